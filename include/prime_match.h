@@ -1,0 +1,281 @@
+/*
+ * prime_match.h — C ABI of the B200-native task<->worker matching engine.
+ *
+ * Drop-in boundary for the Prime Protocol orchestrator's scheduling hot path.
+ * Every entry point below names the reference interface (file:line under the
+ * reference checkout, crates/...) that it replaces or feeds.  Plain pointers
+ * and sizes only; no C++/torch types cross this boundary.  All functions
+ * return 0 (PM_OK) or a negative pm_status, never unwind, never abort
+ * (reference error convention: failures are swallowed to an empty answer and
+ * retried next tick — crates/orchestrator/src/plugins/node_groups/
+ * scheduler_impl.rs:24-30,86-104 and mod.rs:188-194).
+ *
+ * Vocabulary follows the reference: worker == OrchestratorNode
+ * (crates/orchestrator/src/models/node.rs:10-37), ask == one
+ * NodeGroupConfiguration row {min,max,ComputeRequirements}
+ * (crates/orchestrator/src/plugins/node_groups/mod.rs:30-37), evaluation ==
+ * one is_node_compatible_with_config call (mod.rs:206-215).
+ */
+#ifndef PRIME_MATCH_H
+#define PRIME_MATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1u
+#define PM_NONE 0xFFFFFFFFu
+#define PM_COST_INF INT64_MAX
+
+typedef enum pm_status {
+  PM_OK = 0,
+  PM_E_INVALID = -1,     /* bad argument / table shape                        */
+  PM_E_CUDA = -2,        /* CUDA runtime error; text in pm_last_error         */
+  PM_E_NO_DEVICE = -3,   /* no sm_100 device visible: the engine never falls  */
+                         /* back to a CPU path                                */
+  PM_E_STATE = -4,       /* call order violated (e.g. match before tables)    */
+  PM_E_NOMEM = -5,
+  PM_E_UNSUPPORTED = -6,
+  PM_E_PARSE = -7        /* requirement string rejected (node.rs:180-374)     */
+} pm_status;
+
+/* ------------------------------------------------------------------------ */
+/* Worker table: SoA mirror of OrchestratorNode + ComputeSpecs               */
+/* (crates/shared/src/models/node.rs:25-35,72-78,153-157).  Two 16-byte      */
+/* planes so that one worker is exactly two coalesced 128-bit loads.         */
+/* ------------------------------------------------------------------------ */
+enum pm_worker_flag {
+  PM_W_HEALTHY        = 1u << 0,  /* status == NodeStatus::Healthy  (mod.rs:494) */
+  PM_W_P2P            = 1u << 1,  /* p2p_id.is_some()               (mod.rs:495) */
+  PM_W_ASSIGNED       = 1u << 2,  /* present in node_to_group       (mod.rs:496) */
+  PM_W_HAS_SPECS      = 1u << 3,  /* compute_specs.is_some()                     */
+  PM_W_HAS_GPU        = 1u << 4,  /* specs.gpu.is_some()                         */
+  PM_W_HAS_GPU_COUNT  = 1u << 5,
+  PM_W_HAS_GPU_MEM    = 1u << 6,
+  PM_W_HAS_GPU_MODEL  = 1u << 7,
+  PM_W_HAS_CPU        = 1u << 8,  /* specs.cpu.is_some()                         */
+  PM_W_HAS_CPU_CORES  = 1u << 9,
+  PM_W_HAS_RAM        = 1u << 10,
+  PM_W_HAS_STORAGE    = 1u << 11,
+  PM_W_HAS_LOC        = 1u << 12  /* location.is_some()                          */
+};
+
+typedef struct pm_worker_a {   /* plane A, 16 B */
+  uint32_t gpu_count;          /* GpuSpecs.count      */
+  uint32_t gpu_mem_mb;         /* GpuSpecs.memory_mb  */
+  uint32_t model_id;           /* interned GpuSpecs.model (pm_intern_model)  */
+  uint32_t flags;              /* pm_worker_flag bits */
+} pm_worker_a;
+
+typedef struct pm_worker_b {   /* plane B, 16 B */
+  uint32_t cpu_cores;          /* CpuSpecs.cores */
+  uint32_t ram_mb;
+  uint32_t storage_gb;
+  uint32_t ext_ask_price;      /* north-star extension column; 0 when unused */
+} pm_worker_b;
+
+/* ------------------------------------------------------------------------ */
+/* Ask table: one row per enabled NodeGroupConfiguration in PRIORITY ORDER   */
+/* (mod.rs:150-164 then :399-418; pm_sort_configs reproduces it), plus a     */
+/* CSR list of GpuRequirements OR-options (node.rs:58-70).                   */
+/* ------------------------------------------------------------------------ */
+enum pm_ask_flag {
+  PM_A_HAS_REQ        = 1u << 0,  /* compute_requirements.is_some()  (mod.rs:210-214) */
+  PM_A_REQ_CPU        = 1u << 1,  /* requirements.cpu.is_some()      (node.rs:381)    */
+  PM_A_REQ_CPU_CORES  = 1u << 2,  /* requirements.cpu.cores.is_some  (node.rs:533)    */
+  PM_A_REQ_RAM        = 1u << 3,
+  PM_A_REQ_STORAGE    = 1u << 4
+};
+
+typedef struct pm_ask {        /* 32 B */
+  uint32_t flags;              /* pm_ask_flag bits */
+  uint32_t n_opts;             /* requirements.gpu.len() */
+  uint32_t opt_off;            /* first pm_gpu_opt of this ask */
+  uint32_t cpu_cores;
+  uint32_t ram_mb;
+  uint32_t storage_gb;
+  uint32_t min_group_size;
+  uint32_t max_group_size;
+} pm_ask;
+
+enum pm_opt_present {
+  PM_O_COUNT   = 1u << 0,
+  PM_O_MODEL   = 1u << 1,
+  PM_O_MEM     = 1u << 2,   /* memory_mb        */
+  PM_O_MEM_MIN = 1u << 3,   /* memory_mb_min    */
+  PM_O_MEM_MAX = 1u << 4,   /* memory_mb_max    */
+  PM_O_TOT_MIN = 1u << 5,   /* total_memory_min */
+  PM_O_TOT_MAX = 1u << 6    /* total_memory_max */
+};
+
+typedef struct pm_gpu_opt {    /* 32 B; field-for-field GpuRequirements */
+  uint32_t present;            /* pm_opt_present bits */
+  uint32_t count;
+  uint32_t memory_mb;
+  uint32_t memory_mb_min;
+  uint32_t memory_mb_max;
+  uint32_t total_memory_min;
+  uint32_t total_memory_max;
+  uint32_t pattern_id;         /* interned requirement model list (pm_intern_pattern) */
+} pm_gpu_opt;
+
+/* ------------------------------------------------------------------------ */
+/* Host-side model-string interning.  The substring predicate of            */
+/* GpuSpecs::meets (node.rs:463-484) is evaluated once per distinct          */
+/* (requirement pattern, worker model) pair on the host and shipped to the   */
+/* device as a bit table; per (ask, worker) pair the device does one bit     */
+/* test.  No GPU needed for these calls.                                     */
+/* ------------------------------------------------------------------------ */
+typedef struct pm_interner pm_interner;
+pm_interner* pm_interner_create(void);
+void         pm_interner_destroy(pm_interner*);
+uint32_t     pm_intern_model(pm_interner*, const char* spec_model);      /* worker side */
+uint32_t     pm_intern_pattern(pm_interner*, const char* req_model);     /* ask side    */
+/* bits[p * words + (m >> 5)] >> (m & 31) & 1  <=>  pattern p accepts model m;  */
+/* words = ceil(n_models / 32).  Pointer is valid until the next intern call.   */
+int pm_interner_table(pm_interner*, const uint32_t** bits, uint32_t* n_patterns,
+                      uint32_t* n_models, uint32_t* words_per_pattern);
+
+/* ComputeRequirements::from_str (node.rs:180-374).  Fills *ask (flags, n_opts,
+ * cpu/ram/storage; opt_off/min/max untouched) and up to max_opts options.   */
+int pm_parse_requirements(const char* s, pm_interner* interner, pm_ask* ask,
+                          pm_gpu_opt* opts, uint32_t max_opts, uint32_t* n_opts,
+                          char* err, size_t err_len);
+
+/* NodeGroupsPlugin::new_with_policy sort (mod.rs:150-164): stable, by
+ * min_group_size desc, then with-requirements before without.  perm_out[i] =
+ * index of the config that lands at priority i.                             */
+int pm_sort_configs(const uint32_t* min_group_size, const uint8_t* has_requirements,
+                    uint32_t n, uint32_t* perm_out);
+
+/* ------------------------------------------------------------------------ */
+/* Engine                                                                     */
+/* ------------------------------------------------------------------------ */
+typedef struct pm_engine pm_engine;
+
+enum pm_cfg_flag {
+  PM_CFG_TIMING = 1u << 0     /* record CUDA events per kernel class (pm_stats.ms_*) */
+};
+
+typedef struct pm_cfg {
+  uint32_t abi_version;        /* PM_ABI_VERSION */
+  int32_t  device;             /* CUDA ordinal */
+  uint32_t flags;              /* pm_cfg_flag */
+  uint32_t reserved0;
+  uint64_t cost_tile_bytes;    /* HBM budget for one materialised cost tile; 0 = 8 GiB */
+  /* Worker sharding across GPUs: this engine evaluates the        */
+  /* contiguous canonical-order range [shard_first, shard_first+shard_count)   */
+  /* of the global worker table; shard_count == 0 means "all".                 */
+  uint32_t shard_first;
+  uint32_t shard_count;
+  void*    stream;             /* cudaStream_t to launch on (e.g. the caller's torch     */
+                               /* stream, so its CUDA events bracket the kernels);        */
+                               /* NULL = the engine creates a private non-blocking stream */
+} pm_cfg;
+
+int         pm_create(const pm_cfg* cfg, pm_engine** out);
+void        pm_destroy(pm_engine*);
+const char* pm_last_error(const pm_engine*);   /* NULL engine -> last create error */
+
+/* Pinned host memory for the caller-owned tables (SURVEY 8b "ownership").   */
+void* pm_alloc_pinned(size_t bytes);
+void  pm_free_pinned(void*);
+
+/* replaces the per-pass TaskStore/config reads (mod.rs:399-418)             */
+int pm_set_asks(pm_engine*, const pm_ask* asks, uint32_t n_asks,
+                const pm_gpu_opt* opts, uint32_t n_opts);
+int pm_set_model_table(pm_engine*, const uint32_t* bits, uint32_t n_patterns,
+                       uint32_t n_models, uint32_t words_per_pattern);
+/* replaces NodeStore::get_nodes per pass (store/domains/node_store.rs:163-209);
+ * row index == canonical order (SURVEY 8c determinisation rule 1).          */
+int pm_set_worker_count(pm_engine*, uint32_t n_workers);
+int pm_upsert_workers(pm_engine*, const pm_worker_a* a, const pm_worker_b* b,
+                      uint32_t first, uint32_t n);
+/* NodeLocation.latitude/longitude (node.rs:543-550); only read in proximity mode */
+int pm_set_worker_locations(pm_engine*, const double* lat, const double* lon,
+                            uint32_t first, uint32_t n);
+/* rank of the worker's address string in BTreeSet<String> order
+ * (mod.rs:63-69,424-434); decides member order inside a group               */
+int pm_set_worker_addr_rank(pm_engine*, const uint32_t* rank, uint32_t first, uint32_t n);
+/* status / assigned deltas (status_update_impl.rs:8-39, mod.rs:1423-1487)   */
+int pm_set_flags(pm_engine*, const uint32_t* idx, const uint32_t* flags, uint32_t n);
+
+enum pm_mode {
+  PM_MODE_FIRST_FIT = 0,   /* try_form_new_groups, ProximityOptimizationPolicy{enabled:false} */
+  PM_MODE_PROXIMITY = 1,   /* ... {enabled:true}  (mod.rs:524-552), the reference default     */
+  PM_MODE_AUCTION   = 2    /* north-star extension (price-capped e-scaling auction); no       */
+                           /* reference counterpart, self-oracle only                         */
+};
+enum pm_path {
+  PM_PATH_MATERIALIZED = 0,      /* build int64 cost tile in HBM, then argmin over it */
+  PM_PATH_FUSED        = 1u << 8 /* evaluate + reduce on chip, matrix never written   */
+};
+
+typedef struct pm_stats {
+  uint64_t evals;            /* predicate evaluations executed on the device        */
+  uint64_t cost_bytes_written;
+  uint64_t cost_bytes_read;
+  uint32_t n_tiles;
+  uint32_t n_launches;       /* kernels of this library launched by the last match  */
+  uint32_t n_bumped;         /* workers displaced by an under-filled tail group     */
+  uint32_t n_rounds;         /* auction rounds (extension mode)                     */
+  float ms_build;            /* sum over launches, CUDA events on the engine stream */
+  float ms_argmin;
+  float ms_fused;
+  float ms_resolve;
+  float ms_total;
+  uint32_t n_build_launches;
+  uint32_t n_argmin_launches;
+  uint32_t n_fused_launches;
+  uint32_t reserved;
+} pm_stats;
+
+typedef struct pm_result {
+  uint32_t n_workers;
+  uint32_t n_asks;
+  uint32_t n_groups;
+  uint32_t n_members;
+  /* all arrays are engine-owned pinned host memory, valid until the next
+   * pm_fetch_result / pm_destroy on this engine                             */
+  const uint32_t* worker_group;   /* [n_workers] group index or PM_NONE                 */
+  const uint32_t* worker_ask;     /* [n_workers] ask (config) index or PM_NONE          */
+  const uint32_t* group_ask;      /* [n_groups]  configuration of the group             */
+  const uint32_t* group_off;      /* [n_groups+1] CSR offsets into group_members        */
+  const uint32_t* group_members;  /* worker indices, BTreeSet (addr_rank) order         */
+  const int64_t*  ask_best;       /* [n_asks] row argmin: cost<<32 | worker, PM_COST_INF */
+  const uint32_t* ask_count;      /* [n_asks] feasible candidate workers of the ask      */
+  pm_stats stats;
+} pm_result;
+
+/* The management pass (replaces try_form_new_groups, mod.rs:478-628).
+ * mode = pm_mode | pm_path.  Device compute only: tables must be resident.  */
+int pm_match(pm_engine*, uint32_t mode);
+/* D2H of the last match into engine-owned pinned buffers.                   */
+int pm_fetch_result(pm_engine*, pm_result* out);
+int pm_get_stats(const pm_engine*, pm_stats* out);
+/* Build the cost rows of asks [t0, t0+nt) against this engine's worker range and
+ * copy them to host_out[nt * n_cols] (row-major, n_cols = shard width): the
+ * materialised matrix itself, for external solvers and for bit-exact checks.  */
+int pm_build_cost_tile(pm_engine*, uint32_t t0, uint32_t nt, int64_t* host_out);
+
+/* Multi-GPU plumbing: between pm_match_local and pm_match_finish
+ * the host all-reduces/all-gathers these device buffers with NCCL.          */
+enum pm_buffer {
+  PM_BUF_WORKER_FIRST_ASK = 0,  /* uint32[n_workers] global; only the shard range is written */
+  PM_BUF_ASK_BEST         = 1,  /* int64 [n_asks] packed row argmin (allreduce MIN)          */
+  PM_BUF_ASK_COUNT        = 2   /* uint32[n_asks] (allreduce SUM)                            */
+};
+int pm_match_local(pm_engine*, uint32_t mode);    /* evaluation over this shard only */
+int pm_match_finish(pm_engine*, uint32_t mode);   /* resolution sweep over the global arrays */
+int pm_device_buffer(pm_engine*, uint32_t which, void** dev_ptr, size_t* bytes);
+int pm_stream_sync(pm_engine*);
+
+uint32_t pm_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIME_MATCH_H */

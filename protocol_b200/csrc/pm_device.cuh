@@ -1,0 +1,152 @@
+// pm_device.cuh — device-side table layouts and the feasibility predicate.
+//
+// The predicate restates, on the SoA tables of include/prime_match.h,
+//   NodeGroupsPlugin::is_node_compatible_with_config
+//     (crates/orchestrator/src/plugins/node_groups/mod.rs:206-215)
+//   ComputeSpecs::meets / GpuSpecs::meets / CpuSpecs::meets
+//     (crates/shared/src/models/node.rs:377-541)
+// with every Option<> folded into (a) one presence-mask test and (b) unsigned
+// interval compares, so that one (ask, worker) evaluation is a handful of
+// integer instructions and no string work (the model clause, node.rs:463-484,
+// is a bit test against the host-interned table).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/prime_match.h"
+
+namespace pm {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr long long kInf = 0x7FFFFFFFFFFFFFFFll;
+
+// Device form of one ask row (32 B).  `need` = presence bits the worker must
+// carry: HAS_SPECS when the config has requirements (mod.rs:210-214), HAS_CPU /
+// HAS_CPU_CORES / HAS_RAM / HAS_STORAGE for the scalar clauses (node.rs:381-418),
+// HAS_GPU when requirements.gpu is non-empty (node.rs:420-425).  Thresholds of
+// absent clauses are 0 so the unsigned >= compares pass.
+struct __align__(16) DevAsk {
+  uint32_t need;
+  uint32_t n_opts;
+  uint32_t opt_off;
+  uint32_t cpu_cores;
+  uint32_t ram_mb;
+  uint32_t storage_gb;
+  uint32_t pad0, pad1;
+};
+
+// Device form of one GpuRequirements option (32 B).  memory_mb / memory_mb_min
+// fold into mem_lo (both are "spec >= req", node.rs:487-498), memory_mb_max into
+// mem_hi (:499-503); `need` carries HAS_GPU_MODEL / HAS_GPU_MEM when the clause
+// is present (a None spec field fails a present clause, is_none_or).
+struct __align__(16) DevOpt {
+  uint32_t need;
+  uint32_t count_mask;   // 0xFFFFFFFF when gpu:count is required, else 0
+  uint32_t count;
+  uint32_t mem_lo, mem_hi;
+  uint32_t tot_lo, tot_hi;
+  uint32_t pattern_row;  // row in the device bit table; row 0 is all-ones (no model clause)
+};
+
+// One worker held in registers.
+struct WorkerReg {
+  uint32_t flags;
+  uint32_t count_eff;  // None behaves exactly like Some(0) in the count clause (node.rs:447-461)
+  uint32_t mem_eff;
+  uint32_t tot;        // count * memory_mb, wrapping (release-build u32 multiply, node.rs:509,518)
+  uint32_t tot_valid;  // both count and memory_mb are Some (node.rs:506-507,515-516)
+  uint32_t cores, ram, storage;
+  uint32_t mword, mbit;
+  uint32_t price;
+  bool candidate;      // Healthy && p2p_id.is_some() && !assigned (mod.rs:492-497)
+};
+
+__device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
+  WorkerReg w;
+  w.flags = a.w;
+  const bool hc = (a.w & PM_W_HAS_GPU_COUNT) != 0, hm = (a.w & PM_W_HAS_GPU_MEM) != 0;
+  w.count_eff = hc ? a.x : 0u;
+  w.mem_eff = hm ? a.y : 0u;
+  w.tot = a.x * a.y;
+  w.tot_valid = (hc && hm) ? 1u : 0u;
+  w.cores = b.x;
+  w.ram = b.y;
+  w.storage = b.z;
+  w.price = b.w;
+  const uint32_t mid = (a.w & PM_W_HAS_GPU_MODEL) ? a.z : 0u;
+  w.mword = mid >> 5;
+  w.mbit = mid & 31u;
+  w.candidate = (a.w & (PM_W_HEALTHY | PM_W_P2P | PM_W_ASSIGNED)) == (PM_W_HEALTHY | PM_W_P2P);
+  return w;
+}
+
+__device__ __forceinline__ WorkerReg null_worker() {
+  WorkerReg w;
+  w.flags = 0; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_valid = 0;
+  w.cores = 0; w.ram = 0; w.storage = 0; w.mword = 0; w.mbit = 0; w.price = 0;
+  w.candidate = false;
+  return w;
+}
+
+// GpuSpecs::meets for one option (node.rs:443-527).
+__device__ __forceinline__ bool opt_meets(const DevOpt& q, const WorkerReg& w,
+                                          const uint32_t* __restrict__ bits, uint32_t words) {
+  bool ok = (w.flags & q.need) == q.need;
+  ok &= (w.count_eff & q.count_mask) == q.count;
+  ok &= (w.mem_eff >= q.mem_lo) & (w.mem_eff <= q.mem_hi);
+  ok &= (w.tot_valid == 0u) | ((w.tot >= q.tot_lo) & (w.tot <= q.tot_hi));
+  if (q.pattern_row != 0u)  // uniform across the warp in the hot kernels
+    ok &= ((bits[size_t(q.pattern_row) * words + w.mword] >> w.mbit) & 1u) != 0u;
+  return ok;
+}
+
+// is_node_compatible_with_config + ComputeSpecs::meets.
+__device__ __forceinline__ bool ask_meets(const DevAsk& a, const DevOpt* __restrict__ opts,
+                                          const WorkerReg& w, const uint32_t* __restrict__ bits,
+                                          uint32_t words) {
+  bool ok = ((w.flags & a.need) == a.need) & (w.cores >= a.cpu_cores) & (w.ram >= a.ram_mb) &
+            (w.storage >= a.storage_gb);
+  if (a.n_opts != 0u) {
+    bool any = false;
+    for (uint32_t o = 0; o < a.n_opts; ++o) any |= opt_meets(opts[a.opt_off + o], w, bits, words);
+    ok &= any;
+  }
+  return ok;
+}
+
+// ---- Hopper/Blackwell bulk async copy (TMA, 1-D) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+}  // namespace pm

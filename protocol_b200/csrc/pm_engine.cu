@@ -1,0 +1,790 @@
+// pm_engine.cu — the engine behind include/prime_match.h.
+//
+// One engine = one CUDA device + one stream.  pm_match() is the management pass
+// that replaces NodeGroupsPlugin::try_form_new_groups (reference
+// crates/orchestrator/src/plugins/node_groups/mod.rs:478-628): for tiles of asks
+// (configurations, priority order) x all candidate workers it builds the int64
+// cost matrix in HBM, reduces it (per-ask argmin, per-worker first feasible ask)
+// and then runs the resolution sweep that reproduces the reference's sequential
+// greedy allocation bit for bit.  There is no CPU fallback: without an sm_100
+// device pm_create fails with PM_E_NO_DEVICE.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pm_kernels.cuh"
+
+struct pm_engine;
+
+namespace {
+
+std::string g_create_error;
+
+template <class T> struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (want == 0) want = 1;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+template <class T> struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n && p) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    if (want == 0) want = 1;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+struct pm_engine {
+  pm_cfg cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::mutex mu;
+
+  // tables
+  uint32_t n_workers = 0, n_asks = 0, n_opts = 0;
+  uint32_t n_patterns = 0, n_models = 0, words = 1;
+  uint32_t max_pattern_row = 0;
+  bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
+  bool all_solo = true;  // every ask has min == max == 1
+  DevBuf<uint4> wa, wb;
+  DevBuf<double> lat, lon;
+  DevBuf<uint32_t> addr_rank;
+  DevBuf<pm::DevAsk> asks;
+  DevBuf<pm::DevOpt> opts;
+  DevBuf<uint32_t> amin, amax, bits;
+  DevBuf<uint32_t> scratch_idx, scratch_flags;
+
+  // evaluation
+  DevBuf<long long> cost;
+  DevBuf<uint32_t> first_ask, ask_count;
+  DevBuf<long long> ask_best;
+
+  // resolution
+  DevBuf<uint32_t> keys, keys_sorted, iota, order, hist, seg_start, ngroups, group_base;
+  DevBuf<uint32_t> base_len, xhead, xnext, xcount, popped, counters;  // counters: [0]=any_bad [1]=n_bumped
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<uint32_t> worker_group, worker_ask, group_ask, group_off, members;
+  PinBuf<uint32_t> h_scalars;  // small D2H mailbox
+
+  // result (pinned host)
+  PinBuf<uint32_t> r_worker_group, r_worker_ask, r_group_ask, r_group_off, r_members, r_ask_count;
+  PinBuf<long long> r_ask_best;
+  uint32_t n_groups = 0, n_assigned = 0;
+  bool matched = false, local_done = false;
+
+  pm_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool own_stream = true;
+  struct TimedRegion { cudaEvent_t a, b; float* acc; };
+  std::vector<cudaEvent_t> ev_pool;     // grows on demand, reused across matches
+  std::vector<TimedRegion> ev_pending;
+  size_t ev_used = 0;
+  cudaEvent_t take_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t ev = nullptr;
+      if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+      ev_pool.push_back(ev);
+    }
+    return ev_pool[ev_used++];
+  }
+  void resolve_timers() {  // caller has synchronised the stream
+    for (auto& r : ev_pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) *r.acc += ms;
+    }
+    ev_pending.clear();
+    ev_used = 0;
+  }
+
+  int fail(pm_status st, const std::string& msg) {
+    err = msg;
+    return st;
+  }
+};
+
+#define PM_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      return e->fail(PM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));    \
+    }                                                                                   \
+  } while (0)
+
+#define PM_LAUNCH_CHECK(name)                                                           \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return e->fail(PM_E_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+    ++e->stats.n_launches;                                                              \
+  } while (0)
+
+namespace {
+
+// Per-launch CUDA-event timing without host synchronisation: start/stop events
+// are recorded on the engine stream around a region and resolved in one go at
+// the end of the match (which synchronises anyway to read the group count).
+struct Timer {
+  pm_engine* e;
+  float* acc;
+  bool on;
+  size_t slot = 0;
+  Timer(pm_engine* e_, float* acc_);
+  void stop();
+};
+
+Timer::Timer(pm_engine* e_, float* acc_) : e(e_), acc(acc_), on((e_->cfg.flags & PM_CFG_TIMING) != 0) {
+  if (!on) return;
+  cudaEvent_t a = e->take_event(), b = e->take_event();
+  if (!a || !b) { on = false; return; }
+  slot = e->ev_pending.size();
+  e->ev_pending.push_back({a, b, acc});
+  cudaEventRecord(a, e->stream);
+}
+void Timer::stop() {
+  if (!on) return;
+  cudaEventRecord(e->ev_pending[slot].b, e->stream);
+  on = false;
+}
+
+pm::EvalParams eval_params(pm_engine* e) {
+  pm::EvalParams p;
+  p.wa = e->wa.p;
+  p.wb = e->wb.p;
+  p.asks = e->asks.p;
+  p.opts = e->opts.p;
+  p.bits = e->bits.p;
+  p.words = e->words;
+  p.n_workers = e->n_workers;
+  p.n_asks = e->n_asks;
+  p.n_opts = e->n_opts;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* pm_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void pm_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int pm_create(const pm_cfg* cfg, pm_engine** out) {
+  if (!cfg || !out) {
+    g_create_error = "pm_create: null argument";
+    return PM_E_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != PM_ABI_VERSION) {
+    g_create_error = "pm_create: ABI version mismatch";
+    return PM_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "pm_create: no CUDA device visible (this engine has no CPU path)";
+    return PM_E_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "pm_create: device ordinal out of range";
+    return PM_E_INVALID;
+  }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) {
+    cudaGetLastError();
+    g_create_error = "pm_create: device is not sm_100 or newer (kernels are built for sm_100a only)";
+    return PM_E_NO_DEVICE;
+  }
+  pm_engine* e = new (std::nothrow) pm_engine;
+  if (!e) return PM_E_NOMEM;
+  e->cfg = *cfg;
+  if (e->cfg.cost_tile_bytes == 0) e->cfg.cost_tile_bytes = 8ull << 30;
+  e->device = cfg->device;
+  bool ok = cudaSetDevice(e->device) == cudaSuccess;
+  if (ok && cfg->stream) {
+    e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
+    e->own_stream = false;
+  } else if (ok) {
+    ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+  }
+  ok = ok &&
+            cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
+            e->h_scalars.ensure(16) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("pm_create: ") + cudaGetErrorString(cudaGetLastError());
+    delete e;
+    return PM_E_CUDA;
+  }
+  *out = e;
+  return PM_OK;
+}
+
+void pm_destroy(pm_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  e->wa.release(); e->wb.release(); e->lat.release(); e->lon.release(); e->addr_rank.release();
+  e->asks.release(); e->opts.release(); e->amin.release(); e->amax.release(); e->bits.release();
+  e->scratch_idx.release(); e->scratch_flags.release();
+  e->cost.release(); e->first_ask.release(); e->ask_count.release(); e->ask_best.release();
+  e->keys.release(); e->keys_sorted.release(); e->iota.release(); e->order.release();
+  e->hist.release(); e->seg_start.release(); e->ngroups.release(); e->group_base.release();
+  e->base_len.release(); e->xhead.release(); e->xnext.release(); e->xcount.release();
+  e->popped.release(); e->counters.release(); e->cub_tmp.release();
+  e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
+  e->group_off.release(); e->members.release(); e->h_scalars.release();
+  e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
+  e->r_group_off.release(); e->r_members.release(); e->r_ask_count.release(); e->r_ask_best.release();
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* pm_last_error(const pm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                uint32_t n_opts) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if ((n_asks && !asks) || (n_opts && !opts)) return e->fail(PM_E_INVALID, "pm_set_asks: null table");
+  if (n_asks >= (1u << 30)) return e->fail(PM_E_INVALID, "pm_set_asks: too many asks");
+  std::vector<pm::DevAsk> da(n_asks);
+  std::vector<pm::DevOpt> dopt;
+  std::vector<uint32_t> mn(n_asks), mx(n_asks);
+  dopt.reserve(n_opts);
+  uint32_t max_row = 0;
+  bool solo = true;
+  for (uint32_t t = 0; t < n_asks; ++t) {
+    const pm_ask& a = asks[t];
+    // NodeGroupConfiguration::is_valid, mod.rs:55-60 (the reference panics at construction)
+    if (a.max_group_size < a.min_group_size)
+      return e->fail(PM_E_INVALID, "pm_set_asks: max_group_size < min_group_size (Plugin configuration is invalid)");
+    if ((uint64_t)a.opt_off + a.n_opts > n_opts)
+      return e->fail(PM_E_INVALID, "pm_set_asks: option range out of bounds");
+    pm::DevAsk d{};
+    const bool has_req = (a.flags & PM_A_HAS_REQ) != 0;
+    uint32_t need = 0;
+    if (has_req) {
+      need |= PM_W_HAS_SPECS;
+      if (a.flags & PM_A_REQ_CPU) need |= PM_W_HAS_CPU;
+      if ((a.flags & PM_A_REQ_CPU) && (a.flags & PM_A_REQ_CPU_CORES)) {
+        need |= PM_W_HAS_CPU_CORES;
+        d.cpu_cores = a.cpu_cores;
+      }
+      if (a.flags & PM_A_REQ_RAM) { need |= PM_W_HAS_RAM; d.ram_mb = a.ram_mb; }
+      if (a.flags & PM_A_REQ_STORAGE) { need |= PM_W_HAS_STORAGE; d.storage_gb = a.storage_gb; }
+      if (a.n_opts) need |= PM_W_HAS_GPU;
+      d.n_opts = a.n_opts;
+    }
+    // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
+    if (a.max_group_size == 0) need = 0xFFFFFFFFu;
+    d.need = need;
+    d.opt_off = (uint32_t)dopt.size();
+    for (uint32_t o = 0; has_req && o < a.n_opts; ++o) {
+      const pm_gpu_opt& q = opts[a.opt_off + o];
+      pm::DevOpt x{};
+      x.count_mask = (q.present & PM_O_COUNT) ? 0xFFFFFFFFu : 0u;
+      x.count = (q.present & PM_O_COUNT) ? q.count : 0u;
+      x.mem_lo = 0; x.mem_hi = 0xFFFFFFFFu; x.tot_lo = 0; x.tot_hi = 0xFFFFFFFFu;
+      if (q.present & PM_O_MEM) x.mem_lo = std::max(x.mem_lo, q.memory_mb);
+      if (q.present & PM_O_MEM_MIN) x.mem_lo = std::max(x.mem_lo, q.memory_mb_min);
+      if (q.present & PM_O_MEM_MAX) x.mem_hi = q.memory_mb_max;
+      if (q.present & (PM_O_MEM | PM_O_MEM_MIN | PM_O_MEM_MAX)) x.need |= PM_W_HAS_GPU_MEM;
+      if (q.present & PM_O_TOT_MIN) x.tot_lo = q.total_memory_min;
+      if (q.present & PM_O_TOT_MAX) x.tot_hi = q.total_memory_max;
+      if (q.present & PM_O_MODEL) {
+        x.need |= PM_W_HAS_GPU_MODEL;
+        x.pattern_row = q.pattern_id + 1;
+        max_row = std::max(max_row, x.pattern_row);
+      }
+      dopt.push_back(x);
+    }
+    da[t] = d;
+    mn[t] = a.min_group_size;
+    mx[t] = a.max_group_size;
+    if (!(a.min_group_size == 1 && a.max_group_size == 1)) solo = false;
+  }
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->asks.ensure(n_asks));
+  PM_CUDA(e->opts.ensure(dopt.size()));
+  PM_CUDA(e->amin.ensure(n_asks));
+  PM_CUDA(e->amax.ensure(n_asks));
+  if (n_asks) {
+    PM_CUDA(cudaMemcpyAsync(e->asks.p, da.data(), n_asks * sizeof(pm::DevAsk), cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->amin.p, mn.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->amax.p, mx.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (!dopt.empty())
+    PM_CUDA(cudaMemcpyAsync(e->opts.p, dopt.data(), dopt.size() * sizeof(pm::DevOpt), cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));  // staging vectors die here
+  e->n_asks = n_asks;
+  e->n_opts = (uint32_t)dopt.size();
+  e->max_pattern_row = max_row;
+  e->all_solo = solo;
+  e->have_asks = true;
+  e->matched = e->local_done = false;
+  return PM_OK;
+}
+
+int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, uint32_t n_models,
+                       uint32_t words) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (words == 0) words = 1;
+  if (n_patterns && !bits) return e->fail(PM_E_INVALID, "pm_set_model_table: null table");
+  if ((uint64_t)words * 32 < n_models) return e->fail(PM_E_INVALID, "pm_set_model_table: words too small");
+  std::vector<uint32_t> tbl((size_t)(n_patterns + 1) * words, 0u);
+  for (uint32_t i = 0; i < words; ++i) tbl[i] = 0xFFFFFFFFu;  // row 0: no model clause
+  if (n_patterns) std::memcpy(tbl.data() + words, bits, (size_t)n_patterns * words * 4);
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->bits.ensure(tbl.size()));
+  PM_CUDA(cudaMemcpyAsync(e->bits.p, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  e->n_patterns = n_patterns;
+  e->n_models = n_models;
+  e->words = words;
+  e->have_bits = true;
+  e->matched = e->local_done = false;
+  return PM_OK;
+}
+
+int pm_set_worker_count(pm_engine* e, uint32_t n_workers) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PM_CUDA(cudaSetDevice(e->device));
+  if (n_workers > e->wa.n || !e->wa.p) {
+    // grow, preserving nothing: callers upsert after (re)sizing
+    PM_CUDA(e->wa.ensure(n_workers));
+    PM_CUDA(e->wb.ensure(n_workers));
+  }
+  PM_CUDA(cudaMemsetAsync(e->wa.p, 0, (size_t)std::max<uint32_t>(n_workers, 1) * 16, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->wb.p, 0, (size_t)std::max<uint32_t>(n_workers, 1) * 16, e->stream));
+  e->n_workers = n_workers;
+  e->have_workers = true;
+  e->have_loc = e->have_rank = false;
+  e->matched = e->local_done = false;
+  return PM_OK;
+}
+
+int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, uint32_t first,
+                      uint32_t n) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_upsert_workers: call pm_set_worker_count first");
+  if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_upsert_workers: range out of bounds");
+  if (n && (!a || !b)) return e->fail(PM_E_INVALID, "pm_upsert_workers: null plane");
+  PM_CUDA(cudaSetDevice(e->device));
+  if (n) {
+    PM_CUDA(cudaMemcpyAsync(e->wa.p + first, a, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->wb.p + first, b, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  }
+  e->matched = e->local_done = false;
+  return PM_OK;
+}
+
+int pm_set_worker_locations(pm_engine* e, const double* lat, const double* lon, uint32_t first,
+                            uint32_t n) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_locations: no worker table");
+  if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_set_worker_locations: range");
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->lat.ensure(e->n_workers));
+  PM_CUDA(e->lon.ensure(e->n_workers));
+  if (n) {
+    PM_CUDA(cudaMemcpyAsync(e->lat.p + first, lat, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->lon.p + first, lon, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  }
+  e->have_loc = true;
+  return PM_OK;
+}
+
+int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, uint32_t n) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_addr_rank: no worker table");
+  if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_set_worker_addr_rank: range");
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->addr_rank.ensure(e->n_workers));
+  if (n) PM_CUDA(cudaMemcpyAsync(e->addr_rank.p + first, rank, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  e->have_rank = true;
+  return PM_OK;
+}
+
+int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint32_t n) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_flags: no worker table");
+  if (n == 0) return PM_OK;
+  if (!idx || !flags) return e->fail(PM_E_INVALID, "pm_set_flags: null");
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->scratch_idx.ensure(n));
+  PM_CUDA(e->scratch_flags.ensure(n));
+  PM_CUDA(cudaMemcpyAsync(e->scratch_idx.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->scratch_flags.p, flags, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  pm::pm_scatter_flags<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->wa.p, e->scratch_idx.p, e->scratch_flags.p, n, e->n_workers);
+  PM_LAUNCH_CHECK("pm_scatter_flags");
+  e->matched = e->local_done = false;
+  return PM_OK;
+}
+
+// ------------------------------------------------------------------ evaluation
+static int match_local_locked(pm_engine* e, uint32_t mode) {
+  if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_match: worker and ask tables must be set first");
+  if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
+    return e->fail(PM_E_STATE, "pm_match: an ask references a model pattern missing from the model table");
+  const uint32_t base_mode = mode & 0xFFu;
+  if (base_mode == PM_MODE_AUCTION) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is not built yet");
+  if (base_mode != PM_MODE_FIRST_FIT && base_mode != PM_MODE_PROXIMITY) return e->fail(PM_E_INVALID, "pm_match: unknown mode");
+  if (base_mode == PM_MODE_PROXIMITY && !e->all_solo)
+    return e->fail(PM_E_UNSUPPORTED, "pm_match: proximity mode currently requires min_group_size == max_group_size == 1");
+  PM_CUDA(cudaSetDevice(e->device));
+  const uint32_t W = e->n_workers, T = e->n_asks;
+  const uint32_t w0 = e->cfg.shard_first;
+  const uint32_t nw = e->cfg.shard_count ? e->cfg.shard_count : (W > w0 ? W - w0 : 0);
+  if ((uint64_t)w0 + nw > W) return e->fail(PM_E_INVALID, "pm_match: shard range exceeds the worker table");
+  if (!e->have_bits) {  // tables without any model clause: a one-row all-ones table
+    PM_CUDA(e->bits.ensure(1));
+    PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
+    e->words = 1;
+  }
+
+  e->stats = pm_stats{};
+  e->ev_pending.clear();
+  e->ev_used = 0;
+  const bool timing = (e->cfg.flags & PM_CFG_TIMING) != 0;
+  if (timing) PM_CUDA(cudaEventRecord(e->ev0, e->stream));
+
+  PM_CUDA(e->first_ask.ensure(W));
+  PM_CUDA(e->ask_best.ensure(T));
+  PM_CUDA(e->ask_count.ensure(T));
+  PM_CUDA(cudaMemsetAsync(e->first_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->ask_count.p, 0, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
+  if (T) {
+    pm::pm_fill_i64<<<std::min(blocks_for(T, 256), 1184u), 256, 0, e->stream>>>(e->ask_best.p, pm::kInf, T);
+    PM_LAUNCH_CHECK("pm_fill_i64");
+  }
+
+  if (T && nw) {
+    pm::EvalParams p = eval_params(e);
+    if (mode & PM_PATH_FUSED) {
+      Timer tm(e, &e->stats.ms_fused);
+      const uint32_t rows_per_launch = 65535u * pm::kFusedRows;
+      for (uint32_t t0 = 0; t0 < T; t0 += rows_per_launch) {
+        const uint32_t nt = std::min(rows_per_launch, T - t0);
+        dim3 grid(blocks_for(nw, pm::kBuildCols), blocks_for(nt, pm::kFusedRows));
+        pm::pm_fused_eval<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+        PM_LAUNCH_CHECK("pm_fused_eval");
+        ++e->stats.n_fused_launches;
+      }
+      tm.stop();
+      e->stats.n_tiles = 1;
+    } else {
+      const size_t ld = ((size_t)nw + 1) & ~(size_t)1;
+      uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
+      if (rows == 0) rows = 1;
+      rows = std::min<uint64_t>(rows, T);
+      rows = std::min<uint64_t>(rows, 65535ull * pm::kArgRows);
+      cudaError_t ce = e->cost.ensure((size_t)rows * ld);
+      if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return e->fail(PM_E_NOMEM, "pm_match: cannot allocate the cost tile; lower pm_cfg.cost_tile_bytes");
+      }
+      for (uint32_t t0 = 0; t0 < T; t0 += (uint32_t)rows) {
+        const uint32_t nt = (uint32_t)std::min<uint64_t>(rows, T - t0);
+        {
+          Timer tm(e, &e->stats.ms_build);
+          dim3 grid(blocks_for(ld, pm::kBuildCols), blocks_for(nt, pm::kBuildRows));
+          pm::pm_build_cost<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+          PM_LAUNCH_CHECK("pm_build_cost");
+          tm.stop();
+          ++e->stats.n_build_launches;
+        }
+        {
+          Timer tm(e, &e->stats.ms_argmin);
+          dim3 grid(blocks_for(ld, pm::kArgCols), blocks_for(nt, pm::kArgRows));
+          pm::pm_argmin<<<grid, pm::kArgThreads, 0, e->stream>>>(e->cost.p, ld, nt, t0, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+          PM_LAUNCH_CHECK("pm_argmin");
+          tm.stop();
+          ++e->stats.n_argmin_launches;
+        }
+        ++e->stats.n_tiles;
+        e->stats.cost_bytes_written += (uint64_t)nt * ld * 8;
+        e->stats.cost_bytes_read += (uint64_t)nt * ld * 8;
+      }
+    }
+    e->stats.evals = (uint64_t)T * nw;
+  }
+  e->local_done = true;
+  e->matched = false;
+  return PM_OK;
+}
+
+// ------------------------------------------------------------------ resolution
+static int sort_and_scan(pm_engine* e, uint32_t n_bins, uint32_t shift) {
+  const uint32_t W = e->n_workers;
+  PM_CUDA(cudaMemsetAsync(e->hist.p, 0, ((size_t)n_bins + 1) * 4, e->stream));
+  if (W) {
+    pm::pm_make_keys<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->first_ask.p, e->wa.p, W, shift, e->keys.p, e->hist.p);
+    PM_LAUNCH_CHECK("pm_make_keys");
+  }
+  size_t tmp_scan = 0, tmp_sort = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, e->hist.p, e->seg_start.p, (int)(n_bins + 1), e->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, e->keys.p, e->keys_sorted.p, e->iota.p, e->order.p, (int)W, 0, 32, e->stream);
+  size_t tmp = std::max(tmp_scan, tmp_sort);
+  PM_CUDA(e->cub_tmp.ensure(tmp));
+  PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->hist.p, e->seg_start.p, (int)(n_bins + 1), e->stream));
+  if (W) PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->keys.p, e->keys_sorted.p, e->iota.p, e->order.p, (int)W, 0, 32, e->stream));
+  return PM_OK;
+}
+
+static int match_finish_locked(pm_engine* e, uint32_t mode) {
+  if (!e->local_done) return e->fail(PM_E_STATE, "pm_match_finish: pm_match_local has not run");
+  PM_CUDA(cudaSetDevice(e->device));
+  const uint32_t base_mode = mode & 0xFFu;
+  const uint32_t W = e->n_workers, T = e->n_asks;
+  const uint32_t shift = (base_mode == PM_MODE_PROXIMITY) ? 1u : 0u;
+  const uint32_t n_bins = T << shift;
+  Timer tm(e, &e->stats.ms_resolve);
+
+  PM_CUDA(e->keys.ensure(W)); PM_CUDA(e->keys_sorted.ensure(W)); PM_CUDA(e->iota.ensure(W));
+  PM_CUDA(e->order.ensure(W)); PM_CUDA(e->hist.ensure((size_t)n_bins + 1));
+  PM_CUDA(e->seg_start.ensure((size_t)n_bins + 1)); PM_CUDA(e->ngroups.ensure((size_t)n_bins + 1));
+  PM_CUDA(e->group_base.ensure((size_t)n_bins + 1));
+  PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(W));
+  PM_CUDA(cudaMemsetAsync(e->counters.p, 0, 16 * 4, e->stream));
+  if (W) {
+    pm::pm_iota_u32<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->iota.p, W);
+    PM_LAUNCH_CHECK("pm_iota_u32");
+  }
+  int rc = sort_and_scan(e, n_bins, shift);
+  if (rc != PM_OK) return rc;
+
+  if (shift == 0 && T && !e->all_solo) {
+    pm::pm_check_tails<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, T, e->counters.p);
+    PM_LAUNCH_CHECK("pm_check_tails");
+    PM_CUDA(cudaMemcpyAsync(e->h_scalars.p, e->counters.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_scalars.p[0]) {
+      PM_CUDA(e->base_len.ensure(T)); PM_CUDA(e->xhead.ensure(T)); PM_CUDA(e->xcount.ensure(T));
+      PM_CUDA(e->xnext.ensure(W)); PM_CUDA(e->popped.ensure(W));
+      PM_CUDA(cudaMemcpyAsync(e->base_len.p, e->hist.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, e->stream));
+      PM_CUDA(cudaMemsetAsync(e->xhead.p, 0xFF, (size_t)T * 4, e->stream));
+      PM_CUDA(cudaMemsetAsync(e->xcount.p, 0, (size_t)T * 4, e->stream));
+      pm::SweepParams sp;
+      sp.ev = eval_params(e);
+      sp.cur = e->first_ask.p; sp.base_len = e->base_len.p; sp.seg_start = e->seg_start.p;
+      sp.order = e->order.p; sp.xhead = e->xhead.p; sp.xnext = e->xnext.p; sp.xcount = e->xcount.p;
+      sp.amin = e->amin.p; sp.amax = e->amax.p; sp.popped = e->popped.p; sp.n_bumped = e->counters.p + 1;
+      pm::pm_sweep<<<1, 1024, 0, e->stream>>>(sp);
+      PM_LAUNCH_CHECK("pm_sweep");
+      rc = sort_and_scan(e, n_bins, shift);
+      if (rc != PM_OK) return rc;
+    }
+  }
+
+  if (n_bins) {
+    pm::pm_count_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, n_bins, shift, e->ngroups.p);
+    PM_LAUNCH_CHECK("pm_count_groups");
+  }
+  PM_CUDA(cudaMemsetAsync(e->ngroups.p + n_bins, 0, 4, e->stream));
+  {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream);
+    PM_CUDA(e->cub_tmp.ensure(tmp));
+    PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream));
+  }
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 1, e->group_base.p + n_bins, 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 2, e->seg_start.p + n_bins, 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 3, e->counters.p + 1, 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  const uint32_t G = e->h_scalars.p[1], n_assigned = e->h_scalars.p[2];
+  e->stats.n_bumped = e->h_scalars.p[3];
+  e->n_groups = G;
+  e->n_assigned = n_assigned;
+
+  PM_CUDA(e->group_ask.ensure((size_t)G + 1));
+  PM_CUDA(e->group_off.ensure((size_t)G + 1));
+  PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+  if (n_assigned) {
+    pm::pm_emit_workers<<<blocks_for(n_assigned, 256), 256, 0, e->stream>>>(
+        e->keys_sorted.p, e->order.p, n_assigned, e->hist.p, e->seg_start.p, e->group_base.p, e->amin.p,
+        e->amax.p, shift, e->worker_group.p, e->worker_ask.p, e->group_ask.p, e->group_off.p);
+    PM_LAUNCH_CHECK("pm_emit_workers");
+  }
+  if (n_bins && !e->all_solo) {
+    pm::pm_emit_empty_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(
+        e->hist.p, e->seg_start.p, e->group_base.p, e->ngroups.p, e->amin.p, n_bins, shift, e->group_ask.p, e->group_off.p);
+    PM_LAUNCH_CHECK("pm_emit_empty_groups");
+  }
+  PM_CUDA(cudaMemcpyAsync(e->group_off.p + G, &e->h_scalars.p[2], 4, cudaMemcpyHostToDevice, e->stream));
+  if (n_assigned) {
+    pm::pm_order_members<<<blocks_for(n_assigned, 256), 256, 0, e->stream>>>(
+        e->order.p, n_assigned, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
+    PM_LAUNCH_CHECK("pm_order_members");
+  }
+  tm.stop();
+  if (e->cfg.flags & PM_CFG_TIMING) {
+    PM_CUDA(cudaEventRecord(e->ev1, e->stream));
+    PM_CUDA(cudaEventSynchronize(e->ev1));
+    PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
+    e->resolve_timers();
+  }
+  e->matched = true;
+  return PM_OK;
+}
+
+int pm_match_local(pm_engine* e, uint32_t mode) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return match_local_locked(e, mode);
+}
+int pm_match_finish(pm_engine* e, uint32_t mode) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return match_finish_locked(e, mode);
+}
+int pm_match(pm_engine* e, uint32_t mode) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc = match_local_locked(e, mode);
+  if (rc != PM_OK) return rc;
+  return match_finish_locked(e, mode);
+}
+
+int pm_fetch_result(pm_engine* e, pm_result* out) {
+  if (!e || !out) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->matched) return e->fail(PM_E_STATE, "pm_fetch_result: no completed match");
+  PM_CUDA(cudaSetDevice(e->device));
+  const uint32_t W = e->n_workers, T = e->n_asks, G = e->n_groups, M = e->n_assigned;
+  PM_CUDA(e->r_worker_group.ensure(W)); PM_CUDA(e->r_worker_ask.ensure(W));
+  PM_CUDA(e->r_group_ask.ensure(G)); PM_CUDA(e->r_group_off.ensure((size_t)G + 1));
+  PM_CUDA(e->r_members.ensure(M)); PM_CUDA(e->r_ask_best.ensure(T)); PM_CUDA(e->r_ask_count.ensure(T));
+  if (W) {
+    PM_CUDA(cudaMemcpyAsync(e->r_worker_group.p, e->worker_group.p, (size_t)W * 4, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->r_worker_ask.p, e->worker_ask.p, (size_t)W * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (G) PM_CUDA(cudaMemcpyAsync(e->r_group_ask.p, e->group_ask.p, (size_t)G * 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->r_group_off.p, e->group_off.p, ((size_t)G + 1) * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (M) PM_CUDA(cudaMemcpyAsync(e->r_members.p, e->members.p, (size_t)M * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (T) {
+    PM_CUDA(cudaMemcpyAsync(e->r_ask_best.p, e->ask_best.p, (size_t)T * 8, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->r_ask_count.p, e->ask_count.p, (size_t)T * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  out->n_workers = W; out->n_asks = T; out->n_groups = G; out->n_members = M;
+  out->worker_group = e->r_worker_group.p; out->worker_ask = e->r_worker_ask.p;
+  out->group_ask = e->r_group_ask.p; out->group_off = e->r_group_off.p; out->group_members = e->r_members.p;
+  out->ask_best = (const int64_t*)e->r_ask_best.p; out->ask_count = e->r_ask_count.p;
+  out->stats = e->stats;
+  return PM_OK;
+}
+
+int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out) {
+  if (!e || !host_out) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_build_cost_tile: tables not set");
+  if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
+    return e->fail(PM_E_STATE, "pm_build_cost_tile: model table missing");
+  if ((uint64_t)t0 + nt > e->n_asks || nt == 0) return e->fail(PM_E_INVALID, "pm_build_cost_tile: ask range");
+  PM_CUDA(cudaSetDevice(e->device));
+  const uint32_t W = e->n_workers, w0 = e->cfg.shard_first;
+  const uint32_t nw = e->cfg.shard_count ? e->cfg.shard_count : (W > w0 ? W - w0 : 0);
+  if (nw == 0 || (uint64_t)w0 + nw > W) return e->fail(PM_E_INVALID, "pm_build_cost_tile: empty worker range");
+  if (!e->have_bits) {
+    PM_CUDA(e->bits.ensure(1));
+    PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
+    e->words = 1;
+  }
+  const size_t ld = ((size_t)nw + 1) & ~(size_t)1;
+  if (nt > 65535u * pm::kBuildRows) return e->fail(PM_E_INVALID, "pm_build_cost_tile: too many rows");
+  if (e->cost.ensure((size_t)nt * ld) != cudaSuccess) {
+    cudaGetLastError();
+    return e->fail(PM_E_NOMEM, "pm_build_cost_tile: cannot allocate the tile");
+  }
+  pm::EvalParams p = eval_params(e);
+  dim3 grid(blocks_for(ld, pm::kBuildCols), blocks_for(nt, pm::kBuildRows));
+  pm::pm_build_cost<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  PM_LAUNCH_CHECK("pm_build_cost");
+  PM_CUDA(cudaMemcpy2DAsync(host_out, (size_t)nw * 8, e->cost.p, ld * 8, (size_t)nw * 8, nt,
+                            cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_get_stats(const pm_engine* e, pm_stats* out) {
+  if (!e || !out) return PM_E_INVALID;
+  *out = e->stats;
+  return PM_OK;
+}
+
+int pm_device_buffer(pm_engine* e, uint32_t which, void** dev_ptr, size_t* bytes) {
+  if (!e || !dev_ptr || !bytes) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  switch (which) {
+    case PM_BUF_WORKER_FIRST_ASK: *dev_ptr = e->first_ask.p; *bytes = (size_t)e->n_workers * 4; break;
+    case PM_BUF_ASK_BEST: *dev_ptr = e->ask_best.p; *bytes = (size_t)e->n_asks * 8; break;
+    case PM_BUF_ASK_COUNT: *dev_ptr = e->ask_count.p; *bytes = (size_t)e->n_asks * 4; break;
+    default: return e->fail(PM_E_INVALID, "pm_device_buffer: unknown buffer");
+  }
+  if (!*dev_ptr) return e->fail(PM_E_STATE, "pm_device_buffer: buffer not allocated yet (run pm_match_local)");
+  return PM_OK;
+}
+
+int pm_stream_sync(pm_engine* e) {
+  if (!e) return PM_E_INVALID;
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI.  Bit-exact
+(integer/index work).  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+
+import kat_vectors as kv
+from helpers import TableBuilder, groups_equal, load_engine
+from oracle import pm_oracle as orc
+from protocol_b200 import abi, synth
+from protocol_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+MAT, FUSED = abi.PM_PATH_MATERIALIZED, abi.PM_PATH_FUSED
+
+
+def synth_tables(n_asks, n_workers, kind="mixed", group_sizes=None, seed_shift=0, with_addresses=False):
+    w = synth.make_workers(n_workers, seed=synth.SEED_WORKERS + seed_shift, with_addresses=with_addresses)
+    a = synth.make_asks(n_asks, kind, seed=synth.SEED_ASKS + seed_shift, group_sizes=group_sizes)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    return w, a, dict(asks=a.asks, opts=a.opts, wa=w.a, wb=w.b, bits=bits, n_patterns=npat, n_models=nmod,
+                      words=words, lat=w.lat, lon=w.lon)
+
+
+def check_against_oracle(eng, t, mode, addr_rank=None, proximity=False, check_rows=True):
+    eng.match(mode)
+    res = eng.fetch()
+    og = orc.soa_form_groups(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], addr_rank=addr_rank,
+                             lat=t["lat"], lon=t["lon"], proximity=proximity)
+    assert groups_equal(res, og), f"groups differ: engine {res.n_groups} vs oracle {len(og)}"
+    # per-worker view is consistent with the group table
+    wg = np.full(len(t["wa"]), abi.PM_NONE, dtype=np.uint32)
+    wk = np.full(len(t["wa"]), abi.PM_NONE, dtype=np.uint32)
+    for g in range(len(og.cfg)):
+        m = og.members[og.off[g]:og.off[g + 1]]
+        wg[m] = g
+        wk[m] = og.cfg[g]
+    assert np.array_equal(res.worker_group, wg) and np.array_equal(res.worker_ask, wk)
+    if check_rows:
+        T, W = len(t["asks"]), len(t["wa"])
+        ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 0, T, 0, W, threads=8)
+        assert np.array_equal(res.ask_best, ev["row_best"])
+        assert np.array_equal(res.ask_count, ev["row_count"])
+    return res, og
+
+
+def test_kat_vectors_on_device():
+    """Every meets() vector of node.rs:659-1241 as one (ask, worker) pair: entry [i][i] of the
+    materialised cost matrix is finite iff the reference test expects meets() == true."""
+    tb = TableBuilder()
+    for name, line, specs, req, expected in kv.MEETS:
+        tb.add_config(req)
+        tb.add_node(specs)
+    t = tb.tables()
+    eng = Engine()
+    load_engine(eng, t)
+    n = len(kv.MEETS)
+    cost = eng.cost_tile(0, n)
+    for i, (name, line, specs, req, expected) in enumerate(kv.MEETS):
+        assert (cost[i, i] != abi.PM_COST_INF) is expected, name
+        if expected:
+            assert cost[i, i] == i
+    ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 0, n, 0, n, want_cost=True)
+    assert np.array_equal(cost, ev["cost"])
+    eng.close()
+
+
+@pytest.mark.parametrize("path", [MAT, FUSED], ids=["materialized", "fused"])
+def test_cfg1_uniform_1k_x_10k(path):
+    """BASELINE configs[0]: 1k tasks x 10k workers, uniform single-GPU asks."""
+    w, a, t = synth_tables(1000, 10000, "uniform1")
+    eng = Engine()
+    load_engine(eng, t)
+    res, og = check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT | path)
+    assert res.stats["evals"] == 1000 * 10000
+    eng.close()
+
+
+def test_cost_matrix_bit_exact_cfg1():
+    w, a, t = synth_tables(1000, 10000, "mixed")
+    eng = Engine()
+    load_engine(eng, t)
+    cost = eng.cost_tile(0, 1000)
+    ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 0, 1000, 0, 10000,
+                             threads=8, want_cost=True)
+    assert np.array_equal(cost, ev["cost"])
+    eng.close()
+
+
+@pytest.mark.parametrize("path", [MAT, FUSED], ids=["materialized", "fused"])
+@pytest.mark.parametrize("nt,nw", [(1, 1), (3, 2), (129, 513), (257, 1023), (700, 4099)])
+def test_ragged_shapes(path, nt, nw):
+    w, a, t = synth_tables(nt, nw, "mixed", seed_shift=nt * 7 + nw)
+    eng = Engine(cost_tile_bytes=64 * 1024)   # forces several row tiles
+    load_engine(eng, t)
+    check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT | path)
+    eng.close()
+
+
+@pytest.mark.parametrize("path", [MAT, FUSED], ids=["materialized", "fused"])
+def test_group_sizes_with_underfilled_tails(path):
+    """min/max > 1: the sweep that hands under-filled tails to later configurations."""
+    sizes = [(1, 1), (2, 2), (2, 4), (3, 3), (4, 8), (1, 3), (5, 16)]
+    w, a, t = synth_tables(300, 6000, "mixed", group_sizes=sizes, with_addresses=True)
+    eng = Engine()
+    load_engine(eng, t, addr_rank=w.addr_rank)
+    res, og = check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT | path, addr_rank=w.addr_rank)
+    assert res.stats["n_bumped"] > 0, "test input should exercise the tail sweep"
+    eng.close()
+
+
+def test_degenerate_group_sizes():
+    """min_group_size == 0 yields a trailing empty group; max_group_size == 0 takes nobody
+    (mod.rs:507-566,606)."""
+    tb = TableBuilder()
+    tb.add_config("gpu:count=8", 0, 0)
+    tb.add_config("gpu:count=1", 0, 2)
+    tb.add_config(None, 2, 3)
+    for c in (1, 1, 1, 8, 2, 2, 2, 2, 4):
+        tb.add_node(kv.specs(c, "A100", 40000, 8, 1000, 10))
+    t = tb.tables()
+    eng = Engine()
+    load_engine(eng, t)
+    check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT)
+    eng.close()
+
+
+def test_no_asks_no_workers_and_nobody_feasible():
+    eng = Engine()
+    w, a, t = synth_tables(5, 50, "mixed")
+    # nobody healthy
+    t2 = dict(t)
+    wa = t["wa"].copy()
+    wa["flags"] &= ~np.uint32(abi.PM_W_HEALTHY)
+    t2["wa"] = wa
+    load_engine(eng, t2)
+    res, og = check_against_oracle(eng, t2, abi.PM_MODE_FIRST_FIT)
+    assert res.n_groups == 0 and (res.worker_group == abi.PM_NONE).all()
+    # empty ask table
+    t3 = dict(t)
+    t3["asks"] = t["asks"][:0]
+    t3["opts"] = t["opts"][:0]
+    load_engine(eng, t3)
+    eng.match()
+    assert eng.fetch().n_groups == 0
+    eng.close()
+
+
+def test_flag_deltas_and_rematch():
+    """pm_set_flags: a worker going Dead / being assigned drops out on the next pass
+    (status_update_impl.rs:8-39)."""
+    w, a, t = synth_tables(50, 2000, "mixed")
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match()
+    r0 = eng.fetch()
+    taken = np.flatnonzero(r0.worker_group != abi.PM_NONE)[:100].astype(np.uint32)
+    new_flags = (t["wa"]["flags"][taken] | abi.PM_W_ASSIGNED).astype(np.uint32)
+    eng.set_flags(taken, new_flags)
+    t2 = dict(t)
+    wa = t["wa"].copy()
+    wa["flags"][taken] = new_flags
+    t2["wa"] = wa
+    res, og = check_against_oracle(eng, t2, abi.PM_MODE_FIRST_FIT)
+    assert (res.worker_group[taken] == abi.PM_NONE).all()
+    eng.close()
+
+
+def test_proximity_solo_groups_order():
+    """ProximityOptimizationPolicy enabled with min=max=1: the seed rule orders located
+    workers first (mod.rs:526-530)."""
+    w, a, t = synth_tables(40, 3000, "mixed")
+    eng = Engine()
+    load_engine(eng, t, locations=True)
+    check_against_oracle(eng, t, abi.PM_MODE_PROXIMITY, proximity=True)
+    eng.close()
+
+
+def test_materialized_and_fused_agree_multi_tile():
+    w, a, t = synth_tables(5000, 20000, "skewed")
+    eng = Engine(cost_tile_bytes=32 << 20)
+    load_engine(eng, t)
+    eng.match(abi.PM_MODE_FIRST_FIT | MAT)
+    r1 = eng.fetch()
+    assert r1.stats["n_tiles"] > 1
+    eng.match(abi.PM_MODE_FIRST_FIT | FUSED)
+    r2 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_best", "ask_count"):
+        assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+    eng.close()
+
+
+def test_cfg2_100k_x_100k_mixed_bit_exact():
+    """BASELINE configs[1] at full size: assignment bit-identical to the CPU scheduler."""
+    w, a, t = synth_tables(100_000, 100_000, "mixed")
+    eng = Engine()
+    load_engine(eng, t)
+    check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT, check_rows=False)
+    # row results on a sampled band of asks (full 1e10-pair check is minutes of CPU)
+    res = eng.fetch()
+    for t0 in (0, 50_000, 99_000):
+        ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], t0, t0 + 1000,
+                                 0, 100_000, threads=8)
+        assert np.array_equal(res.ask_best[t0:t0 + 1000], ev["row_best"])
+        assert np.array_equal(res.ask_count[t0:t0 + 1000], ev["row_count"])
+    eng.close()
