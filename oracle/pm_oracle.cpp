@@ -847,7 +847,9 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b, const p
       for (u32 c = 0; c < nw; ++c) {
         const u32 w = w0 + c;
         int64_t cost = PM_COST_INF;
-        if (soa_candidate(a[w].flags) &&
+        // a first-fit configuration with max_group_size == 0 can never take a worker
+        // (ng/mod.rs:555-556): its row of the cost matrix is masked
+        if (ask.max_group_size != 0 && soa_candidate(a[w].flags) &&
             orc_soa_compatible(&a[w], &b[w], &ask, opts, model_bits, words)) {
           cost = int64_t(w);
           ++count;

@@ -140,7 +140,8 @@ orc_groups* orc_soa_form_groups(const pm_worker_a* a, const pm_worker_b* b, uint
 
 /* Full evaluation of the sub-matrix asks[t0,t1) x workers[w0,w1) over `threads`
  * host threads: cost[t][w] = compat && candidate ? (price<<32 | w) : INF with
- * price = 0 (reference modes).  Any out pointer may be NULL.
+ * price = 0 (reference modes); rows of asks with max_group_size == 0 are all INF
+ * (such a configuration never takes a worker).  Any out pointer may be NULL.
  *   cost_out      [(t1-t0) * (w1-w0)] row-major
  *   row_best_out  [t1-t0] min over w      row_count_out [t1-t0] #feasible
  *   col_first_out [w1-w0] first feasible ask index (global) or PM_NONE

@@ -20,11 +20,17 @@ namespace pm {
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr long long kInf = 0x7FFFFFFFFFFFFFFFll;
 
+// Synthetic presence bits added on the device side (never part of the ABI):
+constexpr uint32_t kCandBit = 1u << 31;        // Healthy && p2p_id.is_some() && !assigned (mod.rs:492-497)
+constexpr uint32_t kNeverBit = 1u << 30;       // no worker carries it: "this clause can never pass"
+constexpr uint32_t kTotInvalidBit = 1u << 29;  // count or memory_mb is None: total-memory clauses are skipped
+
 // Device form of one ask row (32 B).  `need` = presence bits the worker must
-// carry: HAS_SPECS when the config has requirements (mod.rs:210-214), HAS_CPU /
-// HAS_CPU_CORES / HAS_RAM / HAS_STORAGE for the scalar clauses (node.rs:381-418),
-// HAS_GPU when requirements.gpu is non-empty (node.rs:420-425).  Thresholds of
-// absent clauses are 0 so the unsigned >= compares pass.
+// carry: the candidate bit always; HAS_SPECS when the config has requirements
+// (mod.rs:210-214); HAS_CPU / HAS_CPU_CORES / HAS_RAM / HAS_STORAGE for the scalar
+// clauses (node.rs:381-418); HAS_GPU when requirements.gpu is non-empty
+// (node.rs:420-425).  Thresholds of absent clauses are 0 so the unsigned >=
+// compares pass.
 struct __align__(16) DevAsk {
   uint32_t need;
   uint32_t n_opts;
@@ -37,70 +43,71 @@ struct __align__(16) DevAsk {
 
 // Device form of one GpuRequirements option (32 B).  memory_mb / memory_mb_min
 // fold into mem_lo (both are "spec >= req", node.rs:487-498), memory_mb_max into
-// mem_hi (:499-503); `need` carries HAS_GPU_MODEL / HAS_GPU_MEM when the clause
-// is present (a None spec field fails a present clause, is_none_or).
+// the span (:499-503): lo <= x <= hi  <=>  (x - lo) <= (hi - lo) unsigned.  `need`
+// carries HAS_GPU_MODEL / HAS_GPU_MEM when the clause is present (a None spec field
+// fails a present clause, is_none_or); an empty interval becomes kNeverBit (memory)
+// or kTotInvalidBit (total memory: only workers that skip the clause can pass).
 struct __align__(16) DevOpt {
   uint32_t need;
   uint32_t count_mask;   // 0xFFFFFFFF when gpu:count is required, else 0
   uint32_t count;
-  uint32_t mem_lo, mem_hi;
-  uint32_t tot_lo, tot_hi;
-  uint32_t pattern_row;  // row in the device bit table; row 0 is all-ones (no model clause)
+  uint32_t mem_lo, mem_span;
+  uint32_t tot_lo, tot_span;
+  uint32_t pattern_row;  // row in the device bit table; 0 = no model clause
 };
 
 // One worker held in registers.
 struct WorkerReg {
-  uint32_t flags;
+  uint32_t flags;      // ABI presence bits + kCandBit / kTotInvalidBit
   uint32_t count_eff;  // None behaves exactly like Some(0) in the count clause (node.rs:447-461)
   uint32_t mem_eff;
   uint32_t tot;        // count * memory_mb, wrapping (release-build u32 multiply, node.rs:509,518)
-  uint32_t tot_valid;  // both count and memory_mb are Some (node.rs:506-507,515-516)
+  uint32_t tot_keep;   // all-ones when both count and memory_mb are Some, else 0 (clause skipped)
   uint32_t cores, ram, storage;
-  uint32_t mword, mbit;
+  uint32_t mword, mmask;
   uint32_t price;
-  bool candidate;      // Healthy && p2p_id.is_some() && !assigned (mod.rs:492-497)
 };
 
 __device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
   WorkerReg w;
-  w.flags = a.w;
   const bool hc = (a.w & PM_W_HAS_GPU_COUNT) != 0, hm = (a.w & PM_W_HAS_GPU_MEM) != 0;
+  const bool cand = (a.w & (PM_W_HEALTHY | PM_W_P2P | PM_W_ASSIGNED)) == (PM_W_HEALTHY | PM_W_P2P);
+  w.flags = (a.w & 0x1FFFFFFFu) | (cand ? kCandBit : 0u) | ((hc && hm) ? 0u : kTotInvalidBit);
   w.count_eff = hc ? a.x : 0u;
   w.mem_eff = hm ? a.y : 0u;
   w.tot = a.x * a.y;
-  w.tot_valid = (hc && hm) ? 1u : 0u;
+  w.tot_keep = (hc && hm) ? 0xFFFFFFFFu : 0u;
   w.cores = b.x;
   w.ram = b.y;
   w.storage = b.z;
   w.price = b.w;
   const uint32_t mid = (a.w & PM_W_HAS_GPU_MODEL) ? a.z : 0u;
   w.mword = mid >> 5;
-  w.mbit = mid & 31u;
-  w.candidate = (a.w & (PM_W_HEALTHY | PM_W_P2P | PM_W_ASSIGNED)) == (PM_W_HEALTHY | PM_W_P2P);
+  w.mmask = 1u << (mid & 31u);
   return w;
 }
 
 __device__ __forceinline__ WorkerReg null_worker() {
   WorkerReg w;
-  w.flags = 0; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_valid = 0;
-  w.cores = 0; w.ram = 0; w.storage = 0; w.mword = 0; w.mbit = 0; w.price = 0;
-  w.candidate = false;
+  w.flags = kTotInvalidBit; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_keep = 0;
+  w.cores = 0; w.ram = 0; w.storage = 0; w.mword = 0; w.mmask = 1u; w.price = 0;
   return w;
 }
 
-// GpuSpecs::meets for one option (node.rs:443-527).
+// GpuSpecs::meets for one option (node.rs:443-527).  `row` points at the
+// option's row of the acceptance bit table (any address space).
 __device__ __forceinline__ bool opt_meets(const DevOpt& q, const WorkerReg& w,
                                           const uint32_t* __restrict__ bits, uint32_t words) {
   bool ok = (w.flags & q.need) == q.need;
   ok &= (w.count_eff & q.count_mask) == q.count;
-  ok &= (w.mem_eff >= q.mem_lo) & (w.mem_eff <= q.mem_hi);
-  ok &= (w.tot_valid == 0u) | ((w.tot >= q.tot_lo) & (w.tot <= q.tot_hi));
+  ok &= (w.mem_eff - q.mem_lo) <= q.mem_span;
+  ok &= (((w.tot - q.tot_lo) & w.tot_keep) <= q.tot_span);
   if (q.pattern_row != 0u)  // uniform across the warp in the hot kernels
-    ok &= ((bits[size_t(q.pattern_row) * words + w.mword] >> w.mbit) & 1u) != 0u;
+    ok &= (bits[q.pattern_row * words + w.mword] & w.mmask) != 0u;
   return ok;
 }
 
-// is_node_compatible_with_config + ComputeSpecs::meets.
+// is_node_compatible_with_config + ComputeSpecs::meets + the candidate filter.
 __device__ __forceinline__ bool ask_meets(const DevAsk& a, const DevOpt* __restrict__ opts,
                                           const WorkerReg& w, const uint32_t* __restrict__ bits,
                                           uint32_t words) {

@@ -194,6 +194,7 @@ pm::EvalParams eval_params(pm_engine* e) {
   p.n_workers = e->n_workers;
   p.n_asks = e->n_asks;
   p.n_opts = e->n_opts;
+  p.n_bits_rows = e->have_bits ? e->n_patterns + 1 : 1;
   return p;
 }
 
@@ -310,7 +311,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
       return e->fail(PM_E_INVALID, "pm_set_asks: option range out of bounds");
     pm::DevAsk d{};
     const bool has_req = (a.flags & PM_A_HAS_REQ) != 0;
-    uint32_t need = 0;
+    uint32_t need = pm::kCandBit;
     if (has_req) {
       need |= PM_W_HAS_SPECS;
       if (a.flags & PM_A_REQ_CPU) need |= PM_W_HAS_CPU;
@@ -324,7 +325,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
       d.n_opts = a.n_opts;
     }
     // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
-    if (a.max_group_size == 0) need = 0xFFFFFFFFu;
+    if (a.max_group_size == 0) need |= pm::kNeverBit;
     d.need = need;
     d.opt_off = (uint32_t)dopt.size();
     for (uint32_t o = 0; has_req && o < a.n_opts; ++o) {
@@ -332,13 +333,17 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
       pm::DevOpt x{};
       x.count_mask = (q.present & PM_O_COUNT) ? 0xFFFFFFFFu : 0u;
       x.count = (q.present & PM_O_COUNT) ? q.count : 0u;
-      x.mem_lo = 0; x.mem_hi = 0xFFFFFFFFu; x.tot_lo = 0; x.tot_hi = 0xFFFFFFFFu;
-      if (q.present & PM_O_MEM) x.mem_lo = std::max(x.mem_lo, q.memory_mb);
-      if (q.present & PM_O_MEM_MIN) x.mem_lo = std::max(x.mem_lo, q.memory_mb_min);
-      if (q.present & PM_O_MEM_MAX) x.mem_hi = q.memory_mb_max;
+      uint32_t mem_lo = 0, mem_hi = 0xFFFFFFFFu, tot_lo = 0, tot_hi = 0xFFFFFFFFu;
+      if (q.present & PM_O_MEM) mem_lo = std::max(mem_lo, q.memory_mb);
+      if (q.present & PM_O_MEM_MIN) mem_lo = std::max(mem_lo, q.memory_mb_min);
+      if (q.present & PM_O_MEM_MAX) mem_hi = q.memory_mb_max;
       if (q.present & (PM_O_MEM | PM_O_MEM_MIN | PM_O_MEM_MAX)) x.need |= PM_W_HAS_GPU_MEM;
-      if (q.present & PM_O_TOT_MIN) x.tot_lo = q.total_memory_min;
-      if (q.present & PM_O_TOT_MAX) x.tot_hi = q.total_memory_max;
+      if (q.present & PM_O_TOT_MIN) tot_lo = q.total_memory_min;
+      if (q.present & PM_O_TOT_MAX) tot_hi = q.total_memory_max;
+      if (mem_lo > mem_hi) { x.need |= pm::kNeverBit; mem_lo = 0; mem_hi = 0xFFFFFFFFu; }
+      if (tot_lo > tot_hi) { x.need |= pm::kTotInvalidBit; tot_lo = 0; tot_hi = 0xFFFFFFFFu; }
+      x.mem_lo = mem_lo; x.mem_span = mem_hi - mem_lo;
+      x.tot_lo = tot_lo; x.tot_span = tot_hi - tot_lo;
       if (q.present & PM_O_MODEL) {
         x.need |= PM_W_HAS_GPU_MODEL;
         x.pattern_row = q.pattern_id + 1;
@@ -514,20 +519,23 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
 
   if (T && nw) {
     pm::EvalParams p = eval_params(e);
+    const int bits_mode = ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0;
     if (mode & PM_PATH_FUSED) {
       Timer tm(e, &e->stats.ms_fused);
-      const uint32_t rows_per_launch = 65535u * pm::kFusedRows;
+      const uint32_t rows_per_launch = 65535u * pm::kEvalRows;
       for (uint32_t t0 = 0; t0 < T; t0 += rows_per_launch) {
         const uint32_t nt = std::min(rows_per_launch, T - t0);
-        dim3 grid(blocks_for(nw, pm::kBuildCols), blocks_for(nt, pm::kFusedRows));
-        pm::pm_fused_eval<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+        dim3 grid(blocks_for(nw, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
+        if (bits_mode == 2) pm::pm_fused_eval<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+        else if (bits_mode == 1) pm::pm_fused_eval<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+        else pm::pm_fused_eval<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
         PM_LAUNCH_CHECK("pm_fused_eval");
         ++e->stats.n_fused_launches;
       }
       tm.stop();
       e->stats.n_tiles = 1;
     } else {
-      const size_t ld = ((size_t)nw + 1) & ~(size_t)1;
+      const size_t ld = ((size_t)nw + 3) & ~(size_t)3;
       uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
       if (rows == 0) rows = 1;
       rows = std::min<uint64_t>(rows, T);
@@ -541,8 +549,10 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
         const uint32_t nt = (uint32_t)std::min<uint64_t>(rows, T - t0);
         {
           Timer tm(e, &e->stats.ms_build);
-          dim3 grid(blocks_for(ld, pm::kBuildCols), blocks_for(nt, pm::kBuildRows));
-          pm::pm_build_cost<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+          dim3 grid(blocks_for(ld, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
+          if (bits_mode == 2) pm::pm_build_cost<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+          else if (bits_mode == 1) pm::pm_build_cost<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+          else pm::pm_build_cost<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
           PM_LAUNCH_CHECK("pm_build_cost");
           tm.stop();
           ++e->stats.n_build_launches;
@@ -745,15 +755,18 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
     PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
     e->words = 1;
   }
-  const size_t ld = ((size_t)nw + 1) & ~(size_t)1;
-  if (nt > 65535u * pm::kBuildRows) return e->fail(PM_E_INVALID, "pm_build_cost_tile: too many rows");
+  const size_t ld = ((size_t)nw + 3) & ~(size_t)3;
+  if (nt > 65535u * pm::kEvalRows) return e->fail(PM_E_INVALID, "pm_build_cost_tile: too many rows");
   if (e->cost.ensure((size_t)nt * ld) != cudaSuccess) {
     cudaGetLastError();
     return e->fail(PM_E_NOMEM, "pm_build_cost_tile: cannot allocate the tile");
   }
   pm::EvalParams p = eval_params(e);
-  dim3 grid(blocks_for(ld, pm::kBuildCols), blocks_for(nt, pm::kBuildRows));
-  pm::pm_build_cost<<<grid, pm::kBuildThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  dim3 grid(blocks_for(ld, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
+  if ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap)
+    pm::pm_build_cost<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  else
+    pm::pm_build_cost<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
   PM_LAUNCH_CHECK("pm_build_cost");
   PM_CUDA(cudaMemcpy2DAsync(host_out, (size_t)nw * 8, e->cost.p, ld * 8, (size_t)nw * 8, nt,
                             cudaMemcpyDeviceToHost, e->stream));

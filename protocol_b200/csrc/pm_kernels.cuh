@@ -25,82 +25,202 @@ struct EvalParams {
   uint32_t n_workers;                 // global
   uint32_t n_asks;
   uint32_t n_opts;
+  uint32_t n_bits_rows;               // n_patterns + 1
 };
 
-// ------------------------------------------------------------------ build
-constexpr int kBuildThreads = 256;
-constexpr int kBuildWPT = 2;                          // workers per thread -> one 16 B store per row
-constexpr int kBuildCols = kBuildThreads * kBuildWPT; // 512 workers per CTA stripe
-constexpr int kBuildRows = 128;                       // asks staged in smem per CTA
-constexpr int kBuildOptCap = 256;                     // options staged per CTA
+// ------------------------------------------------------------------ evaluation core
+constexpr int kEvalThreads = 256;
+constexpr int kEvalWPT = 4;                          // workers per thread: two 16 B stores per row
+constexpr int kEvalCols = kEvalThreads * kEvalWPT;   // 1024 workers per CTA stripe
+constexpr int kEvalRows = 128;                       // asks per CTA (staged in shared memory)
+constexpr int kOptCap = 384;                         // options staged at a time
+constexpr int kBitsCap = 2048;                       // acceptance-table words kept in shared memory
 
-struct AskStage {
-  DevAsk ask[kBuildRows];
-  DevOpt opt[kBuildOptCap];
+struct __align__(128) EvalStage {
+  DevAsk ask[kEvalRows];
+  DevOpt opt[kOptCap];
+  uint32_t bits[kBitsCap];
   uint64_t bar;
 };
 
-// Stage rows [r0, r1) of the ask table (and their option range) into shared
-// memory with two 1-D TMA bulk copies signalled on one mbarrier.  Returns the
-// option base to subtract from DevAsk::opt_off, or kNone when the option range
-// does not fit (then options are read from global memory through L1).
-__device__ __forceinline__ uint32_t stage_asks(AskStage& s, const EvalParams& p, uint32_t r0,
-                                               uint32_t r1) {
-  const uint32_t o0 = p.asks[r0].opt_off;
-  const DevAsk last = p.asks[r1 - 1];
-  const uint32_t o1 = last.opt_off + last.n_opts;
-  const bool fits = (o1 - o0) <= (uint32_t)kBuildOptCap;
-  if (threadIdx.x == 0) {
-    mbar_init(&s.bar, 1);
-    uint32_t bytes = (r1 - r0) * (uint32_t)sizeof(DevAsk);
-    uint32_t obytes = (fits && o1 > o0) ? (o1 - o0) * (uint32_t)sizeof(DevOpt) : 0u;
-    mbar_expect_tx(&s.bar, bytes + obytes);
-    bulk_g2s(s.ask, p.asks + r0, bytes, &s.bar);
-    if (obytes) bulk_g2s(s.opt, p.opts + o0, obytes, &s.bar);
-  }
-  __syncthreads();          // barrier init visible to all waiters
-  mbar_wait(&s.bar, 0);
-  return fits ? o0 : kNone;
+// The predicate for one staged ask against WPT register-resident workers, as
+// all-ones / zero masks.  Ask and option operands are warp-uniform shared-memory
+// reads; each clause is one subtract/and plus one ISETP chained on a single
+// predicate (inline PTX keeps ptxas from materialising booleans in registers).
+__device__ __forceinline__ uint32_t base_mask(const DevAsk& a, const WorkerReg& w) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.eq.u32 p, t, %2;\n\t"
+      "setp.ge.and.u32 p, %3, %4, p;\n\t"
+      "setp.ge.and.u32 p, %5, %6, p;\n\t"
+      "setp.ge.and.u32 p, %7, %8, p;\n\t"
+      "selp.b32 %0, -1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(w.flags), "r"(a.need), "r"(w.cores), "r"(a.cpu_cores), "r"(w.ram), "r"(a.ram_mb),
+        "r"(w.storage), "r"(a.storage_gb));
+  return r;
 }
 
-// grid = (ceil(ld / 512), ceil(nt / 128)); each thread owns 2 adjacent workers in
-// registers and walks the staged asks, emitting one 128-bit streaming store per
-// row: a warp writes 512 contiguous bytes, the CTA 4 KB contiguous per row.
-__global__ void __launch_bounds__(kBuildThreads)
+// GpuSpecs::meets for one option (node.rs:443-527).  `word` is the worker's word
+// of the option's acceptance row (row 0 is all-ones: no model clause).
+__device__ __forceinline__ uint32_t opt_mask(const DevOpt& q, const WorkerReg& w, uint32_t word) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.eq.u32 p, t, %2;\n\t"            // presence bits
+      "and.b32 t, %3, %4;\n\t"
+      "setp.eq.and.u32 p, t, %5, p;\n\t"     // count == (or unconstrained)
+      "sub.u32 t, %6, %7;\n\t"
+      "setp.le.and.u32 p, t, %8, p;\n\t"     // memory_mb in [lo, hi]
+      "sub.u32 t, %9, %11;\n\t"
+      "and.b32 t, t, %10;\n\t"               // workers without count*memory skip the clause
+      "setp.le.and.u32 p, t, %12, p;\n\t"    // count * memory_mb in [lo, hi]
+      "and.b32 t, %13, %14;\n\t"
+      "setp.ne.and.u32 p, t, 0, p;\n\t"      // model accepted
+      "selp.b32 %0, -1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(w.flags), "r"(q.need), "r"(w.count_eff), "r"(q.count_mask), "r"(q.count),
+        "r"(w.mem_eff), "r"(q.mem_lo), "r"(q.mem_span), "r"(w.tot), "r"(w.tot_keep), "r"(q.tot_lo),
+        "r"(q.tot_span), "r"(word), "r"(w.mmask));
+  return r;
+}
+
+// BITS: 0 = acceptance table in global memory, 1 = in shared memory, 2 = in shared
+// memory with one word per row (<= 32 worker models): the word is warp-uniform.
+template <int WPT, int BITS>
+__device__ __forceinline__ void eval_row(const EvalStage& s, const DevAsk& a, uint32_t obegin,
+                                         const WorkerReg (&w)[WPT],
+                                         const uint32_t* __restrict__ gbits, uint32_t words,
+                                         uint32_t (&f)[WPT]) {
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) f[k] = base_mask(a, w[k]);
+  if (a.n_opts != 0u) {
+    uint32_t any[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) any[k] = 0u;
+    const uint32_t o0 = a.opt_off - obegin;
+    for (uint32_t o = 0; o < a.n_opts; ++o) {
+      const DevOpt q = s.opt[o0 + o];
+      if (BITS == 2) {
+        const uint32_t word = s.bits[q.pattern_row];
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) any[k] |= opt_mask(q, w[k], word);
+      } else {
+        const uint32_t rowoff = q.pattern_row * words;
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+          const uint32_t word = (BITS == 1) ? s.bits[rowoff + w[k].mword] : __ldg(gbits + rowoff + w[k].mword);
+          any[k] |= opt_mask(q, w[k], word);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) f[k] &= any[k];
+  }
+}
+
+// Slow path for an ask whose option list alone exceeds the staging capacity.
+template <int WPT>
+__device__ __noinline__ void eval_row_global(const EvalParams& p, const DevAsk& a,
+                                             const WorkerReg (&w)[WPT], uint32_t (&f)[WPT]) {
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) f[k] = ask_meets(a, p.opts, w[k], p.bits, p.words) ? 0xFFFFFFFFu : 0u;
+}
+
+template <int WPT>
+__device__ __forceinline__ void load_workers(const EvalParams& p, uint32_t w0, uint32_t nw,
+                                             uint32_t c, WorkerReg (&w)[WPT]) {
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const uint32_t col = c + k;
+    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+    else w[k] = null_worker();
+  }
+}
+
+// Drives `body(row_in_tile, ask, obegin, staged)` over rows [r0, r1) of the tile:
+// ask headers, then as many option rows as fit, arrive in shared memory through
+// 1-D TMA bulk copies signalled on one mbarrier.
+template <class Body>
+__device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalParams& p, uint32_t t0,
+                                                    uint32_t r0, uint32_t r1, Body&& body) {
+  if (threadIdx.x == 0) mbar_init(&s.bar, 1);
+  const uint32_t total_words = (p.n_bits_rows)*p.words;
+  if (total_words <= (uint32_t)kBitsCap)
+    for (uint32_t i = threadIdx.x; i < total_words; i += blockDim.x) s.bits[i] = __ldg(p.bits + i);
+  __syncthreads();
+  uint32_t phase = 0;
+  const uint32_t nrows = r1 - r0;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&s.bar, nrows * (uint32_t)sizeof(DevAsk));
+    bulk_g2s(s.ask, p.asks + t0 + r0, nrows * (uint32_t)sizeof(DevAsk), &s.bar);
+  }
+  mbar_wait(&s.bar, phase);
+  phase ^= 1u;
+  uint32_t row = 0;
+  while (row < nrows) {
+    const uint32_t obegin = s.ask[row].opt_off;
+    // rows [row, row+n) whose options fit (option offsets are non-decreasing in ask order)
+    const uint32_t r = row + threadIdx.x;
+    const bool fits = r < nrows && (s.ask[r].opt_off + s.ask[r].n_opts - obegin) <= (uint32_t)kOptCap;
+    const uint32_t n = (uint32_t)__syncthreads_count(fits);
+    if (n == 0) {  // one ask with more options than the stage holds
+      body(row, s.ask[row], 0u, false);
+      ++row;
+      continue;
+    }
+    const uint32_t oend = s.ask[row + n - 1].opt_off + s.ask[row + n - 1].n_opts;
+    if (oend > obegin) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&s.bar, (oend - obegin) * (uint32_t)sizeof(DevOpt));
+        bulk_g2s(s.opt, p.opts + obegin, (oend - obegin) * (uint32_t)sizeof(DevOpt), &s.bar);
+      }
+      mbar_wait(&s.bar, phase);
+      phase ^= 1u;
+    }
+    for (uint32_t i = 0; i < n; ++i) body(row + i, s.ask[row + i], obegin, true);
+    row += n;
+    if (row < nrows) __syncthreads();  // everyone is done with s.opt before it is overwritten
+  }
+}
+
+// ------------------------------------------------------------------ build
+// grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 adjacent workers in
+// registers and walks the staged asks, emitting two 128-bit streaming stores per
+// row: a warp writes 1 KB contiguous, the CTA 8 KB contiguous per row.
+template <int BITS>
+__global__ void __launch_bounds__(kEvalThreads)
 pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               long long* __restrict__ cost, size_t ld) {
-  __shared__ __align__(128) AskStage s;
-  const uint32_t r0 = blockIdx.y * kBuildRows;
-  const uint32_t r1 = min(nt, r0 + (uint32_t)kBuildRows);
-  const uint32_t obase = stage_asks(s, p, t0 + r0, t0 + r1);
-  const DevOpt* optp = (obase == kNone) ? p.opts : (s.opt - obase);
-
-  const uint32_t c = blockIdx.x * kBuildCols + threadIdx.x * kBuildWPT;  // column in tile
-  if (c >= ld) return;
-  WorkerReg w[kBuildWPT];
-  long long feas_cost[kBuildWPT];
+  __shared__ EvalStage s;
+  const uint32_t r0 = blockIdx.y * kEvalRows;
+  const uint32_t r1 = min(nt, r0 + (uint32_t)kEvalRows);
+  const uint32_t c = blockIdx.x * kEvalCols + threadIdx.x * kEvalWPT;  // column in tile
+  WorkerReg w[kEvalWPT];
+  load_workers<kEvalWPT>(p, w0, nw, c, w);
+  const bool in_range = c < ld;   // ld is a multiple of 4: a thread's 4 columns are all in or all out
+  uint32_t gw[kEvalWPT];
 #pragma unroll
-  for (int k = 0; k < kBuildWPT; ++k) {
-    const uint32_t col = c + k;
-    if (col < nw) {
-      const uint32_t gw = w0 + col;
-      w[k] = make_worker(__ldg(p.wa + gw), __ldg(p.wb + gw));
-      feas_cost[k] = ((long long)w[k].price << 32) | (long long)gw;
-    } else {
-      w[k] = null_worker();
-      feas_cost[k] = kInf;
+  for (int k = 0; k < kEvalWPT; ++k) gw[k] = w0 + c + k;
+  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + (in_range ? c : 0));
+  const size_t row_stride = ld / 2;   // in 16-byte units; rows are visited in increasing order
+  for_each_staged_row(s, p, t0, r0, r1, [&](uint32_t, const DevAsk& a, uint32_t obegin, bool staged) {
+    uint32_t f[kEvalWPT];
+    if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
+    else eval_row_global<kEvalWPT>(p, a, w, f);
+    if (in_range) {
+      // feasible: (price << 32) | worker ; infeasible: 0x7FFFFFFF_FFFFFFFF — pure bit selects
+      uint4 v0, v1;
+      v0.x = gw[0] | ~f[0]; v0.y = (w[0].price & f[0]) | (0x7FFFFFFFu & ~f[0]);
+      v0.z = gw[1] | ~f[1]; v0.w = (w[1].price & f[1]) | (0x7FFFFFFFu & ~f[1]);
+      v1.x = gw[2] | ~f[2]; v1.y = (w[2].price & f[2]) | (0x7FFFFFFFu & ~f[2]);
+      v1.z = gw[3] | ~f[3]; v1.w = (w[3].price & f[3]) | (0x7FFFFFFFu & ~f[3]);
+      __stcs(out, v0);
+      __stcs(out + 1, v1);
     }
-  }
-  longlong2* out = reinterpret_cast<longlong2*>(cost + (size_t)r0 * ld + c);
-  const size_t ld2 = ld / 2;
-#pragma unroll 4
-  for (uint32_t r = 0; r < r1 - r0; ++r) {
-    const DevAsk a = s.ask[r];
-    longlong2 v;
-    v.x = (w[0].candidate && ask_meets(a, optp, w[0], p.bits, p.words)) ? feas_cost[0] : kInf;
-    v.y = (w[1].candidate && ask_meets(a, optp, w[1], p.bits, p.words)) ? feas_cost[1] : kInf;
-    __stcs(out + (size_t)r * ld2, v);
-  }
+    out += row_stride;
+  });
 }
 
 // ------------------------------------------------------------------ argmin
@@ -174,66 +294,54 @@ pm_argmin(const long long* __restrict__ cost, size_t ld, uint32_t nt, uint32_t t
 
 // ------------------------------------------------------------------ fused
 // Same stripe/row decomposition as pm_build_cost, but the int64 cost never
-// leaves the SM: per-row results go through a ballot (first-fit cost is the
+// leaves the SM: per-row results go through ballots (first-fit cost is the
 // worker index, so the row minimum is the lowest set bit), per-worker results
 // stay in registers.  Integer-issue-bound, not HBM-bound.
-constexpr int kFusedRows = 128;
-__global__ void __launch_bounds__(kBuildThreads)
+template <int BITS>
+__global__ void __launch_bounds__(kEvalThreads)
 pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               uint32_t* __restrict__ first_ask, long long* __restrict__ ask_best,
               uint32_t* __restrict__ ask_count) {
-  __shared__ __align__(128) AskStage s;
-  __shared__ uint32_t s_cnt[kFusedRows];
-  __shared__ unsigned long long s_best[kFusedRows];
-  const uint32_t r0 = blockIdx.y * kFusedRows;
-  const uint32_t r1 = min(nt, r0 + (uint32_t)kFusedRows);
-  const uint32_t obase = stage_asks(s, p, t0 + r0, t0 + r1);
-  const DevOpt* optp = (obase == kNone) ? p.opts : (s.opt - obase);
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kFusedRows; i += kBuildThreads) {
+  __shared__ EvalStage s;
+  __shared__ uint32_t s_cnt[kEvalRows];
+  __shared__ uint32_t s_best[kEvalRows];
+  const uint32_t r0 = blockIdx.y * kEvalRows;
+  const uint32_t r1 = min(nt, r0 + (uint32_t)kEvalRows);
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kEvalRows; i += kEvalThreads) {
     s_cnt[i] = 0;
-    s_best[i] = (unsigned long long)kInf;
+    s_best[i] = kNone;
   }
-  __syncthreads();
-
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t c = blockIdx.x * kBuildCols + threadIdx.x * kBuildWPT;
-  WorkerReg w[kBuildWPT];
+  const uint32_t c = blockIdx.x * kEvalCols + threadIdx.x * kEvalWPT;
+  WorkerReg w[kEvalWPT];
+  load_workers<kEvalWPT>(p, w0, nw, c, w);
+  uint32_t first[kEvalWPT];
 #pragma unroll
-  for (int k = 0; k < kBuildWPT; ++k) {
-    const uint32_t col = c + k;
-    if (col < nw) {
-      const uint32_t gw = w0 + col;
-      w[k] = make_worker(__ldg(p.wa + gw), __ldg(p.wb + gw));
-    } else {
-      w[k] = null_worker();
-    }
-  }
-  uint32_t first[kBuildWPT] = {kNone, kNone};
-  const bool uniform_price = true;  // reference modes: cost = worker index
-  (void)uniform_price;
-#pragma unroll 2
-  for (uint32_t r = 0; r < r1 - r0; ++r) {
-    const DevAsk a = s.ask[r];
-    const bool f0 = w[0].candidate && ask_meets(a, optp, w[0], p.bits, p.words);
-    const bool f1 = w[1].candidate && ask_meets(a, optp, w[1], p.bits, p.words);
+  for (int k = 0; k < kEvalWPT; ++k) first[k] = kNone;
+  const uint32_t warp_gw0 = w0 + (c - lane * kEvalWPT);
+  for_each_staged_row(s, p, t0, r0, r1, [&](uint32_t r, const DevAsk& a, uint32_t obegin, bool staged) {
+    uint32_t f[kEvalWPT];
+    if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
+    else eval_row_global<kEvalWPT>(p, a, w, f);
     const uint32_t t = t0 + r0 + r;
-    first[0] = (f0 && first[0] == kNone) ? t : first[0];
-    first[1] = (f1 && first[1] == kNone) ? t : first[1];
-    const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-    if ((b0 | b1) != 0u && lane == 0) {
-      // lowest worker index among the warp's 64 columns
-      const uint32_t l0 = b0 ? (uint32_t)__ffs(b0) - 1u : 64u, l1 = b1 ? (uint32_t)__ffs(b1) - 1u : 64u;
-      const uint32_t rel = min(l0 * 2u, l1 * 2u + 1u);
-      const uint32_t gw = w0 + (c - lane * kBuildWPT) + rel;
-      atomicAdd(&s_cnt[r], (uint32_t)__popc(b0) + (uint32_t)__popc(b1));
-      atomicMin(&s_best[r], (unsigned long long)gw);
-    }
-  }
+    uint32_t cnt = 0, best = kNone;
 #pragma unroll
-  for (int k = 0; k < kBuildWPT; ++k)
+    for (int k = 0; k < kEvalWPT; ++k) {
+      first[k] = min(first[k], t | ~f[k]);
+      const uint32_t b = __ballot_sync(0xffffffffu, f[k] != 0u);
+      cnt += (uint32_t)__popc(b);
+      if (b) best = min(best, ((uint32_t)__ffs(b) - 1u) * kEvalWPT + k);
+    }
+    if (cnt && lane == 0) {
+      atomicAdd(&s_cnt[r], cnt);
+      atomicMin(&s_best[r], warp_gw0 + best);
+    }
+  });
+#pragma unroll
+  for (int k = 0; k < kEvalWPT; ++k)
     if (first[k] != kNone) atomicMin(first_ask + w0 + c + k, first[k]);
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < r1 - r0; i += kBuildThreads) {
+  for (uint32_t i = threadIdx.x; i < r1 - r0; i += kEvalThreads) {
     if (s_cnt[i]) {
       atomicAdd(ask_count + t0 + r0 + i, s_cnt[i]);
       atomicMin(ask_best + t0 + r0 + i, (long long)s_best[i]);

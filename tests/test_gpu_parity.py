@@ -57,7 +57,7 @@ def test_kat_vectors_on_device():
     n = len(kv.MEETS)
     cost = eng.cost_tile(0, n)
     for i, (name, line, specs, req, expected) in enumerate(kv.MEETS):
-        assert (cost[i, i] != abi.PM_COST_INF) is expected, name
+        assert bool(cost[i, i] != abi.PM_COST_INF) is expected, name
         if expected:
             assert cost[i, i] == i
     ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 0, n, 0, n, want_cost=True)
