@@ -56,9 +56,28 @@ struct __align__(16) DevOpt {
   uint32_t pattern_row;  // row in the device bit table; 0 = no model clause
 };
 
+// Fast-path form of an option (same 32 B slot as DevOpt, separate array).  Valid
+// when every numeric operand on both sides is < 2^31 and every gpu count < 2^16
+// (checked at upload; otherwise the generic predicate is used).  The worker's
+// presence flags and gpu count are packed into one `key` word (count in bits
+// 13..28), so presence + count is ONE masked equality ((key & m) ^ v) == 0, where
+// m/v also carry the owning ask's `need` bits; range clauses are sign tests of
+// (x - lo) | (hi - x), which run on the FMA pipe (IMAD) instead of the ALU pipe.
+struct __align__(16) DevOptF {
+  uint32_t m, v;
+  uint32_t mem_lo, mem_hi;
+  uint32_t tot_lo, tot_hi;
+  uint32_t pattern_row;
+  uint32_t pad;
+};
+constexpr uint32_t kKeyCountShift = 13;
+constexpr uint32_t kKeyFlagMask = 0xE0001FFFu;
+constexpr uint32_t kSign = 0x80000000u;
+
 // One worker held in registers.
 struct WorkerReg {
   uint32_t flags;      // ABI presence bits + kCandBit / kTotInvalidBit
+  uint32_t key;        // fast path: flags | count << 13
   uint32_t count_eff;  // None behaves exactly like Some(0) in the count clause (node.rs:447-461)
   uint32_t mem_eff;
   uint32_t tot;        // count * memory_mb, wrapping (release-build u32 multiply, node.rs:509,518)
@@ -74,6 +93,7 @@ __device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
   const bool cand = (a.w & (PM_W_HEALTHY | PM_W_P2P | PM_W_ASSIGNED)) == (PM_W_HEALTHY | PM_W_P2P);
   w.flags = (a.w & 0x1FFFFFFFu) | (cand ? kCandBit : 0u) | ((hc && hm) ? 0u : kTotInvalidBit);
   w.count_eff = hc ? a.x : 0u;
+  w.key = (w.flags & kKeyFlagMask) | (w.count_eff << kKeyCountShift);
   w.mem_eff = hm ? a.y : 0u;
   w.tot = a.x * a.y;
   w.tot_keep = (hc && hm) ? 0xFFFFFFFFu : 0u;
@@ -89,7 +109,7 @@ __device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
 
 __device__ __forceinline__ WorkerReg null_worker() {
   WorkerReg w;
-  w.flags = kTotInvalidBit; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_keep = 0;
+  w.flags = kTotInvalidBit; w.key = kTotInvalidBit; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_keep = 0;
   w.cores = 0; w.ram = 0; w.storage = 0; w.mword = 0; w.mmask = 1u; w.price = 0;
   return w;
 }

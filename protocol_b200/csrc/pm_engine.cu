@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -83,11 +84,16 @@ struct pm_engine {
   uint32_t max_pattern_row = 0;
   bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
   bool all_solo = true;  // every ask has min == max == 1
+  int tune_argmin = 0, tune_generic = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
   DevBuf<uint4> wa, wb;
   DevBuf<double> lat, lon;
   DevBuf<uint32_t> addr_rank;
   DevBuf<pm::DevAsk> asks;
   DevBuf<pm::DevOpt> opts;
+  DevBuf<pm::DevOptF> opts_fast;
+  bool asks_small = true;      // every ask operand fits the fast predicate (pm_device.cuh DevOptF)
+  bool workers_small = false;  // ... and every worker operand (checked on the device)
+  bool workers_checked = false;
   DevBuf<uint32_t> amin, amax, bits;
   DevBuf<uint32_t> scratch_idx, scratch_flags;
 
@@ -189,6 +195,7 @@ pm::EvalParams eval_params(pm_engine* e) {
   p.wb = e->wb.p;
   p.asks = e->asks.p;
   p.opts = e->opts.p;
+  p.opts_fast = e->opts_fast.p;
   p.bits = e->bits.p;
   p.words = e->words;
   p.n_workers = e->n_workers;
@@ -246,6 +253,8 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   e->cfg = *cfg;
   if (e->cfg.cost_tile_bytes == 0) e->cfg.cost_tile_bytes = 8ull << 30;
   e->device = cfg->device;
+  if (const char* t = std::getenv("PM_TUNE_ARGMIN")) e->tune_argmin = std::atoi(t);
+  if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
     e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
@@ -270,7 +279,7 @@ void pm_destroy(pm_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->wa.release(); e->wb.release(); e->lat.release(); e->lon.release(); e->addr_rank.release();
-  e->asks.release(); e->opts.release(); e->amin.release(); e->amax.release(); e->bits.release();
+  e->asks.release(); e->opts.release(); e->opts_fast.release(); e->amin.release(); e->amax.release(); e->bits.release();
   e->scratch_idx.release(); e->scratch_flags.release();
   e->cost.release(); e->first_ask.release(); e->ask_count.release(); e->ask_best.release();
   e->keys.release(); e->keys_sorted.release(); e->iota.release(); e->order.release();
@@ -298,6 +307,8 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   if (n_asks >= (1u << 30)) return e->fail(PM_E_INVALID, "pm_set_asks: too many asks");
   std::vector<pm::DevAsk> da(n_asks);
   std::vector<pm::DevOpt> dopt;
+  std::vector<pm::DevOptF> doptf;
+  bool small = true;
   std::vector<uint32_t> mn(n_asks), mx(n_asks);
   dopt.reserve(n_opts);
   uint32_t max_row = 0;
@@ -327,6 +338,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
     // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
     if (a.max_group_size == 0) need |= pm::kNeverBit;
     d.need = need;
+    if ((d.cpu_cores | d.ram_mb | d.storage_gb) >= pm::kSign) small = false;
     d.opt_off = (uint32_t)dopt.size();
     for (uint32_t o = 0; has_req && o < a.n_opts; ++o) {
       const pm_gpu_opt& q = opts[a.opt_off + o];
@@ -350,6 +362,21 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
         max_row = std::max(max_row, x.pattern_row);
       }
       dopt.push_back(x);
+      // fast-path form (pm_device.cuh DevOptF): presence + count as one masked equality
+      pm::DevOptF f{};
+      const uint32_t need_all = need | x.need;
+      f.m = need_all;
+      f.v = need_all;
+      if (q.present & PM_O_COUNT) {
+        if (q.count >= 65536u) small = false;
+        f.m |= 0xFFFFu << pm::kKeyCountShift;
+        f.v |= (q.count & 0xFFFFu) << pm::kKeyCountShift;
+      }
+      if (mem_lo >= pm::kSign || tot_lo >= pm::kSign) small = false;
+      f.mem_lo = mem_lo; f.mem_hi = std::min(mem_hi, 0x7FFFFFFFu);
+      f.tot_lo = tot_lo; f.tot_hi = std::min(tot_hi, 0x7FFFFFFFu);
+      f.pattern_row = x.pattern_row;
+      doptf.push_back(f);
     }
     da[t] = d;
     mn[t] = a.min_group_size;
@@ -359,6 +386,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   PM_CUDA(cudaSetDevice(e->device));
   PM_CUDA(e->asks.ensure(n_asks));
   PM_CUDA(e->opts.ensure(dopt.size()));
+  PM_CUDA(e->opts_fast.ensure(doptf.size()));
   PM_CUDA(e->amin.ensure(n_asks));
   PM_CUDA(e->amax.ensure(n_asks));
   if (n_asks) {
@@ -366,13 +394,16 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
     PM_CUDA(cudaMemcpyAsync(e->amin.p, mn.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
     PM_CUDA(cudaMemcpyAsync(e->amax.p, mx.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
   }
-  if (!dopt.empty())
+  if (!dopt.empty()) {
     PM_CUDA(cudaMemcpyAsync(e->opts.p, dopt.data(), dopt.size() * sizeof(pm::DevOpt), cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->opts_fast.p, doptf.data(), doptf.size() * sizeof(pm::DevOptF), cudaMemcpyHostToDevice, e->stream));
+  }
   PM_CUDA(cudaStreamSynchronize(e->stream));  // staging vectors die here
   e->n_asks = n_asks;
   e->n_opts = (uint32_t)dopt.size();
   e->max_pattern_row = max_row;
   e->all_solo = solo;
+  e->asks_small = small;
   e->have_asks = true;
   e->matched = e->local_done = false;
   return PM_OK;
@@ -412,6 +443,7 @@ int pm_set_worker_count(pm_engine* e, uint32_t n_workers) {
   PM_CUDA(cudaMemsetAsync(e->wa.p, 0, (size_t)std::max<uint32_t>(n_workers, 1) * 16, e->stream));
   PM_CUDA(cudaMemsetAsync(e->wb.p, 0, (size_t)std::max<uint32_t>(n_workers, 1) * 16, e->stream));
   e->n_workers = n_workers;
+  e->workers_checked = false;
   e->have_workers = true;
   e->have_loc = e->have_rank = false;
   e->matched = e->local_done = false;
@@ -430,6 +462,7 @@ int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, 
     PM_CUDA(cudaMemcpyAsync(e->wa.p + first, a, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
     PM_CUDA(cudaMemcpyAsync(e->wb.p + first, b, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
   }
+  e->workers_checked = false;
   e->matched = e->local_done = false;
   return PM_OK;
 }
@@ -476,11 +509,76 @@ int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint3
   PM_CUDA(cudaMemcpyAsync(e->scratch_flags.p, flags, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   pm::pm_scatter_flags<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->wa.p, e->scratch_idx.p, e->scratch_flags.p, n, e->n_workers);
   PM_LAUNCH_CHECK("pm_scatter_flags");
+  e->workers_checked = false;
   e->matched = e->local_done = false;
   return PM_OK;
 }
 
 // ------------------------------------------------------------------ evaluation
+// Fast predicate only when both tables fit its operand limits; decided per match.
+static int decide_fast(pm_engine* e, bool* fast) {
+  *fast = false;
+  if (e->tune_generic || !e->asks_small) return PM_OK;
+  if (!e->workers_checked) {
+    uint32_t one = 1;
+    PM_CUDA(cudaMemcpyAsync(e->counters.p + 2, &one, 4, cudaMemcpyHostToDevice, e->stream));
+    if (e->n_workers) {
+      pm::pm_check_worker_ranges<<<blocks_for(e->n_workers, 256), 256, 0, e->stream>>>(e->wa.p, e->wb.p, e->n_workers, e->counters.p + 2);
+      PM_LAUNCH_CHECK("pm_check_worker_ranges");
+    }
+    PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 4, e->counters.p + 2, 4, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(cudaStreamSynchronize(e->stream));
+    e->workers_small = e->h_scalars.p[4] != 0;
+    e->workers_checked = true;
+  }
+  *fast = e->workers_small;
+  return PM_OK;
+}
+
+static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, dim3 grid,
+                         uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw, size_t ld) {
+#define PM_BUILD_CASE(B, F) pm::pm_build_cost<B, F><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld)
+  if (fast) {
+    if (bits_mode == 2) PM_BUILD_CASE(2, true); else if (bits_mode == 1) PM_BUILD_CASE(1, true); else PM_BUILD_CASE(0, true);
+  } else {
+    if (bits_mode == 2) PM_BUILD_CASE(2, false); else if (bits_mode == 1) PM_BUILD_CASE(1, false); else PM_BUILD_CASE(0, false);
+  }
+#undef PM_BUILD_CASE
+}
+
+static void launch_fused(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, dim3 grid,
+                         uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw) {
+#define PM_FUSED_CASE(B, F) pm::pm_fused_eval<B, F><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p)
+  if (fast) {
+    if (bits_mode == 2) PM_FUSED_CASE(2, true); else if (bits_mode == 1) PM_FUSED_CASE(1, true); else PM_FUSED_CASE(0, true);
+  } else {
+    if (bits_mode == 2) PM_FUSED_CASE(2, false); else if (bits_mode == 1) PM_FUSED_CASE(1, false); else PM_FUSED_CASE(0, false);
+  }
+#undef PM_FUSED_CASE
+}
+
+static void launch_argmin(pm_engine* e, size_t ld, uint32_t nt, uint32_t t0, uint32_t w0, uint32_t nw) {
+#define PM_ARGMIN_CASE(S, RPW)                                                                      \
+  {                                                                                                  \
+    dim3 grid(blocks_for(ld, (S) * 64), blocks_for(nt, pm::kArgRows));                               \
+    pm::pm_argmin<S, RPW><<<grid, pm::kArgThreads, 0, e->stream>>>(e->cost.p, ld, nt, t0, w0, nw,    \
+                                                                   e->first_ask.p, e->ask_best.p,   \
+                                                                   e->ask_count.p);                 \
+  }
+  switch (e->tune_argmin) {
+    case 1: PM_ARGMIN_CASE(4, 1) break;
+    case 2: PM_ARGMIN_CASE(4, 2) break;
+    case 3: PM_ARGMIN_CASE(8, 2) break;
+    case 4: PM_ARGMIN_CASE(4, 4) break;
+    case 5: PM_ARGMIN_CASE(8, 1) break;
+    case 6: PM_ARGMIN_CASE(8, 4) break;
+    case 7: PM_ARGMIN_CASE(16, 1) break;
+    case 8: PM_ARGMIN_CASE(16, 2) break;
+    default: PM_ARGMIN_CASE(8, 2) break;
+  }
+#undef PM_ARGMIN_CASE
+}
+
 static int match_local_locked(pm_engine* e, uint32_t mode) {
   if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_match: worker and ask tables must be set first");
   if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
@@ -520,22 +618,25 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
   if (T && nw) {
     pm::EvalParams p = eval_params(e);
     const int bits_mode = ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0;
+    bool fast = false;
+    {
+      int rc = decide_fast(e, &fast);
+      if (rc != PM_OK) return rc;
+    }
     if (mode & PM_PATH_FUSED) {
       Timer tm(e, &e->stats.ms_fused);
       const uint32_t rows_per_launch = 65535u * pm::kEvalRows;
       for (uint32_t t0 = 0; t0 < T; t0 += rows_per_launch) {
         const uint32_t nt = std::min(rows_per_launch, T - t0);
         dim3 grid(blocks_for(nw, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
-        if (bits_mode == 2) pm::pm_fused_eval<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
-        else if (bits_mode == 1) pm::pm_fused_eval<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
-        else pm::pm_fused_eval<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+        launch_fused(e, p, bits_mode, fast, grid, t0, nt, w0, nw);
         PM_LAUNCH_CHECK("pm_fused_eval");
         ++e->stats.n_fused_launches;
       }
       tm.stop();
       e->stats.n_tiles = 1;
     } else {
-      const size_t ld = ((size_t)nw + 3) & ~(size_t)3;
+      const size_t ld = ((size_t)nw + 15) & ~(size_t)15;  // 128-byte rows
       uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
       if (rows == 0) rows = 1;
       rows = std::min<uint64_t>(rows, T);
@@ -550,17 +651,14 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
         {
           Timer tm(e, &e->stats.ms_build);
           dim3 grid(blocks_for(ld, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
-          if (bits_mode == 2) pm::pm_build_cost<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
-          else if (bits_mode == 1) pm::pm_build_cost<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
-          else pm::pm_build_cost<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+          launch_build(e, p, bits_mode, fast, grid, t0, nt, w0, nw, ld);
           PM_LAUNCH_CHECK("pm_build_cost");
           tm.stop();
           ++e->stats.n_build_launches;
         }
         {
           Timer tm(e, &e->stats.ms_argmin);
-          dim3 grid(blocks_for(ld, pm::kArgCols), blocks_for(nt, pm::kArgRows));
-          pm::pm_argmin<<<grid, pm::kArgThreads, 0, e->stream>>>(e->cost.p, ld, nt, t0, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p);
+          launch_argmin(e, ld, nt, t0, w0, nw);
           PM_LAUNCH_CHECK("pm_argmin");
           tm.stop();
           ++e->stats.n_argmin_launches;
@@ -755,7 +853,7 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
     PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
     e->words = 1;
   }
-  const size_t ld = ((size_t)nw + 3) & ~(size_t)3;
+  const size_t ld = ((size_t)nw + 15) & ~(size_t)15;
   if (nt > 65535u * pm::kEvalRows) return e->fail(PM_E_INVALID, "pm_build_cost_tile: too many rows");
   if (e->cost.ensure((size_t)nt * ld) != cudaSuccess) {
     cudaGetLastError();
@@ -763,10 +861,12 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
   }
   pm::EvalParams p = eval_params(e);
   dim3 grid(blocks_for(ld, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
-  if ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap)
-    pm::pm_build_cost<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
-  else
-    pm::pm_build_cost<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  bool fast = false;
+  {
+    int rc = decide_fast(e, &fast);
+    if (rc != PM_OK) return rc;
+  }
+  launch_build(e, p, ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0, fast, grid, t0, nt, w0, nw, ld);
   PM_LAUNCH_CHECK("pm_build_cost");
   PM_CUDA(cudaMemcpy2DAsync(host_out, (size_t)nw * 8, e->cost.p, ld * 8, (size_t)nw * 8, nt,
                             cudaMemcpyDeviceToHost, e->stream));

@@ -20,6 +20,7 @@ struct EvalParams {
   const uint4* __restrict__ wb;       // plane B [n_workers]
   const DevAsk* __restrict__ asks;    // [n_asks] priority order
   const DevOpt* __restrict__ opts;    // CSR, ask order
+  const DevOptF* __restrict__ opts_fast;  // same CSR, fast-path form
   const uint32_t* __restrict__ bits;  // [(n_patterns+1) * words], row 0 all-ones
   uint32_t words;
   uint32_t n_workers;                 // global
@@ -120,6 +121,46 @@ __device__ __forceinline__ void eval_row(const EvalStage& s, const DevAsk& a, ui
   }
 }
 
+// Fast path (all operands < 2^31, counts < 2^16): `fail == 0` <=> feasible.
+// Per worker and option: 2 LOP3 for presence+count+model, 4 IMAD subtractions and
+// 2 LOP3 for the two range clauses, 1 LOP3 to merge — half the ALU-pipe work of the
+// generic chain, which is what bounds pm_build_cost on the integer side.
+template <int WPT, int BITS>
+__device__ __forceinline__ void eval_row_fast(const EvalStage& s, const DevAsk& a, uint32_t obegin,
+                                              const WorkerReg (&w)[WPT],
+                                              const uint32_t* __restrict__ gbits, uint32_t words,
+                                              uint32_t (&fail)[WPT]) {
+  uint32_t sb[WPT];
+#pragma unroll
+  for (int k = 0; k < WPT; ++k)
+    sb[k] = ((w[k].cores - a.cpu_cores) | (w[k].ram - a.ram_mb) | (w[k].storage - a.storage_gb)) & kSign;
+  if (a.n_opts == 0u) {
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) fail[k] = (~w[k].key & a.need) | sb[k];
+    return;
+  }
+  const DevOptF* optf = reinterpret_cast<const DevOptF*>(s.opt);
+  const uint32_t o0 = a.opt_off - obegin;
+  uint32_t um[WPT];
+  for (uint32_t o = 0; o < a.n_opts; ++o) {
+    const DevOptF q = optf[o0 + o];
+    const uint32_t rowoff = q.pattern_row * words;
+    const uint32_t uword = (BITS == 2) ? s.bits[q.pattern_row] : 0u;
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const uint32_t word = (BITS == 2) ? uword
+                            : (BITS == 1) ? s.bits[rowoff + w[k].mword] : __ldg(gbits + rowoff + w[k].mword);
+      const uint32_t z = ((w[k].key & q.m) ^ q.v) | (~word & w[k].mmask);
+      const uint32_t r = (w[k].mem_eff - q.mem_lo) | (q.mem_hi - w[k].mem_eff) |
+                         (((w[k].tot - q.tot_lo) | (q.tot_hi - w[k].tot)) & w[k].tot_keep);
+      const uint32_t u = z | (r & kSign);
+      um[k] = (o == 0u) ? u : min(um[k], u);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) fail[k] = um[k] | sb[k];
+}
+
 // Slow path for an ask whose option list alone exceeds the staging capacity.
 template <int WPT>
 __device__ __noinline__ void eval_row_global(const EvalParams& p, const DevAsk& a,
@@ -143,8 +184,9 @@ __device__ __forceinline__ void load_workers(const EvalParams& p, uint32_t w0, u
 // ask headers, then as many option rows as fit, arrive in shared memory through
 // 1-D TMA bulk copies signalled on one mbarrier.
 template <class Body>
-__device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalParams& p, uint32_t t0,
-                                                    uint32_t r0, uint32_t r1, Body&& body) {
+__device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalParams& p, bool fast,
+                                                    uint32_t t0, uint32_t r0, uint32_t r1, Body&& body) {
+  const DevOpt* opt_src = fast ? reinterpret_cast<const DevOpt*>(p.opts_fast) : p.opts;
   if (threadIdx.x == 0) mbar_init(&s.bar, 1);
   const uint32_t total_words = (p.n_bits_rows)*p.words;
   if (total_words <= (uint32_t)kBitsCap)
@@ -174,7 +216,7 @@ __device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalPara
     if (oend > obegin) {
       if (threadIdx.x == 0) {
         mbar_expect_tx(&s.bar, (oend - obegin) * (uint32_t)sizeof(DevOpt));
-        bulk_g2s(s.opt, p.opts + obegin, (oend - obegin) * (uint32_t)sizeof(DevOpt), &s.bar);
+        bulk_g2s(s.opt, opt_src + obegin, (oend - obegin) * (uint32_t)sizeof(DevOpt), &s.bar);
       }
       mbar_wait(&s.bar, phase);
       phase ^= 1u;
@@ -189,8 +231,8 @@ __device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalPara
 // grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 adjacent workers in
 // registers and walks the staged asks, emitting two 128-bit streaming stores per
 // row: a warp writes 1 KB contiguous, the CTA 8 KB contiguous per row.
-template <int BITS>
-__global__ void __launch_bounds__(kEvalThreads)
+template <int BITS, bool FAST>
+__global__ void __launch_bounds__(kEvalThreads, 2)
 pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               long long* __restrict__ cost, size_t ld) {
   __shared__ EvalStage s;
@@ -205,17 +247,26 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
   for (int k = 0; k < kEvalWPT; ++k) gw[k] = w0 + c + k;
   uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + (in_range ? c : 0));
   const size_t row_stride = ld / 2;   // in 16-byte units; rows are visited in increasing order
-  for_each_staged_row(s, p, t0, r0, r1, [&](uint32_t, const DevAsk& a, uint32_t obegin, bool staged) {
-    uint32_t f[kEvalWPT];
-    if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
-    else eval_row_global<kEvalWPT>(p, a, w, f);
-    if (in_range) {
-      // feasible: (price << 32) | worker ; infeasible: 0x7FFFFFFF_FFFFFFFF — pure bit selects
-      uint4 v0, v1;
+  for_each_staged_row(s, p, FAST, t0, r0, r1, [&](uint32_t, const DevAsk& a, uint32_t obegin, bool staged) {
+    uint4 v0, v1;
+    // feasible: (price << 32) | worker ; infeasible: 0x7FFFFFFF_FFFFFFFF
+    if (FAST && staged) {
+      uint32_t fail[kEvalWPT];
+      eval_row_fast<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, fail);
+      v0.x = fail[0] ? 0xFFFFFFFFu : gw[0]; v0.y = fail[0] ? 0x7FFFFFFFu : w[0].price;
+      v0.z = fail[1] ? 0xFFFFFFFFu : gw[1]; v0.w = fail[1] ? 0x7FFFFFFFu : w[1].price;
+      v1.x = fail[2] ? 0xFFFFFFFFu : gw[2]; v1.y = fail[2] ? 0x7FFFFFFFu : w[2].price;
+      v1.z = fail[3] ? 0xFFFFFFFFu : gw[3]; v1.w = fail[3] ? 0x7FFFFFFFu : w[3].price;
+    } else {
+      uint32_t f[kEvalWPT];
+      if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
+      else eval_row_global<kEvalWPT>(p, a, w, f);
       v0.x = gw[0] | ~f[0]; v0.y = (w[0].price & f[0]) | (0x7FFFFFFFu & ~f[0]);
       v0.z = gw[1] | ~f[1]; v0.w = (w[1].price & f[1]) | (0x7FFFFFFFu & ~f[1]);
       v1.x = gw[2] | ~f[2]; v1.y = (w[2].price & f[2]) | (0x7FFFFFFFu & ~f[2]);
       v1.z = gw[3] | ~f[3]; v1.w = (w[3].price & f[3]) | (0x7FFFFFFFu & ~f[3]);
+    }
+    if (in_range) {
       __stcs(out, v0);
       __stcs(out + 1, v1);
     }
@@ -225,68 +276,77 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
 
 // ------------------------------------------------------------------ argmin
 constexpr int kArgThreads = 256;
-constexpr int kArgStripes = 8;                   // 16 B loads in flight per lane per row
-constexpr int kArgCols = kArgStripes * 64;       // 512 columns per CTA
 constexpr int kArgRows = 64;                     // rows per CTA (8 per warp)
 
-// grid = (ceil(ld / 512), ceil(nt / 64)).  Warp j reduces rows j, j+8, ...; for a
-// row it issues 8 independent 128-bit streaming loads (4 KB per warp in flight),
-// folds them lane-locally, then one shuffle reduction per row.
+// grid = (ceil(ld / (S*64)), ceil(nt / 64)).  Warp j reduces rows j, j+8, ...; for
+// RPW rows at a time it issues S independent 128-bit streaming loads per row
+// (S*RPW*512 B per warp in flight), folds them lane-locally, then one shuffle
+// reduction per row.  Per-column "first feasible ask" lives in registers and is
+// merged across the CTA's warps through shared memory.
+template <int S, int RPW>
 __global__ void __launch_bounds__(kArgThreads)
 pm_argmin(const long long* __restrict__ cost, size_t ld, uint32_t nt, uint32_t t0, uint32_t w0,
           uint32_t nw, uint32_t* __restrict__ first_ask, long long* __restrict__ ask_best,
           uint32_t* __restrict__ ask_count) {
-  __shared__ uint32_t s_cm[kArgCols];
+  constexpr int kCols = S * 64;
+  constexpr int kWarps = kArgThreads / 32;
+  __shared__ uint32_t s_cm[kCols];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t c0 = blockIdx.x * kArgCols;
+  const uint32_t c0 = blockIdx.x * kCols;
   const uint32_t r0 = blockIdx.y * kArgRows;
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kArgCols; i += kArgThreads) s_cm[i] = kNone;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kCols; i += kArgThreads) s_cm[i] = kNone;
   __syncthreads();
 
-  uint32_t cm[kArgStripes][2];
+  uint32_t cm[S][2];
 #pragma unroll
-  for (int s = 0; s < kArgStripes; ++s) cm[s][0] = cm[s][1] = kNone;
+  for (int s = 0; s < S; ++s) cm[s][0] = cm[s][1] = kNone;
 
-  for (uint32_t rr = warp; rr < (uint32_t)kArgRows; rr += kArgThreads / 32) {
-    const uint32_t r = r0 + rr;
-    if (r >= nt) break;
-    const longlong2* rowp = reinterpret_cast<const longlong2*>(cost + (size_t)r * ld);
-    longlong2 v[kArgStripes];
+  for (uint32_t rr = warp; rr < (uint32_t)kArgRows; rr += kWarps * RPW) {
+    longlong2 v[RPW][S];
 #pragma unroll
-    for (int s = 0; s < kArgStripes; ++s) {
-      const uint32_t col = c0 + s * 64 + lane * 2;
-      if (col < ld) v[s] = __ldcs(rowp + (col >> 1));
-      else v[s] = make_longlong2(kInf, kInf);
-    }
-    const uint32_t t = t0 + r;
-    long long best = kInf;
-    uint32_t cnt = 0;
+    for (int q = 0; q < RPW; ++q) {
+      const uint32_t r = r0 + rr + q * kWarps;
+      const longlong2* rowp = reinterpret_cast<const longlong2*>(cost + (size_t)r * ld);
 #pragma unroll
-    for (int s = 0; s < kArgStripes; ++s) {
-      best = min(best, min(v[s].x, v[s].y));
-      const bool fx = v[s].x != kInf, fy = v[s].y != kInf;
-      cnt += (uint32_t)fx + (uint32_t)fy;
-      cm[s][0] = fx ? min(cm[s][0], t) : cm[s][0];
-      cm[s][1] = fy ? min(cm[s][1], t) : cm[s][1];
+      for (int s = 0; s < S; ++s) {
+        const uint32_t col = c0 + s * 64 + lane * 2;
+        if (r < nt && col < ld) v[q][s] = __ldcs(rowp + (col >> 1));
+        else v[q][s] = make_longlong2(kInf, kInf);
+      }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    }
-    if (lane == 0 && cnt) {
-      atomicMin(ask_best + t, best);
-      atomicAdd(ask_count + t, cnt);
+    for (int q = 0; q < RPW; ++q) {
+      const uint32_t r = r0 + rr + q * kWarps;
+      const uint32_t t = t0 + r;
+      long long best = kInf;
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        best = min(best, min(v[q][s].x, v[q][s].y));
+        const bool fx = v[q][s].x != kInf, fy = v[q][s].y != kInf;
+        cnt += (uint32_t)fx + (uint32_t)fy;
+        cm[s][0] = fx ? min(cm[s][0], t) : cm[s][0];
+        cm[s][1] = fy ? min(cm[s][1], t) : cm[s][1];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      }
+      if (lane == 0 && cnt) {
+        atomicMin(ask_best + t, best);
+        atomicAdd(ask_count + t, cnt);
+      }
     }
   }
 #pragma unroll
-  for (int s = 0; s < kArgStripes; ++s) {
+  for (int s = 0; s < S; ++s) {
     const uint32_t i = s * 64 + lane * 2;
     if (cm[s][0] != kNone) atomicMin(&s_cm[i], cm[s][0]);
     if (cm[s][1] != kNone) atomicMin(&s_cm[i + 1], cm[s][1]);
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kArgCols; i += kArgThreads) {
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kCols; i += kArgThreads) {
     const uint32_t col = c0 + i;
     if (col < nw && s_cm[i] != kNone) atomicMin(first_ask + w0 + col, s_cm[i]);
   }
@@ -297,8 +357,8 @@ pm_argmin(const long long* __restrict__ cost, size_t ld, uint32_t nt, uint32_t t
 // leaves the SM: per-row results go through ballots (first-fit cost is the
 // worker index, so the row minimum is the lowest set bit), per-worker results
 // stay in registers.  Integer-issue-bound, not HBM-bound.
-template <int BITS>
-__global__ void __launch_bounds__(kEvalThreads)
+template <int BITS, bool FAST>
+__global__ void __launch_bounds__(kEvalThreads, 2)
 pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               uint32_t* __restrict__ first_ask, long long* __restrict__ ask_best,
               uint32_t* __restrict__ ask_count) {
@@ -319,10 +379,18 @@ pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
 #pragma unroll
   for (int k = 0; k < kEvalWPT; ++k) first[k] = kNone;
   const uint32_t warp_gw0 = w0 + (c - lane * kEvalWPT);
-  for_each_staged_row(s, p, t0, r0, r1, [&](uint32_t r, const DevAsk& a, uint32_t obegin, bool staged) {
+  for_each_staged_row(s, p, FAST, t0, r0, r1, [&](uint32_t r, const DevAsk& a, uint32_t obegin, bool staged) {
     uint32_t f[kEvalWPT];
-    if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
-    else eval_row_global<kEvalWPT>(p, a, w, f);
+    if (FAST && staged) {
+      uint32_t fail[kEvalWPT];
+      eval_row_fast<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, fail);
+#pragma unroll
+      for (int k = 0; k < kEvalWPT; ++k) f[k] = fail[k] ? 0u : 0xFFFFFFFFu;
+    } else if (staged) {
+      eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
+    } else {
+      eval_row_global<kEvalWPT>(p, a, w, f);
+    }
     const uint32_t t = t0 + r0 + r;
     uint32_t cnt = 0, best = kNone;
 #pragma unroll
@@ -362,6 +430,21 @@ __global__ void pm_iota_u32(uint32_t* p, size_t n) {
 __global__ void pm_scatter_flags(uint4* wa, const uint32_t* idx, const uint32_t* flags, uint32_t n, uint32_t n_workers) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && idx[i] < n_workers) wa[idx[i]].w = flags[i];
+}
+
+// Do all workers satisfy the fast-path operand limits (values < 2^31, gpu count < 2^16,
+// count * memory_mb < 2^31 without wrapping)?  Clears *ok otherwise.
+__global__ void pm_check_worker_ranges(const uint4* __restrict__ wa, const uint4* __restrict__ wb,
+                                       uint32_t n, uint32_t* __restrict__ ok) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 a = wa[i], b = wb[i];
+  bool small = (b.x | b.y | b.z) < kSign;
+  if (a.w & PM_W_HAS_GPU_COUNT) small &= a.x < 65536u;
+  if (a.w & PM_W_HAS_GPU_MEM) small &= a.y < kSign;
+  if ((a.w & PM_W_HAS_GPU_COUNT) && (a.w & PM_W_HAS_GPU_MEM))
+    small &= (unsigned long long)a.x * (unsigned long long)a.y < (unsigned long long)kSign;
+  if (!small) *ok = 0u;
 }
 
 // ------------------------------------------------------------------ resolution

@@ -204,3 +204,53 @@ def test_cfg2_100k_x_100k_mixed_bit_exact():
         assert np.array_equal(res.ask_best[t0:t0 + 1000], ev["row_best"])
         assert np.array_equal(res.ask_count[t0:t0 + 1000], ev["row_count"])
     eng.close()
+
+
+@pytest.mark.parametrize("path", [MAT, FUSED], ids=["materialized", "fused"])
+def test_generic_predicate_path_forced(path, monkeypatch):
+    """The fast predicate (operands < 2^31) and the generic one must agree; force the generic."""
+    monkeypatch.setenv("PM_TUNE_GENERIC", "1")
+    sizes = [(1, 1), (2, 2), (2, 4), (3, 3)]
+    w, a, t = synth_tables(400, 5000, "mixed", group_sizes=sizes)
+    eng = Engine()
+    load_engine(eng, t)
+    check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT | path)
+    eng.close()
+
+
+@pytest.mark.parametrize("path", [MAT, FUSED], ids=["materialized", "fused"])
+def test_large_operands_fall_back_to_generic(path):
+    """u32 operands >= 2^31, counts >= 2^16 and a wrapping count*memory product: the engine must
+    notice (device-side range check) and stay bit-exact (node.rs:509 wraps in release builds)."""
+    tb = TableBuilder()
+    tb.add_config("ram_mb=3000000000", 1, 1)
+    tb.add_config("gpu:count=70000", 1, 1)
+    tb.add_config("gpu:total_memory_max=10", 1, 1)
+    tb.add_config("gpu:count=2;gpu:memory_mb_min=2500000000", 1, 1)
+    tb.add_config("storage_gb=5", 1, 2)
+    tb.add_node(kv.specs(1, "A100", 40000, 8, 3500000000, 10))
+    tb.add_node(kv.specs(70000, "A100", 10, 8, 1000, 10))
+    tb.add_node(kv.specs(65536, "X", 65536, 8, 1000, 10))          # product wraps to 0
+    tb.add_node(kv.specs(2, "A100", 3000000000, 8, 1000, 10))
+    tb.add_node(kv.specs(2, "A100", 40000, 8, 1000, 10))
+    tb.add_node(kv.specs(4, "H100", 80000, 8, 2999999999, 4000000000))
+    t = tb.tables()
+    eng = Engine()
+    load_engine(eng, t)
+    res, og = check_against_oracle(eng, t, abi.PM_MODE_FIRST_FIT | path)
+    assert res.n_groups >= 4
+    eng.close()
+
+
+def test_fast_and_generic_cost_matrices_identical(monkeypatch):
+    w, a, t = synth_tables(600, 3000, "skewed")
+    eng = Engine()
+    load_engine(eng, t)
+    fast = eng.cost_tile(0, 600)
+    eng.close()
+    monkeypatch.setenv("PM_TUNE_GENERIC", "1")
+    eng = Engine()
+    load_engine(eng, t)
+    generic = eng.cost_tile(0, 600)
+    eng.close()
+    assert np.array_equal(fast, generic)
