@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "pm_kernels.cuh"
+#include "pm_proximity.cuh"
 
 struct pm_engine;
 
@@ -106,6 +107,9 @@ struct pm_engine {
   DevBuf<uint32_t> keys, keys_sorted, iota, order, hist, seg_start, ngroups, group_base;
   DevBuf<uint32_t> base_len, xhead, xnext, xcount, popped, counters;  // counters: [0]=any_bad [1]=n_bumped
   DevBuf<unsigned char> cub_tmp;
+  DevBuf<uint32_t> prox_list, prox_xs, members_raw;
+  DevBuf<double> prox_dist;
+  bool any_max_zero = false;
   DevBuf<uint32_t> worker_group, worker_ask, group_ask, group_off, members;
   PinBuf<uint32_t> h_scalars;  // small D2H mailbox
 
@@ -264,7 +268,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   }
   ok = ok &&
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
-            e->h_scalars.ensure(16) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
+            e->h_scalars.ensure(32) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
   if (!ok) {
     g_create_error = std::string("pm_create: ") + cudaGetErrorString(cudaGetLastError());
     delete e;
@@ -286,6 +290,7 @@ void pm_destroy(pm_engine* e) {
   e->hist.release(); e->seg_start.release(); e->ngroups.release(); e->group_base.release();
   e->base_len.release(); e->xhead.release(); e->xnext.release(); e->xcount.release();
   e->popped.release(); e->counters.release(); e->cub_tmp.release();
+  e->prox_list.release(); e->prox_xs.release(); e->members_raw.release(); e->prox_dist.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
@@ -404,6 +409,9 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   e->max_pattern_row = max_row;
   e->all_solo = solo;
   e->asks_small = small;
+  e->any_max_zero = false;
+  for (uint32_t t = 0; t < n_asks; ++t)
+    if (mx[t] == 0) e->any_max_zero = true;
   e->have_asks = true;
   e->matched = e->local_done = false;
   return PM_OK;
@@ -586,8 +594,11 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
   const uint32_t base_mode = mode & 0xFFu;
   if (base_mode == PM_MODE_AUCTION) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is not built yet");
   if (base_mode != PM_MODE_FIRST_FIT && base_mode != PM_MODE_PROXIMITY) return e->fail(PM_E_INVALID, "pm_match: unknown mode");
-  if (base_mode == PM_MODE_PROXIMITY && !e->all_solo)
-    return e->fail(PM_E_UNSUPPORTED, "pm_match: proximity mode currently requires min_group_size == max_group_size == 1");
+  if (base_mode == PM_MODE_PROXIMITY && !e->all_solo) {
+    if (!e->have_loc) return e->fail(PM_E_STATE, "pm_match: proximity mode needs pm_set_worker_locations");
+    if (e->any_max_zero)
+      return e->fail(PM_E_UNSUPPORTED, "pm_match: max_group_size == 0 is not supported in proximity mode");
+  }
   PM_CUDA(cudaSetDevice(e->device));
   const uint32_t W = e->n_workers, T = e->n_asks;
   const uint32_t w0 = e->cfg.shard_first;
@@ -698,7 +709,8 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   PM_CUDA(cudaSetDevice(e->device));
   const uint32_t base_mode = mode & 0xFFu;
   const uint32_t W = e->n_workers, T = e->n_asks;
-  const uint32_t shift = (base_mode == PM_MODE_PROXIMITY) ? 1u : 0u;
+  const bool prox_general = base_mode == PM_MODE_PROXIMITY && !e->all_solo;
+  const uint32_t shift = (base_mode == PM_MODE_PROXIMITY && !prox_general) ? 1u : 0u;
   const uint32_t n_bins = T << shift;
   Timer tm(e, &e->stats.ms_resolve);
 
@@ -714,6 +726,56 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   }
   int rc = sort_and_scan(e, n_bins, shift);
   if (rc != PM_OK) return rc;
+
+  if (prox_general) {
+    // sequential-per-group nearest-neighbour formation (pm_proximity.cuh)
+    uint32_t P = 1;
+    while (P < std::max<uint32_t>(W, 1)) P <<= 1;
+    const uint32_t cap = W + T + 1;
+    PM_CUDA(e->base_len.ensure(T)); PM_CUDA(e->xhead.ensure(T)); PM_CUDA(e->xcount.ensure(T));
+    PM_CUDA(e->xnext.ensure(W)); PM_CUDA(e->popped.ensure(W));
+    PM_CUDA(e->prox_list.ensure(W)); PM_CUDA(e->prox_xs.ensure(P)); PM_CUDA(e->prox_dist.ensure(W));
+    PM_CUDA(e->members_raw.ensure(W));
+    PM_CUDA(e->group_ask.ensure((size_t)cap + 1)); PM_CUDA(e->group_off.ensure((size_t)cap + 1));
+    PM_CUDA(cudaMemcpyAsync(e->base_len.p, e->hist.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->xhead.p, 0xFF, (size_t)T * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->xcount.p, 0, (size_t)T * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->counters.p + 4, 0, 4 * 4, e->stream));
+    pm::ProxParams pp;
+    pp.ev = eval_params(e);
+    pp.lat = e->lat.p; pp.lon = e->lon.p;
+    pp.cur = e->first_ask.p; pp.base_len = e->base_len.p; pp.seg_start = e->seg_start.p; pp.order = e->order.p;
+    pp.xhead = e->xhead.p; pp.xnext = e->xnext.p; pp.xcount = e->xcount.p; pp.amin = e->amin.p; pp.amax = e->amax.p;
+    pp.list = e->prox_list.p; pp.xs = e->prox_xs.p; pp.dist = e->prox_dist.p; pp.popped = e->popped.p;
+    pp.worker_group = e->worker_group.p; pp.worker_ask = e->worker_ask.p; pp.group_ask = e->group_ask.p;
+    pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = e->counters.p + 4;
+    pp.group_cap = cap;
+    pm::pm_proximity_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
+    PM_LAUNCH_CHECK("pm_proximity_sweep");
+    PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 8, e->counters.p + 4, 16, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_scalars.p[11]) return e->fail(PM_E_CUDA, "pm_match: proximity group table overflow");
+    const uint32_t G = e->h_scalars.p[8], M = e->h_scalars.p[9];
+    e->stats.n_bumped = e->h_scalars.p[10];
+    e->n_groups = G;
+    e->n_assigned = M;
+    if (M) {
+      pm::pm_order_members<<<blocks_for(M, 256), 256, 0, e->stream>>>(
+          e->members_raw.p, M, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
+      PM_LAUNCH_CHECK("pm_order_members");
+    }
+    tm.stop();
+    if (e->cfg.flags & PM_CFG_TIMING) {
+      PM_CUDA(cudaEventRecord(e->ev1, e->stream));
+      PM_CUDA(cudaEventSynchronize(e->ev1));
+      PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
+      e->resolve_timers();
+    }
+    e->matched = true;
+    return PM_OK;
+  }
 
   if (shift == 0 && T && !e->all_solo) {
     pm::pm_check_tails<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, T, e->counters.p);

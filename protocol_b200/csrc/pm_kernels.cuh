@@ -651,11 +651,11 @@ __global__ void pm_order_members(const uint32_t* __restrict__ order, uint32_t n_
   if (g == kNone) { members[pidx] = w; return; }
   const uint32_t gs = group_off[g], ge = group_off[g + 1];
   uint32_t pos = 0;
-  if (addr_rank) {
-    const uint32_t mine = addr_rank[w];
-    for (uint32_t q = gs; q < ge; ++q) pos += (addr_rank[order[q]] < mine) ? 1u : 0u;
-  } else {
-    pos = pidx - gs;
+  // without address ranks the row index stands in for the address order
+  const uint32_t mine = addr_rank ? addr_rank[w] : w;
+  for (uint32_t q = gs; q < ge; ++q) {
+    const uint32_t o = order[q];
+    pos += ((addr_rank ? addr_rank[o] : o) < mine) ? 1u : 0u;
   }
   members[gs + pos] = w;
 }

@@ -254,3 +254,48 @@ def test_fast_and_generic_cost_matrices_identical(monkeypatch):
     generic = eng.cost_tile(0, 600)
     eng.close()
     assert np.array_equal(fast, generic)
+
+
+def _distinct_distance_gap(lat, lon, has_loc):
+    """Parity hazard H: only the ORDER of distances is observable and CUDA's
+    sin/cos/atan2 are not bit-identical to glibc's.  The synthetic swarm places workers on 64
+    well-separated cities, so distinct distances differ by kilometres; assert that margin."""
+    pts = np.unique(np.stack([lat[has_loc], lon[has_loc]], 1), axis=0)
+    d = np.array([[orc.haversine_km(a[0], a[1], b[0], b[1]) for b in pts] for a in pts])
+    gaps = []
+    for row in d:
+        u = np.unique(row)
+        if len(u) > 1:
+            gaps.append(np.min(np.diff(u)))
+    return min(gaps) if gaps else np.inf
+
+
+@pytest.mark.parametrize("sizes", [[(2, 2)], [(1, 1), (2, 2), (2, 4), (3, 3), (4, 8), (1, 3)]], ids=["pairs", "mixed"])
+def test_proximity_groups_general(sizes):
+    """ProximityOptimizationPolicy enabled with max_group_size > 1: seed = first located remaining
+    node, members = the max-1 nearest by haversine, stable ties (mod.rs:524-552, 218-255)."""
+    w, a, t = synth_tables(120, 4000, "mixed", group_sizes=sizes, with_addresses=True, seed_shift=5)
+    has_loc = (w.a["flags"] & abi.PM_W_HAS_LOC) != 0
+    assert _distinct_distance_gap(w.lat, w.lon, has_loc) > 1e-3        # km: no near-ties in this input
+    eng = Engine()
+    load_engine(eng, t, addr_rank=w.addr_rank, locations=True)
+    res, og = check_against_oracle(eng, t, abi.PM_MODE_PROXIMITY, addr_rank=w.addr_rank, proximity=True)
+    assert res.n_groups > 50
+    eng.close()
+
+
+def test_proximity_montreal_dallas_on_device():
+    """The coordinates of node_groups/tests.rs:2861-3064: interleaved arrivals still pair by city."""
+    tb = TableBuilder()
+    tb.add_config(None, 2, 2)
+    A6000 = kv.specs(1, "nvidia rtx a6000", 49140)
+    MONTREAL, DALLAS = (45.5186, -73.5545), (32.7942, -96.7475)
+    for loc in (MONTREAL, DALLAS, MONTREAL, DALLAS):
+        tb.add_node(A6000, location=loc)
+    t = tb.tables()
+    eng = Engine()
+    load_engine(eng, t, locations=True)
+    eng.match(abi.PM_MODE_PROXIMITY)
+    res = eng.fetch()
+    assert sorted(sorted(m) for _, m in res.groups()) == [[0, 2], [1, 3]]
+    eng.close()
