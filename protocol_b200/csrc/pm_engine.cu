@@ -568,7 +568,7 @@ static void launch_fused(pm_engine* e, const pm::EvalParams& p, int bits_mode, b
 static void launch_argmin(pm_engine* e, size_t ld, uint32_t nt, uint32_t t0, uint32_t w0, uint32_t nw) {
 #define PM_ARGMIN_CASE(S, RPW)                                                                      \
   {                                                                                                  \
-    dim3 grid(blocks_for(ld, (S) * 64), blocks_for(nt, pm::kArgRows));                               \
+    dim3 grid(blocks_for(ld, (S) * 64 * pm::kArgWarps), blocks_for(nt, pm::kArgRows));                               \
     pm::pm_argmin<S, RPW><<<grid, pm::kArgThreads, 0, e->stream>>>(e->cost.p, ld, nt, t0, w0, nw,    \
                                                                    e->first_ask.p, e->ask_best.p,   \
                                                                    e->ask_count.p);                 \

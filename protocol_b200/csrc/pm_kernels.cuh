@@ -276,79 +276,89 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
 
 // ------------------------------------------------------------------ argmin
 constexpr int kArgThreads = 256;
-constexpr int kArgRows = 64;                     // rows per CTA (8 per warp)
+constexpr int kArgWarps = kArgThreads / 32;
+constexpr int kArgRows = 64;                     // rows per CTA
 
-// grid = (ceil(ld / (S*64)), ceil(nt / 64)).  Warp j reduces rows j, j+8, ...; for
-// RPW rows at a time it issues S independent 128-bit streaming loads per row
-// (S*RPW*512 B per warp in flight), folds them lane-locally, then one shuffle
-// reduction per row.  Per-column "first feasible ask" lives in registers and is
-// merged across the CTA's warps through shared memory.
+// grid = (ceil(ld / (8*S*64)), ceil(nt / 64)).  All 8 warps of a CTA work on the SAME
+// RPW rows at a time, each on its own S*64-column slice (so a CTA touches RPW DRAM
+// pages / TLB entries at a time even when rows are megabytes apart); a lane issues
+// S*RPW independent 128-bit streaming loads before the first use (8 KB per warp in
+// flight at S=8, RPW=2), folds them lane-locally, then one shuffle reduction per
+// row.  Per-column "first feasible ask" never leaves the lane's registers; per-row
+// (min, count) partials are merged in shared memory and flushed once per CTA.
 template <int S, int RPW>
 __global__ void __launch_bounds__(kArgThreads)
 pm_argmin(const long long* __restrict__ cost, size_t ld, uint32_t nt, uint32_t t0, uint32_t w0,
           uint32_t nw, uint32_t* __restrict__ first_ask, long long* __restrict__ ask_best,
           uint32_t* __restrict__ ask_count) {
-  constexpr int kCols = S * 64;
-  constexpr int kWarps = kArgThreads / 32;
-  __shared__ uint32_t s_cm[kCols];
+  constexpr int kWarpCols = S * 64;
+  __shared__ unsigned long long s_best[kArgRows];
+  __shared__ uint32_t s_cnt[kArgRows];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t c0 = blockIdx.x * kCols;
+  const uint32_t c0 = (blockIdx.x * kArgWarps + warp) * kWarpCols;   // this warp's first column
   const uint32_t r0 = blockIdx.y * kArgRows;
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kCols; i += kArgThreads) s_cm[i] = kNone;
+  const uint32_t rows = min((uint32_t)kArgRows, nt - r0);
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kArgRows; i += kArgThreads) {
+    s_best[i] = (unsigned long long)kInf;
+    s_cnt[i] = 0;
+  }
   __syncthreads();
 
   uint32_t cm[S][2];
 #pragma unroll
   for (int s = 0; s < S; ++s) cm[s][0] = cm[s][1] = kNone;
 
-  for (uint32_t rr = warp; rr < (uint32_t)kArgRows; rr += kWarps * RPW) {
-    longlong2 v[RPW][S];
+  if (c0 < ld) {
+    for (uint32_t rr = 0; rr < rows; rr += RPW) {
+      longlong2 v[RPW][S];
 #pragma unroll
-    for (int q = 0; q < RPW; ++q) {
-      const uint32_t r = r0 + rr + q * kWarps;
-      const longlong2* rowp = reinterpret_cast<const longlong2*>(cost + (size_t)r * ld);
+      for (int q = 0; q < RPW; ++q) {
+        const uint32_t r = r0 + rr + q;
+        const longlong2* rowp = reinterpret_cast<const longlong2*>(cost + (size_t)r * ld);
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const uint32_t col = c0 + s * 64 + lane * 2;
-        if (r < nt && col < ld) v[q][s] = __ldcs(rowp + (col >> 1));
-        else v[q][s] = make_longlong2(kInf, kInf);
+        for (int s = 0; s < S; ++s) {
+          const uint32_t col = c0 + s * 64 + lane * 2;
+          if (rr + q < rows && col < ld) v[q][s] = __ldcs(rowp + (col >> 1));
+          else v[q][s] = make_longlong2(kInf, kInf);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const uint32_t t = t0 + r0 + rr + q;
+        long long best = kInf;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          best = min(best, min(v[q][s].x, v[q][s].y));
+          const bool fx = v[q][s].x != kInf, fy = v[q][s].y != kInf;
+          cnt += (uint32_t)fx + (uint32_t)fy;
+          cm[s][0] = fx ? min(cm[s][0], t) : cm[s][0];
+          cm[s][1] = fy ? min(cm[s][1], t) : cm[s][1];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+          cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        }
+        if (lane == 0 && cnt) {
+          atomicMin(&s_best[rr + q], (unsigned long long)best);
+          atomicAdd(&s_cnt[rr + q], cnt);
+        }
       }
     }
 #pragma unroll
-    for (int q = 0; q < RPW; ++q) {
-      const uint32_t r = r0 + rr + q * kWarps;
-      const uint32_t t = t0 + r;
-      long long best = kInf;
-      uint32_t cnt = 0;
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        best = min(best, min(v[q][s].x, v[q][s].y));
-        const bool fx = v[q][s].x != kInf, fy = v[q][s].y != kInf;
-        cnt += (uint32_t)fx + (uint32_t)fy;
-        cm[s][0] = fx ? min(cm[s][0], t) : cm[s][0];
-        cm[s][1] = fy ? min(cm[s][1], t) : cm[s][1];
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-      }
-      if (lane == 0 && cnt) {
-        atomicMin(ask_best + t, best);
-        atomicAdd(ask_count + t, cnt);
-      }
+    for (int s = 0; s < S; ++s) {
+      const uint32_t col = c0 + s * 64 + lane * 2;
+      if (cm[s][0] != kNone && col < nw) atomicMin(first_ask + w0 + col, cm[s][0]);
+      if (cm[s][1] != kNone && col + 1 < nw) atomicMin(first_ask + w0 + col + 1, cm[s][1]);
     }
-  }
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const uint32_t i = s * 64 + lane * 2;
-    if (cm[s][0] != kNone) atomicMin(&s_cm[i], cm[s][0]);
-    if (cm[s][1] != kNone) atomicMin(&s_cm[i + 1], cm[s][1]);
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kCols; i += kArgThreads) {
-    const uint32_t col = c0 + i;
-    if (col < nw && s_cm[i] != kNone) atomicMin(first_ask + w0 + col, s_cm[i]);
+  for (uint32_t i = threadIdx.x; i < rows; i += kArgThreads) {
+    if (s_cnt[i]) {
+      atomicMin(ask_best + t0 + r0 + i, (long long)s_best[i]);
+      atomicAdd(ask_count + t0 + r0 + i, s_cnt[i]);
+    }
   }
 }
 
