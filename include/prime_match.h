@@ -275,6 +275,75 @@ int pm_stream_sync(pm_engine*);
 
 uint32_t pm_abi_version(void);
 
+/* ------------------------------------------------------------------------ */
+/* Host mirror of the reference's plugin interface for this path              */
+/* (protocol_b200/csrc/pm_plugin.cpp).  In-process tables replace Redis; group */
+/* formation always runs on the engine (no CPU evaluation path).              */
+/* ------------------------------------------------------------------------ */
+typedef struct pm_plugin pm_plugin;
+
+typedef struct pm_plugin_policy {     /* mod.rs:71-98 */
+  uint8_t task_switching_enabled;     /* TaskSwitchingPolicy.enabled               */
+  uint8_t prefer_larger_groups;       /* TaskSwitchingPolicy.prefer_larger_groups  */
+  uint8_t proximity_enabled;          /* ProximityOptimizationPolicy.enabled       */
+  uint8_t reserved;
+} pm_plugin_policy;
+
+typedef struct pm_kv { const char* key; const char* value; } pm_kv;
+
+typedef struct pm_task_desc {         /* shared/src/models/task.rs:162-184 (fields on the path) */
+  const char* id;                     /* Uuid as string */
+  const char* name;
+  const char* image;
+  int64_t created_at;
+  const pm_kv* env_vars;      uint32_t n_env_vars;      int32_t has_env_vars;      /* Option<HashMap> */
+  const char* const* cmd;     uint32_t n_cmd;           int32_t has_cmd;           /* Option<Vec>     */
+  const pm_kv* volume_mounts; uint32_t n_volume_mounts; int32_t has_volume_mounts; /* {host_path, container_path} */
+  /* scheduling_config (task.rs:58-61): 0 = None; 1 = Some, no "node_groups" plugin entry;
+   * 2 = "node_groups" entry without "allowed_topologies"; 3 = allowed_topologies list below */
+  int32_t scheduling;
+  const char* const* allowed_topologies; uint32_t n_allowed_topologies;
+} pm_task_desc;
+
+typedef struct pm_node_desc {         /* orchestrator/src/models/node.rs:10-37 (fields on the path) */
+  const char* address;                /* Address::to_string(), opaque, EIP-55 cased by the caller */
+  uint32_t status;                    /* NodeStatus ordinal: Discovered=0, WaitingForHeartbeat, Healthy=2,
+                                         Unhealthy, Dead=4, Ejected, Banned, LowBalance=7 (node.rs:74-85) */
+  const char* p2p_id;                 /* NULL == None */
+  uint32_t spec_flags;                /* PM_W_HAS_* presence bits of compute_specs */
+  uint32_t gpu_count, gpu_mem_mb;
+  const char* gpu_model;
+  uint32_t cpu_cores, ram_mb, storage_gb;
+  int32_t has_location;
+  double lat, lon;
+} pm_node_desc;
+
+/* NodeGroupsPlugin::new_with_policy (mod.rs:129-175).  engine may be NULL (then
+ * pm_plugin_try_form_new_groups fails with PM_E_NO_DEVICE); policy NULL = defaults. */
+int  pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugin** out);
+void pm_plugin_destroy(pm_plugin*);
+const char* pm_plugin_last_error(const pm_plugin*);
+/* duplicate name / max < min are PM_E_INVALID (the reference panics, mod.rs:141-147);
+ * requirements NULL == compute_requirements: None, else ComputeRequirements::from_str */
+int pm_plugin_add_config(pm_plugin*, const char* name, uint32_t min_group_size, uint32_t max_group_size,
+                         const char* requirements);
+int pm_plugin_seal_configs(pm_plugin*);                                   /* the ctor's sort, mod.rs:150-164 */
+int pm_plugin_enable_configuration(pm_plugin*, const char* name, int enable);   /* mod.rs:1328-1346 */
+int pm_plugin_upsert_node(pm_plugin*, const pm_node_desc*);                /* NodeStore::add_node / update */
+int pm_plugin_set_node_status(pm_plugin*, const char* address, uint32_t status); /* + handle_status_change */
+int pm_plugin_add_task(pm_plugin*, const pm_task_desc*);                   /* TaskStore::add_task + on_task_created */
+int pm_plugin_delete_task(pm_plugin*, const char* id);                     /* delete_task + on_task_deleted */
+int pm_plugin_try_form_new_groups(pm_plugin*, uint32_t* n_formed);         /* mod.rs:478-628 via pm_match */
+/* the "upload:<node>:<group>:<file>" key the storage route records; feeds ${TOTAL_UPLOAD_COUNT} */
+int pm_plugin_record_upload(pm_plugin*, const char* address, const char* group_id, const char* file_name);
+/* JSON out (NUL-terminated into buf): NodeGroup {"id","nodes","configuration_name","task_id"} or null */
+int pm_plugin_get_node_group(pm_plugin*, const char* address, char* buf, size_t len);
+int pm_plugin_get_all_groups(pm_plugin*, char* buf, size_t len);           /* sorted by id, mod.rs:1040 */
+/* Scheduler::get_task_for_node (scheduler/mod.rs:26-74) with the plugin chain
+ * [NodeGroupsPlugin] when configurations exist, else [NewestTaskPlugin]:
+ * writes {"current_task": Task|null} (shared/src/models/heartbeat.rs:7-22). */
+int pm_scheduler_get_task_for_node(pm_plugin*, const char* address, char* buf, size_t len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,21 @@ def load() -> C.CDLL:
         "pm_match_finish": (i32, [vp, u32]),
         "pm_device_buffer": (i32, [vp, u32, P(vp), P(sz)]),
         "pm_stream_sync": (i32, [vp]),
+        "pm_plugin_create": (i32, [vp, P(abi.PmPluginPolicy), P(vp)]),
+        "pm_plugin_destroy": (None, [vp]),
+        "pm_plugin_last_error": (cp, [vp]),
+        "pm_plugin_add_config": (i32, [vp, cp, u32, u32, cp]),
+        "pm_plugin_seal_configs": (i32, [vp]),
+        "pm_plugin_enable_configuration": (i32, [vp, cp, i32]),
+        "pm_plugin_upsert_node": (i32, [vp, P(abi.PmNodeDesc)]),
+        "pm_plugin_set_node_status": (i32, [vp, cp, u32]),
+        "pm_plugin_add_task": (i32, [vp, P(abi.PmTaskDesc)]),
+        "pm_plugin_delete_task": (i32, [vp, cp]),
+        "pm_plugin_record_upload": (i32, [vp, cp, cp, cp]),
+        "pm_plugin_try_form_new_groups": (i32, [vp, P(u32)]),
+        "pm_plugin_get_node_group": (i32, [vp, cp, C.c_char_p, sz]),
+        "pm_plugin_get_all_groups": (i32, [vp, C.c_char_p, sz]),
+        "pm_scheduler_get_task_for_node": (i32, [vp, cp, C.c_char_p, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -112,4 +112,37 @@ EXPORTS = [
     "pm_set_worker_locations", "pm_set_worker_addr_rank", "pm_set_flags",
     "pm_match", "pm_fetch_result", "pm_get_stats", "pm_build_cost_tile",
     "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync",
+    "pm_plugin_create", "pm_plugin_destroy", "pm_plugin_last_error", "pm_plugin_add_config", "pm_plugin_seal_configs",
+    "pm_plugin_enable_configuration", "pm_plugin_upsert_node", "pm_plugin_set_node_status", "pm_plugin_add_task",
+    "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups",
+    "pm_scheduler_get_task_for_node",
 ]
+
+
+class PmPluginPolicy(C.Structure):
+    _fields_ = [("task_switching_enabled", C.c_uint8), ("prefer_larger_groups", C.c_uint8),
+                ("proximity_enabled", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class PmKv(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("value", C.c_char_p)]
+
+
+class PmTaskDesc(C.Structure):
+    _fields_ = [
+        ("id", C.c_char_p), ("name", C.c_char_p), ("image", C.c_char_p), ("created_at", C.c_int64),
+        ("env_vars", C.POINTER(PmKv)), ("n_env_vars", C.c_uint32), ("has_env_vars", C.c_int32),
+        ("cmd", C.POINTER(C.c_char_p)), ("n_cmd", C.c_uint32), ("has_cmd", C.c_int32),
+        ("volume_mounts", C.POINTER(PmKv)), ("n_volume_mounts", C.c_uint32), ("has_volume_mounts", C.c_int32),
+        ("scheduling", C.c_int32),
+        ("allowed_topologies", C.POINTER(C.c_char_p)), ("n_allowed_topologies", C.c_uint32),
+    ]
+
+
+class PmNodeDesc(C.Structure):
+    _fields_ = [
+        ("address", C.c_char_p), ("status", C.c_uint32), ("p2p_id", C.c_char_p), ("spec_flags", C.c_uint32),
+        ("gpu_count", C.c_uint32), ("gpu_mem_mb", C.c_uint32), ("gpu_model", C.c_char_p),
+        ("cpu_cores", C.c_uint32), ("ram_mb", C.c_uint32), ("storage_gb", C.c_uint32),
+        ("has_location", C.c_int32), ("lat", C.c_double), ("lon", C.c_double),
+    ]

@@ -12,10 +12,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libprime_match.so")
-SOURCES = [os.path.join(HERE, "csrc", "pm_engine.cu"), os.path.join(HERE, "csrc", "pm_host.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", "pm_engine.cu"), os.path.join(HERE, "csrc", "pm_host.cpp"),
+           os.path.join(HERE, "csrc", "pm_plugin.cpp")]
 DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "pm_kernels.cuh"),
     os.path.join(HERE, "csrc", "pm_device.cuh"),
+    os.path.join(HERE, "csrc", "pm_proximity.cuh"),
     os.path.join(ROOT, "include", "prime_match.h"),
 ]
 

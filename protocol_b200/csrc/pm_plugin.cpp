@@ -1,0 +1,671 @@
+// pm_plugin.cpp — host-side mirror of the reference's plugin interface for this path,
+// on top of the C-ABI engine (no GPU code here, and no CPU evaluation of the
+// feasibility predicate: group formation always goes through pm_match).
+//
+// Mirrors (names, argument meaning, error behaviour):
+//   NodeGroupsPlugin::new_with_policy      crates/orchestrator/src/plugins/node_groups/mod.rs:129-175
+//   get_available_configurations           mod.rs:399-418
+//   try_form_new_groups                    mod.rs:478-628     (-> pm_match)
+//   get_node_group / get_idx_in_group      mod.rs:324-337, 424-434
+//   get_current_group_task / assign_task_to_group   mod.rs:436-476
+//   dissolve_group / handle_status_change  mod.rs:1423-1487, status_update_impl.rs:8-39
+//   on_task_created / on_task_deleted      mod.rs:1224-1325
+//   NodeGroupsPlugin::filter_tasks         node_groups/scheduler_impl.rs:11-210
+//   NewestTaskPlugin::filter_tasks         plugins/newest_task/mod.rs:8-19
+//   Scheduler::get_task_for_node           scheduler/mod.rs:26-74
+//   TaskStore::get_all_tasks ordering      store/domains/task_store.rs:57-82
+//   NodeStore::get_nodes ordering          store/domains/node_store.rs:163-209
+// Redis is replaced by in-process tables (the engine's tables are "a cache of
+// Redis"); the reference's random choices follow the determinisation
+// rules of SURVEY 8c (newest applicable task; group id = running counter).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/prime_match.h"
+
+namespace {
+
+enum NodeStatus : uint32_t {  // crates/orchestrator/src/models/node.rs:74-85
+  kDiscovered = 0, kWaitingForHeartbeat = 1, kHealthy = 2, kUnhealthy = 3,
+  kDead = 4, kEjected = 5, kBanned = 6, kLowBalance = 7
+};
+
+int status_class(uint32_t st) {  // node_store.rs:195-206
+  if (st == kHealthy) return 0;
+  if (st == kDiscovered) return 1;
+  if (st == kDead) return 3;
+  return 2;
+}
+
+struct Config {
+  std::string name;
+  uint32_t min_group_size = 0, max_group_size = 0;
+  bool has_requirements = false;
+  pm_ask ask{};
+  std::vector<pm_gpu_opt> opts;
+};
+
+struct TaskRec {
+  std::string id, name, image;
+  int64_t created_at = 0;
+  bool has_env = false, has_cmd = false, has_mounts = false;
+  std::vector<std::pair<std::string, std::string>> env, mounts;
+  std::vector<std::string> cmd;
+  int scheduling = 0;  // pm_task_desc::scheduling
+  std::vector<std::string> topologies;
+};
+
+struct NodeRec {
+  std::string address;
+  uint32_t status = kDiscovered;
+  bool has_p2p = false;
+  std::string p2p_id;
+  pm_worker_a a{};
+  pm_worker_b b{};
+  bool has_loc = false;
+  double lat = 0, lon = 0;
+};
+
+struct Group {  // NodeGroup, mod.rs:63-69
+  std::string id;
+  std::vector<std::string> nodes;  // BTreeSet<String> order
+  std::string configuration_name;
+};
+
+std::string replace_all(std::string s, const std::string& from, const std::string& to) {
+  if (from.empty()) return s;
+  size_t pos = 0;
+  while ((pos = s.find(from, pos)) != std::string::npos) {
+    s.replace(pos, from.size(), to);
+    pos += to.size();
+  }
+  return s;
+}
+
+void json_str(std::string& out, const std::string& s) {
+  out += '"';
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': out += "\\\""; break;
+      case '\\': out += "\\\\"; break;
+      case '\n': out += "\\n"; break;
+      case '\r': out += "\\r"; break;
+      case '\t': out += "\\t"; break;
+      default:
+        if (c < 0x20) {
+          char b[8];
+          std::snprintf(b, sizeof b, "\\u%04x", c);
+          out += b;
+        } else {
+          out += char(c);
+        }
+    }
+  }
+  out += '"';
+}
+
+// the topology predicate of scheduler_impl.rs:44-59 == mod.rs:1138-1163
+bool task_applicable(const TaskRec& t, const std::string& configuration_name) {
+  if (t.scheduling != 3) return true;  // None / no node_groups plugin / no allowed_topologies
+  return std::find(t.topologies.begin(), t.topologies.end(), configuration_name) != t.topologies.end();
+}
+
+}  // namespace
+
+struct pm_plugin {
+  pm_engine* engine = nullptr;
+  pm_plugin_policy policy{};
+  pm_interner* interner = nullptr;
+  std::string err;
+  std::mutex mu;
+
+  std::vector<Config> templates;  // sorted at seal (mod.rs:150-164)
+  bool sealed = false;
+  std::set<std::string> available;  // "available_node_group_configs"
+
+  std::vector<NodeRec> nodes;  // insertion order stands in for SMEMBERS order
+  std::unordered_map<std::string, size_t> node_index;
+
+  std::vector<TaskRec> tasks;  // RPUSH order (task_store.rs:41)
+
+  std::map<std::string, Group> groups;                      // node_group:<id>
+  std::unordered_map<std::string, std::string> node_to_group;  // node_to_group
+  std::unordered_map<std::string, std::string> group_task;     // group_task:<id>
+  uint64_t next_group_id = 1;
+  std::set<std::string> upload_keys;                           // "upload:<node>:<group>:<file>" (storage route)
+
+  int fail(int st, const std::string& m) {
+    err = m;
+    return st;
+  }
+
+  std::vector<const TaskRec*> all_tasks() const {  // get_all_tasks: stable sort created_at desc
+    std::vector<const TaskRec*> v;
+    for (const auto& t : tasks) v.push_back(&t);
+    std::stable_sort(v.begin(), v.end(), [](const TaskRec* a, const TaskRec* b) { return a->created_at > b->created_at; });
+    return v;
+  }
+  const TaskRec* find_task(const std::string& id) const {
+    for (const auto& t : tasks)
+      if (t.id == id) return &t;
+    return nullptr;
+  }
+
+  std::vector<const Config*> available_configurations() const {  // mod.rs:399-418
+    std::vector<const Config*> v;
+    for (const auto& c : templates)
+      if (available.count(c.name)) v.push_back(&c);
+    std::stable_sort(v.begin(), v.end(), [](const Config* a, const Config* b) { return a->min_group_size > b->min_group_size; });
+    return v;
+  }
+
+  void dissolve(const std::string& group_id) {  // mod.rs:1423-1487
+    auto it = groups.find(group_id);
+    if (it == groups.end()) return;
+    for (const auto& n : it->second.nodes) node_to_group.erase(n);
+    group_task.erase(group_id);
+    groups.erase(it);
+  }
+
+  // get_current_group_task, mod.rs:436-469 (a claim on a deleted task is garbage-collected)
+  const TaskRec* current_group_task(const std::string& group_id) {
+    auto it = group_task.find(group_id);
+    if (it == group_task.end()) return nullptr;
+    if (const TaskRec* t = find_task(it->second)) return t;
+    group_task.erase(it);
+    return nullptr;
+  }
+};
+
+extern "C" {
+
+int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugin** out) {
+  if (!out) return PM_E_INVALID;
+  pm_plugin* p = new (std::nothrow) pm_plugin;
+  if (!p) return PM_E_NOMEM;
+  p->engine = engine;
+  if (policy) p->policy = *policy;
+  else {  // TaskSwitchingPolicy::default / ProximityOptimizationPolicy::default, mod.rs:85-98
+    p->policy.task_switching_enabled = 1;
+    p->policy.prefer_larger_groups = 1;
+    p->policy.proximity_enabled = 1;
+  }
+  p->interner = pm_interner_create();
+  *out = p;
+  return PM_OK;
+}
+
+void pm_plugin_destroy(pm_plugin* p) {
+  if (!p) return;
+  pm_interner_destroy(p->interner);
+  delete p;
+}
+
+const char* pm_plugin_last_error(const pm_plugin* p) { return p ? p->err.c_str() : ""; }
+
+int pm_plugin_add_config(pm_plugin* p, const char* name, uint32_t min_group_size, uint32_t max_group_size,
+                         const char* requirements) {
+  if (!p || !name) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->sealed) return p->fail(PM_E_STATE, "configurations are sealed");
+  for (const auto& c : p->templates)
+    if (c.name == name) return p->fail(PM_E_INVALID, "Configuration names must be unique");       // mod.rs:142-144
+  if (max_group_size < min_group_size) return p->fail(PM_E_INVALID, "Plugin configuration is invalid");  // :145-147
+  Config c;
+  c.name = name;
+  c.min_group_size = min_group_size;
+  c.max_group_size = max_group_size;
+  if (requirements) {  // deserialize_compute_requirements, mod.rs:39-52
+    c.has_requirements = true;
+    c.opts.resize(64);
+    uint32_t n = 0;
+    char err[256] = {0};
+    int rc = pm_parse_requirements(requirements, p->interner, &c.ask, c.opts.data(), 64, &n, err, sizeof err);
+    if (rc != PM_OK) return p->fail(rc, err);
+    c.opts.resize(n);
+  }
+  c.ask.min_group_size = min_group_size;
+  c.ask.max_group_size = max_group_size;
+  p->templates.push_back(std::move(c));
+  return PM_OK;
+}
+
+int pm_plugin_seal_configs(pm_plugin* p) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  const uint32_t n = (uint32_t)p->templates.size();
+  std::vector<uint32_t> mn(n), perm(n);
+  std::vector<uint8_t> hr(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    mn[i] = p->templates[i].min_group_size;
+    hr[i] = p->templates[i].has_requirements;
+  }
+  if (n) {
+    int rc = pm_sort_configs(mn.data(), hr.data(), n, perm.data());
+    if (rc != PM_OK) return p->fail(rc, "pm_sort_configs");
+    std::vector<Config> sorted;
+    for (uint32_t i = 0; i < n; ++i) sorted.push_back(std::move(p->templates[perm[i]]));
+    p->templates.swap(sorted);
+  }
+  p->sealed = true;
+  return PM_OK;
+}
+
+int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) {  // mod.rs:1328-1346
+  if (!p || !name) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (enable) p->available.insert(name);
+  else p->available.erase(name);
+  return PM_OK;
+}
+
+int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
+  if (!p || !d || !d->address) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  NodeRec* r;
+  auto it = p->node_index.find(d->address);
+  if (it == p->node_index.end()) {
+    p->node_index.emplace(d->address, p->nodes.size());
+    p->nodes.emplace_back();
+    r = &p->nodes.back();
+    r->address = d->address;
+  } else {
+    r = &p->nodes[it->second];
+  }
+  r->status = d->status;
+  r->has_p2p = d->p2p_id != nullptr;
+  r->p2p_id = d->p2p_id ? d->p2p_id : "";
+  const uint32_t keep = PM_W_HAS_SPECS | PM_W_HAS_GPU | PM_W_HAS_GPU_COUNT | PM_W_HAS_GPU_MEM | PM_W_HAS_GPU_MODEL |
+                        PM_W_HAS_CPU | PM_W_HAS_CPU_CORES | PM_W_HAS_RAM | PM_W_HAS_STORAGE;
+  r->a.flags = d->spec_flags & keep;
+  r->a.gpu_count = d->gpu_count;
+  r->a.gpu_mem_mb = d->gpu_mem_mb;
+  r->a.model_id = (d->spec_flags & PM_W_HAS_GPU_MODEL) && d->gpu_model ? pm_intern_model(p->interner, d->gpu_model) : 0;
+  r->b.cpu_cores = d->cpu_cores;
+  r->b.ram_mb = d->ram_mb;
+  r->b.storage_gb = d->storage_gb;
+  r->b.ext_ask_price = 0;
+  r->has_loc = d->has_location != 0;
+  r->lat = d->lat;
+  r->lon = d->lon;
+  return PM_OK;
+}
+
+// StatusUpdatePlugin::handle_status_change (plugins/mod.rs:23-34 -> status_update_impl.rs:8-39)
+int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status) {
+  if (!p || !address) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->node_index.find(address);
+  if (it == p->node_index.end()) return p->fail(PM_E_INVALID, "unknown node");
+  p->nodes[it->second].status = status;
+  if (status == kDead || status == kLowBalance) {
+    auto g = p->node_to_group.find(address);
+    if (g != p->node_to_group.end()) {
+      const std::string gid = g->second;
+      p->dissolve(gid);
+    }
+  }
+  return PM_OK;
+}
+
+int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
+  if (!p || !d || !d->id) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  TaskRec t;
+  t.id = d->id;
+  t.name = d->name ? d->name : "";
+  t.image = d->image ? d->image : "";
+  t.created_at = d->created_at;
+  t.has_env = d->has_env_vars != 0;
+  for (uint32_t i = 0; i < d->n_env_vars; ++i) t.env.emplace_back(d->env_vars[i].key, d->env_vars[i].value);
+  t.has_cmd = d->has_cmd != 0;
+  for (uint32_t i = 0; i < d->n_cmd; ++i) t.cmd.emplace_back(d->cmd[i]);
+  t.has_mounts = d->has_volume_mounts != 0;
+  for (uint32_t i = 0; i < d->n_volume_mounts; ++i) t.mounts.emplace_back(d->volume_mounts[i].key, d->volume_mounts[i].value);
+  t.scheduling = d->scheduling;
+  for (uint32_t i = 0; i < d->n_allowed_topologies; ++i) t.topologies.emplace_back(d->allowed_topologies[i]);
+  // on_task_created: enable the configuration of every allowed topology (mod.rs:1224-1243)
+  if (t.scheduling == 3)
+    for (const auto& topo : t.topologies) p->available.insert(topo);
+  p->tasks.push_back(std::move(t));
+  return PM_OK;
+}
+
+int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_task + on_task_deleted
+  if (!p || !id) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = std::find_if(p->tasks.begin(), p->tasks.end(), [&](const TaskRec& t) { return t.id == id; });
+  if (it == p->tasks.end()) return PM_OK;
+  TaskRec gone = *it;
+  p->tasks.erase(it);
+  // dissolve every group working on the task (mod.rs:1259-1291)
+  std::vector<std::string> doomed;
+  for (const auto& kv : p->group_task)
+    if (kv.second == gone.id) doomed.push_back(kv.first);
+  for (const auto& gid : doomed) p->dissolve(gid);
+  // disable topologies with no remaining task (mod.rs:1295-1320)
+  if (gone.scheduling == 3)
+    for (const auto& topo : gone.topologies) {
+      bool remaining = false;
+      for (const auto& t : p->tasks)
+        if (t.scheduling == 3 && std::find(t.topologies.begin(), t.topologies.end(), topo) != t.topologies.end()) remaining = true;
+      if (!remaining) p->available.erase(topo);
+    }
+  return PM_OK;
+}
+
+// try_form_new_groups (mod.rs:478-628): the evaluation and the allocation run on the GPU.
+int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (n_formed) *n_formed = 0;
+  if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
+  if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
+  const auto configs = p->available_configurations();
+
+  // node_store.get_nodes(): stable status-class sort (node_store.rs:195-206) = canonical order
+  const uint32_t W = (uint32_t)p->nodes.size();
+  std::vector<uint32_t> order(W);
+  for (uint32_t i = 0; i < W; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return status_class(p->nodes[a].status) < status_class(p->nodes[b].status);
+  });
+  // address rank = BTreeSet<String> order (byte-lexicographic)
+  std::vector<uint32_t> by_addr(W), rank(W);
+  for (uint32_t i = 0; i < W; ++i) by_addr[i] = i;
+  std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return p->nodes[a].address < p->nodes[b].address; });
+  for (uint32_t i = 0; i < W; ++i) rank[by_addr[i]] = i;
+
+  std::vector<pm_worker_a> wa(W);
+  std::vector<pm_worker_b> wb(W);
+  std::vector<double> lat(W), lon(W);
+  std::vector<uint32_t> arank(W);
+  for (uint32_t i = 0; i < W; ++i) {
+    const NodeRec& n = p->nodes[order[i]];
+    wa[i] = n.a;
+    wb[i] = n.b;
+    uint32_t f = n.a.flags;
+    if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
+    if (n.has_p2p) f |= PM_W_P2P;                                        // :495
+    if (p->node_to_group.count(n.address)) f |= PM_W_ASSIGNED;           // :496
+    if (n.has_loc) f |= PM_W_HAS_LOC;
+    wa[i].flags = f;
+    lat[i] = n.lat;
+    lon[i] = n.lon;
+    arank[i] = rank[order[i]];
+  }
+  std::vector<pm_ask> asks;
+  std::vector<pm_gpu_opt> opts;
+  for (const Config* c : configs) {
+    pm_ask a = c->ask;
+    a.opt_off = (uint32_t)opts.size();
+    a.min_group_size = c->min_group_size;
+    a.max_group_size = c->max_group_size;
+    opts.insert(opts.end(), c->opts.begin(), c->opts.end());
+    asks.push_back(a);
+  }
+  const uint32_t* bits = nullptr;
+  uint32_t npat = 0, nmod = 0, words = 1;
+  int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
+  if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
+  auto chk = [&](int r, const char* what) {
+    if (r != PM_OK) {
+      const char* m = pm_last_error(p->engine);
+      p->err = std::string(what) + ": " + (m ? m : "");
+    }
+    return r;
+  };
+  if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
+  if ((rc = chk(pm_set_model_table(p->engine, bits, npat, nmod, words), "pm_set_model_table"))) return rc;
+  if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
+  if ((rc = chk(pm_upsert_workers(p->engine, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
+  if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
+  if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
+  if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;   // staging vectors are read asynchronously
+  const uint32_t mode = p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT;
+  if ((rc = chk(pm_match(p->engine, mode), "pm_match"))) return rc;
+  pm_result res{};
+  if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
+
+  for (uint32_t g = 0; g < res.n_groups; ++g) {  // mod.rs:568-581
+    Group grp;
+    char idbuf[32];
+    std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);  // format!("{:x}", ..)
+    grp.id = idbuf;
+    grp.configuration_name = configs[res.group_ask[g]]->name;
+    for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m)
+      grp.nodes.push_back(p->nodes[order[res.group_members[m]]].address);
+    for (const auto& n : grp.nodes) p->node_to_group[n] = grp.id;
+    p->groups.emplace(grp.id, std::move(grp));
+  }
+  if (n_formed) *n_formed = res.n_groups;
+  return PM_OK;
+}
+
+static void group_json(const pm_plugin* p, const Group& g, std::string& out) {
+  out += "{\"id\":";
+  json_str(out, g.id);
+  out += ",\"nodes\":[";
+  for (size_t i = 0; i < g.nodes.size(); ++i) {
+    if (i) out += ',';
+    json_str(out, g.nodes[i]);
+  }
+  out += "],\"configuration_name\":";
+  json_str(out, g.configuration_name);
+  auto it = p->group_task.find(g.id);
+  out += ",\"task_id\":";
+  if (it == p->group_task.end()) out += "null";
+  else json_str(out, it->second);
+  out += '}';
+}
+
+static int emit(pm_plugin* p, const std::string& s, char* buf, size_t len) {
+  if (!buf || len < s.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return PM_OK;
+}
+
+// the key the storage route writes per requested upload (consumed by scheduler_impl.rs:131-157)
+int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group_id, const char* file_name) {
+  if (!p || !address || !group_id || !file_name) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  p->upload_keys.insert(std::string("upload:") + address + ":" + group_id + ":" + file_name);
+  return PM_OK;
+}
+
+// get_node_group (mod.rs:324-337): JSON NodeGroup or "null"
+int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_t len) {
+  if (!p || !address) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  std::string out = "null";
+  auto it = p->node_to_group.find(address);
+  if (it != p->node_to_group.end()) {
+    auto g = p->groups.find(it->second);
+    if (g != p->groups.end()) {
+      out.clear();
+      group_json(p, g->second, out);
+    }
+  }
+  return emit(p, out, buf, len);
+}
+
+// get_all_groups (mod.rs:1006-1044): sorted by id
+int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  std::string out = "[";
+  bool first = true;
+  for (const auto& kv : p->groups) {
+    if (!first) out += ',';
+    first = false;
+    group_json(p, kv.second, out);
+  }
+  out += ']';
+  return emit(p, out, buf, len);
+}
+
+namespace {
+
+struct Expanded {
+  const TaskRec* task = nullptr;
+  std::vector<std::pair<std::string, std::string>> env, mounts;
+  std::vector<std::string> cmd;
+  bool has_env = false, has_cmd = false, has_mounts = false;
+};
+
+// NodeGroupsPlugin::filter_tasks, scheduler_impl.rs:11-210.  Returns false for "no task".
+bool node_groups_filter(pm_plugin* p, const std::vector<const TaskRec*>& tasks, const std::string& addr, Expanded* out) {
+  auto ng = p->node_to_group.find(addr);
+  if (ng == p->node_to_group.end()) return false;            // "Node is not in a group, skipping all tasks"
+  auto git = p->groups.find(ng->second);
+  if (git == p->groups.end()) return false;
+  const Group& group = git->second;
+  auto pos = std::find(group.nodes.begin(), group.nodes.end(), addr);  // get_idx_in_group, mod.rs:424-434
+  if (pos == group.nodes.end()) return false;
+  const size_t idx = size_t(pos - group.nodes.begin());
+
+  const TaskRec* current = p->current_group_task(group.id);
+  if (!current) {
+    if (tasks.empty()) return false;
+    std::vector<const TaskRec*> applicable;
+    for (const TaskRec* t : tasks)
+      if (task_applicable(*t, group.configuration_name)) applicable.push_back(t);
+    if (applicable.empty()) return false;
+    // reference: IteratorRandom::choose (scheduler_impl.rs:67-70); determinised to the NewestTask rule:
+    // max_by_key(created_at) over the desc-sorted list returns the LAST maximum
+    const TaskRec* chosen = applicable[0];
+    for (const TaskRec* t : applicable)
+      if (t->created_at >= chosen->created_at) chosen = t;
+    if (!p->group_task.count(group.id)) p->group_task[group.id] = chosen->id;   // SET NX, mod.rs:471-476
+    current = p->current_group_task(group.id);
+    if (!current) return false;
+  }
+
+  const std::string idx_s = std::to_string(idx), size_s = std::to_string(group.nodes.size());
+  const std::string& next_addr = group.nodes[(idx + 1) % group.nodes.size()];
+  std::string next_p2p;
+  auto ni = p->node_index.find(next_addr);
+  if (ni != p->node_index.end()) next_p2p = p->nodes[ni->second].p2p_id;
+  // SCAN upload:<node>:<group>:*  (scheduler_impl.rs:131-157); LAST_FILE_IDX = count.saturating_sub(1)
+  size_t n_up = 0;
+  {
+    const std::string prefix = "upload:" + addr + ":" + group.id + ":";
+    for (auto it = p->upload_keys.lower_bound(prefix); it != p->upload_keys.end() && it->compare(0, prefix.size(), prefix) == 0; ++it) ++n_up;
+  }
+  const std::string total_upload = std::to_string(n_up), last_file_idx = std::to_string(n_up ? n_up - 1 : 0);
+  auto expand = [&](std::string v) {
+    v = replace_all(v, "${GROUP_INDEX}", idx_s);
+    v = replace_all(v, "${GROUP_SIZE}", size_s);
+    v = replace_all(v, "${NEXT_P2P_ADDRESS}", next_p2p);
+    v = replace_all(v, "${GROUP_ID}", group.id);
+    v = replace_all(v, "${TOTAL_UPLOAD_COUNT}", total_upload);
+    v = replace_all(v, "${LAST_FILE_IDX}", last_file_idx);
+    return v;
+  };
+  out->task = current;
+  out->env = current->env;   // env_vars.unwrap_or_default()
+  bool have_gi = false;
+  for (auto& kv : out->env)
+    if (kv.first == "GROUP_INDEX") { kv.second = idx_s; have_gi = true; }
+  if (!have_gi) out->env.emplace_back("GROUP_INDEX", idx_s);
+  for (auto& kv : out->env) kv.second = expand(kv.second);
+  out->has_env = true;
+  out->has_cmd = current->has_cmd;
+  for (const auto& a : current->cmd) out->cmd.push_back(expand(a));
+  out->has_mounts = current->has_mounts;
+  for (const auto& m : current->mounts)
+    out->mounts.emplace_back(replace_all(m.first, "${GROUP_ID}", group.id), replace_all(m.second, "${GROUP_ID}", group.id));
+  return true;
+}
+
+void task_json(const Expanded& e, std::string& out) {
+  const TaskRec& t = *e.task;
+  out += "{\"name\":"; json_str(out, t.name);
+  out += ",\"id\":"; json_str(out, t.id);
+  out += ",\"image\":"; json_str(out, t.image);
+  out += ",\"env_vars\":";
+  if (!e.has_env) out += "null";
+  else {
+    out += '{';
+    for (size_t i = 0; i < e.env.size(); ++i) {
+      if (i) out += ',';
+      json_str(out, e.env[i].first); out += ':'; json_str(out, e.env[i].second);
+    }
+    out += '}';
+  }
+  out += ",\"cmd\":";
+  if (!e.has_cmd) out += "null";
+  else {
+    out += '[';
+    for (size_t i = 0; i < e.cmd.size(); ++i) { if (i) out += ','; json_str(out, e.cmd[i]); }
+    out += ']';
+  }
+  out += ",\"created_at\":" + std::to_string(t.created_at);
+  out += ",\"volume_mounts\":";
+  if (!e.has_mounts) out += "null";
+  else {
+    out += '[';
+    for (size_t i = 0; i < e.mounts.size(); ++i) {
+      if (i) out += ',';
+      out += "{\"host_path\":"; json_str(out, e.mounts[i].first);
+      out += ",\"container_path\":"; json_str(out, e.mounts[i].second); out += '}';
+    }
+    out += ']';
+  }
+  out += '}';
+}
+
+}  // namespace
+
+// Scheduler::get_task_for_node (scheduler/mod.rs:26-74).  Writes the heartbeat payload
+// {"current_task": Task|null} (crates/shared/src/models/heartbeat.rs:7-22).
+int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) {
+  if (!p || !address) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  const std::string addr(address);
+  auto tasks = p->all_tasks();
+  Expanded e;
+  bool have = false;
+  if (!p->templates.empty()) {  // plugin chain = [NodeGroupsPlugin]
+    have = node_groups_filter(p, tasks, addr, &e);
+  } else if (!tasks.empty()) {  // Scheduler::new pushes NewestTaskPlugin when no plugin is configured
+    const TaskRec* chosen = tasks[0];
+    for (const TaskRec* t : tasks)
+      if (t->created_at >= chosen->created_at) chosen = t;  // max_by_key: last maximum
+    e.task = chosen;
+    e.env = chosen->env; e.has_env = chosen->has_env;
+    e.cmd = chosen->cmd; e.has_cmd = chosen->has_cmd;
+    e.mounts = chosen->mounts; e.has_mounts = chosen->has_mounts;
+    have = true;
+  }
+  std::string out = "{\"current_task\":";
+  if (!have) {
+    out += "null}";
+    return emit(p, out, buf, len);
+  }
+  // scheduler/mod.rs:34-70: ${TASK_ID}, ${NODE_ADDRESS} (+ ${TIMESTAMP} in volume mounts)
+  const std::string& tid = e.task->id;
+  auto expand = [&](std::string v) { return replace_all(replace_all(v, "${TASK_ID}", tid), "${NODE_ADDRESS}", addr); };
+  if (e.has_env) for (auto& kv : e.env) kv.second = expand(kv.second);
+  if (e.has_cmd) for (auto& a : e.cmd) a = expand(a);
+  if (e.has_mounts) {
+    const std::string ts = std::to_string((long long)std::time(nullptr));
+    for (auto& m : e.mounts) {
+      m.first = replace_all(expand(m.first), "${TIMESTAMP}", ts);
+      m.second = replace_all(expand(m.second), "${TIMESTAMP}", ts);
+    }
+  }
+  task_json(e, out);
+  out += '}';
+  return emit(p, out, buf, len);
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""The reference's scenario tests for the path (crates/orchestrator/src/plugins/node_groups/tests.rs),
+re-run against the host mirror + CUDA engine.  Where the reference accepts several outcomes
+(tests.rs:846-861) the determinisation rules of SURVEY 8c pick one and the test says which."""
+import pytest
+
+from protocol_b200.engine import Engine
+from protocol_b200.plugin import (ComputeSpecs, GpuSpecs, NodeGroupConfiguration, NodeGroupsPlugin, NodeStatus,
+                                  OrchestratorNode, Scheduler, Task)
+
+pytestmark = pytest.mark.gpu
+
+A1 = "0x1234567890123456789012345678901234567890"
+A2 = "0x2234567890123456789012345678901234567890"
+A3 = "0x3234567890123456789012345678901234567890"
+RTX = ComputeSpecs(gpu=GpuSpecs(count=8, model="RTX4090", memory_mb=24))
+
+
+@pytest.fixture()
+def engine():
+    e = Engine()
+    yield e
+    e.close()
+
+
+def make(engine, configs, **kw):
+    return NodeGroupsPlugin(configs, engine=engine, **kw)
+
+
+def test_group_formation_and_dissolution(engine):
+    """tests.rs:105-196."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 2)])
+    plugin.add_task(Task(allowed_topologies=["test-config"]))
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.try_form_new_groups()
+    assert plugin.get_node_group(A1) is None
+    plugin.add_node(OrchestratorNode(A2))
+    plugin.try_form_new_groups()
+    g1, g2 = plugin.get_node_group(A1), plugin.get_node_group(A2)
+    assert g1 is not None and g1 == g2 and g1["nodes"] == [A1, A2]
+    plugin.update_node_status(A1, NodeStatus.Dead)           # handle_status_change dissolves the group
+    assert plugin.get_node_group(A1) is None and plugin.get_node_group(A2) is None
+
+
+def test_group_formation_with_requirements_and_multiple_nodes(engine):
+    """tests.rs:387-506."""
+    cfg = NodeGroupConfiguration("test-config-with-requirements", 2, 2, "gpu:count=8;gpu:model=RTX4090;")
+    plugin = make(engine, [cfg])
+    plugin.add_task(Task(allowed_topologies=[cfg.name]))
+    plugin.add_node(OrchestratorNode(A1))                    # compute_specs: None
+    plugin.try_form_new_groups()
+    plugin.add_node(OrchestratorNode(A2, compute_specs=RTX))
+    plugin.try_form_new_groups()
+    assert plugin.get_node_group(A1) is None and plugin.get_node_group(A2) is None
+    plugin.add_node(OrchestratorNode(A3, compute_specs=RTX))
+    plugin.try_form_new_groups()
+    assert plugin.get_node_group(A3) is not None and plugin.get_node_group(A2) is not None
+    assert plugin.get_node_group(A1) is None
+
+
+def test_group_scheduling(engine):
+    """tests.rs:509-676: both members get the same task, distinct GROUP_INDEX, expanded variables."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 2)])
+    sched = Scheduler(plugin)
+    plugin.add_task(Task(allowed_topologies=["test-config"]))
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    env = {"LOCAL_RANK": "0", "RANK": "${GROUP_INDEX}", "WORLD_SIZE": "${GROUP_SIZE}", "GROUP_ID": "${GROUP_ID}",
+           "TOTAL_UPLOAD_COUNT": "${TOTAL_UPLOAD_COUNT}", "LAST_FILE_IDX": "${LAST_FILE_IDX}"}
+    cmd = ["uv", "run", "generate.py", "--model", "model/Qwen3-14B-${GROUP_INDEX}.${GROUP_SIZE}", "--top-p", "0.95",
+           "--group-id", "${GROUP_ID}", "--upload-count", "${TOTAL_UPLOAD_COUNT}", "--file-number", "${LAST_FILE_IDX}"]
+    for _ in range(3):
+        plugin.add_task(Task(image="prime-vllm", name="test-task", env_vars=dict(env), cmd=list(cmd), created_at=0))
+    assert sched.get_task_for_node(A1) is None                # not in a group yet
+    plugin.try_form_new_groups()
+    group = plugin.get_node_group(A1)
+    assert group is not None
+    plugin.record_upload(A1, group["id"], "test.txt")
+    t1, t2 = sched.get_task_for_node(A1), sched.get_task_for_node(A2)
+    e1, e2 = t1["env_vars"], t2["env_vars"]
+    assert (e1["GROUP_INDEX"], e1["RANK"], e1["WORLD_SIZE"]) == ("0", "0", "2")
+    assert t1["cmd"][4] == "model/Qwen3-14B-0.2"
+    assert e1["GROUP_ID"] == group["id"] != "${GROUP_ID}"
+    assert (e1["TOTAL_UPLOAD_COUNT"], e1["LAST_FILE_IDX"], t1["cmd"][10]) == ("1", "0", "1")
+    assert (e2["GROUP_INDEX"], e2["RANK"], e2["WORLD_SIZE"]) == ("1", "1", "2")
+    assert t2["cmd"][4] == "model/Qwen3-14B-1.2"
+    assert (e2["TOTAL_UPLOAD_COUNT"], e2["LAST_FILE_IDX"], t2["cmd"][10]) == ("0", "0", "0")
+    assert t1["id"] == t2["id"]
+
+
+def test_group_formation_with_max_size(engine):
+    """tests.rs:734-885: three nodes, min=max=2 -> one pair, the third node gets no task."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 2)])
+    sched = Scheduler(plugin)
+    plugin.add_task(Task(allowed_topologies=["test-config"]))
+    for a in (A1, A2, A3):
+        plugin.add_node(OrchestratorNode(a))
+    plugin.try_form_new_groups()
+    plugin.add_task(Task(image="test-image", name="test-task", env_vars={"RANK": "${GROUP_INDEX}"},
+                         cmd=["run", "--index", "${GROUP_INDEX}"]))
+    groups = [plugin.get_node_group(a) for a in (A1, A2, A3)]
+    assert sum(g is not None for g in groups) == 2
+    assert groups[0] == groups[1] and groups[2] is None       # canonical order picks the first two
+    for a, g in zip((A1, A2, A3), groups):
+        assert (sched.get_task_for_node(a) is not None) == (g is not None)
+
+
+def test_node_groups_with_allowed_topologies(engine):
+    """tests.rs:888-990: a task restricted to another topology is not handed to the group."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 1, 1)])
+    sched = Scheduler(plugin)
+    plugin.enable_configuration("test-config")
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.try_form_new_groups()
+    t_no = Task(name="test-task", allowed_topologies=["no-match-config"])
+    plugin.add_task(t_no)
+    assert sched.get_task_for_node(A1) is None
+    t_ok = Task(name="test-task", allowed_topologies=["test-config"])
+    plugin.add_task(t_ok)
+    assert sched.get_task_for_node(A1)["id"] == t_ok.id
+
+
+def test_reformation_on_death(engine):
+    """tests.rs:1215-1332: after a member dies the survivors regroup with a new node."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 2)])
+    plugin.add_task(Task(allowed_topologies=["test-config"]))
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    plugin.try_form_new_groups()
+    first = plugin.get_node_group(A1)
+    assert first is not None and first["nodes"] == [A1, A2]
+    plugin.update_node_status(A2, NodeStatus.Dead)
+    assert plugin.get_node_group(A1) is None
+    plugin.add_node(OrchestratorNode(A3))
+    plugin.try_form_new_groups()
+    again = plugin.get_node_group(A1)
+    assert again is not None and again["nodes"] == [A1, A3] and again["id"] != first["id"]
+    assert plugin.get_node_group(A2) is None
+
+
+def test_task_observer(engine):
+    """tests.rs:1467-1627: configurations are enabled by tasks and disabled/dissolved with them."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 1, 1)])
+    sched = Scheduler(plugin)
+    plugin.add_node(OrchestratorNode(A1))
+    assert plugin.try_form_new_groups() == 0                   # no task -> configuration not enabled
+    task = Task(name="t", allowed_topologies=["test-config"])
+    plugin.add_task(task)
+    assert plugin.try_form_new_groups() == 1
+    assert sched.get_task_for_node(A1)["id"] == task.id        # claims the task for the group
+    plugin.delete_task(task.id)                                # groups working on it dissolve immediately
+    assert plugin.get_node_group(A1) is None
+    assert plugin.try_form_new_groups() == 0                   # configuration disabled again
+
+
+def test_group_formation_priority(engine):
+    """tests.rs:1803-1904: one 3-node group + one solo group, not four solos."""
+    plugin = make(engine, [NodeGroupConfiguration("solo", 1, 1), NodeGroupConfiguration("trio", 3, 3)])
+    plugin.add_task(Task(allowed_topologies=["solo", "trio"]))
+    addrs = [f"0x{i + 1}234567890123456789012345678901234567890" for i in range(4)]
+    for a in addrs:
+        plugin.add_node(OrchestratorNode(a))
+    assert plugin.try_form_new_groups() == 2
+    sizes = sorted(len(g["nodes"]) for g in plugin.get_all_groups())
+    assert sizes == [1, 3]
+    assert sorted(n for g in plugin.get_all_groups() for n in g["nodes"]) == sorted(addrs)
+
+
+def test_proximity_pairs_by_city(engine):
+    """Coordinates and specs of tests.rs:2861-3064 through the formation pass (policy enabled)."""
+    a6000 = ComputeSpecs(gpu=GpuSpecs(count=1, model="nvidia rtx a6000", memory_mb=49140))
+    montreal, dallas = (45.5186, -73.5545), (32.7942, -96.7475)
+    m1, m2 = "0xB2631de00e6120969d34456b9c7Ee22352f13b02", "0x2C490CAdf3A8C2Ab67b00831973da8b9d18e5b6D"
+    d1, d2 = "0x7ec9d3bc276B74969341c03dc00B9f70c0EadFd5", "0x32d7cd9b8F6eA556a67E0c9386cdd911Da3AD3E5"
+    plugin = make(engine, [NodeGroupConfiguration("2x40-48GB", 2, 2)])
+    plugin.add_task(Task(allowed_topologies=["2x40-48GB"]))
+    for addr, loc in ((m1, montreal), (d1, dallas), (m2, montreal), (d2, dallas)):
+        plugin.add_node(OrchestratorNode(addr, compute_specs=a6000, location=loc))
+    assert plugin.try_form_new_groups() == 2
+    assert plugin.get_node_group(m1) == plugin.get_node_group(m2) != plugin.get_node_group(d1)
+    assert plugin.get_node_group(d1) == plugin.get_node_group(d2)
+    g = plugin.get_node_group(m1)
+    assert g["nodes"] == sorted([m1, m2], key=lambda s: s.encode())    # BTreeSet<String> order
