@@ -133,7 +133,7 @@ def run_reference(args):
         return
     from oracle import pm_oracle as orc
 
-    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, 1)
+    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, max(args.gpus, 1))
     cores = os.cpu_count() or 1
     # bounded sample: a band of asks against every worker, ~2e9 pair evaluations per step at most
     sample_rows = max(1, min(T, int(2.0e9 // max(W, 1)), 20_000))
@@ -158,7 +158,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/int64",
         "data": "synthetic (splitmix64, seeds 0xB2000001/0xB2000002)",
-        "config": {"workload": f"{args.workload}: {desc}", "n_asks": T, "n_workers": W},
+        "config": {"workload": f"{args.workload}: {desc}", "n_asks": T, "n_workers": W, "workers_per_gpu": Wg,
+                   "path": "cpu (oracle/pm_oracle.cpp, SoA restatement, all pairs)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"asks [{t0},{t0 + sample_rows}) x all {W} workers, all pairs, {cores} threads",
                          "faithful_single_thread": faithful},

@@ -203,11 +203,17 @@ int pm_set_worker_addr_rank(pm_engine*, const uint32_t* rank, uint32_t first, ui
 /* status / assigned deltas (status_update_impl.rs:8-39, mod.rs:1423-1487)   */
 int pm_set_flags(pm_engine*, const uint32_t* idx, const uint32_t* flags, uint32_t n);
 
+/* NORTH-STAR EXTENSION columns (no reference counterpart; only PM_MODE_AUCTION reads them):
+ * per-ask price cap against pm_worker_b.ext_ask_price, and the auction's parameters
+ * (value = -(ask_price * cost_scale) - price; eps runs eps_start, /eps_div, ..., 1).       */
+int pm_set_ask_price_caps(pm_engine*, const uint32_t* price_cap, uint32_t n_asks);
+int pm_set_auction_params(pm_engine*, uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div);
+
 enum pm_mode {
   PM_MODE_FIRST_FIT = 0,   /* try_form_new_groups, ProximityOptimizationPolicy{enabled:false} */
   PM_MODE_PROXIMITY = 1,   /* ... {enabled:true}  (mod.rs:524-552), the reference default     */
-  PM_MODE_AUCTION   = 2    /* north-star extension (price-capped e-scaling auction); no       */
-                           /* reference counterpart, self-oracle only                         */
+  PM_MODE_AUCTION   = 2    /* north-star extension: price-capped forward auction, one worker  */
+                           /* per ask (pm_auction.cuh); no reference counterpart, self-oracle */
 };
 enum pm_path {
   PM_PATH_MATERIALIZED = 0,      /* build int64 cost tile in HBM, then argmin over it */

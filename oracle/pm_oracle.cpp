@@ -873,4 +873,76 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b, const p
   return u64(nt) * nw;
 }
 
+
+// EXTENSION, self-oracle (see pm_oracle.h): synchronous forward auction, sequentially.
+uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                         const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                         const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
+                         uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
+                         uint32_t* ask_worker_out, int64_t* worker_price_out) {
+  const int64_t S = cost_scale ? int64_t(cost_scale) : 1;
+  const int64_t NEG = INT64_MIN / 4;
+  std::vector<int64_t> price(n_workers, 0);
+  std::vector<u32> owner(n_workers, PM_NONE), assigned(n_asks, PM_NONE);
+  std::vector<char> withdrawn(n_asks, 0);
+  // feasibility lists (so every round costs only the feasible pairs)
+  std::vector<std::vector<u32>> feas(n_asks);
+  for (u32 t = 0; t < n_asks; ++t)
+    for (u32 w = 0; w < n_workers; ++w)
+      if (soa_candidate(a[w].flags) && b[w].ext_ask_price <= price_cap[t] &&
+          orc_soa_compatible(&a[w], &b[w], &asks[t], opts, model_bits, words))
+        feas[t].push_back(w);
+  u32 rounds = 0;
+  if (eps_start == 0) eps_start = 1;
+  if (eps_div < 2) eps_div = 2;
+  for (uint64_t eps = eps_start;; eps = std::max<uint64_t>(1, eps / eps_div)) {
+    std::fill(owner.begin(), owner.end(), PM_NONE);
+    std::fill(assigned.begin(), assigned.end(), PM_NONE);
+    std::fill(withdrawn.begin(), withdrawn.end(), 0);
+    for (;;) {
+      std::vector<u32> bid_w(n_asks, PM_NONE);
+      std::vector<int64_t> bid_p(n_asks, 0);
+      bool any = false;
+      for (u32 t = 0; t < n_asks; ++t) {
+        if (assigned[t] != PM_NONE || withdrawn[t]) continue;
+        const int64_t outside = -((int64_t(price_cap[t]) + 1) * S);
+        int64_t b1 = NEG, b2 = NEG;
+        u32 w1 = PM_NONE;
+        for (u32 w : feas[t]) {
+          const int64_t v = -(int64_t(b[w].ext_ask_price) * S) - price[w];
+          if (v > b1) { b2 = b1; b1 = v; w1 = w; }
+          else if (v > b2) b2 = v;
+        }
+        if (w1 == PM_NONE || b1 < outside) { withdrawn[t] = 1; continue; }
+        if (b2 < outside) b2 = outside;
+        bid_w[t] = w1;
+        bid_p[t] = price[w1] + (b1 - b2) + int64_t(eps);
+        any = true;
+      }
+      if (!any) break;
+      ++rounds;
+      // a worker takes the highest bid; ties go to the lowest task index
+      std::vector<u32> winner(n_workers, PM_NONE);
+      for (u32 t = 0; t < n_asks; ++t) {
+        const u32 w = bid_w[t];
+        if (w == PM_NONE) continue;
+        if (winner[w] == PM_NONE || bid_p[t] > bid_p[winner[w]]) winner[w] = t;
+      }
+      for (u32 w = 0; w < n_workers; ++w) {
+        const u32 t = winner[w];
+        if (t == PM_NONE) continue;
+        if (owner[w] != PM_NONE) assigned[owner[w]] = PM_NONE;
+        owner[w] = t;
+        assigned[t] = w;
+        price[w] = bid_p[t];
+      }
+    }
+    if (eps == 1) break;
+  }
+  for (u32 t = 0; t < n_asks; ++t) ask_worker_out[t] = assigned[t];
+  if (worker_price_out)
+    for (u32 w = 0; w < n_workers; ++w) worker_price_out[w] = price[w];
+  return rounds;
+}
+
 }  // extern "C"

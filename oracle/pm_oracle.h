@@ -153,6 +153,23 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b,
                              uint32_t threads, int64_t* cost_out, int64_t* row_best_out,
                              uint32_t* row_count_out, uint32_t* col_first_out);
 
+/* ---- north-star EXTENSION: price-capped auction.  SELF-ORACLE: the reference has no
+ * prices, caps or auction; parity for this mode is UNPINNED BY THE REFERENCE.
+ * Sequential restatement of the synchronous (Jacobi) forward auction the engine runs:
+ *   feasible(t,w) = candidate(w) && compatible(t,w) && ask_price[w] <= price_cap[t]
+ *   value(t,w)    = -(ask_price[w] * S) - price[w];  outside option = -((price_cap[t]+1) * S)
+ *   (S = cost_scale: 1 gives an assignment within T*eps of the optimum; T+1 with eps = 1 the optimum)
+ *   each round every unassigned task bids price[w1] + (best - second) + eps on its best worker
+ *   (ties: lowest worker index); a worker takes the highest bid (ties: lowest task index) and
+ *   releases its previous owner; a task whose best value drops below its outside option withdraws.
+ * eps runs eps_start, eps_start/eps_div, ..., 1 (assignment cleared between phases, prices kept).
+ * ask_worker_out[T]: assigned worker or PM_NONE.  Returns the number of bidding rounds.     */
+uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                         const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                         const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
+                         uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
+                         uint32_t* ask_worker_out, int64_t* worker_price_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,7 @@ def load() -> C.CDLL:
         "orc_idx_in_group": (C.c_int64, [P(cp), u32, cp]),
         "orc_soa_compatible": (i32, [vp, vp, vp, vp, vp, u32]),
         "orc_soa_form_groups": (vp, [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, i32]),
+        "orc_soa_auction": (u32, [vp, vp, u32, vp, u32, vp, vp, u32, vp, C.c_uint64, C.c_uint64, u32, vp, vp]),
         "orc_soa_eval_matrix": (C.c_uint64, [vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -318,3 +319,17 @@ def soa_eval_matrix(a, b, asks, opts, bits, words, t0, t1, w0, w1, threads=1,
         cost.ctypes.data if cost is not None else None, rb.ctypes.data if rb is not None else None,
         rc.ctypes.data if rc is not None else None, cf.ctypes.data if cf is not None else None)
     return {"evals": int(evals), "cost": cost, "row_best": rb, "row_count": rc, "col_first": cf}
+
+
+def soa_auction(a, b, asks, opts, bits, words, price_cap, cost_scale=1, eps_start=1, eps_div=4):
+    """EXTENSION self-oracle (no reference counterpart): returns (ask_worker u32[T], worker_price i64[W], rounds)."""
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    asks = np.ascontiguousarray(asks); opts = np.ascontiguousarray(opts)
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    cap = np.ascontiguousarray(price_cap, dtype=np.uint32)
+    out = np.empty(len(asks), dtype=np.uint32)
+    price = np.empty(len(a), dtype=np.int64)
+    rounds = load().orc_soa_auction(a.ctypes.data, b.ctypes.data, len(a), asks.ctypes.data, len(asks), opts.ctypes.data,
+                                    bits.ctypes.data, words, cap.ctypes.data, cost_scale, eps_start, eps_div, out.ctypes.data,
+                                    price.ctypes.data)
+    return out, price, rounds

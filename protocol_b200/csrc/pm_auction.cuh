@@ -1,0 +1,181 @@
+// pm_auction.cuh — NORTH-STAR EXTENSION: price-capped forward auction (one worker per ask).
+//
+// The reference orchestrator has no prices, caps, reputation or auction:
+// nothing here restates reference code, and parity for this mode is against the
+// builder's own sequential restatement (the auction checker of the test oracle) —
+// "self-oracle, parity unpinned by the reference".  The mode is inert unless
+// PM_MODE_AUCTION is requested; the reference modes never read ext_ask_price.
+//
+// Synchronous (Jacobi) Bertsekas auction:
+//   feasible(t,w) = candidate(w) && compatible(t,w) && ask_price[w] <= price_cap[t]
+//   value(t,w)    = -(ask_price[w] * S) - price[w]      outside(t) = -((price_cap[t] + 1) * S)
+//   bid(t)        = price[w1] + (best - max(second, outside)) + eps    on the best worker w1
+//   a worker takes the highest bid (ties: lowest ask index), releasing its previous owner.
+//
+// pm_auction_bid: one warp per unassigned ask; the CTA's 8 warps share stripes of the
+// worker table (planes A, B) and of the per-worker price vector, staged into shared
+// memory with 1-D TMA bulk copies; collisions are resolved by atomicMax on the bid and
+// atomicMin on the bidder (the claim), applied by the single winner of each worker.
+#pragma once
+#include "pm_kernels.cuh"
+
+namespace pm {
+
+constexpr int kAucThreads = 256;
+constexpr int kAucWarps = kAucThreads / 32;
+constexpr int kAucStripe = 1024;  // workers staged per step: 16 KB + 16 KB + 8 KB
+constexpr long long kAucNeg = (long long)(0x8000000000000000ull) / 4;
+
+struct AuctionParams {
+  EvalParams ev;
+  const uint32_t* price_cap;   // [T]
+  long long* price;            // [W] dual price of each worker
+  uint32_t* owner;             // [W] ask currently holding the worker
+  uint32_t* assigned;          // [T] worker held by the ask
+  uint32_t* withdrawn;         // [T]
+  const uint32_t* active;      // [n_active] unassigned, not withdrawn asks
+  uint32_t n_active;
+  uint32_t* bid_w;             // [T]
+  long long* bid_p;            // [T]
+  long long* bid_max;          // [W] highest bid of the round (reset by the winner)
+  uint32_t* winner;            // [W]
+  long long scale, eps;
+};
+
+struct __align__(128) AuctionStage {
+  uint4 a[kAucStripe];
+  uint4 b[kAucStripe];
+  long long price[kAucStripe];
+  uint64_t bar;
+};
+
+struct Top2 {
+  long long b1, b2;
+  uint32_t w1;
+};
+__device__ __forceinline__ Top2 top2_merge(const Top2& x, const Top2& y) {
+  Top2 r;
+  r.b1 = max(x.b1, y.b1);
+  r.w1 = (x.b1 > y.b1) ? x.w1 : (y.b1 > x.b1) ? y.w1 : min(x.w1, y.w1);
+  r.b2 = max(min(x.b1, y.b1), max(x.b2, y.b2));
+  return r;
+}
+
+__global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AuctionStage& s = *reinterpret_cast<AuctionStage*>(smem_raw);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * kAucWarps + warp;
+  const bool live = slot < p.n_active;
+  const uint32_t t = live ? p.active[slot] : 0u;
+  const DevAsk ask = p.ev.asks[t];
+  const uint32_t cap = p.price_cap[t];
+  Top2 best{kAucNeg, kAucNeg, kNone};
+
+  if (threadIdx.x == 0) mbar_init(&s.bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  const uint32_t W = p.ev.n_workers;
+  for (uint32_t w0 = 0; w0 < W; w0 += kAucStripe) {
+    const uint32_t n = min((uint32_t)kAucStripe, W - w0);
+    const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price[] is padded
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&s.bar, n * 32u + np * 8u);
+      bulk_g2s(s.a, p.ev.wa + w0, n * 16u, &s.bar);
+      bulk_g2s(s.b, p.ev.wb + w0, n * 16u, &s.bar);
+      bulk_g2s(s.price, p.price + w0, np * 8u, &s.bar);
+    }
+    mbar_wait(&s.bar, phase);
+    phase ^= 1u;
+    if (live) {
+      for (uint32_t i = lane; i < n; i += 32) {
+        const WorkerReg wr = make_worker(s.a[i], s.b[i]);
+        if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
+          const long long v = -((long long)wr.price * p.scale) - s.price[i];
+          const uint32_t w = w0 + i;
+          if (v > best.b1) { best.b2 = best.b1; best.b1 = v; best.w1 = w; }   // w ascends per lane
+          else if (v > best.b2) best.b2 = v;
+        }
+      }
+    }
+    __syncthreads();  // stripe fully consumed before the next bulk copy overwrites it
+  }
+  if (!live) return;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Top2 o;
+    o.b1 = __shfl_xor_sync(0xffffffffu, best.b1, off);
+    o.b2 = __shfl_xor_sync(0xffffffffu, best.b2, off);
+    o.w1 = __shfl_xor_sync(0xffffffffu, best.w1, off);
+    best = top2_merge(best, o);
+  }
+  if (lane == 0) {
+    const long long outside = -(((long long)cap + 1) * p.scale);
+    if (best.w1 == kNone || best.b1 < outside) {
+      p.withdrawn[t] = 1u;       // prices only rise: it can never come back
+      p.bid_w[t] = kNone;
+    } else {
+      const long long second = max(best.b2, outside);
+      const long long bid = p.price[best.w1] + (best.b1 - second) + p.eps;
+      p.bid_w[t] = best.w1;
+      p.bid_p[t] = bid;
+      atomicMax(p.bid_max + best.w1, bid);
+    }
+  }
+}
+
+// the claim: among the highest bidders of a worker the lowest ask index wins
+__global__ void pm_auction_claim(AuctionParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_active) return;
+  const uint32_t t = p.active[i], w = p.bid_w[t];
+  if (w != kNone && p.bid_p[t] == p.bid_max[w]) atomicMin(p.winner + w, t);
+}
+
+__global__ void pm_auction_apply(AuctionParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_active) return;
+  const uint32_t t = p.active[i], w = p.bid_w[t];
+  if (w == kNone || p.winner[w] != t) return;
+  const uint32_t prev = p.owner[w];
+  if (prev != kNone) p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
+  p.owner[w] = t;
+  p.assigned[t] = w;
+  p.price[w] = p.bid_p[t];
+  p.bid_max[w] = kAucNeg;
+  p.winner[w] = kNone;
+}
+
+__global__ void pm_auction_compact(const uint32_t* __restrict__ assigned, const uint32_t* __restrict__ withdrawn,
+                                   uint32_t n_asks, uint32_t* __restrict__ active, uint32_t* __restrict__ n_active) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_asks) return;
+  if (assigned[t] == kNone && !withdrawn[t]) active[atomicAdd(n_active, 1u)] = t;
+}
+
+// result in the engine's group form: one solo group per assigned ask, in ask order
+__global__ void pm_auction_flags(const uint32_t* __restrict__ assigned, uint32_t n_asks, uint32_t* __restrict__ flag) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_asks) flag[t] = assigned[t] != kNone ? 1u : 0u;
+  if (t == n_asks) flag[t] = 0u;
+}
+__global__ void pm_auction_emit(const uint32_t* __restrict__ assigned, const uint32_t* __restrict__ gidx,
+                                const uint4* __restrict__ wb, uint32_t n_asks, uint32_t* __restrict__ worker_group,
+                                uint32_t* __restrict__ worker_ask, uint32_t* __restrict__ group_ask,
+                                uint32_t* __restrict__ group_off, uint32_t* __restrict__ members,
+                                long long* __restrict__ ask_best, uint32_t* __restrict__ ask_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_asks) return;
+  const uint32_t w = assigned[t];
+  if (w == kNone) { ask_best[t] = kInf; ask_count[t] = 0; return; }
+  const uint32_t g = gidx[t];
+  worker_group[w] = g;
+  worker_ask[w] = t;
+  group_ask[g] = t;
+  group_off[g] = g;
+  members[g] = w;
+  ask_best[t] = ((long long)wb[w].w << 32) | (long long)w;
+  ask_count[t] = 1;
+}
+
+}  // namespace pm

@@ -22,6 +22,7 @@
 
 #include "pm_kernels.cuh"
 #include "pm_proximity.cuh"
+#include "pm_auction.cuh"
 
 struct pm_engine;
 
@@ -110,6 +111,12 @@ struct pm_engine {
   DevBuf<uint32_t> prox_list, prox_xs, members_raw;
   DevBuf<double> prox_dist;
   bool any_max_zero = false;
+  // extension (auction) state
+  DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
+  DevBuf<long long> auc_price, auc_bid_p, auc_bid_max;
+  bool have_caps = false;
+  uint64_t auc_scale = 1, auc_eps_start = 1;
+  uint32_t auc_eps_div = 4;
   DevBuf<uint32_t> worker_group, worker_ask, group_ask, group_off, members;
   PinBuf<uint32_t> h_scalars;  // small D2H mailbox
 
@@ -268,7 +275,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   }
   ok = ok &&
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
-            e->h_scalars.ensure(32) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
+            e->h_scalars.ensure(64) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
   if (!ok) {
     g_create_error = std::string("pm_create: ") + cudaGetErrorString(cudaGetLastError());
     delete e;
@@ -291,6 +298,9 @@ void pm_destroy(pm_engine* e) {
   e->base_len.release(); e->xhead.release(); e->xnext.release(); e->xcount.release();
   e->popped.release(); e->counters.release(); e->cub_tmp.release();
   e->prox_list.release(); e->prox_xs.release(); e->members_raw.release(); e->prox_dist.release();
+  e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
+  e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
+  e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
@@ -409,6 +419,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   e->max_pattern_row = max_row;
   e->all_solo = solo;
   e->asks_small = small;
+  e->have_caps = false;
   e->any_max_zero = false;
   for (uint32_t t = 0; t < n_asks; ++t)
     if (mx[t] == 0) e->any_max_zero = true;
@@ -592,7 +603,7 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
   if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
     return e->fail(PM_E_STATE, "pm_match: an ask references a model pattern missing from the model table");
   const uint32_t base_mode = mode & 0xFFu;
-  if (base_mode == PM_MODE_AUCTION) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is not built yet");
+  if (base_mode == PM_MODE_AUCTION) return e->fail(PM_E_INVALID, "pm_match: auction mode goes through pm_match");
   if (base_mode != PM_MODE_FIRST_FIT && base_mode != PM_MODE_PROXIMITY) return e->fail(PM_E_INVALID, "pm_match: unknown mode");
   if (base_mode == PM_MODE_PROXIMITY && !e->all_solo) {
     if (!e->have_loc) return e->fail(PM_E_STATE, "pm_match: proximity mode needs pm_set_worker_locations");
@@ -852,9 +863,139 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   return PM_OK;
 }
 
+// ------------------------------------------------------------------ extension: auction
+static int match_auction_locked(pm_engine* e) {
+  if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_match: worker and ask tables must be set first");
+  if (!e->have_caps) return e->fail(PM_E_STATE, "pm_match: auction mode needs pm_set_ask_price_caps");
+  if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
+    return e->fail(PM_E_STATE, "pm_match: an ask references a model pattern missing from the model table");
+  if (e->cfg.shard_count) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is single-GPU");
+  PM_CUDA(cudaSetDevice(e->device));
+  const uint32_t W = e->n_workers, T = e->n_asks;
+  if (!e->have_bits) {
+    PM_CUDA(e->bits.ensure(1));
+    PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
+    e->words = 1;
+  }
+  e->stats = pm_stats{};
+  e->ev_pending.clear();
+  e->ev_used = 0;
+  if (e->cfg.flags & PM_CFG_TIMING) PM_CUDA(cudaEventRecord(e->ev0, e->stream));
+  Timer tm(e, &e->stats.ms_fused);
+  PM_CUDA(e->auc_price.ensure((size_t)W + 2)); PM_CUDA(e->auc_owner.ensure(W)); PM_CUDA(e->auc_bid_max.ensure(W));
+  PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
+  PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
+  PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
+  PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(std::max(W, T)));
+  PM_CUDA(e->group_ask.ensure((size_t)T + 1)); PM_CUDA(e->group_off.ensure((size_t)T + 2));
+  PM_CUDA(e->ask_best.ensure(T)); PM_CUDA(e->ask_count.ensure(T)); PM_CUDA(e->first_ask.ensure(W));
+  PM_CUDA(cudaMemsetAsync(e->auc_price.p, 0, ((size_t)W + 2) * 8, e->stream));
+  if (W) {
+    pm::pm_fill_i64<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->auc_bid_max.p, pm::kAucNeg, W);
+    PM_LAUNCH_CHECK("pm_fill_i64");
+  }
+  PM_CUDA(cudaMemsetAsync(e->auc_winner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+
+  pm::AuctionParams ap;
+  ap.ev = eval_params(e);
+  ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
+  ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
+  ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
+  const size_t smem = sizeof(pm::AuctionStage);
+  uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
+  const uint32_t div = e->auc_eps_div < 2 ? 2 : e->auc_eps_div;
+  for (;;) {  // eps phases: assignment cleared, prices kept
+    PM_CUDA(cudaMemsetAsync(e->auc_owner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->auc_assigned.p, 0xFF, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->auc_withdrawn.p, 0, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
+    ap.eps = (long long)eps;
+    for (;;) {
+      PM_CUDA(cudaMemsetAsync(e->counters.p + 8, 0, 4, e->stream));
+      if (T) {
+        pm::pm_auction_compact<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->auc_assigned.p, e->auc_withdrawn.p, T, e->auc_active.p, e->counters.p + 8);
+        PM_LAUNCH_CHECK("pm_auction_compact");
+      }
+      PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 16, e->counters.p + 8, 4, cudaMemcpyDeviceToHost, e->stream));
+      PM_CUDA(cudaStreamSynchronize(e->stream));
+      const uint32_t n_active = e->h_scalars.p[16];
+      if (n_active == 0) break;
+      ap.n_active = n_active;
+      pm::pm_auction_bid<<<blocks_for(n_active, pm::kAucWarps), pm::kAucThreads, smem, e->stream>>>(ap);
+      PM_LAUNCH_CHECK("pm_auction_bid");
+      pm::pm_auction_claim<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
+      PM_LAUNCH_CHECK("pm_auction_claim");
+      pm::pm_auction_apply<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
+      PM_LAUNCH_CHECK("pm_auction_apply");
+      ++e->stats.n_rounds;
+      ++e->stats.n_fused_launches;
+      e->stats.evals += (uint64_t)n_active * W;
+      if (e->stats.n_rounds > 50u * 1000u * 1000u) return e->fail(PM_E_CUDA, "pm_match: auction did not terminate");
+    }
+    if (eps == 1) break;
+    eps = std::max<uint64_t>(1, eps / div);
+  }
+  tm.stop();
+  Timer tr(e, &e->stats.ms_resolve);
+  // result: one solo group per assigned ask, ask order
+  pm::pm_auction_flags<<<blocks_for((size_t)T + 1, 256), 256, 0, e->stream>>>(e->auc_assigned.p, T, e->auc_flag.p);
+  PM_LAUNCH_CHECK("pm_auction_flags");
+  {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->auc_flag.p, e->auc_gidx.p, (int)(T + 1), e->stream);
+    PM_CUDA(e->cub_tmp.ensure(tmp));
+    PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->auc_flag.p, e->auc_gidx.p, (int)(T + 1), e->stream));
+  }
+  PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+  if (T) {
+    pm::pm_auction_emit<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->auc_assigned.p, e->auc_gidx.p, e->wb.p, T, e->worker_group.p,
+                                                                    e->worker_ask.p, e->group_ask.p, e->group_off.p, e->members.p,
+                                                                    e->ask_best.p, e->ask_count.p);
+    PM_LAUNCH_CHECK("pm_auction_emit");
+  }
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 17, e->auc_gidx.p + T, 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  const uint32_t G = e->h_scalars.p[17];
+  PM_CUDA(cudaMemcpyAsync(e->group_off.p + G, e->h_scalars.p + 17, 4, cudaMemcpyHostToDevice, e->stream));
+  tr.stop();
+  e->n_groups = G;
+  e->n_assigned = G;
+  if (e->cfg.flags & PM_CFG_TIMING) {
+    PM_CUDA(cudaEventRecord(e->ev1, e->stream));
+    PM_CUDA(cudaEventSynchronize(e->ev1));
+    PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
+    e->resolve_timers();
+  }
+  e->matched = true;
+  e->local_done = false;
+  return PM_OK;
+}
+
+int pm_set_ask_price_caps(pm_engine* e, const uint32_t* price_cap, uint32_t n_asks) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_asks || n_asks != e->n_asks) return e->fail(PM_E_INVALID, "pm_set_ask_price_caps: one cap per ask, after pm_set_asks");
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->price_cap.ensure(n_asks));
+  if (n_asks) PM_CUDA(cudaMemcpyAsync(e->price_cap.p, price_cap, (size_t)n_asks * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_caps = true;
+  return PM_OK;
+}
+
+int pm_set_auction_params(pm_engine* e, uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div) {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->auc_scale = cost_scale ? cost_scale : 1;
+  e->auc_eps_start = eps_start ? eps_start : 1;
+  e->auc_eps_div = eps_div < 2 ? 2 : eps_div;
+  return PM_OK;
+}
+
 int pm_match_local(pm_engine* e, uint32_t mode) {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  if ((mode & 0xFFu) == PM_MODE_AUCTION) return e->fail(PM_E_UNSUPPORTED, "pm_match_local: auction mode is single-GPU (use pm_match)");
   return match_local_locked(e, mode);
 }
 int pm_match_finish(pm_engine* e, uint32_t mode) {
@@ -865,6 +1006,7 @@ int pm_match_finish(pm_engine* e, uint32_t mode) {
 int pm_match(pm_engine* e, uint32_t mode) {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  if ((mode & 0xFFu) == PM_MODE_AUCTION) return match_auction_locked(e);
   int rc = match_local_locked(e, mode);
   if (rc != PM_OK) return rc;
   return match_finish_locked(e, mode);

@@ -183,6 +183,14 @@ class Engine:
         self._check(self._lib.pm_set_flags(self._h, _ptr(idx), _ptr(flags), len(idx)))
         self.sync()
 
+    # ---- north-star extension columns (PM_MODE_AUCTION only) ---------------
+    def set_price_caps(self, caps: np.ndarray):
+        caps = np.ascontiguousarray(caps, dtype=np.uint32)
+        self._check(self._lib.pm_set_ask_price_caps(self._h, _ptr(caps), len(caps)))
+
+    def set_auction_params(self, cost_scale: int = 1, eps_start: int = 1, eps_div: int = 4):
+        self._check(self._lib.pm_set_auction_params(self._h, cost_scale, eps_start, eps_div))
+
     # ---- the pass ---------------------------------------------------------
     def match(self, mode: int = abi.PM_MODE_FIRST_FIT):
         self._check(self._lib.pm_match(self._h, mode))

@@ -299,3 +299,60 @@ def test_proximity_montreal_dallas_on_device():
     res = eng.fetch()
     assert sorted(sorted(m) for _, m in res.groups()) == [[0, 2], [1, 3]]
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# NORTH-STAR EXTENSION (no reference counterpart): parity is against the builder's own sequential
+# auction — "self-oracle, parity unpinned by the reference" (SURVEY 0, 8c).
+def _auction_tables(n_asks, n_workers, seed):
+    w, a, t = synth_tables(n_asks, n_workers, "mixed", seed_shift=seed)
+    rng = np.random.default_rng(seed)
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = rng.integers(10, 1000, n_workers).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(50, 1500, n_asks).astype(np.uint32)
+    return t, cap
+
+
+@pytest.mark.parametrize("n_asks,n_workers,seed", [(1, 5, 1), (50, 700, 2), (300, 2500, 3), (64, 1025, 4)])
+def test_extension_auction_matches_self_oracle(n_asks, n_workers, seed):
+    t, cap = _auction_tables(n_asks, n_workers, seed)
+    eng = Engine()
+    load_engine(eng, t)
+    eng.set_price_caps(cap)
+    eng.match(abi.PM_MODE_AUCTION)
+    res = eng.fetch()
+    want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap)
+    got = np.full(n_asks, abi.PM_NONE, dtype=np.uint32)
+    for g, (ask, members) in enumerate(res.groups()):
+        assert len(members) == 1
+        got[ask] = members[0]
+    assert np.array_equal(got, want)
+    assert res.stats["n_rounds"] == rounds
+    # every assignment respects feasibility and the cap; no worker is used twice
+    used = got[got != abi.PM_NONE]
+    assert len(set(used.tolist())) == len(used)
+    for tk in np.flatnonzero(got != abi.PM_NONE):
+        wk = got[tk]
+        assert t["wb"]["ext_ask_price"][wk] <= cap[tk]
+        assert orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][tk], t["opts"], t["bits"], t["words"])
+    eng.close()
+
+
+def test_extension_columns_are_neutral_in_reference_modes():
+    """ext_ask_price only occupies the high word of the packed cost; groups do not depend on it."""
+    w, a, t = synth_tables(200, 3000, "mixed")
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match()
+    r0 = eng.fetch()
+    t2 = dict(t)
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = 7
+    t2["wb"] = wb
+    load_engine(eng, t2)
+    eng.match()
+    r1 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_count"):
+        assert np.array_equal(getattr(r0, f), getattr(r1, f)), f
+    eng.close()
