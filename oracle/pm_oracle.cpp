@@ -902,7 +902,11 @@ uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_
     for (;;) {
       std::vector<u32> bid_w(n_asks, PM_NONE);
       std::vector<int64_t> bid_p(n_asks, 0);
-      bool any = false;
+      u32 n_active = 0;
+      for (u32 t = 0; t < n_asks; ++t)
+        if (assigned[t] == PM_NONE && !withdrawn[t]) ++n_active;
+      if (n_active == 0) break;
+      ++rounds;  // a round = one bidding pass over the unassigned, not-withdrawn asks
       for (u32 t = 0; t < n_asks; ++t) {
         if (assigned[t] != PM_NONE || withdrawn[t]) continue;
         const int64_t outside = -((int64_t(price_cap[t]) + 1) * S);
@@ -917,10 +921,7 @@ uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_
         if (b2 < outside) b2 = outside;
         bid_w[t] = w1;
         bid_p[t] = price[w1] + (b1 - b2) + int64_t(eps);
-        any = true;
       }
-      if (!any) break;
-      ++rounds;
       // a worker takes the highest bid; ties go to the lowest task index
       std::vector<u32> winner(n_workers, PM_NONE);
       for (u32 t = 0; t < n_asks; ++t) {
