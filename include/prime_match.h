@@ -212,6 +212,8 @@ int pm_set_auction_params(pm_engine*, uint64_t cost_scale, uint64_t eps_start, u
 enum pm_mode {
   PM_MODE_FIRST_FIT = 0,   /* try_form_new_groups, ProximityOptimizationPolicy{enabled:false} */
   PM_MODE_PROXIMITY = 1,   /* ... {enabled:true}  (mod.rs:524-552), the reference default     */
+  PM_MODE_PROXIMITY_MERGE = 3, /* try_merge_solo_groups' batch selection (mod.rs:752-848) over a table that  */
+                           /* holds only the nodes of solo groups, in get_all_groups() order               */
   PM_MODE_AUCTION   = 2    /* north-star extension: price-capped forward auction, one worker  */
                            /* per ask (pm_auction.cuh); no reference counterpart, self-oracle */
 };
@@ -340,6 +342,7 @@ int pm_plugin_set_node_status(pm_plugin*, const char* address, uint32_t status);
 int pm_plugin_add_task(pm_plugin*, const pm_task_desc*);                   /* TaskStore::add_task + on_task_created */
 int pm_plugin_delete_task(pm_plugin*, const char* id);                     /* delete_task + on_task_deleted */
 int pm_plugin_try_form_new_groups(pm_plugin*, uint32_t* n_formed);         /* mod.rs:478-628 via pm_match */
+int pm_plugin_try_merge_solo_groups(pm_plugin*, uint32_t* n_merged);       /* mod.rs:631-971 via pm_match */
 /* the "upload:<node>:<group>:<file>" key the storage route records; feeds ${TOTAL_UPLOAD_COUNT} */
 int pm_plugin_record_upload(pm_plugin*, const char* address, const char* group_id, const char* file_name);
 /* JSON out (NUL-terminated into buf): NodeGroup {"id","nodes","configuration_name","task_id"} or null */

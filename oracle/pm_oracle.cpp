@@ -625,6 +625,104 @@ const uint32_t* orc_groups_off(const orc_groups* g) { return g->off.data(); }
 const uint32_t* orc_groups_members(const orc_groups* g) { return g->members.data(); }
 uint64_t orc_groups_evals(const orc_groups* g) { return g->evals; }
 
+// try_merge_solo_groups / try_merge_groups_for_config / find_compatible_solo_groups /
+// attempt_group_merge / is_merge_beneficial / should_switch_tasks, ng/mod.rs:631-873, 257-296.
+orc_groups* orc_merge_solo_groups(const orc_node* c_nodes, uint32_t n_nodes, const orc_solo* c_solos,
+                                  uint32_t n_solos, const orc_config* cfgs, uint32_t n_cfgs,
+                                  int proximity, int task_switching_enabled, int prefer_larger_groups) {
+  auto* out = new orc_groups;
+  out->off.push_back(0);
+  std::vector<Node> nodes;
+  for (u32 i = 0; i < n_nodes; ++i) nodes.push_back(node_from_c(c_nodes[i], i));
+  struct Solo { std::string id; u32 node; bool has_task; };
+  std::vector<Solo> all;  // get_all_groups(): sorted by id (:1040); only solo groups matter here
+  for (u32 i = 0; i < n_solos; ++i) all.push_back({c_solos[i].id, c_solos[i].node, c_solos[i].has_task != 0});
+  std::sort(all.begin(), all.end(), [](const Solo& a, const Solo& b) { return a.id < b.id; });
+  if (all.size() < 2) return out;  // :640-644
+
+  for (u32 ci = 0; ci < n_cfgs; ++ci) {  // :654-661, current_groups refreshed per configuration
+    const orc_config& config = cfgs[ci];
+    const ComputeRequirements* reqs = config.req ? &config.req->r : nullptr;
+    // find_compatible_solo_groups (:712-749): specs only, no health/p2p filter
+    std::vector<Solo> remaining;
+    for (const Solo& g : all) {
+      ++out->evals;
+      if (is_node_compatible_with_config(reqs, nodes[g.node])) remaining.push_back(g);
+    }
+    if (remaining.size() < config.min_group_size) continue;  // :687-690
+    while (remaining.size() >= config.min_group_size) {       // :694
+      // attempt_group_merge (:752-860)
+      std::vector<const Solo*> merge_batch;
+      std::set<std::string> total_nodes;
+      auto in_batch = [&](const Solo* g) {
+        for (const Solo* b : merge_batch)
+          if (b->id == g->id) return true;
+        return false;
+      };
+      if (proximity) {
+        const Solo* seed = nullptr;
+        for (const Solo& g : remaining)
+          if (nodes[g.node].location) { seed = &g; break; }
+        if (seed) {
+          merge_batch.push_back(seed);
+          total_nodes.insert(nodes[seed->node].address);
+          const Location& sl = *nodes[seed->node].location;
+          std::vector<std::pair<double, const Solo*>> with_distance;
+          for (const Solo& g : remaining)
+            if (g.id != seed->id && nodes[g.node].location)
+              with_distance.push_back({calculate_distance(sl, *nodes[g.node].location), &g});
+          std::stable_sort(with_distance.begin(), with_distance.end(),
+                           [](const auto& a, const auto& b) { return a.first < b.first; });
+          for (const auto& dg : with_distance) {
+            if (total_nodes.size() + 1 <= config.max_group_size) {
+              merge_batch.push_back(dg.second);
+              total_nodes.insert(nodes[dg.second->node].address);
+              if (total_nodes.size() >= config.max_group_size) break;
+            }
+          }
+        }
+      }
+      if (merge_batch.empty() ||
+          (total_nodes.size() < config.max_group_size && total_nodes.size() < config.min_group_size)) {  // :823-848
+        if (total_nodes.size() < config.min_group_size) {
+          merge_batch.clear();
+          total_nodes.clear();
+        }
+        for (const Solo& g : remaining) {
+          if (!in_batch(&g) && total_nodes.size() + 1 <= config.max_group_size) {
+            merge_batch.push_back(&g);
+            total_nodes.insert(nodes[g.node].address);
+            if (total_nodes.size() >= config.max_group_size) break;
+          }
+        }
+      }
+      // is_merge_beneficial (:863-873) + should_switch_tasks (:257-296)
+      bool ok = merge_batch.size() >= 2 && total_nodes.size() >= 2 && task_switching_enabled;
+      if (ok && !prefer_larger_groups)
+        for (const Solo* g : merge_batch)
+          if (g->has_task) ok = false;
+      if (!ok) break;  // :704
+      out->cfg.push_back(ci);
+      for (const std::string& addr : total_nodes)
+        for (const Solo* g : merge_batch)
+          if (nodes[g->node].address == addr) { out->members.push_back(g->node); break; }
+      out->off.push_back(u32(out->members.size()));
+      std::set<std::string> used;
+      for (const Solo* g : merge_batch) used.insert(g->id);
+      std::vector<Solo> next;
+      for (const Solo& g : remaining)
+        if (!used.count(g.id)) next.push_back(g);
+      remaining.swap(next);
+      // the merged groups leave `all` (they are no longer solo groups in the next get_all_groups())
+      std::vector<Solo> all_next;
+      for (const Solo& g : all)
+        if (!used.count(g.id)) all_next.push_back(g);
+      all.swap(all_next);
+    }
+  }
+  return out;
+}
+
 // newest_task/mod.rs:8-19; Iterator::max_by_key returns the LAST maximum.
 uint32_t orc_newest_task(const int64_t* created_at, uint32_t n) {
   if (n == 0) return PM_NONE;

@@ -117,6 +117,20 @@ const uint32_t* orc_groups_off(const orc_groups*);      /* [G+1]                
 const uint32_t* orc_groups_members(const orc_groups*);  /* node idx, BTreeSet address order */
 uint64_t        orc_groups_evals(const orc_groups*);    /* compat predicate executions     */
 
+/* try_merge_solo_groups + helpers, mod.rs:631-971 (faithful).  solos = the groups with exactly
+ * one node (get_all_groups order is re-established here: sorted by id string, mod.rs:1040);
+ * has_task = get_current_group_task(id).is_some() (only read when !prefer_larger_groups).
+ * Returns the merged groups in creation order: cfg index, members = node indices in BTreeSet
+ * address order.  A solo group is dissolved iff its node appears in a merged group.          */
+typedef struct orc_solo {
+  const char* id;
+  uint32_t node;      /* index into nodes */
+  uint32_t has_task;
+} orc_solo;
+orc_groups* orc_merge_solo_groups(const orc_node* nodes, uint32_t n_nodes, const orc_solo* solos,
+                                  uint32_t n_solos, const orc_config* cfgs, uint32_t n_cfgs,
+                                  int proximity, int task_switching_enabled, int prefer_larger_groups);
+
 /* NewestTaskPlugin::filter_tasks, newest_task/mod.rs:8-19: index of the task
  * max_by_key(created_at) returns (LAST maximum), or PM_NONE if n == 0.        */
 uint32_t orc_newest_task(const int64_t* created_at, uint32_t n);

@@ -32,6 +32,10 @@ class OrcNode(C.Structure):
     ]
 
 
+class OrcSolo(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("node", C.c_uint32), ("has_task", C.c_uint32)]
+
+
 class OrcConfig(C.Structure):
     _fields_ = [("name", C.c_char_p), ("min_group_size", C.c_uint64), ("max_group_size", C.c_uint64),
                 ("req", C.c_void_p)]
@@ -77,6 +81,7 @@ def load() -> C.CDLL:
         "orc_groups_off": (P(u32), [vp]),
         "orc_groups_members": (P(u32), [vp]),
         "orc_groups_evals": (C.c_uint64, [vp]),
+        "orc_merge_solo_groups": (vp, [P(OrcNode), u32, P(OrcSolo), u32, P(OrcConfig), u32, i32, i32, i32]),
         "orc_newest_task": (u32, [vp, u32]),
         "orc_sort_tasks": (None, [vp, u32, vp]),
         "orc_idx_in_group": (C.c_int64, [P(cp), u32, cp]),
@@ -257,6 +262,18 @@ def form_groups(nodes, cfgs, proximity: bool) -> Groups:
     arr = (OrcNode * max(len(nodes), 1))(*nodes)
     carr = _configs(cfgs)
     h = load().orc_form_groups(arr, len(nodes), carr, len(cfgs), 1 if proximity else 0)
+    return Groups(h)
+
+
+def merge_solo_groups(nodes, solos, cfgs, proximity=True, task_switching_enabled=True, prefer_larger_groups=True) -> Groups:
+    """Faithful try_merge_solo_groups.  solos: list of (group id, node index, has_task)."""
+    arr = (OrcNode * max(len(nodes), 1))(*nodes)
+    sarr = (OrcSolo * max(len(solos), 1))()
+    for i, (gid, node, has_task) in enumerate(solos):
+        sarr[i].id, sarr[i].node, sarr[i].has_task = gid.encode(), node, int(has_task)
+    carr = _configs(cfgs)
+    h = load().orc_merge_solo_groups(arr, len(nodes), sarr, len(solos), carr, len(cfgs), int(proximity),
+                                     int(task_switching_enabled), int(prefer_larger_groups))
     return Groups(h)
 
 

@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         "pm_plugin_delete_task": (i32, [vp, cp]),
         "pm_plugin_record_upload": (i32, [vp, cp, cp, cp]),
         "pm_plugin_try_form_new_groups": (i32, [vp, P(u32)]),
+        "pm_plugin_try_merge_solo_groups": (i32, [vp, P(u32)]),
         "pm_plugin_get_node_group": (i32, [vp, cp, C.c_char_p, sz]),
         "pm_plugin_get_all_groups": (i32, [vp, C.c_char_p, sz]),
         "pm_scheduler_get_task_for_node": (i32, [vp, cp, C.c_char_p, sz]),

@@ -45,7 +45,7 @@ PM_O_TOT_MAX = 1 << 6
 
 PM_CFG_TIMING = 1 << 0
 
-PM_MODE_FIRST_FIT, PM_MODE_PROXIMITY, PM_MODE_AUCTION = 0, 1, 2
+PM_MODE_FIRST_FIT, PM_MODE_PROXIMITY, PM_MODE_AUCTION, PM_MODE_PROXIMITY_MERGE = 0, 1, 2, 3
 PM_PATH_MATERIALIZED, PM_PATH_FUSED = 0, 1 << 8
 
 PM_BUF_WORKER_FIRST_ASK, PM_BUF_ASK_BEST, PM_BUF_ASK_COUNT = 0, 1, 2
@@ -115,7 +115,7 @@ EXPORTS = [
     "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync",
     "pm_plugin_create", "pm_plugin_destroy", "pm_plugin_last_error", "pm_plugin_add_config", "pm_plugin_seal_configs",
     "pm_plugin_enable_configuration", "pm_plugin_upsert_node", "pm_plugin_set_node_status", "pm_plugin_add_task",
-    "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups",
+    "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_try_merge_solo_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups",
     "pm_scheduler_get_task_for_node",
 ]
 

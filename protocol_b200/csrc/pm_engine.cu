@@ -604,8 +604,9 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
     return e->fail(PM_E_STATE, "pm_match: an ask references a model pattern missing from the model table");
   const uint32_t base_mode = mode & 0xFFu;
   if (base_mode == PM_MODE_AUCTION) return e->fail(PM_E_INVALID, "pm_match: auction mode goes through pm_match");
-  if (base_mode != PM_MODE_FIRST_FIT && base_mode != PM_MODE_PROXIMITY) return e->fail(PM_E_INVALID, "pm_match: unknown mode");
-  if (base_mode == PM_MODE_PROXIMITY && !e->all_solo) {
+  if (base_mode != PM_MODE_FIRST_FIT && base_mode != PM_MODE_PROXIMITY && base_mode != PM_MODE_PROXIMITY_MERGE)
+    return e->fail(PM_E_INVALID, "pm_match: unknown mode");
+  if ((base_mode == PM_MODE_PROXIMITY && !e->all_solo) || base_mode == PM_MODE_PROXIMITY_MERGE) {
     if (!e->have_loc) return e->fail(PM_E_STATE, "pm_match: proximity mode needs pm_set_worker_locations");
     if (e->any_max_zero)
       return e->fail(PM_E_UNSUPPORTED, "pm_match: max_group_size == 0 is not supported in proximity mode");
@@ -720,7 +721,8 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   PM_CUDA(cudaSetDevice(e->device));
   const uint32_t base_mode = mode & 0xFFu;
   const uint32_t W = e->n_workers, T = e->n_asks;
-  const bool prox_general = base_mode == PM_MODE_PROXIMITY && !e->all_solo;
+  const bool merge_mode = base_mode == PM_MODE_PROXIMITY_MERGE;
+  const bool prox_general = (base_mode == PM_MODE_PROXIMITY && !e->all_solo) || merge_mode;
   const uint32_t shift = (base_mode == PM_MODE_PROXIMITY && !prox_general) ? 1u : 0u;
   const uint32_t n_bins = T << shift;
   Timer tm(e, &e->stats.ms_resolve);
@@ -763,7 +765,8 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     pp.worker_group = e->worker_group.p; pp.worker_ask = e->worker_ask.p; pp.group_ask = e->group_ask.p;
     pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = e->counters.p + 4;
     pp.group_cap = cap;
-    pm::pm_proximity_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
+    if (merge_mode) pm::pm_merge_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
+    else pm::pm_proximity_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
     PM_LAUNCH_CHECK("pm_proximity_sweep");
     PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 8, e->counters.p + 4, 16, cudaMemcpyDeviceToHost, e->stream));
     PM_CUDA(cudaStreamSynchronize(e->stream));

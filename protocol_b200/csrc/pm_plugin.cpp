@@ -450,6 +450,138 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   return PM_OK;
 }
 
+// try_merge_solo_groups (mod.rs:631-971).  Compatibility of the solo groups' nodes with each
+// configuration, and the batch selection, run on the engine over a temporary table that holds only
+// those nodes in get_all_groups() order (sorted by id, mod.rs:1040).
+static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, const std::vector<std::string>& solo_ids,
+                      std::vector<std::pair<const Config*, std::vector<std::string>>>* merged /* (config, solo group ids) */) {
+  const uint32_t W = (uint32_t)solo_ids.size();
+  std::vector<pm_worker_a> wa(W);
+  std::vector<pm_worker_b> wb(W);
+  std::vector<double> lat(W), lon(W);
+  std::vector<uint32_t> by_addr(W), arank(W);
+  std::vector<const NodeRec*> recs(W);
+  for (uint32_t i = 0; i < W; ++i) {
+    const Group& g = p->groups.at(solo_ids[i]);
+    const NodeRec& n = p->nodes[p->node_index.at(g.nodes[0])];
+    recs[i] = &n;
+    wa[i] = n.a;
+    wb[i] = n.b;
+    // find_compatible_solo_groups (mod.rs:712-749) looks at compute specs only
+    wa[i].flags = n.a.flags | PM_W_HEALTHY | PM_W_P2P | (n.has_loc ? PM_W_HAS_LOC : 0u);
+    lat[i] = n.lat;
+    lon[i] = n.lon;
+    by_addr[i] = i;
+  }
+  std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return recs[a]->address < recs[b]->address; });
+  for (uint32_t i = 0; i < W; ++i) arank[by_addr[i]] = i;
+
+  const bool prox = p->policy.proximity_enabled != 0;
+  std::vector<pm_ask> asks;
+  std::vector<pm_gpu_opt> opts;
+  std::vector<const Config*> ask_cfg;
+  for (const Config* c : configs) {
+    if (c->max_group_size < 2) continue;          // a batch of one group is never beneficial (mod.rs:868)
+    pm_ask a = c->ask;
+    a.opt_off = (uint32_t)opts.size();
+    // first-fit batches are cut like formation chunks; a tail merges iff it has >= max(min, 2) groups
+    a.min_group_size = prox ? c->min_group_size : std::max<uint32_t>(c->min_group_size, 2);
+    a.max_group_size = c->max_group_size;
+    opts.insert(opts.end(), c->opts.begin(), c->opts.end());
+    asks.push_back(a);
+    ask_cfg.push_back(c);
+  }
+  if (asks.empty()) return PM_OK;
+  const uint32_t* bits = nullptr;
+  uint32_t npat = 0, nmod = 0, words = 1;
+  int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
+  if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
+  auto chk = [&](int r, const char* what) {
+    if (r != PM_OK) {
+      const char* m = pm_last_error(p->engine);
+      p->err = std::string(what) + ": " + (m ? m : "");
+    }
+    return r;
+  };
+  if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
+  if ((rc = chk(pm_set_model_table(p->engine, bits, npat, nmod, words), "pm_set_model_table"))) return rc;
+  if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
+  if ((rc = chk(pm_upsert_workers(p->engine, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
+  if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
+  if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
+  if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;
+  if ((rc = chk(pm_match(p->engine, prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT), "pm_match"))) return rc;
+  pm_result res{};
+  if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
+  for (uint32_t g = 0; g < res.n_groups; ++g) {
+    std::vector<std::string> ids;
+    for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m) ids.push_back(solo_ids[res.group_members[m]]);
+    merged->emplace_back(ask_cfg[res.group_ask[g]], std::move(ids));
+  }
+  return PM_OK;
+}
+
+int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (n_merged) *n_merged = 0;
+  if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: merging has no CPU path");
+  auto solo_list = [&]() {
+    std::vector<std::string> ids;  // std::map iterates in id order == get_all_groups() order
+    for (const auto& kv : p->groups)
+      if (kv.second.nodes.size() == 1) ids.push_back(kv.first);
+    return ids;
+  };
+  if (solo_list().size() < 2) return PM_OK;                      // mod.rs:640-644
+  if (!p->policy.task_switching_enabled) return PM_OK;            // should_switch_tasks, mod.rs:263-265
+  const auto configs = p->available_configurations();
+
+  // execute_group_merge (mod.rs:876-971)
+  auto apply = [&](const Config* cfg, const std::vector<std::string>& ids) {
+    Group merged;
+    char idbuf[32];
+    std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);
+    merged.id = idbuf;
+    merged.configuration_name = cfg->name;
+    for (const auto& gid : ids) merged.nodes.push_back(p->groups.at(gid).nodes[0]);
+    std::sort(merged.nodes.begin(), merged.nodes.end());           // BTreeSet<String>
+    // find_best_task_for_group (mod.rs:1122-1189), determinised to the NewestTask rule
+    const TaskRec* chosen = nullptr;
+    for (const TaskRec* t : p->all_tasks())
+      if (task_applicable(*t, cfg->name) && (!chosen || t->created_at >= chosen->created_at)) chosen = t;
+    for (const auto& gid : ids) p->dissolve(gid);
+    for (const auto& n : merged.nodes) p->node_to_group[n] = merged.id;
+    if (chosen) p->group_task[merged.id] = chosen->id;              // SET NX on a fresh key
+    p->groups.emplace(merged.id, std::move(merged));
+    if (n_merged) ++*n_merged;
+  };
+
+  if (p->policy.prefer_larger_groups) {
+    std::vector<std::pair<const Config*, std::vector<std::string>>> merged;
+    int rc = merge_pass(p, configs, solo_list(), &merged);
+    if (rc != PM_OK) return rc;
+    for (const auto& m : merged) apply(m.first, m.second);
+  } else {
+    // a batch that contains a group holding a task is refused and ends the configuration
+    // (mod.rs:277-287, :704): one pass per configuration, truncated at the first such batch
+    for (const Config* c : configs) {
+      const auto solos = solo_list();
+      if (solos.size() < 2) break;
+      std::vector<std::pair<const Config*, std::vector<std::string>>> merged;
+      int rc = merge_pass(p, {c}, solos, &merged);
+      if (rc != PM_OK) return rc;
+      for (const auto& m : merged) {
+        bool tasked = false;
+        for (const auto& gid : m.second)
+          if (p->current_group_task(gid)) tasked = true;
+        if (tasked) break;
+        apply(m.first, m.second);
+      }
+    }
+  }
+  return PM_OK;
+}
+
 static void group_json(const pm_plugin* p, const Group& g, std::string& out) {
   out += "{\"id\":";
   json_str(out, g.id);

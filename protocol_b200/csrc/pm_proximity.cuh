@@ -21,7 +21,8 @@ namespace pm {
 
 constexpr uint32_t kTakenBit = 1u << 31;
 constexpr uint32_t kLocBit = 1u << 30;
-constexpr uint32_t kIdxMask = 0x3FFFFFFFu;
+constexpr uint32_t kTentBit = 1u << 29;   // merge sweep: tentatively in the current batch
+constexpr uint32_t kIdxMask = 0x1FFFFFFFu;
 constexpr int kProxThreads = 1024;
 
 struct ProxParams {
@@ -91,13 +92,16 @@ __device__ __forceinline__ uint32_t block_find_first(ProxShared& sh, const uint3
   return n;
 }
 
-// lexicographic (distance, position) arg-min over the not-yet-taken entries
+// lexicographic (distance, position) arg-min over the entries with (e & skip) == 0 and, when
+// need != 0, (e & need) != 0; kNone when there is none
 __device__ __forceinline__ uint32_t block_argmin(ProxShared& sh, const uint32_t* list,
-                                                 const double* dist, uint32_t n) {
+                                                 const double* dist, uint32_t n,
+                                                 uint32_t skip = kTakenBit, uint32_t need = 0u) {
   double bd = 1.7976931348623157e308;
   uint32_t bi = kNone;
   for (uint32_t i = threadIdx.x; i < n; i += kProxThreads) {
-    if (list[i] & kTakenBit) continue;
+    const uint32_t e = list[i];
+    if ((e & skip) != 0u || (need != 0u && (e & need) == 0u)) continue;
     const double d = dist[i];
     if (bi == kNone || d < bd) { bd = d; bi = i; }  // i increases: ties keep the smaller position
   }
@@ -315,6 +319,197 @@ __global__ void __launch_bounds__(kProxThreads) pm_proximity_sweep(ProxParams p)
           atomicAdd(&p.xcount[found], 1u);
         }
         atomicAdd(&p.out_counts[2], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { p.base_len[c] = 0; p.xcount[c] = 0; p.xhead[c] = kNone; }
+    __syncthreads();
+    c_lo = c + 1;
+  }
+  if (tid == 0) {
+    p.out_counts[0] = g;
+    p.out_counts[1] = mpos;
+    if (g < p.group_cap + 1) p.group_off[g] = mpos;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// try_merge_solo_groups with ProximityOptimizationPolicy enabled (mod.rs:631-873).  The caller
+// passes ONLY the nodes of solo groups, in get_all_groups() order (sorted by group id), all
+// marked as candidates; "configurations" and the hand-down of unmerged nodes work as in
+// pm_proximity_sweep.  Batch selection follows attempt_group_merge (mod.rs:752-848):
+//   seed = first remaining LOCATED node; then the nearest LOCATED nodes while size + 1 <= max;
+//   if there was no seed, or size < max && size < min: (clear if size < min and) fill in list order;
+//   the merge happens iff the batch has >= 2 groups (is_merge_beneficial, :863-873), else the
+//   configuration is done (:704).  Task-switching policy is applied by the host.
+__global__ void __launch_bounds__(kProxThreads) pm_merge_sweep(ProxParams p) {
+  __shared__ ProxShared sh;
+  const uint32_t T = p.ev.n_asks;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  uint32_t g = 0, mpos = 0, c_lo = 0;
+  uint32_t* pickpos = p.xs;  // positions of the tentative batch (xs is free after the merge step)
+
+  while (c_lo < T) {
+    if (tid == 0) sh.u[0] = kNone;
+    __syncthreads();
+    {
+      const uint32_t c = c_lo + tid;
+      if (c < T && (p.base_len[c] + p.xcount[c] != 0u)) atomicMin(&sh.u[0], c);
+    }
+    __syncthreads();
+    const uint32_t c = sh.u[0];
+    __syncthreads();
+    if (c == kNone) { c_lo += kProxThreads; continue; }
+    const uint32_t mn = p.amin[c], mx = p.amax[c];
+    const uint32_t bl = p.base_len[c], xc = p.xcount[c];
+    const uint32_t n = bl + xc;
+    const uint32_t* base = p.order + p.seg_start[c];
+
+    uint32_t P = 1;
+    while (P < xc) P <<= 1;
+    if (xc) {
+      if (tid == 0) {
+        uint32_t j = 0;
+        for (uint32_t x = p.xhead[c]; x != kNone; x = p.xnext[x]) p.xs[j++] = x;
+      }
+      for (uint32_t j = xc + tid; j < P; j += kProxThreads) p.xs[j] = kNone;
+      __syncthreads();
+      for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = tid; i < P; i += kProxThreads) {
+            const uint32_t l = i ^ j;
+            if (l > i) {
+              const uint32_t a = p.xs[i], b = p.xs[l];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { p.xs[i] = b; p.xs[l] = a; }
+            }
+          }
+          __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < bl; i += kProxThreads) {
+      const uint32_t w = base[i];
+      p.list[i + lower_bound_u32(p.xs, xc, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+    }
+    for (uint32_t j = tid; j < xc; j += kProxThreads) {
+      const uint32_t w = p.xs[j];
+      p.list[j + lower_bound_u32(base, bl, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+    }
+    __syncthreads();
+
+    uint32_t remaining = n, ploc = 0;
+    if (remaining >= mn) {   // "if compatible_groups.len() < min_group_size return" (:687)
+      for (;;) {
+        if (remaining < mn || remaining == 0) break;                       // :694
+        uint32_t size = 0;
+        // --- proximity phase
+        uint32_t seed_pos = n;
+        if (ploc < n) {
+          seed_pos = block_find_first(sh, p.list, n, ploc,
+                                      [](uint32_t e) { return (e & (kTakenBit | kLocBit)) == kLocBit; });
+          ploc = seed_pos;
+        }
+        if (seed_pos < n) {
+          const uint32_t seed_w = p.list[seed_pos] & kIdxMask;
+          __syncthreads();
+          if (tid == 0) { p.list[seed_pos] |= kTentBit; pickpos[0] = seed_pos; }
+          size = 1;
+          if (mx > 1) {
+            const double slat = p.lat[seed_w], slon = p.lon[seed_w];
+            for (uint32_t i = tid; i < n; i += kProxThreads) {
+              const uint32_t e = p.list[i];
+              if ((e & kTakenBit) || !(e & kLocBit)) continue;
+              p.dist[i] = haversine_km(slat, slon, p.lat[e & kIdxMask], p.lon[e & kIdxMask]);
+            }
+            __syncthreads();
+            while (size < mx) {                                           // total + 1 <= max
+              const uint32_t bi = block_argmin(sh, p.list, p.dist, n, kTakenBit | kTentBit, kLocBit);
+              if (bi == kNone) break;
+              if (tid == 0) { p.list[bi] |= kTentBit; pickpos[size] = bi; }
+              ++size;
+              __syncthreads();
+            }
+          }
+          __syncthreads();
+        }
+        // --- fallback to list order (:823-848)
+        if (size == 0 || (size < mx && size < mn)) {
+          if (size < mn) {
+            for (uint32_t j = tid; j < size; j += kProxThreads) p.list[pickpos[j]] &= ~kTentBit;
+            __syncthreads();
+            size = 0;
+          }
+          uint32_t pos = block_find_first(sh, p.list, n, 0, [](uint32_t e) { return (e & kTakenBit) == 0u; });
+          while (size < mx && pos < n) {
+            const uint32_t i = pos + tid;
+            const bool live = i < n && (p.list[i] & (kTakenBit | kTentBit)) == 0u;
+            const uint32_t b = __ballot_sync(0xffffffffu, live);
+            if (lane == 0) sh.warp_cnt[warp] = (uint32_t)__popc(b);
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+            for (uint32_t q = 0; q < (uint32_t)kProxThreads / 32; ++q) {
+              const uint32_t v = sh.warp_cnt[q];
+              if (q < warp) before += v;
+              total += v;
+            }
+            const uint32_t rank = size + before + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (live && rank < mx) { p.list[i] |= kTentBit; pickpos[rank] = i; }
+            size = min(mx, size + total);
+            pos += kProxThreads;
+            __syncthreads();
+          }
+        }
+        // --- is_merge_beneficial: at least two groups
+        if (size < 2) {
+          for (uint32_t j = tid; j < size; j += kProxThreads) p.list[pickpos[j]] &= ~kTentBit;
+          __syncthreads();
+          break;                                                           // :704
+        }
+        if (g >= p.group_cap) { if (tid == 0) p.out_counts[3] = 1u; break; }
+        for (uint32_t j = tid; j < size; j += kProxThreads) {
+          const uint32_t pos = pickpos[j];
+          const uint32_t w = p.list[pos] & kIdxMask;
+          p.list[pos] = (p.list[pos] & ~kTentBit) | kTakenBit;
+          p.members[mpos + j] = w;
+          p.worker_group[w] = g;
+          p.worker_ask[w] = c;
+        }
+        if (tid == 0) { p.group_ask[g] = c; p.group_off[g] = mpos; }
+        __syncthreads();
+        remaining -= size;
+        mpos += size;
+        ++g;
+      }
+    }
+
+    // unmerged nodes stay solo and are considered by the following configurations
+    if (tid == 0) sh.u[1] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kProxThreads) {
+      const uint32_t e = p.list[i];
+      if ((e & kTakenBit) == 0u) p.popped[atomicAdd(&sh.u[1], 1u)] = e & kIdxMask;
+    }
+    __syncthreads();
+    const uint32_t npop = sh.u[1];
+    for (uint32_t i = warp; i < npop; i += kProxThreads / 32) {
+      const uint32_t w = p.popped[i];
+      const WorkerReg wr = make_worker(p.ev.wa[w], p.ev.wb[w]);
+      uint32_t found = kNone;
+      for (uint32_t cbase = c + 1; cbase < T; cbase += 32) {
+        const uint32_t c2 = cbase + lane;
+        bool ok = false;
+        if (c2 < T) ok = ask_meets(p.ev.asks[c2], p.ev.opts, wr, p.ev.bits, p.ev.words);
+        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+        if (b) { found = cbase + (uint32_t)__ffs(b) - 1u; break; }
+      }
+      if (lane == 0) {
+        p.cur[w] = found;
+        if (found != kNone) {
+          const uint32_t old = atomicExch(&p.xhead[found], w);
+          p.xnext[w] = old;
+          atomicAdd(&p.xcount[found], 1u);
+        }
       }
     }
     __syncthreads();

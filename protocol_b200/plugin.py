@@ -193,6 +193,11 @@ class NodeGroupsPlugin:
         self._check(self._lib.pm_plugin_try_form_new_groups(self._h, C.byref(n)))
         return n.value
 
+    def try_merge_solo_groups(self) -> int:
+        n = C.c_uint32()
+        self._check(self._lib.pm_plugin_try_merge_solo_groups(self._h, C.byref(n)))
+        return n.value
+
     def get_node_group(self, address: str):
         return self._json(self._lib.pm_plugin_get_node_group, address.encode())
 

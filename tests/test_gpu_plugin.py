@@ -180,3 +180,133 @@ def test_proximity_pairs_by_city(engine):
     assert plugin.get_node_group(d1) == plugin.get_node_group(d2)
     g = plugin.get_node_group(m1)
     assert g["nodes"] == sorted([m1, m2], key=lambda s: s.encode())    # BTreeSet<String> order
+
+
+# ------------------------------------------------------------------------------------------------
+# try_merge_solo_groups (mod.rs:631-971)
+def test_proximity_merging_prevents_wrong_nodes_grouping(engine):
+    """tests.rs:2861-3064 verbatim: each arrival forms a solo group (the 2-node configuration cannot
+    fill yet), then the merge pass pairs Montreal with Montreal and Dallas with Dallas."""
+    a6000 = ComputeSpecs(gpu=GpuSpecs(count=1, model="nvidia rtx a6000", memory_mb=49140))
+    montreal, dallas = (45.5186, -73.5545), (32.7942, -96.7475)
+    m1, m2 = "0xB2631de00e6120969d34456b9c7Ee22352f13b02", "0x2C490CAdf3A8C2Ab67b00831973da8b9d18e5b6D"
+    d1, d2 = "0x7ec9d3bc276B74969341c03dc00B9f70c0EadFd5", "0x32d7cd9b8F6eA556a67E0c9386cdd911Da3AD3E5"
+    plugin = make(engine, [NodeGroupConfiguration("1x40-48GB", 1, 1), NodeGroupConfiguration("2x40-48GB", 2, 2)])
+    plugin.add_task(Task(allowed_topologies=["1x40-48GB", "2x40-48GB"]))
+    for addr, loc in ((m1, montreal), (m2, montreal), (d1, dallas), (d2, dallas)):
+        plugin.add_node(OrchestratorNode(addr, compute_specs=a6000, location=loc))
+        assert plugin.try_form_new_groups() == 1, "Should form 1 solo group"
+    assert plugin.try_merge_solo_groups() == 2
+    gm, gd = plugin.get_node_group(m1), plugin.get_node_group(d1)
+    assert sorted(gm["nodes"]) == sorted([m1, m2]) and sorted(gd["nodes"]) == sorted([d1, d2])
+    assert gm["configuration_name"] == gd["configuration_name"] == "2x40-48GB"
+    assert gm["task_id"] is not None        # find_best_task_for_group + SET NX
+
+
+def test_no_merge_when_policy_disabled(engine):
+    """tests.rs:2636-2710."""
+    plugin = make(engine, [NodeGroupConfiguration("merge-config", 1, 3)], task_switching_enabled=False)
+    plugin.add_task(Task(allowed_topologies=["merge-config"]))
+    for a in (A1, A2, A3):
+        plugin.add_node(OrchestratorNode(a))
+        plugin.try_form_new_groups()
+    before = plugin.get_all_groups()
+    assert plugin.try_merge_solo_groups() == 0
+    assert plugin.get_all_groups() == before
+
+
+def test_merge_solo_groups_first_fit_and_prefer_larger(engine):
+    """tests.rs:2171-2338 shape: three solo groups, configuration {1..3}: one merged group of three."""
+    plugin = make(engine, [NodeGroupConfiguration("merge-config", 1, 3)], proximity_enabled=False)
+    sched = Scheduler(plugin)
+    task = Task(name="t", allowed_topologies=["merge-config"])
+    plugin.add_task(task)
+    for a in (A1, A2, A3):
+        plugin.add_node(OrchestratorNode(a))
+        assert plugin.try_form_new_groups() == 1
+    assert sched.get_task_for_node(A1)["id"] == task.id          # a solo group already works on the task
+    assert plugin.try_merge_solo_groups() == 1
+    g = plugin.get_node_group(A1)
+    assert g["nodes"] == [A1, A2, A3] and g == plugin.get_node_group(A3)
+    t1 = sched.get_task_for_node(A2)
+    assert t1["env_vars"]["GROUP_INDEX"] == "1" and t1["id"] == task.id
+    # with prefer_larger_groups = false the group holding a task blocks the batch (mod.rs:277-287)
+    plugin2 = make(engine, [NodeGroupConfiguration("merge-config", 1, 3)], proximity_enabled=False,
+                   prefer_larger_groups=False)
+    plugin2.add_task(Task(name="t", allowed_topologies=["merge-config"]))
+    for a in (A1, A2, A3):
+        plugin2.add_node(OrchestratorNode(a))
+        plugin2.try_form_new_groups()
+    assert Scheduler(plugin2).get_task_for_node(A1) is not None
+    assert plugin2.try_merge_solo_groups() == 0
+
+
+def test_merge_only_compatible_groups(engine):
+    """tests.rs:2471-2635."""
+    a100 = ComputeSpecs(gpu=GpuSpecs(count=8, model="A100", memory_mb=80000))
+    other = ComputeSpecs(gpu=GpuSpecs(count=8, model="RTX 3090", memory_mb=24000))
+    a4 = "0x4234567890123456789012345678901234567890"
+    plugin = make(engine, [NodeGroupConfiguration("solo", 1, 1), NodeGroupConfiguration("a100-pair", 2, 2, "gpu:count=8;gpu:model=A100")])
+    plugin.add_task(Task(allowed_topologies=["solo", "a100-pair"]))
+    for addr, spec in ((A1, a100), (A2, None), (A3, a100), (a4, other)):
+        plugin.add_node(OrchestratorNode(addr, compute_specs=spec))
+        plugin.try_form_new_groups()
+    assert len(plugin.get_all_groups()) == 4
+    assert plugin.try_merge_solo_groups() == 1
+    assert plugin.get_node_group(A1)["nodes"] == [A1, A3]
+    assert len(plugin.get_node_group(A2)["nodes"]) == 1 and len(plugin.get_node_group(a4)["nodes"]) == 1
+
+
+@pytest.mark.parametrize("proximity", [False, True], ids=["first_fit", "proximity"])
+def test_merge_matches_oracle_on_random_swarm(engine, proximity):
+    """Host mirror + engine vs the faithful oracle merge (orc_merge_solo_groups) on a random swarm of
+    solo groups with mixed requirements, locations and group sizes."""
+    import numpy as np
+
+    from helpers import spec_to_orc_node
+    from oracle import pm_oracle as orc
+    from protocol_b200 import abi, synth
+
+    n = 400
+    w = synth.make_workers(n, seed=777, with_addresses=True, healthy_frac=1.0)
+    reqs = ["gpu:count=8", "gpu:count=4;gpu:model=a100,h100", "gpu:count=2", "gpu:count=1;gpu:memory_mb_min=24000", None]
+    sizes = [(4, 6), (3, 3), (2, 5), (1, 2), (2, 4)]
+    cfgs = [NodeGroupConfiguration(f"cfg{i}", mn, mx, r) for i, ((mn, mx), r) in enumerate(zip(sizes, reqs))]
+    cfgs.append(NodeGroupConfiguration("solo", 1, 1))
+    plugin = make(engine, cfgs, proximity_enabled=proximity)
+    plugin.add_task(Task(allowed_topologies=["solo"]))           # only the solo configuration is enabled at first
+    onodes = []
+    for i in range(n):
+        f = int(w.a["flags"][i])
+        has = lambda b: bool(f & b)
+        if not has(abi.PM_W_P2P):
+            continue
+        spec = None
+        kw = {}
+        if has(abi.PM_W_HAS_SPECS):
+            spec = ComputeSpecs(gpu=GpuSpecs(count=int(w.a["gpu_count"][i]), model=w.model_strings[int(w.a["model_id"][i])],
+                                             memory_mb=int(w.a["gpu_mem_mb"][i]) if has(abi.PM_W_HAS_GPU_MEM) else None),
+                                cpu_cores=int(w.b["cpu_cores"][i]), ram_mb=int(w.b["ram_mb"][i]), storage_gb=int(w.b["storage_gb"][i]))
+            kw = dict(gpu_count=spec.gpu.count, gpu_model=spec.gpu.model, gpu_mem=spec.gpu.memory_mb,
+                      cpu_cores=spec.cpu_cores, ram=spec.ram_mb, storage=spec.storage_gb)
+        loc = (float(w.lat[i]), float(w.lon[i])) if has(abi.PM_W_HAS_LOC) else None
+        plugin.add_node(OrchestratorNode(w.addresses[i], compute_specs=spec, location=loc))
+        onodes.append(orc.make_node(address=w.addresses[i], specs=spec is not None, location=loc, **kw))
+    formed = plugin.try_form_new_groups()
+    assert formed == len(onodes)                                  # everybody sits in a solo group
+    groups = plugin.get_all_groups()
+    addr_to_idx = {nd.address.decode(): i for i, nd in enumerate(onodes)}
+    solos = [(g["id"], addr_to_idx[g["nodes"][0]], False) for g in groups]
+    for c in cfgs[:-1]:
+        plugin.enable_configuration(c.name)
+    # available configurations: templates sorted (mod.rs:150-164) then filtered + sorted by min desc (:399-418)
+    oreqs = [orc.Req(c.compute_requirements) if c.compute_requirements else None for c in cfgs]
+    ocfgs = [(c.name, c.min_group_size, c.max_group_size, r) for c, r in zip(cfgs, oreqs)]
+    sorted_cfgs = [ocfgs[i] for i in orc.sort_configs(ocfgs)]
+    avail = [sorted_cfgs[i] for i in orc.available_configs(sorted_cfgs, [1] * len(sorted_cfgs))]
+    want = orc.merge_solo_groups(onodes, solos, avail, proximity=proximity)
+    n_merged = plugin.try_merge_solo_groups()
+    assert n_merged == len(want) and n_merged > 10
+    got = sorted((g["configuration_name"], tuple(g["nodes"])) for g in plugin.get_all_groups() if len(g["nodes"]) > 1)
+    exp = sorted((avail[c][0], tuple(onodes[m].address.decode() for m in ms)) for c, ms in want.as_list())
+    assert got == exp

@@ -213,3 +213,51 @@ def test_faithful_loop_counts_the_quadratic_refilter():
     g = orc.form_groups(nodes, [("solo", 1, 1, None)], False)
     assert len(g) == 40
     assert g.evals == sum(range(41))            # 40 + 39 + ... + 1 (+0 for the last, empty filter)
+
+
+# ---------------------------------------------------------------------------------------------
+# try_merge_solo_groups (mod.rs:631-971)
+def test_proximity_merging_prevents_wrong_nodes_grouping():
+    """tests.rs:2861-3064 verbatim: four solo groups (Montreal, Montreal, Dallas, Dallas in arrival
+    order M1, M2, D1, D2) merge into exactly two 2-node groups, one per city."""
+    nodes = [spec_to_orc_node(A6000, address=M1, location=MONTREAL), spec_to_orc_node(A6000, address=M2, location=MONTREAL),
+             spec_to_orc_node(A6000, address=D1, location=DALLAS), spec_to_orc_node(A6000, address=D2, location=DALLAS)]
+    cfgs = [("2x40-48GB", 2, 2, None), ("1x40-48GB", 1, 1, None)]          # priority order (min desc)
+    for ids in (["1", "2", "3", "4"], ["9", "3", "7", "1"], ["a", "10", "2", "1f"]):   # any id order
+        solos = [(ids[i], i, False) for i in range(4)]
+        g = orc.merge_solo_groups(nodes, solos, cfgs, proximity=True)
+        assert sorted(sorted(m) for _, m in g.as_list()) == [[0, 1], [2, 3]]
+        assert all(c == 0 for c, _ in g.as_list())
+
+
+def test_no_merge_when_policy_disabled_or_single_solo():
+    """tests.rs:2636-2710 (TaskSwitchingPolicy.enabled = false) and mod.rs:640-644."""
+    nodes = [plain(A1), plain(A2), plain(A3)]
+    cfgs = [("c", 1, 3, None)]
+    solos = [("1", 0, True), ("2", 1, True), ("3", 2, False)]
+    assert len(orc.merge_solo_groups(nodes, solos, cfgs, task_switching_enabled=False)) == 0
+    assert len(orc.merge_solo_groups(nodes, solos[:1], cfgs)) == 0
+    g = orc.merge_solo_groups(nodes, solos, cfgs, proximity=False)
+    assert g.as_list() == [(0, [0, 1, 2])]
+    # prefer_larger_groups = false: a batch containing a group that holds a task is refused
+    assert len(orc.merge_solo_groups(nodes, solos, cfgs, proximity=False, prefer_larger_groups=False)) == 0
+
+
+def test_merge_only_compatible_groups():
+    """tests.rs:2471-2635: only solo groups whose node meets the requirements are merged."""
+    a100 = kv.specs(8, "A100", 80000)
+    nodes = [spec_to_orc_node(a100, address=A1), plain(A2), spec_to_orc_node(a100, address=A3),
+             spec_to_orc_node(kv.specs(8, "RTX 3090", 24000), address="0x4234567890123456789012345678901234567890")]
+    req = orc.Req("gpu:count=8;gpu:model=A100")
+    solos = [(str(i + 1), i, False) for i in range(4)]
+    g = orc.merge_solo_groups(nodes, solos, [("a100-pair", 2, 2, req)], proximity=True)
+    assert g.as_list() == [(0, [0, 2])]
+
+
+def test_merge_chunks_and_leftovers():
+    nodes = [plain(f"0x{i + 1:040x}") for i in range(7)]
+    solos = [(f"{i + 1:x}", i, False) for i in range(7)]
+    g = orc.merge_solo_groups(nodes, solos, [("trio", 3, 3, None), ("pair", 2, 2, None)], proximity=False)
+    assert [(c, sorted(m)) for c, m in g.as_list()] == [(0, [0, 1, 2]), (0, [3, 4, 5])]   # the 7th stays solo
+    g = orc.merge_solo_groups(nodes, solos, [("upto4", 1, 4, None)], proximity=False)
+    assert [sorted(m) for _, m in g.as_list()] == [[0, 1, 2, 3], [4, 5, 6]]
