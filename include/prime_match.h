@@ -324,7 +324,20 @@ typedef struct pm_node_desc {         /* orchestrator/src/models/node.rs:10-37 (
   uint32_t cpu_cores, ram_mb, storage_gb;
   int32_t has_location;
   double lat, lon;
+  const char* ip_address;             /* NULL keeps the stored value */
+  uint16_t port;
+  uint16_t reserved;
+  int64_t last_status_change_ms;      /* 0 keeps the stored value (Option<DateTime<Utc>>) */
 } pm_node_desc;
+
+typedef struct pm_discovery_node {    /* shared/src/models/node.rs:552-570 (fields the monitor reads) */
+  pm_node_desc node;                  /* id (as address), compute_specs, location; status/p2p ignored */
+  const char* ip_address;
+  uint16_t port;
+  uint8_t is_validated, is_active, is_provider_whitelisted, is_blacklisted;
+  uint8_t has_latest_balance, latest_balance_is_zero;
+  int64_t last_updated_ms;            /* < 0 == None */
+} pm_discovery_node;
 
 /* NodeGroupsPlugin::new_with_policy (mod.rs:129-175).  engine may be NULL (then
  * pm_plugin_try_form_new_groups fails with PM_E_NO_DEVICE); policy NULL = defaults. */
@@ -339,6 +352,11 @@ int pm_plugin_seal_configs(pm_plugin*);                                   /* the
 int pm_plugin_enable_configuration(pm_plugin*, const char* name, int enable);   /* mod.rs:1328-1346 */
 int pm_plugin_upsert_node(pm_plugin*, const pm_node_desc*);                /* NodeStore::add_node / update */
 int pm_plugin_set_node_status(pm_plugin*, const char* address, uint32_t status); /* + handle_status_change */
+/* DiscoveryMonitor: reconcile validated discovery nodes into the table
+ * (discovery/monitor.rs:195-435); the Theta(N^2) same-endpoint scan is a hash lookup here. */
+int pm_plugin_sync_discovery(pm_plugin*, const pm_discovery_node* nodes, uint32_t n, int64_t now_ms,
+                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new);
+int pm_plugin_get_node(pm_plugin*, const char* address, char* buf, size_t len);   /* JSON or null */
 int pm_plugin_add_task(pm_plugin*, const pm_task_desc*);                   /* TaskStore::add_task + on_task_created */
 int pm_plugin_delete_task(pm_plugin*, const char* id);                     /* delete_task + on_task_deleted */
 int pm_plugin_try_form_new_groups(pm_plugin*, uint32_t* n_formed);         /* mod.rs:478-628 via pm_match */
@@ -348,6 +366,9 @@ int pm_plugin_record_upload(pm_plugin*, const char* address, const char* group_i
 /* JSON out (NUL-terminated into buf): NodeGroup {"id","nodes","configuration_name","task_id"} or null */
 int pm_plugin_get_node_group(pm_plugin*, const char* address, char* buf, size_t len);
 int pm_plugin_get_all_groups(pm_plugin*, char* buf, size_t len);           /* sorted by id, mod.rs:1040 */
+/* Redis write-back in the reference's key formats (mod.rs:25-28,299-322,471-476), as a JSON array of
+ * commands, so /groups, /nodes, storage routes and the metrics sync keep working unchanged.        */
+int pm_plugin_redis_writeback(pm_plugin*, char* buf, size_t len);
 /* Scheduler::get_task_for_node (scheduler/mod.rs:26-74) with the plugin chain
  * [NodeGroupsPlugin] when configurations exist, else [NewestTaskPlugin]:
  * writes {"current_task": Task|null} (shared/src/models/heartbeat.rs:7-22). */

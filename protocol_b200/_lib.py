@@ -73,6 +73,8 @@ def load() -> C.CDLL:
         "pm_plugin_enable_configuration": (i32, [vp, cp, i32]),
         "pm_plugin_upsert_node": (i32, [vp, P(abi.PmNodeDesc)]),
         "pm_plugin_set_node_status": (i32, [vp, cp, u32]),
+        "pm_plugin_sync_discovery": (i32, [vp, vp, u32, C.c_int64, u32, P(u32)]),
+        "pm_plugin_get_node": (i32, [vp, cp, C.c_char_p, sz]),
         "pm_plugin_add_task": (i32, [vp, P(abi.PmTaskDesc)]),
         "pm_plugin_delete_task": (i32, [vp, cp]),
         "pm_plugin_record_upload": (i32, [vp, cp, cp, cp]),
@@ -80,6 +82,7 @@ def load() -> C.CDLL:
         "pm_plugin_try_merge_solo_groups": (i32, [vp, P(u32)]),
         "pm_plugin_get_node_group": (i32, [vp, cp, C.c_char_p, sz]),
         "pm_plugin_get_all_groups": (i32, [vp, C.c_char_p, sz]),
+        "pm_plugin_redis_writeback": (i32, [vp, C.c_char_p, sz]),
         "pm_scheduler_get_task_for_node": (i32, [vp, cp, C.c_char_p, sz]),
     }
     for name, (res, args) in sig.items():

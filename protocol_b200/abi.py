@@ -114,8 +114,8 @@ EXPORTS = [
     "pm_match", "pm_fetch_result", "pm_get_stats", "pm_build_cost_tile",
     "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync",
     "pm_plugin_create", "pm_plugin_destroy", "pm_plugin_last_error", "pm_plugin_add_config", "pm_plugin_seal_configs",
-    "pm_plugin_enable_configuration", "pm_plugin_upsert_node", "pm_plugin_set_node_status", "pm_plugin_add_task",
-    "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_try_merge_solo_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups",
+    "pm_plugin_enable_configuration", "pm_plugin_upsert_node", "pm_plugin_set_node_status", "pm_plugin_sync_discovery", "pm_plugin_get_node", "pm_plugin_add_task",
+    "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_try_merge_solo_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups", "pm_plugin_redis_writeback",
     "pm_scheduler_get_task_for_node",
 ]
 
@@ -146,4 +146,15 @@ class PmNodeDesc(C.Structure):
         ("gpu_count", C.c_uint32), ("gpu_mem_mb", C.c_uint32), ("gpu_model", C.c_char_p),
         ("cpu_cores", C.c_uint32), ("ram_mb", C.c_uint32), ("storage_gb", C.c_uint32),
         ("has_location", C.c_int32), ("lat", C.c_double), ("lon", C.c_double),
+        ("ip_address", C.c_char_p), ("port", C.c_uint16), ("reserved", C.c_uint16),
+        ("last_status_change_ms", C.c_int64),
+    ]
+
+
+class PmDiscoveryNode(C.Structure):
+    _fields_ = [
+        ("node", PmNodeDesc), ("ip_address", C.c_char_p), ("port", C.c_uint16),
+        ("is_validated", C.c_uint8), ("is_active", C.c_uint8), ("is_provider_whitelisted", C.c_uint8),
+        ("is_blacklisted", C.c_uint8), ("has_latest_balance", C.c_uint8), ("latest_balance_is_zero", C.c_uint8),
+        ("last_updated_ms", C.c_int64),
     ]

@@ -65,6 +65,10 @@ struct TaskRec {
 
 struct NodeRec {
   std::string address;
+  std::string ip_address;
+  uint16_t port = 0;
+  int64_t last_status_change_ms = -1;  // Option<DateTime<Utc>>
+  int64_t first_seen_ms = -1;
   uint32_t status = kDiscovered;
   bool has_p2p = false;
   std::string p2p_id;
@@ -78,6 +82,7 @@ struct Group {  // NodeGroup, mod.rs:63-69
   std::string id;
   std::vector<std::string> nodes;  // BTreeSet<String> order
   std::string configuration_name;
+  int64_t created_at_ms = 0;       // chrono::Utc::now() at creation (mod.rs:575)
 };
 
 std::string replace_all(std::string s, const std::string& from, const std::string& to) {
@@ -141,6 +146,33 @@ struct pm_plugin {
   std::unordered_map<std::string, std::string> group_task;     // group_task:<id>
   uint64_t next_group_id = 1;
   std::set<std::string> upload_keys;                           // "upload:<node>:<group>:<file>" (storage route)
+  // (ip, port) -> number of Healthy nodes: replaces the per-node full scan of
+  // count_healthy_nodes_with_same_endpoint (discovery/monitor.rs:218-234, Theta(N^2) per sync)
+  std::unordered_map<std::string, uint32_t> healthy_at;
+
+  static std::string endpoint_key(const std::string& ip, uint16_t port) { return ip + ":" + std::to_string(port); }
+  void index_remove(const NodeRec& n) {
+    if (n.status != kHealthy) return;
+    auto it = healthy_at.find(endpoint_key(n.ip_address, n.port));
+    if (it != healthy_at.end() && it->second) --it->second;
+  }
+  void index_add(const NodeRec& n) {
+    if (n.status == kHealthy) ++healthy_at[endpoint_key(n.ip_address, n.port)];
+  }
+  // NodeStore::update_node_status (node_store.rs:284-305) + handle_status_change
+  void set_status(NodeRec& n, uint32_t status, int64_t now_ms) {
+    index_remove(n);
+    n.status = status;
+    n.last_status_change_ms = now_ms;
+    index_add(n);
+    if (status == kDead || status == kLowBalance) {
+      auto g = node_to_group.find(n.address);
+      if (g != node_to_group.end()) {
+        const std::string gid = g->second;
+        dissolve(gid);
+      }
+    }
+  }
 
   int fail(int st, const std::string& m) {
     err = m;
@@ -280,9 +312,13 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
   } else {
     r = &p->nodes[it->second];
   }
+  p->index_remove(*r);
   r->status = d->status;
   r->has_p2p = d->p2p_id != nullptr;
   r->p2p_id = d->p2p_id ? d->p2p_id : "";
+  if (d->ip_address) r->ip_address = d->ip_address;
+  r->port = d->port;
+  if (d->last_status_change_ms) r->last_status_change_ms = d->last_status_change_ms;
   const uint32_t keep = PM_W_HAS_SPECS | PM_W_HAS_GPU | PM_W_HAS_GPU_COUNT | PM_W_HAS_GPU_MEM | PM_W_HAS_GPU_MODEL |
                         PM_W_HAS_CPU | PM_W_HAS_CPU_CORES | PM_W_HAS_RAM | PM_W_HAS_STORAGE;
   r->a.flags = d->spec_flags & keep;
@@ -296,6 +332,7 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
   r->has_loc = d->has_location != 0;
   r->lat = d->lat;
   r->lon = d->lon;
+  p->index_add(*r);
   return PM_OK;
 }
 
@@ -305,14 +342,127 @@ int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status
   std::lock_guard<std::mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   if (it == p->node_index.end()) return p->fail(PM_E_INVALID, "unknown node");
-  p->nodes[it->second].status = status;
-  if (status == kDead || status == kLowBalance) {
-    auto g = p->node_to_group.find(address);
-    if (g != p->node_to_group.end()) {
-      const std::string gid = g->second;
-      p->dissolve(gid);
+  p->set_status(p->nodes[it->second], status, (int64_t)std::time(nullptr) * 1000);
+  return PM_OK;
+}
+
+// DiscoveryMonitor::get_nodes -> sync_single_node_with_discovery (discovery/monitor.rs:236-435):
+// reconcile the validated nodes reported by the discovery service into the node table.
+int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
+                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
+  if (!p || (n && !dn)) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (n_new) *n_new = 0;
+  std::set<std::string> seen;  // "Remove duplicates based on node ID" (:203-210)
+  for (uint32_t i = 0; i < n; ++i) {
+    const pm_discovery_node& d = dn[i];
+    if (!d.node.address || !d.ip_address) return p->fail(PM_E_INVALID, "discovery node without id / ip");
+    if (!d.is_validated) continue;                       // fetch keeps validated nodes only
+    if (!seen.insert(d.node.address).second) continue;
+    const std::string addr(d.node.address), ip(d.ip_address);
+    auto it = p->node_index.find(addr);
+    const bool exists = it != p->node_index.end();
+    // count_healthy_nodes_with_same_endpoint (:218-234) through the endpoint index
+    uint32_t same = 0;
+    {
+      auto h = p->healthy_at.find(pm_plugin::endpoint_key(ip, d.port));
+      if (h != p->healthy_at.end()) same = h->second;
+      if (exists) {
+        const NodeRec& e = p->nodes[it->second];
+        if (e.status == kHealthy && e.ip_address == ip && e.port == d.port && same) --same;
+      }
+    }
+    if (exists) {
+      NodeRec& node = p->nodes[it->second];
+      const NodeRec existing = node;                     // the snapshot the reference keeps testing against
+      if (same > 0 && existing.status != kHealthy) {     // :254-268
+        p->set_status(node, kDead, now_ms);
+        continue;
+      }
+      if (d.is_validated && !d.is_provider_whitelisted) p->set_status(node, kEjected, now_ms);          // :270-281
+      if (d.is_validated && d.is_provider_whitelisted && existing.status == kEjected)                   // :285-299
+        p->set_status(node, kDead, now_ms);
+      if (!d.is_active && existing.status == kHealthy) {                                                 // :300-338
+        const bool should_mark_inactive =
+            existing.last_status_change_ms < 0 || (now_ms - existing.last_status_change_ms) > 5 * 60 * 1000;
+        if (should_mark_inactive) p->set_status(node, d.is_provider_whitelisted ? kDead : kEjected, now_ms);
+      }
+      if (existing.ip_address != ip) {                                                                   // :340-348
+        p->index_remove(node);
+        node.ip_address = ip;
+        p->index_add(node);
+      }
+      if (!existing.has_loc && d.node.has_location) {                                                    // :349-362
+        node.has_loc = true;
+        node.lat = d.node.lat;
+        node.lon = d.node.lon;
+      }
+      if (existing.status == kDead && existing.last_status_change_ms >= 0 && d.last_updated_ms >= 0 &&
+          existing.last_status_change_ms < d.last_updated_ms) {                                          // :364-389
+        const uint32_t keep = PM_W_HAS_SPECS | PM_W_HAS_GPU | PM_W_HAS_GPU_COUNT | PM_W_HAS_GPU_MEM | PM_W_HAS_GPU_MODEL |
+                              PM_W_HAS_CPU | PM_W_HAS_CPU_CORES | PM_W_HAS_RAM | PM_W_HAS_STORAGE;
+        node.a.flags = d.node.spec_flags & keep;
+        node.a.gpu_count = d.node.gpu_count;
+        node.a.gpu_mem_mb = d.node.gpu_mem_mb;
+        node.a.model_id = (d.node.spec_flags & PM_W_HAS_GPU_MODEL) && d.node.gpu_model ? pm_intern_model(p->interner, d.node.gpu_model) : 0;
+        node.b.cpu_cores = d.node.cpu_cores;
+        node.b.ram_mb = d.node.ram_mb;
+        node.b.storage_gb = d.node.storage_gb;
+        p->set_status(node, kDiscovered, now_ms);
+      }
+      if (d.has_latest_balance && d.latest_balance_is_zero) p->set_status(node, kLowBalance, now_ms);    // :391-402
+    } else {
+      if (same >= max_healthy_nodes_with_same_endpoint) continue;                                        // :405-415
+      NodeRec node;                                      // OrchestratorNode::from(DiscoveryNode), models/node.rs:46-66
+      node.address = addr;
+      node.ip_address = ip;
+      node.port = d.port;
+      node.status = kDiscovered;
+      node.has_p2p = false;                              // p2p_id: None until the first heartbeat
+      node.first_seen_ms = now_ms;
+      const uint32_t keep = PM_W_HAS_SPECS | PM_W_HAS_GPU | PM_W_HAS_GPU_COUNT | PM_W_HAS_GPU_MEM | PM_W_HAS_GPU_MODEL |
+                            PM_W_HAS_CPU | PM_W_HAS_CPU_CORES | PM_W_HAS_RAM | PM_W_HAS_STORAGE;
+      node.a.flags = d.node.spec_flags & keep;
+      node.a.gpu_count = d.node.gpu_count;
+      node.a.gpu_mem_mb = d.node.gpu_mem_mb;
+      node.a.model_id = (d.node.spec_flags & PM_W_HAS_GPU_MODEL) && d.node.gpu_model ? pm_intern_model(p->interner, d.node.gpu_model) : 0;
+      node.b.cpu_cores = d.node.cpu_cores;
+      node.b.ram_mb = d.node.ram_mb;
+      node.b.storage_gb = d.node.storage_gb;
+      node.has_loc = d.node.has_location != 0;
+      node.lat = d.node.lat;
+      node.lon = d.node.lon;
+      p->node_index.emplace(addr, p->nodes.size());
+      p->nodes.push_back(std::move(node));
+      if (n_new) ++*n_new;
     }
   }
+  return PM_OK;
+}
+
+// node as the /nodes route would show it (fields on this path): JSON or null
+int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len) {
+  if (!p || !address) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->node_index.find(address);
+  std::string out = "null";
+  if (it != p->node_index.end()) {
+    static const char* kNames[] = {"Discovered", "WaitingForHeartbeat", "Healthy", "Unhealthy", "Dead", "Ejected", "Banned", "LowBalance"};
+    const NodeRec& n = p->nodes[it->second];
+    out = "{\"address\":";
+    json_str(out, n.address);
+    out += ",\"ip_address\":";
+    json_str(out, n.ip_address);
+    out += ",\"port\":" + std::to_string(n.port);
+    out += std::string(",\"status\":\"") + kNames[n.status & 7] + "\"";
+    out += ",\"first_seen_ms\":" + (n.first_seen_ms < 0 ? std::string("null") : std::to_string(n.first_seen_ms));
+    out += ",\"last_status_change_ms\":" + (n.last_status_change_ms < 0 ? std::string("null") : std::to_string(n.last_status_change_ms));
+    out += std::string(",\"has_location\":") + (n.has_loc ? "true" : "false");
+    out += std::string(",\"has_compute_specs\":") + ((n.a.flags & PM_W_HAS_SPECS) ? "true" : "false");
+    out += ",\"ram_mb\":" + std::to_string(n.b.ram_mb) + "}";
+  }
+  if (!buf || len < out.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
   return PM_OK;
 }
 
@@ -441,6 +591,7 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
     std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);  // format!("{:x}", ..)
     grp.id = idbuf;
     grp.configuration_name = configs[res.group_ask[g]]->name;
+    grp.created_at_ms = (int64_t)std::time(nullptr) * 1000;
     for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m)
       grp.nodes.push_back(p->nodes[order[res.group_members[m]]].address);
     for (const auto& n : grp.nodes) p->node_to_group[n] = grp.id;
@@ -543,6 +694,7 @@ int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
     std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);
     merged.id = idbuf;
     merged.configuration_name = cfg->name;
+    merged.created_at_ms = (int64_t)std::time(nullptr) * 1000;
     for (const auto& gid : ids) merged.nodes.push_back(p->groups.at(gid).nodes[0]);
     std::sort(merged.nodes.begin(), merged.nodes.end());           // BTreeSet<String>
     // find_best_task_for_group (mod.rs:1122-1189), determinised to the NewestTask rule
@@ -642,6 +794,64 @@ int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
   }
   out += ']';
   return emit(p, out, buf, len);
+}
+
+// The keys a drop-in must leave in Redis for /groups, /nodes, storage routes and the metrics sync to
+// keep working unchanged (mod.rs:25-28, 299-322, 471-476): a JSON array of commands
+//   ["SET","node_group:<id>","<NodeGroup json>"], ["SADD","orchestrator:groups_index","<id>"],
+//   ["HSET","node_to_group","<node>","<id>"], ["SET","group_task:<id>","<task id>"],
+//   ["SADD","available_node_group_configs","<name>"].
+int pm_plugin_redis_writeback(pm_plugin* p, char* buf, size_t len) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  std::string out = "[";
+  bool first = true;
+  auto cmd = [&](std::initializer_list<std::string> parts) {
+    if (!first) out += ',';
+    first = false;
+    out += '[';
+    bool f2 = true;
+    for (const auto& s : parts) {
+      if (!f2) out += ',';
+      f2 = false;
+      json_str(out, s);
+    }
+    out += ']';
+  };
+  for (const auto& kv : p->groups) {
+    const Group& g = kv.second;
+    // serde shape of NodeGroup (mod.rs:63-69); created_at as chrono's RFC 3339
+    std::string j = "{\"id\":";
+    json_str(j, g.id);
+    j += ",\"nodes\":[";
+    for (size_t i = 0; i < g.nodes.size(); ++i) {
+      if (i) j += ',';
+      json_str(j, g.nodes[i]);
+    }
+    j += "],\"created_at\":";
+    {
+      std::time_t secs = (std::time_t)(g.created_at_ms / 1000);
+      std::tm tmv{};
+      gmtime_r(&secs, &tmv);
+      char tb[64];
+      std::snprintf(tb, sizeof tb, "%04d-%02d-%02dT%02d:%02d:%02d.%03dZ", tmv.tm_year + 1900, tmv.tm_mon + 1, tmv.tm_mday,
+                    tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (int)(g.created_at_ms % 1000));
+      json_str(j, tb);
+    }
+    j += ",\"configuration_name\":";
+    json_str(j, g.configuration_name);
+    j += '}';
+    cmd({"SET", "node_group:" + g.id, j});
+    cmd({"SADD", "orchestrator:groups_index", g.id});
+    for (const auto& n : g.nodes) cmd({"HSET", "node_to_group", n, g.id});
+    auto t = p->group_task.find(g.id);
+    if (t != p->group_task.end()) cmd({"SET", "group_task:" + g.id, t->second});
+  }
+  for (const auto& name : p->available) cmd({"SADD", "available_node_group_configs", name});
+  out += ']';
+  if (!buf || len < out.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return PM_OK;
 }
 
 namespace {

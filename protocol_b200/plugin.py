@@ -60,6 +60,24 @@ class OrchestratorNode:  # orchestrator/src/models/node.rs:10-37 (fields on the 
     p2p_id: str | None = "test_p2p_id"
     compute_specs: ComputeSpecs | None = None
     location: tuple | None = None
+    ip_address: str = ""
+    port: int = 0
+    last_status_change_ms: int | None = None
+
+
+@dataclass
+class DiscoveryNode:  # shared/src/models/node.rs:552-570 (fields the monitor reads)
+    id: str
+    ip_address: str = "127.0.0.1"
+    port: int = 8080
+    compute_specs: ComputeSpecs | None = None
+    is_validated: bool = False
+    is_active: bool = False
+    is_provider_whitelisted: bool = False
+    is_blacklisted: bool = False
+    last_updated_ms: int | None = None
+    location: tuple | None = None
+    latest_balance: int | None = None
 
 
 def _b(s):
@@ -105,13 +123,9 @@ class NodeGroupsPlugin:
         return json.loads(buf.value.decode())
 
     # ---- stores ------------------------------------------------------------
-    def add_node(self, node: OrchestratorNode):
-        d = abi.PmNodeDesc()
-        d.address = node.address.encode()
-        d.status = node.status
-        d.p2p_id = _b(node.p2p_id)
+    @staticmethod
+    def _fill_specs(d, s, location):
         f = 0
-        s = node.compute_specs
         if s is not None:
             f |= abi.PM_W_HAS_SPECS
             if s.gpu is not None:
@@ -138,10 +152,42 @@ class NodeGroupsPlugin:
                 f |= abi.PM_W_HAS_STORAGE
                 d.storage_gb = s.storage_gb
         d.spec_flags = f
-        if node.location is not None:
+        if location is not None:
             d.has_location = 1
-            d.lat, d.lon = node.location
+            d.lat, d.lon = location
+
+    def add_node(self, node: OrchestratorNode):
+        d = abi.PmNodeDesc()
+        d.address = node.address.encode()
+        d.status = node.status
+        d.p2p_id = _b(node.p2p_id)
+        d.ip_address = node.ip_address.encode()
+        d.port = node.port
+        d.last_status_change_ms = node.last_status_change_ms or 0
+        self._fill_specs(d, node.compute_specs, node.location)
         self._check(self._lib.pm_plugin_upsert_node(self._h, C.byref(d)))
+
+    def sync_discovery(self, discovery_nodes, now_ms: int, max_healthy_nodes_with_same_endpoint: int = 1) -> int:
+        """DiscoveryMonitor::get_nodes (discovery/monitor.rs:422-435) for one fetch."""
+        arr = (abi.PmDiscoveryNode * max(len(discovery_nodes), 1))()
+        for i, dn in enumerate(discovery_nodes):
+            d = arr[i]
+            d.node.address = dn.id.encode()
+            self._fill_specs(d.node, dn.compute_specs, dn.location)
+            d.ip_address = dn.ip_address.encode()
+            d.port = dn.port
+            d.is_validated, d.is_active = int(dn.is_validated), int(dn.is_active)
+            d.is_provider_whitelisted, d.is_blacklisted = int(dn.is_provider_whitelisted), int(dn.is_blacklisted)
+            d.has_latest_balance = int(dn.latest_balance is not None)
+            d.latest_balance_is_zero = int(dn.latest_balance == 0)
+            d.last_updated_ms = -1 if dn.last_updated_ms is None else dn.last_updated_ms
+        n_new = C.c_uint32()
+        self._check(self._lib.pm_plugin_sync_discovery(self._h, arr, len(discovery_nodes), now_ms,
+                                                       max_healthy_nodes_with_same_endpoint, C.byref(n_new)))
+        return n_new.value
+
+    def get_node(self, address: str):
+        return self._json(self._lib.pm_plugin_get_node, address.encode())
 
     def update_node_status(self, address: str, status: int):
         """NodeStore::update_node_status followed by StatusUpdatePlugin::handle_status_change."""
@@ -203,6 +249,10 @@ class NodeGroupsPlugin:
 
     def get_all_groups(self):
         return self._json(self._lib.pm_plugin_get_all_groups)
+
+    def redis_writeback(self):
+        """[[cmd, key, ...], ...] in the reference's key formats (mod.rs:25-28, 299-322)."""
+        return self._json(self._lib.pm_plugin_redis_writeback, cap=1 << 24)
 
 
 class Scheduler:

@@ -310,3 +310,26 @@ def test_merge_matches_oracle_on_random_swarm(engine, proximity):
     got = sorted((g["configuration_name"], tuple(g["nodes"])) for g in plugin.get_all_groups() if len(g["nodes"]) > 1)
     exp = sorted((avail[c][0], tuple(onodes[m].address.decode() for m in ms)) for c, ms in want.as_list())
     assert got == exp
+
+
+def test_redis_writeback_format(engine):
+    """The keys downstream routes read (mod.rs:25-28, 299-322, 471-476; groups.rs, nodes.rs, sync_service.rs)."""
+    import json
+
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 2)])
+    task = Task(allowed_topologies=["test-config"])
+    plugin.add_task(task)
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    plugin.try_form_new_groups()
+    Scheduler(plugin).get_task_for_node(A1)
+    cmds = plugin.redis_writeback()
+    gid = plugin.get_node_group(A1)["id"]
+    by_key = {(c[0], c[1]): c[2:] for c in cmds}
+    group = json.loads(by_key[("SET", f"node_group:{gid}")][0])
+    assert set(group) == {"id", "nodes", "created_at", "configuration_name"}
+    assert group["nodes"] == [A1, A2] and group["configuration_name"] == "test-config" and group["created_at"].endswith("Z")
+    assert ["SADD", "orchestrator:groups_index", gid] in cmds
+    assert ["HSET", "node_to_group", A1, gid] in cmds and ["HSET", "node_to_group", A2, gid] in cmds
+    assert ["SET", f"group_task:{gid}", task.id] in cmds
+    assert ["SADD", "available_node_group_configs", "test-config"] in cmds

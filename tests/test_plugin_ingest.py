@@ -1,0 +1,92 @@
+"""Discovery ingest: the reference's DiscoveryMonitor tests
+(crates/orchestrator/src/discovery/monitor.rs:449-800) against the host mirror, plus the
+status-transition table of sync_single_node_with_discovery (:236-420).  CPU only."""
+from protocol_b200.plugin import ComputeSpecs, DiscoveryNode, NodeGroupsPlugin, NodeStatus, OrchestratorNode
+
+A1 = "0x1234567890123456789012345678901234567890"
+A2 = "0x2234567890123456789012345678901234567890"
+A3 = "0x3234567890123456789012345678901234567890"
+SPECS = ComputeSpecs(ram_mb=1024, storage_gb=10)
+NOW = 1_700_000_000_000
+
+
+def test_sync_single_node_with_discovery():
+    """monitor.rs:449-560: store has the node Ejected; discovery says validated + whitelisted (inactive)
+    -> the node is marked Dead so it can recover."""
+    plugin = NodeGroupsPlugin([])
+    plugin.add_node(OrchestratorNode(A1, status=NodeStatus.Ejected, compute_specs=SPECS, ip_address="127.0.0.1", port=8080))
+    assert plugin.get_node(A1)["status"] == "Ejected"
+    plugin.sync_discovery([DiscoveryNode(A1, "127.0.0.1", 8080, SPECS, is_validated=True, is_provider_whitelisted=True,
+                                         is_active=False)], NOW)
+    assert plugin.get_node(A1)["status"] == "Dead"
+
+
+def test_first_seen_timestamp_set_on_new_node():
+    """monitor.rs:562-674."""
+    plugin = NodeGroupsPlugin([])
+    dn = DiscoveryNode(A1, "192.168.1.100", 8080, SPECS, is_validated=True, is_provider_whitelisted=True, is_active=True)
+    assert plugin.sync_discovery([dn], NOW) == 1
+    node = plugin.get_node(A1)
+    assert node["first_seen_ms"] == NOW and node["status"] == "Discovered" and node["ip_address"] == "192.168.1.100"
+    dn.ip_address = "192.168.1.101"
+    assert plugin.sync_discovery([dn], NOW + 60_000) == 0
+    node = plugin.get_node(A1)
+    assert node["first_seen_ms"] == NOW and node["ip_address"] == "192.168.1.101" and node["status"] == "Discovered"
+
+
+def test_sync_node_with_same_endpoint():
+    """monitor.rs:676-800: a new node on the endpoint of a healthy node is not added; another port is."""
+    plugin = NodeGroupsPlugin([])
+    plugin.add_node(OrchestratorNode(A1, status=NodeStatus.Healthy, compute_specs=SPECS, ip_address="127.0.0.1", port=8080))
+    mk = lambda a, port: DiscoveryNode(a, "127.0.0.1", port, SPECS, is_validated=True, is_provider_whitelisted=True, is_active=True)
+    assert plugin.sync_discovery([mk(A2, 8080)], NOW) == 0
+    assert plugin.get_node(A2) is None
+    assert plugin.sync_discovery([mk(A3, 8081)], NOW) == 1
+    assert plugin.get_node(A3) is not None
+
+
+def test_transitions_table():
+    plugin = NodeGroupsPlugin([])
+    mk = lambda a, **kw: DiscoveryNode(a, "10.0.0.1", 1000 + int(a[2]), SPECS, is_validated=True, **kw)
+    # validated but not whitelisted -> Ejected (:270-281)
+    plugin.add_node(OrchestratorNode(A1, status=NodeStatus.Healthy, ip_address="10.0.0.1", port=1001, last_status_change_ms=NOW))
+    plugin.sync_discovery([mk(A1, is_provider_whitelisted=False, is_active=True)], NOW + 1000)
+    assert plugin.get_node(A1)["status"] == "Ejected"
+    # healthy but no longer active on chain: grace period of 5 minutes (:300-338)
+    plugin.add_node(OrchestratorNode(A2, status=NodeStatus.Healthy, ip_address="10.0.0.1", port=1002, last_status_change_ms=NOW))
+    plugin.sync_discovery([mk(A2, is_provider_whitelisted=True, is_active=False)], NOW + 60_000)
+    assert plugin.get_node(A2)["status"] == "Healthy"
+    plugin.sync_discovery([mk(A2, is_provider_whitelisted=True, is_active=False)], NOW + 6 * 60_000)
+    assert plugin.get_node(A2)["status"] == "Dead"
+    # dead node updated on discovery after its death -> Discovered again, with the new specs (:364-389)
+    last_change = plugin.get_node(A2)["last_status_change_ms"]
+    plugin.sync_discovery([DiscoveryNode(A2, "10.0.0.1", 1002, ComputeSpecs(ram_mb=2048), is_validated=True,
+                                         is_provider_whitelisted=True, is_active=True, last_updated_ms=last_change + 1)],
+                          last_change + 10)
+    n2 = plugin.get_node(A2)
+    assert n2["status"] == "Discovered" and n2["ram_mb"] == 2048
+    # zero balance -> LowBalance (:391-402); not validated -> ignored; duplicates by id -> first wins (:203-210)
+    plugin.add_node(OrchestratorNode(A3, status=NodeStatus.Healthy, ip_address="10.0.0.1", port=1003, last_status_change_ms=NOW))
+    plugin.sync_discovery([mk(A3, is_provider_whitelisted=True, is_active=True, latest_balance=0)], NOW + 1000)
+    assert plugin.get_node(A3)["status"] == "LowBalance"
+    a4 = "0x4234567890123456789012345678901234567890"
+    assert plugin.sync_discovery([DiscoveryNode(a4, "10.0.0.9", 9, SPECS, is_validated=False)], NOW) == 0
+    first = DiscoveryNode(a4, "10.0.0.9", 9, SPECS, is_validated=True, is_provider_whitelisted=True, is_active=True)
+    dup = DiscoveryNode(a4, "10.0.0.10", 10, SPECS, is_validated=True, is_provider_whitelisted=True, is_active=True)
+    assert plugin.sync_discovery([first, dup], NOW) == 1
+    assert plugin.get_node(a4)["ip_address"] == "10.0.0.9"
+
+
+def test_endpoint_index_scales_linearly():
+    """The reference re-reads every node for every synced node (Theta(N^2), monitor.rs:218-234);
+    20k nodes over 2k shared endpoints sync in well under a second through the endpoint index."""
+    import time
+
+    plugin = NodeGroupsPlugin([])
+    n = 20_000
+    nodes = [DiscoveryNode(f"0x{i:040x}", f"10.1.{(i % 2000) // 250}.{i % 250}", 8000 + (i % 3), SPECS, is_validated=True,
+                           is_provider_whitelisted=True, is_active=True) for i in range(n)]
+    t0 = time.perf_counter()
+    assert plugin.sync_discovery(nodes, NOW, max_healthy_nodes_with_same_endpoint=1) == n   # nobody healthy yet
+    plugin.sync_discovery(nodes, NOW + 1000)
+    assert time.perf_counter() - t0 < 5.0
