@@ -140,6 +140,25 @@ struct pm_plugin {
   std::unordered_map<std::string, size_t> node_index;
 
   std::vector<TaskRec> tasks;  // RPUSH order (task_store.rs:41)
+  // heartbeat fast path: the reference re-reads and re-filters every task on every
+  // heartbeat (scheduler/mod.rs:27, scheduler_impl.rs:42-61: O(T*K) string compares); here the
+  // task a fresh group of a configuration would claim is cached until the task list changes
+  std::unordered_map<std::string, std::string> claim_cache;  // configuration name -> task id ("" = none)
+  bool claim_cache_valid = false;
+  const TaskRec* task_for_configuration(const std::string& configuration_name) {
+    if (!claim_cache_valid) {
+      claim_cache.clear();
+      claim_cache_valid = true;
+    }
+    auto it = claim_cache.find(configuration_name);
+    if (it == claim_cache.end()) {
+      const TaskRec* chosen = nullptr;  // NewestTask rule over the desc-sorted list: last maximum
+      for (const TaskRec* t : all_tasks())
+        if (task_applicable(*t, configuration_name) && (!chosen || t->created_at >= chosen->created_at)) chosen = t;
+      it = claim_cache.emplace(configuration_name, chosen ? chosen->id : std::string()).first;
+    }
+    return it->second.empty() ? nullptr : find_task(it->second);
+  }
 
   std::map<std::string, Group> groups;                      // node_group:<id>
   std::unordered_map<std::string, std::string> node_to_group;  // node_to_group
@@ -486,6 +505,7 @@ int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
   if (t.scheduling == 3)
     for (const auto& topo : t.topologies) p->available.insert(topo);
   p->tasks.push_back(std::move(t));
+  p->claim_cache_valid = false;
   return PM_OK;
 }
 
@@ -496,6 +516,7 @@ int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_
   if (it == p->tasks.end()) return PM_OK;
   TaskRec gone = *it;
   p->tasks.erase(it);
+  p->claim_cache_valid = false;
   // dissolve every group working on the task (mod.rs:1259-1291)
   std::vector<std::string> doomed;
   for (const auto& kv : p->group_task)
@@ -698,9 +719,7 @@ int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
     for (const auto& gid : ids) merged.nodes.push_back(p->groups.at(gid).nodes[0]);
     std::sort(merged.nodes.begin(), merged.nodes.end());           // BTreeSet<String>
     // find_best_task_for_group (mod.rs:1122-1189), determinised to the NewestTask rule
-    const TaskRec* chosen = nullptr;
-    for (const TaskRec* t : p->all_tasks())
-      if (task_applicable(*t, cfg->name) && (!chosen || t->created_at >= chosen->created_at)) chosen = t;
+    const TaskRec* chosen = p->task_for_configuration(cfg->name);
     for (const auto& gid : ids) p->dissolve(gid);
     for (const auto& n : merged.nodes) p->node_to_group[n] = merged.id;
     if (chosen) p->group_task[merged.id] = chosen->id;              // SET NX on a fresh key
@@ -864,7 +883,7 @@ struct Expanded {
 };
 
 // NodeGroupsPlugin::filter_tasks, scheduler_impl.rs:11-210.  Returns false for "no task".
-bool node_groups_filter(pm_plugin* p, const std::vector<const TaskRec*>& tasks, const std::string& addr, Expanded* out) {
+bool node_groups_filter(pm_plugin* p, const std::string& addr, Expanded* out) {
   auto ng = p->node_to_group.find(addr);
   if (ng == p->node_to_group.end()) return false;            // "Node is not in a group, skipping all tasks"
   auto git = p->groups.find(ng->second);
@@ -876,16 +895,11 @@ bool node_groups_filter(pm_plugin* p, const std::vector<const TaskRec*>& tasks, 
 
   const TaskRec* current = p->current_group_task(group.id);
   if (!current) {
-    if (tasks.empty()) return false;
-    std::vector<const TaskRec*> applicable;
-    for (const TaskRec* t : tasks)
-      if (task_applicable(*t, group.configuration_name)) applicable.push_back(t);
-    if (applicable.empty()) return false;
-    // reference: IteratorRandom::choose (scheduler_impl.rs:67-70); determinised to the NewestTask rule:
-    // max_by_key(created_at) over the desc-sorted list returns the LAST maximum
-    const TaskRec* chosen = applicable[0];
-    for (const TaskRec* t : applicable)
-      if (t->created_at >= chosen->created_at) chosen = t;
+    if (p->tasks.empty()) return false;
+    // reference: filter by allowed_topologies then IteratorRandom::choose (scheduler_impl.rs:42-70);
+    // determinised to the NewestTask rule (max_by_key over the desc-sorted list = LAST maximum)
+    const TaskRec* chosen = p->task_for_configuration(group.configuration_name);
+    if (!chosen) return false;
     if (!p->group_task.count(group.id)) p->group_task[group.id] = chosen->id;   // SET NX, mod.rs:471-476
     current = p->current_group_task(group.id);
     if (!current) return false;
@@ -973,12 +987,12 @@ int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf,
   if (!p || !address) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
   const std::string addr(address);
-  auto tasks = p->all_tasks();
   Expanded e;
   bool have = false;
   if (!p->templates.empty()) {  // plugin chain = [NodeGroupsPlugin]
-    have = node_groups_filter(p, tasks, addr, &e);
-  } else if (!tasks.empty()) {  // Scheduler::new pushes NewestTaskPlugin when no plugin is configured
+    have = node_groups_filter(p, addr, &e);
+  } else if (!p->tasks.empty()) {  // Scheduler::new pushes NewestTaskPlugin when no plugin is configured
+    const auto tasks = p->all_tasks();
     const TaskRec* chosen = tasks[0];
     for (const TaskRec* t : tasks)
       if (t->created_at >= chosen->created_at) chosen = t;  // max_by_key: last maximum

@@ -333,3 +333,23 @@ def test_redis_writeback_format(engine):
     assert ["HSET", "node_to_group", A1, gid] in cmds and ["HSET", "node_to_group", A2, gid] in cmds
     assert ["SET", f"group_task:{gid}", task.id] in cmds
     assert ["SADD", "available_node_group_configs", "test-config"] in cmds
+
+
+def test_heartbeat_fast_path_is_constant_time(engine):
+    """per-heartbeat cost must not grow with the number of tasks once groups hold a claim."""
+    import time
+
+    plugin = make(engine, [NodeGroupConfiguration("c", 1, 1)])
+    sched = Scheduler(plugin)
+    for i in range(2000):
+        plugin.add_task(Task(name=f"t{i}", created_at=i, allowed_topologies=["c"] if i % 2 else ["other"]))
+    addrs = [f"0x{i + 1:040x}" for i in range(200)]
+    for a in addrs:
+        plugin.add_node(OrchestratorNode(a))
+    assert plugin.try_form_new_groups() == 200
+    t0 = time.perf_counter()
+    for _ in range(10):
+        for a in addrs:
+            assert sched.get_task_for_node(a)["name"] == "t1999"
+    dt = time.perf_counter() - t0
+    assert dt < 2.0, f"2000 heartbeats over 2000 tasks took {dt:.2f}s"
