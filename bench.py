@@ -286,12 +286,17 @@ def run_ours(args):
         lo = rank * Wg if world > 1 else 0
         pa[:] = w.a[lo:lo + len(pa)]
         pb[:] = w.b[lo:lo + len(pb)]
+        # caller-owned tables live in pinned host memory (pm_alloc_pinned), SURVEY 8b "ownership"
+        p_asks = pinned_empty(len(a.asks), abi.ASK)
+        p_opts = pinned_empty(len(a.opts), abi.GPU_OPT)
+        p_asks[:] = a.asks
+        p_opts[:] = a.opts
         h2d = len(pa) * 32 + len(a.asks) * 32 + len(a.opts) * 32
         d2h = 0
 
         def e2e_step():
             nonlocal d2h
-            eng.set_asks(a.asks, a.opts)
+            eng.set_asks(p_asks, p_opts)
             eng.upsert_workers(pa, pb, first=lo, sync=False)
             if world > 1:
                 # other shards' rows are needed only by the (replicated) resolution sweep

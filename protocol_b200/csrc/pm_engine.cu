@@ -86,13 +86,16 @@ struct pm_engine {
   uint32_t max_pattern_row = 0;
   bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
   bool all_solo = true;  // every ask has min == max == 1
-  int tune_argmin = 0, tune_generic = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
+  int tune_argmin = 0, tune_generic = 0, tune_build = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
   DevBuf<uint4> wa, wb;
   DevBuf<double> lat, lon;
   DevBuf<uint32_t> addr_rank;
   DevBuf<pm::DevAsk> asks;
   DevBuf<pm::DevOpt> opts;
   DevBuf<pm::DevOptF> opts_fast;
+  DevBuf<pm_ask> raw_asks;
+  DevBuf<pm_gpu_opt> raw_opts;
+  DevBuf<uint32_t> ask_counts, ask_newoff;
   bool asks_small = true;      // every ask operand fits the fast predicate (pm_device.cuh DevOptF)
   bool workers_small = false;  // ... and every worker operand (checked on the device)
   bool workers_checked = false;
@@ -266,6 +269,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   e->device = cfg->device;
   if (const char* t = std::getenv("PM_TUNE_ARGMIN")) e->tune_argmin = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
+  if (const char* t = std::getenv("PM_TUNE_BUILD")) e->tune_build = std::atoi(t);
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
     e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
@@ -275,7 +279,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   }
   ok = ok &&
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
-            e->h_scalars.ensure(64) == cudaSuccess && e->counters.ensure(16) == cudaSuccess;
+            e->h_scalars.ensure(64) == cudaSuccess && e->counters.ensure(32) == cudaSuccess;
   if (!ok) {
     g_create_error = std::string("pm_create: ") + cudaGetErrorString(cudaGetLastError());
     delete e;
@@ -290,7 +294,8 @@ void pm_destroy(pm_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->wa.release(); e->wb.release(); e->lat.release(); e->lon.release(); e->addr_rank.release();
-  e->asks.release(); e->opts.release(); e->opts_fast.release(); e->amin.release(); e->amax.release(); e->bits.release();
+  e->asks.release(); e->opts.release(); e->opts_fast.release();
+  e->raw_asks.release(); e->raw_opts.release(); e->ask_counts.release(); e->ask_newoff.release(); e->amin.release(); e->amax.release(); e->bits.release();
   e->scratch_idx.release(); e->scratch_flags.release();
   e->cost.release(); e->first_ask.release(); e->ask_count.release(); e->ask_best.release();
   e->keys.release(); e->keys_sorted.release(); e->iota.release(); e->order.release();
@@ -320,109 +325,45 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   std::lock_guard<std::mutex> lk(e->mu);
   if ((n_asks && !asks) || (n_opts && !opts)) return e->fail(PM_E_INVALID, "pm_set_asks: null table");
   if (n_asks >= (1u << 30)) return e->fail(PM_E_INVALID, "pm_set_asks: too many asks");
-  std::vector<pm::DevAsk> da(n_asks);
-  std::vector<pm::DevOpt> dopt;
-  std::vector<pm::DevOptF> doptf;
-  bool small = true;
-  std::vector<uint32_t> mn(n_asks), mx(n_asks);
-  dopt.reserve(n_opts);
-  uint32_t max_row = 0;
-  bool solo = true;
-  for (uint32_t t = 0; t < n_asks; ++t) {
-    const pm_ask& a = asks[t];
-    // NodeGroupConfiguration::is_valid, mod.rs:55-60 (the reference panics at construction)
-    if (a.max_group_size < a.min_group_size)
-      return e->fail(PM_E_INVALID, "pm_set_asks: max_group_size < min_group_size (Plugin configuration is invalid)");
-    if ((uint64_t)a.opt_off + a.n_opts > n_opts)
-      return e->fail(PM_E_INVALID, "pm_set_asks: option range out of bounds");
-    pm::DevAsk d{};
-    const bool has_req = (a.flags & PM_A_HAS_REQ) != 0;
-    uint32_t need = pm::kCandBit;
-    if (has_req) {
-      need |= PM_W_HAS_SPECS;
-      if (a.flags & PM_A_REQ_CPU) need |= PM_W_HAS_CPU;
-      if ((a.flags & PM_A_REQ_CPU) && (a.flags & PM_A_REQ_CPU_CORES)) {
-        need |= PM_W_HAS_CPU_CORES;
-        d.cpu_cores = a.cpu_cores;
-      }
-      if (a.flags & PM_A_REQ_RAM) { need |= PM_W_HAS_RAM; d.ram_mb = a.ram_mb; }
-      if (a.flags & PM_A_REQ_STORAGE) { need |= PM_W_HAS_STORAGE; d.storage_gb = a.storage_gb; }
-      if (a.n_opts) need |= PM_W_HAS_GPU;
-      d.n_opts = a.n_opts;
-    }
-    // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
-    if (a.max_group_size == 0) need |= pm::kNeverBit;
-    d.need = need;
-    if ((d.cpu_cores | d.ram_mb | d.storage_gb) >= pm::kSign) small = false;
-    d.opt_off = (uint32_t)dopt.size();
-    for (uint32_t o = 0; has_req && o < a.n_opts; ++o) {
-      const pm_gpu_opt& q = opts[a.opt_off + o];
-      pm::DevOpt x{};
-      x.count_mask = (q.present & PM_O_COUNT) ? 0xFFFFFFFFu : 0u;
-      x.count = (q.present & PM_O_COUNT) ? q.count : 0u;
-      uint32_t mem_lo = 0, mem_hi = 0xFFFFFFFFu, tot_lo = 0, tot_hi = 0xFFFFFFFFu;
-      if (q.present & PM_O_MEM) mem_lo = std::max(mem_lo, q.memory_mb);
-      if (q.present & PM_O_MEM_MIN) mem_lo = std::max(mem_lo, q.memory_mb_min);
-      if (q.present & PM_O_MEM_MAX) mem_hi = q.memory_mb_max;
-      if (q.present & (PM_O_MEM | PM_O_MEM_MIN | PM_O_MEM_MAX)) x.need |= PM_W_HAS_GPU_MEM;
-      if (q.present & PM_O_TOT_MIN) tot_lo = q.total_memory_min;
-      if (q.present & PM_O_TOT_MAX) tot_hi = q.total_memory_max;
-      if (mem_lo > mem_hi) { x.need |= pm::kNeverBit; mem_lo = 0; mem_hi = 0xFFFFFFFFu; }
-      if (tot_lo > tot_hi) { x.need |= pm::kTotInvalidBit; tot_lo = 0; tot_hi = 0xFFFFFFFFu; }
-      x.mem_lo = mem_lo; x.mem_span = mem_hi - mem_lo;
-      x.tot_lo = tot_lo; x.tot_span = tot_hi - tot_lo;
-      if (q.present & PM_O_MODEL) {
-        x.need |= PM_W_HAS_GPU_MODEL;
-        x.pattern_row = q.pattern_id + 1;
-        max_row = std::max(max_row, x.pattern_row);
-      }
-      dopt.push_back(x);
-      // fast-path form (pm_device.cuh DevOptF): presence + count as one masked equality
-      pm::DevOptF f{};
-      const uint32_t need_all = need | x.need;
-      f.m = need_all;
-      f.v = need_all;
-      if (q.present & PM_O_COUNT) {
-        if (q.count >= 65536u) small = false;
-        f.m |= 0xFFFFu << pm::kKeyCountShift;
-        f.v |= (q.count & 0xFFFFu) << pm::kKeyCountShift;
-      }
-      if (mem_lo >= pm::kSign || tot_lo >= pm::kSign) small = false;
-      f.mem_lo = mem_lo; f.mem_hi = std::min(mem_hi, 0x7FFFFFFFu);
-      f.tot_lo = tot_lo; f.tot_hi = std::min(tot_hi, 0x7FFFFFFFu);
-      f.pattern_row = x.pattern_row;
-      doptf.push_back(f);
-    }
-    da[t] = d;
-    mn[t] = a.min_group_size;
-    mx[t] = a.max_group_size;
-    if (!(a.min_group_size == 1 && a.max_group_size == 1)) solo = false;
-  }
   PM_CUDA(cudaSetDevice(e->device));
-  PM_CUDA(e->asks.ensure(n_asks));
-  PM_CUDA(e->opts.ensure(dopt.size()));
-  PM_CUDA(e->opts_fast.ensure(doptf.size()));
-  PM_CUDA(e->amin.ensure(n_asks));
-  PM_CUDA(e->amax.ensure(n_asks));
+  // the caller's tables go up as they are; the device converts them (pm_ask_convert)
+  PM_CUDA(e->raw_asks.ensure(n_asks)); PM_CUDA(e->raw_opts.ensure(n_opts));
+  PM_CUDA(e->ask_counts.ensure((size_t)n_asks + 1)); PM_CUDA(e->ask_newoff.ensure((size_t)n_asks + 1));
+  PM_CUDA(e->asks.ensure(n_asks)); PM_CUDA(e->amin.ensure(n_asks)); PM_CUDA(e->amax.ensure(n_asks));
+  PM_CUDA(e->opts.ensure(n_opts)); PM_CUDA(e->opts_fast.ensure(n_opts));
+  if (n_asks) PM_CUDA(cudaMemcpyAsync(e->raw_asks.p, asks, (size_t)n_asks * sizeof(pm_ask), cudaMemcpyHostToDevice, e->stream));
+  if (n_opts) PM_CUDA(cudaMemcpyAsync(e->raw_opts.p, opts, (size_t)n_opts * sizeof(pm_gpu_opt), cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->counters.p + 12, 0, 8, e->stream));
+  pm::pm_ask_counts<<<blocks_for((size_t)n_asks + 1, 256), 256, 0, e->stream>>>(e->raw_asks.p, n_asks, n_opts, e->ask_counts.p, e->counters.p + 12);
+  PM_LAUNCH_CHECK("pm_ask_counts");
+  {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->ask_counts.p, e->ask_newoff.p, (int)(n_asks + 1), e->stream);
+    PM_CUDA(e->cub_tmp.ensure(tmp));
+    PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->ask_counts.p, e->ask_newoff.p, (int)(n_asks + 1), e->stream));
+  }
   if (n_asks) {
-    PM_CUDA(cudaMemcpyAsync(e->asks.p, da.data(), n_asks * sizeof(pm::DevAsk), cudaMemcpyHostToDevice, e->stream));
-    PM_CUDA(cudaMemcpyAsync(e->amin.p, mn.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
-    PM_CUDA(cudaMemcpyAsync(e->amax.p, mx.data(), n_asks * 4, cudaMemcpyHostToDevice, e->stream));
+    pm::pm_ask_convert<<<blocks_for(n_asks, 256), 256, 0, e->stream>>>(e->raw_asks.p, e->raw_opts.p, n_asks, e->ask_newoff.p, e->asks.p,
+                                                                        e->opts.p, e->opts_fast.p, e->amin.p, e->amax.p,
+                                                                        e->counters.p + 12, e->counters.p + 13);
+    PM_LAUNCH_CHECK("pm_ask_convert");
   }
-  if (!dopt.empty()) {
-    PM_CUDA(cudaMemcpyAsync(e->opts.p, dopt.data(), dopt.size() * sizeof(pm::DevOpt), cudaMemcpyHostToDevice, e->stream));
-    PM_CUDA(cudaMemcpyAsync(e->opts_fast.p, doptf.data(), doptf.size() * sizeof(pm::DevOptF), cudaMemcpyHostToDevice, e->stream));
-  }
-  PM_CUDA(cudaStreamSynchronize(e->stream));  // staging vectors die here
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 20, e->counters.p + 12, 8, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 22, e->ask_newoff.p + n_asks, 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));  // also: the caller's tables are no longer read after return
+  const uint32_t st = e->h_scalars.p[20];
+  e->have_asks = false;
+  // NodeGroupConfiguration::is_valid, mod.rs:55-60 (the reference panics at construction)
+  if (st & pm::kAskBadSizes)
+    return e->fail(PM_E_INVALID, "pm_set_asks: max_group_size < min_group_size (Plugin configuration is invalid)");
+  if (st & pm::kAskBadRange) return e->fail(PM_E_INVALID, "pm_set_asks: option range out of bounds");
   e->n_asks = n_asks;
-  e->n_opts = (uint32_t)dopt.size();
-  e->max_pattern_row = max_row;
-  e->all_solo = solo;
-  e->asks_small = small;
+  e->n_opts = e->h_scalars.p[22];
+  e->max_pattern_row = e->h_scalars.p[21];
+  e->all_solo = (st & pm::kAskNotSolo) == 0;
+  e->asks_small = (st & pm::kAskNotSmall) == 0;
+  e->any_max_zero = (st & pm::kAskMaxZero) != 0;
   e->have_caps = false;
-  e->any_max_zero = false;
-  for (uint32_t t = 0; t < n_asks; ++t)
-    if (mx[t] == 0) e->any_max_zero = true;
   e->have_asks = true;
   e->matched = e->local_done = false;
   return PM_OK;
@@ -557,7 +498,11 @@ static int decide_fast(pm_engine* e, bool* fast) {
 static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, dim3 grid,
                          uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw, size_t ld) {
 #define PM_BUILD_CASE(B, F) pm::pm_build_cost<B, F><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld)
-  if (fast) {
+  if (fast && bits_mode == 2 && e->tune_build == 3) {
+    pm::pm_build_cost<2, true, 3><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  } else if (fast && bits_mode == 2 && e->tune_build == 4) {
+    pm::pm_build_cost<2, true, 4><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  } else if (fast) {
     if (bits_mode == 2) PM_BUILD_CASE(2, true); else if (bits_mode == 1) PM_BUILD_CASE(1, true); else PM_BUILD_CASE(0, true);
   } else {
     if (bits_mode == 2) PM_BUILD_CASE(2, false); else if (bits_mode == 1) PM_BUILD_CASE(1, false); else PM_BUILD_CASE(0, false);

@@ -231,8 +231,8 @@ __device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalPara
 // grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 adjacent workers in
 // registers and walks the staged asks, emitting two 128-bit streaming stores per
 // row: a warp writes 1 KB contiguous, the CTA 8 KB contiguous per row.
-template <int BITS, bool FAST>
-__global__ void __launch_bounds__(kEvalThreads, 2)
+template <int BITS, bool FAST, int MINB = 2>
+__global__ void __launch_bounds__(kEvalThreads, MINB)
 pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               long long* __restrict__ cost, size_t ld) {
   __shared__ EvalStage s;
@@ -425,6 +425,106 @@ pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
       atomicMin(ask_best + t0 + r0 + i, (long long)s_best[i]);
     }
   }
+}
+
+// ------------------------------------------------------------------ ask-table conversion
+// pm_ask / pm_gpu_opt (ABI form, field-for-field NodeGroupConfiguration + GpuRequirements) ->
+// DevAsk / DevOpt / DevOptF, on the device: the upload is a plain memcpy of the caller's tables
+// and one pass of these two kernels instead of a host loop.
+enum AskStatusBit : uint32_t {
+  kAskBadSizes = 1u << 0,   // max_group_size < min_group_size (is_valid, mod.rs:55-60)
+  kAskBadRange = 1u << 1,   // opt_off + n_opts out of bounds
+  kAskNotSmall = 1u << 2,   // an operand does not fit the fast predicate
+  kAskNotSolo = 1u << 3,    // some ask is not min == max == 1
+  kAskMaxZero = 1u << 4     // some ask has max_group_size == 0
+};
+
+__global__ void pm_ask_counts(const pm_ask* __restrict__ asks, uint32_t n_asks, uint32_t n_opts,
+                              uint32_t* __restrict__ counts, uint32_t* __restrict__ status) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_asks) return;
+  if (t == n_asks) { counts[t] = 0; return; }
+  const pm_ask a = asks[t];
+  uint32_t st = 0;
+  if (a.max_group_size < a.min_group_size) st |= kAskBadSizes;
+  if ((unsigned long long)a.opt_off + a.n_opts > n_opts) st |= kAskBadRange;
+  if (!(a.min_group_size == 1 && a.max_group_size == 1)) st |= kAskNotSolo;
+  if (a.max_group_size == 0) st |= kAskMaxZero;
+  if (st) atomicOr(status, st);
+  counts[t] = ((a.flags & PM_A_HAS_REQ) && !(st & kAskBadRange)) ? a.n_opts : 0u;
+}
+
+__global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt* __restrict__ opts,
+                               uint32_t n_asks, const uint32_t* __restrict__ new_off,
+                               DevAsk* __restrict__ dasks, DevOpt* __restrict__ dopts,
+                               DevOptF* __restrict__ doptsf, uint32_t* __restrict__ amin,
+                               uint32_t* __restrict__ amax, uint32_t* __restrict__ status,
+                               uint32_t* __restrict__ max_row) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_asks) return;
+  const pm_ask a = asks[t];
+  DevAsk d;
+  d.n_opts = 0; d.cpu_cores = 0; d.ram_mb = 0; d.storage_gb = 0; d.pad0 = 0; d.pad1 = 0;
+  const bool has_req = (a.flags & PM_A_HAS_REQ) != 0;
+  uint32_t need = kCandBit;
+  const uint32_t n_eff = new_off[t + 1] - new_off[t];
+  if (has_req) {
+    need |= PM_W_HAS_SPECS;
+    if (a.flags & PM_A_REQ_CPU) need |= PM_W_HAS_CPU;
+    if ((a.flags & PM_A_REQ_CPU) && (a.flags & PM_A_REQ_CPU_CORES)) { need |= PM_W_HAS_CPU_CORES; d.cpu_cores = a.cpu_cores; }
+    if (a.flags & PM_A_REQ_RAM) { need |= PM_W_HAS_RAM; d.ram_mb = a.ram_mb; }
+    if (a.flags & PM_A_REQ_STORAGE) { need |= PM_W_HAS_STORAGE; d.storage_gb = a.storage_gb; }
+    if (a.n_opts) need |= PM_W_HAS_GPU;
+    d.n_opts = n_eff;
+  }
+  if (a.max_group_size == 0) need |= kNeverBit;   // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
+  d.need = need;
+  d.opt_off = new_off[t];
+  uint32_t st = 0, mrow = 0;
+  if ((d.cpu_cores | d.ram_mb | d.storage_gb) >= kSign) st |= kAskNotSmall;
+  for (uint32_t o = 0; o < n_eff; ++o) {
+    const pm_gpu_opt q = opts[a.opt_off + o];
+    DevOpt x;
+    x.need = 0;
+    x.count_mask = (q.present & PM_O_COUNT) ? 0xFFFFFFFFu : 0u;
+    x.count = (q.present & PM_O_COUNT) ? q.count : 0u;
+    uint32_t mem_lo = 0, mem_hi = 0xFFFFFFFFu, tot_lo = 0, tot_hi = 0xFFFFFFFFu;
+    if (q.present & PM_O_MEM) mem_lo = max(mem_lo, q.memory_mb);
+    if (q.present & PM_O_MEM_MIN) mem_lo = max(mem_lo, q.memory_mb_min);
+    if (q.present & PM_O_MEM_MAX) mem_hi = q.memory_mb_max;
+    if (q.present & (PM_O_MEM | PM_O_MEM_MIN | PM_O_MEM_MAX)) x.need |= PM_W_HAS_GPU_MEM;
+    if (q.present & PM_O_TOT_MIN) tot_lo = q.total_memory_min;
+    if (q.present & PM_O_TOT_MAX) tot_hi = q.total_memory_max;
+    if (mem_lo > mem_hi) { x.need |= kNeverBit; mem_lo = 0; mem_hi = 0xFFFFFFFFu; }
+    if (tot_lo > tot_hi) { x.need |= kTotInvalidBit; tot_lo = 0; tot_hi = 0xFFFFFFFFu; }
+    x.mem_lo = mem_lo; x.mem_span = mem_hi - mem_lo;
+    x.tot_lo = tot_lo; x.tot_span = tot_hi - tot_lo;
+    x.pattern_row = 0;
+    if (q.present & PM_O_MODEL) {
+      x.need |= PM_W_HAS_GPU_MODEL;
+      x.pattern_row = q.pattern_id + 1;
+      mrow = max(mrow, x.pattern_row);
+    }
+    dopts[d.opt_off + o] = x;
+    DevOptF f;
+    const uint32_t need_all = need | x.need;
+    f.m = need_all; f.v = need_all;
+    if (q.present & PM_O_COUNT) {
+      if (q.count >= 65536u) st |= kAskNotSmall;
+      f.m |= 0xFFFFu << kKeyCountShift;
+      f.v |= (q.count & 0xFFFFu) << kKeyCountShift;
+    }
+    if (mem_lo >= kSign || tot_lo >= kSign) st |= kAskNotSmall;
+    f.mem_lo = mem_lo; f.mem_hi = min(mem_hi, 0x7FFFFFFFu);
+    f.tot_lo = tot_lo; f.tot_hi = min(tot_hi, 0x7FFFFFFFu);
+    f.pattern_row = x.pattern_row; f.pad = 0;
+    doptsf[d.opt_off + o] = f;
+  }
+  dasks[t] = d;
+  amin[t] = a.min_group_size;
+  amax[t] = a.max_group_size;
+  if (st) atomicOr(status, st);
+  if (mrow) atomicMax(max_row, mrow);
 }
 
 // ------------------------------------------------------------------ small utilities
