@@ -356,6 +356,9 @@ int pm_plugin_set_node_status(pm_plugin*, const char* address, uint32_t status);
  * (discovery/monitor.rs:195-435); the Theta(N^2) same-endpoint scan is a hash lookup here. */
 int pm_plugin_sync_discovery(pm_plugin*, const pm_discovery_node* nodes, uint32_t n, int64_t now_ms,
                              uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new);
+/* same, from the discovery service's wire format: {"success":true,"data":[DiscoveryNode,...]} */
+int pm_plugin_sync_discovery_json(pm_plugin*, const char* json, size_t len, int64_t now_ms,
+                                  uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new);
 int pm_plugin_get_node(pm_plugin*, const char* address, char* buf, size_t len);   /* JSON or null */
 int pm_plugin_add_task(pm_plugin*, const pm_task_desc*);                   /* TaskStore::add_task + on_task_created */
 int pm_plugin_delete_task(pm_plugin*, const char* id);                     /* delete_task + on_task_deleted */

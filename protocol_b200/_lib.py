@@ -74,6 +74,7 @@ def load() -> C.CDLL:
         "pm_plugin_upsert_node": (i32, [vp, P(abi.PmNodeDesc)]),
         "pm_plugin_set_node_status": (i32, [vp, cp, u32]),
         "pm_plugin_sync_discovery": (i32, [vp, vp, u32, C.c_int64, u32, P(u32)]),
+        "pm_plugin_sync_discovery_json": (i32, [vp, cp, sz, C.c_int64, u32, P(u32)]),
         "pm_plugin_get_node": (i32, [vp, cp, C.c_char_p, sz]),
         "pm_plugin_add_task": (i32, [vp, P(abi.PmTaskDesc)]),
         "pm_plugin_delete_task": (i32, [vp, cp]),

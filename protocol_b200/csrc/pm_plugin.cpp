@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../../include/prime_match.h"
+#include "pm_json.hpp"
 
 namespace {
 
@@ -457,6 +458,111 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
     }
   }
   return PM_OK;
+}
+
+namespace {
+
+bool json_u32(const pmjson::Value* v, uint32_t* out) {   // Option<u32>
+  if (!v || v->kind != pmjson::Value::Number || v->num < 0 || v->num > 4294967295.0) return false;
+  *out = (uint32_t)v->num;
+  return true;
+}
+bool json_bool(const pmjson::Value* v, bool dflt) { return (v && v->kind == pmjson::Value::Bool) ? v->b : dflt; }
+
+// chrono DateTime<Utc> serde form (RFC 3339) -> unix milliseconds; -1 when absent/unparsable
+int64_t rfc3339_ms(const pmjson::Value* v) {
+  if (!v || v->kind != pmjson::Value::String) return -1;
+  int Y, M, D, h, m;
+  double sec;
+  if (std::sscanf(v->str.c_str(), "%d-%d-%dT%d:%d:%lf", &Y, &M, &D, &h, &m, &sec) != 6) return -1;
+  std::tm t{};
+  t.tm_year = Y - 1900; t.tm_mon = M - 1; t.tm_mday = D; t.tm_hour = h; t.tm_min = m; t.tm_sec = 0;
+  const std::time_t base = timegm(&t);
+  int64_t ms = (int64_t)base * 1000 + (int64_t)(sec * 1000.0 + 0.5);
+  // numeric offset ("+02:00"); 'Z' means none
+  const std::string& s = v->str;
+  const size_t tpos = s.find('T');
+  const size_t sign = s.find_first_of("+-", tpos == std::string::npos ? 0 : tpos);
+  if (sign != std::string::npos) {
+    int oh = 0, om = 0;
+    if (std::sscanf(s.c_str() + sign + 1, "%d:%d", &oh, &om) >= 1) ms -= (s[sign] == '+' ? 1 : -1) * (int64_t)(oh * 60 + om) * 60000;
+  }
+  return ms;
+}
+
+}  // namespace
+
+// The discovery service's wire format: `{"success":true,"data":[DiscoveryNode,...]}` (or a bare
+// array), DiscoveryNode = flattened Node + flags (shared/src/models/node.rs:10-23, 552-570).
+int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, int64_t now_ms,
+                                  uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
+  if (!p || !json) return PM_E_INVALID;
+  pmjson::Value root;
+  std::string err;
+  if (!pmjson::Parser(json, len).parse(&root, &err)) return p->fail(PM_E_PARSE, "discovery JSON: " + err);
+  const pmjson::Value* list = &root;
+  if (root.kind == pmjson::Value::Object) list = root.get("data");
+  if (!list || list->kind != pmjson::Value::Array) return p->fail(PM_E_PARSE, "discovery JSON: no node array");
+  std::vector<pm_discovery_node> nodes(list->arr.size());
+  for (size_t i = 0; i < list->arr.size(); ++i) {
+    const pmjson::Value& n = list->arr[i];
+    pm_discovery_node& d = nodes[i];
+    std::memset(&d, 0, sizeof d);
+    const pmjson::Value* id = n.get("id");
+    const pmjson::Value* ip = n.get("ip_address");
+    if (!id || id->kind != pmjson::Value::String || !ip || ip->kind != pmjson::Value::String)
+      return p->fail(PM_E_PARSE, "discovery JSON: node without id / ip_address");
+    d.node.address = id->str.c_str();
+    d.ip_address = ip->str.c_str();
+    uint32_t port = 0;
+    json_u32(n.get("port"), &port);
+    d.port = (uint16_t)port;
+    uint32_t f = 0;
+    const pmjson::Value* specs = n.get("compute_specs");
+    if (specs && specs->kind == pmjson::Value::Object) {
+      f |= PM_W_HAS_SPECS;
+      const pmjson::Value* gpu = specs->get("gpu");
+      if (gpu && gpu->kind == pmjson::Value::Object) {
+        f |= PM_W_HAS_GPU;
+        if (json_u32(gpu->get("count"), &d.node.gpu_count)) f |= PM_W_HAS_GPU_COUNT;
+        if (json_u32(gpu->get("memory_mb"), &d.node.gpu_mem_mb)) f |= PM_W_HAS_GPU_MEM;
+        const pmjson::Value* model = gpu->get("model");
+        if (model && model->kind == pmjson::Value::String) { f |= PM_W_HAS_GPU_MODEL; d.node.gpu_model = model->str.c_str(); }
+      }
+      const pmjson::Value* cpu = specs->get("cpu");
+      if (cpu && cpu->kind == pmjson::Value::Object) {
+        f |= PM_W_HAS_CPU;
+        if (json_u32(cpu->get("cores"), &d.node.cpu_cores)) f |= PM_W_HAS_CPU_CORES;
+      }
+      if (json_u32(specs->get("ram_mb"), &d.node.ram_mb)) f |= PM_W_HAS_RAM;
+      if (json_u32(specs->get("storage_gb"), &d.node.storage_gb)) f |= PM_W_HAS_STORAGE;
+    }
+    d.node.spec_flags = f;
+    const pmjson::Value* loc = n.get("location");
+    if (loc && loc->kind == pmjson::Value::Object) {
+      const pmjson::Value *la = loc->get("latitude"), *lo = loc->get("longitude");
+      if (la && lo && la->kind == pmjson::Value::Number && lo->kind == pmjson::Value::Number) {
+        d.node.has_location = 1;
+        d.node.lat = la->num;
+        d.node.lon = lo->num;
+      }
+    }
+    d.is_validated = json_bool(n.get("is_validated"), false);
+    d.is_active = json_bool(n.get("is_active"), false);
+    d.is_provider_whitelisted = json_bool(n.get("is_provider_whitelisted"), false);   // #[serde(default)]
+    d.is_blacklisted = json_bool(n.get("is_blacklisted"), false);
+    d.last_updated_ms = rfc3339_ms(n.get("last_updated"));
+    const pmjson::Value* bal = n.get("latest_balance");                                 // Option<U256>
+    if (bal && !bal->is_null()) {
+      d.has_latest_balance = 1;
+      const std::string& t = bal->str;   // decimal, hex quantity ("0x0") or a JSON number
+      bool zero = !t.empty();
+      for (size_t k = (t.rfind("0x", 0) == 0 ? 2 : 0); k < t.size(); ++k)
+        if (t[k] != '0') zero = false;
+      d.latest_balance_is_zero = zero;
+    }
+  }
+  return pm_plugin_sync_discovery(p, nodes.data(), (uint32_t)nodes.size(), now_ms, max_healthy_nodes_with_same_endpoint, n_new);
 }
 
 // node as the /nodes route would show it (fields on this path): JSON or null

@@ -186,6 +186,14 @@ class NodeGroupsPlugin:
                                                        max_healthy_nodes_with_same_endpoint, C.byref(n_new)))
         return n_new.value
 
+    def sync_discovery_json(self, body: str, now_ms: int, max_healthy_nodes_with_same_endpoint: int = 1) -> int:
+        """The body of `GET {discovery}/api/pool/{id}` (discovery/monitor.rs:109-193)."""
+        raw = body.encode()
+        n_new = C.c_uint32()
+        self._check(self._lib.pm_plugin_sync_discovery_json(self._h, raw, len(raw), now_ms,
+                                                            max_healthy_nodes_with_same_endpoint, C.byref(n_new)))
+        return n_new.value
+
     def get_node(self, address: str):
         return self._json(self._lib.pm_plugin_get_node, address.encode())
 

@@ -90,3 +90,43 @@ def test_endpoint_index_scales_linearly():
     assert plugin.sync_discovery(nodes, NOW, max_healthy_nodes_with_same_endpoint=1) == n   # nobody healthy yet
     plugin.sync_discovery(nodes, NOW + 1000)
     assert time.perf_counter() - t0 < 5.0
+
+
+def test_sync_from_discovery_wire_format():
+    """The JSON the discovery service returns (ApiResponse<Vec<DiscoveryNode>>, node.rs:10-23, 552-570)."""
+    import json
+
+    import pytest
+
+    from protocol_b200 import abi
+    from protocol_b200._lib import PrimeMatchError
+
+    body = json.dumps({"success": True, "data": [
+        {"id": A1, "provider_address": A1, "ip_address": "192.168.1.100", "port": 8080, "compute_pool_id": 1,
+         "compute_specs": {"gpu": {"count": 8, "model": "NVIDIA H100", "memory_mb": 80000, "indices": [0, 1]},
+                           "cpu": {"cores": 64, "model": "x"}, "ram_mb": 1024, "storage_gb": 10, "storage_path": "/var/lib"},
+         "is_validated": True, "is_active": True, "is_provider_whitelisted": True, "is_blacklisted": False,
+         "last_updated": "2024-05-01T12:00:00.250Z", "created_at": None,
+         "location": {"latitude": 45.5186, "longitude": -73.5545, "city": "Montr\\u00e9al", "region": None, "country": "CA"},
+         "latest_balance": "0x0"},
+        {"id": A2, "provider_address": A2, "ip_address": "192.168.1.101", "port": 8081, "compute_pool_id": 1,
+         "compute_specs": None, "is_validated": False, "is_active": True},
+        {"id": A3, "provider_address": A3, "ip_address": "192.168.1.102", "port": 8082, "compute_pool_id": 1,
+         "compute_specs": {"gpu": None, "cpu": None, "ram_mb": 2048, "storage_gb": None, "storage_path": "/x"},
+         "is_validated": True, "is_active": True, "is_provider_whitelisted": True, "latest_balance": "1000000000000000000"},
+    ]})
+    plugin = NodeGroupsPlugin([])
+    assert plugin.sync_discovery_json(body, NOW) == 2                  # the unvalidated node is skipped
+    n1 = plugin.get_node(A1)
+    assert n1["ip_address"] == "192.168.1.100" and n1["port"] == 8080 and n1["status"] == "Discovered"
+    assert n1["has_location"] and n1["has_compute_specs"] and n1["ram_mb"] == 1024
+    assert plugin.get_node(A2) is None
+    assert plugin.get_node(A3)["ram_mb"] == 2048 and not plugin.get_node(A3)["has_location"]
+    # second sync: the zero balance now applies to the existing node (monitor.rs:391-402)
+    assert plugin.sync_discovery_json(body, NOW + 1000) == 0
+    assert plugin.get_node(A1)["status"] == "LowBalance" and plugin.get_node(A3)["status"] == "Discovered"
+    assert plugin.sync_discovery_json("[]", NOW) == 0
+    for bad in ("{", '{"data": 3}', '[{"id": 1}]', '[] trailing'):
+        with pytest.raises(PrimeMatchError) as e:
+            plugin.sync_discovery_json(bad, NOW)
+        assert e.value.status == abi.PM_E_PARSE
