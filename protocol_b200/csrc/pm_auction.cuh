@@ -12,6 +12,13 @@
 //   bid(t)        = price[w1] + (best - max(second, outside)) + eps    on the best worker w1
 //   a worker takes the highest bid (ties: lowest ask index), releasing its previous owner.
 //
+// Rounds are cheap because every ask keeps a cache of its 32 best feasible workers (at the
+// prices of its last full scan) and the value theta that bounds every worker outside the cache:
+// prices only rise, so while the second-best cached value stays above theta the cached top-2 IS
+// the global top-2 (pm_auction_bid_cached: 32 gathers per ask); otherwise the ask rescans all
+// workers at the current prices in the same round (pm_auction_bid) — bids are bit-identical to a
+// full scan every round, which is what the sequential checker does.
+//
 // pm_auction_bid: one warp per unassigned ask; the CTA's 8 warps share stripes of the
 // worker table (planes A, B) and of the per-worker price vector, staged into shared
 // memory with 1-D TMA bulk copies; collisions are resolved by atomicMax on the bid and
@@ -39,8 +46,17 @@ struct AuctionParams {
   long long* bid_p;            // [T]
   long long* bid_max;          // [W] highest bid of the round (reset by the winner)
   uint32_t* winner;            // [W]
+  uint32_t* cand;              // [T * 32] cached best feasible workers of each ask
+  long long* theta;            // [T] upper bound of every non-cached worker's value (INT64_MIN: cache is complete)
+  uint32_t* rescan;            // [T] asks whose cache could not decide this round
+  uint32_t* n_rescan;
+  const uint32_t* scan_list;   // asks pm_auction_bid scans (= rescan)
+  uint32_t n_scan;
   long long scale, eps;
 };
+constexpr int kAucCache = 32;
+constexpr long long kThetaComplete = (long long)0x8000000000000000ull;
+constexpr long long kThetaInvalid = 0x7FFFFFFFFFFFFFFFll;
 
 struct __align__(128) AuctionStage {
   uint4 a[kAucStripe];
@@ -61,16 +77,50 @@ __device__ __forceinline__ Top2 top2_merge(const Top2& x, const Top2& y) {
   return r;
 }
 
+__device__ __forceinline__ void auction_place_bid(const AuctionParams& p, uint32_t t, uint32_t cap,
+                                                  long long b1, uint32_t w1, long long b2) {
+  const long long outside = -(((long long)cap + 1) * p.scale);
+  if (w1 == kNone || b1 < outside) {
+    p.withdrawn[t] = 1u;       // prices only rise: it can never come back
+    p.bid_w[t] = kNone;
+  } else {
+    const long long second = max(b2, outside);
+    const long long bid = p.price[w1] + (b1 - second) + p.eps;
+    p.bid_w[t] = w1;
+    p.bid_p[t] = bid;
+    atomicMax(p.bid_max + w1, bid);
+  }
+}
+
+// (value desc, worker asc) arg-max across the warp; returns the winning lane
+__device__ __forceinline__ uint32_t warp_argbest(long long v, uint32_t w, long long* bv, uint32_t* bw) {
+  uint32_t lane_id = threadIdx.x & 31u;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const long long ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const uint32_t ow = __shfl_xor_sync(0xffffffffu, w, off);
+    const uint32_t ol = __shfl_xor_sync(0xffffffffu, lane_id, off);
+    if (ov > v || (ov == v && ow < w)) { v = ov; w = ow; lane_id = ol; }
+  }
+  *bv = v;
+  *bw = w;
+  return lane_id;
+}
+
+// Full scan of every worker for the asks in scan_list: exact top-2 -> bid, and the ask's cache.
 __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AuctionStage& s = *reinterpret_cast<AuctionStage*>(smem_raw);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t slot = blockIdx.x * kAucWarps + warp;
-  const bool live = slot < p.n_active;
-  const uint32_t t = live ? p.active[slot] : 0u;
+  const bool live = slot < p.n_scan;
+  const uint32_t t = live ? p.scan_list[slot] : 0u;
   const DevAsk ask = p.ev.asks[t];
   const uint32_t cap = p.price_cap[t];
-  Top2 best{kAucNeg, kAucNeg, kNone};
+  // per lane: its 4 best (value, worker) in order, and the best value it did not keep
+  long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
+  uint32_t cw[4] = {kNone, kNone, kNone, kNone};
+  long long dropped = kAucNeg;
 
   if (threadIdx.x == 0) mbar_init(&s.bar, 1);
   __syncthreads();
@@ -92,15 +142,61 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
         if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
           const long long v = -((long long)wr.price * p.scale) - s.price[i];
-          const uint32_t w = w0 + i;
-          if (v > best.b1) { best.b2 = best.b1; best.b1 = v; best.w1 = w; }   // w ascends per lane
-          else if (v > best.b2) best.b2 = v;
+          const uint32_t w = w0 + i;                     // ascends per lane: strict '>' keeps ties in index order
+          if (v > cv[3]) {
+            dropped = max(dropped, cv[3]);
+            cv[3] = v; cw[3] = w;
+            if (cv[3] > cv[2]) { const long long tv = cv[2]; const uint32_t tw = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = tv; cw[3] = tw; }
+            if (cv[2] > cv[1]) { const long long tv = cv[1]; const uint32_t tw = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = tv; cw[2] = tw; }
+            if (cv[1] > cv[0]) { const long long tv = cv[0]; const uint32_t tw = cw[0]; cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = tv; cw[1] = tw; }
+          } else {
+            dropped = max(dropped, v);
+          }
         }
       }
     }
     __syncthreads();  // stripe fully consumed before the next bulk copy overwrites it
   }
   if (!live) return;
+  // 32 selection rounds over the warp's 128 candidates: lane r keeps the r-th best
+  long long b1 = kAucNeg, b2 = kAucNeg;
+  uint32_t w1 = kNone, mine = kNone;
+#pragma unroll 1
+  for (int r = 0; r < kAucCache; ++r) {
+    long long bv;
+    uint32_t bw;
+    const uint32_t win = warp_argbest(cv[0], cw[0], &bv, &bw);
+    if (r == 0) { b1 = bv; w1 = bw; }
+    if (r == 1) b2 = bv;
+    if ((int)lane == r) mine = (bv > kAucNeg) ? bw : kNone;
+    if (lane == win) { cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = kAucNeg; cw[3] = kNone; }
+  }
+  long long next_v;
+  uint32_t next_w;
+  warp_argbest(cv[0], cw[0], &next_v, &next_w);       // the 33rd best candidate
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dropped = max(dropped, __shfl_xor_sync(0xffffffffu, dropped, off));
+  const long long bound = max(next_v, dropped);
+  p.cand[(size_t)t * kAucCache + lane] = mine;
+  if (lane == 0) {
+    p.theta[t] = (bound == kAucNeg) ? kThetaComplete : bound;
+    auction_place_bid(p, t, cap, b1, w1, b2);
+  }
+}
+
+// One round for an ask from its cache: 32 gathers instead of a scan of every worker.
+__global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionParams p) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * kAucWarps + warp;
+  if (slot >= p.n_active) return;
+  const uint32_t t = p.active[slot];
+  const long long theta = p.theta[t];
+  const uint32_t w = p.cand[(size_t)t * kAucCache + lane];
+  Top2 best{kAucNeg, kAucNeg, kNone};
+  if (theta != kThetaInvalid && w != kNone) {
+    best.b1 = -((long long)p.ev.wb[w].w * p.scale) - p.price[w];
+    best.w1 = w;
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     Top2 o;
@@ -110,17 +206,10 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
     best = top2_merge(best, o);
   }
   if (lane == 0) {
-    const long long outside = -(((long long)cap + 1) * p.scale);
-    if (best.w1 == kNone || best.b1 < outside) {
-      p.withdrawn[t] = 1u;       // prices only rise: it can never come back
-      p.bid_w[t] = kNone;
-    } else {
-      const long long second = max(best.b2, outside);
-      const long long bid = p.price[best.w1] + (best.b1 - second) + p.eps;
-      p.bid_w[t] = best.w1;
-      p.bid_p[t] = bid;
-      atomicMax(p.bid_max + best.w1, bid);
-    }
+    // every worker outside the cache is worth at most theta (its value at scan time; prices only rise)
+    const bool decided = theta == kThetaComplete || (theta != kThetaInvalid && best.b2 > theta);
+    if (decided) auction_place_bid(p, t, p.price_cap[t], best.b1, best.w1, best.b2);
+    else { p.bid_w[t] = kNone; p.rescan[atomicAdd(p.n_rescan, 1u)] = t; }
   }
 }
 

@@ -116,7 +116,8 @@ struct pm_engine {
   bool any_max_zero = false;
   // extension (auction) state
   DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
-  DevBuf<long long> auc_price, auc_bid_p, auc_bid_max;
+  DevBuf<long long> auc_price, auc_bid_p, auc_bid_max, auc_theta;
+  DevBuf<uint32_t> auc_cand, auc_rescan;
   bool have_caps = false;
   uint64_t auc_scale = 1, auc_eps_start = 1;
   uint32_t auc_eps_div = 4;
@@ -306,6 +307,7 @@ void pm_destroy(pm_engine* e) {
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
+  e->auc_theta.release(); e->auc_cand.release(); e->auc_rescan.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
@@ -834,6 +836,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
   PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
+  PM_CUDA(e->auc_theta.ensure(T)); PM_CUDA(e->auc_cand.ensure((size_t)T * pm::kAucCache)); PM_CUDA(e->auc_rescan.ensure(T));
   PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(std::max(W, T)));
   PM_CUDA(e->group_ask.ensure((size_t)T + 1)); PM_CUDA(e->group_off.ensure((size_t)T + 2));
   PM_CUDA(e->ask_best.ensure(T)); PM_CUDA(e->ask_count.ensure(T)); PM_CUDA(e->first_ask.ensure(W));
@@ -849,6 +852,8 @@ static int match_auction_locked(pm_engine* e) {
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
   ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
+  ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.rescan = e->auc_rescan.p; ap.n_rescan = e->counters.p + 9;
+  ap.scan_list = e->auc_rescan.p; ap.n_scan = 0;
   const size_t smem = sizeof(pm::AuctionStage);
   uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
   const uint32_t div = e->auc_eps_div < 2 ? 2 : e->auc_eps_div;
@@ -856,6 +861,10 @@ static int match_auction_locked(pm_engine* e) {
     PM_CUDA(cudaMemsetAsync(e->auc_owner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->auc_assigned.p, 0xFF, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->auc_withdrawn.p, 0, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
+    if (T) {  // no cache yet: theta = "invalid" sends every ask to a full scan in its first round
+      pm::pm_fill_i64<<<std::min(blocks_for(T, 256), 1184u), 256, 0, e->stream>>>(e->auc_theta.p, pm::kThetaInvalid, T);
+      PM_LAUNCH_CHECK("pm_fill_i64");
+    }
     ap.eps = (long long)eps;
     for (;;) {
       PM_CUDA(cudaMemsetAsync(e->counters.p + 8, 0, 4, e->stream));
@@ -868,15 +877,24 @@ static int match_auction_locked(pm_engine* e) {
       const uint32_t n_active = e->h_scalars.p[16];
       if (n_active == 0) break;
       ap.n_active = n_active;
-      pm::pm_auction_bid<<<blocks_for(n_active, pm::kAucWarps), pm::kAucThreads, smem, e->stream>>>(ap);
-      PM_LAUNCH_CHECK("pm_auction_bid");
+      PM_CUDA(cudaMemsetAsync(e->counters.p + 9, 0, 4, e->stream));
+      pm::pm_auction_bid_cached<<<blocks_for(n_active, pm::kAucWarps), pm::kAucThreads, 0, e->stream>>>(ap);
+      PM_LAUNCH_CHECK("pm_auction_bid_cached");
+      PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 18, e->counters.p + 9, 4, cudaMemcpyDeviceToHost, e->stream));
+      PM_CUDA(cudaStreamSynchronize(e->stream));
+      const uint32_t n_scan = e->h_scalars.p[18];
+      if (n_scan) {
+        ap.n_scan = n_scan;
+        pm::pm_auction_bid<<<blocks_for(n_scan, pm::kAucWarps), pm::kAucThreads, smem, e->stream>>>(ap);
+        PM_LAUNCH_CHECK("pm_auction_bid");
+        e->stats.evals += (uint64_t)n_scan * W;
+      }
       pm::pm_auction_claim<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
       PM_LAUNCH_CHECK("pm_auction_claim");
       pm::pm_auction_apply<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
       PM_LAUNCH_CHECK("pm_auction_apply");
       ++e->stats.n_rounds;
       ++e->stats.n_fused_launches;
-      e->stats.evals += (uint64_t)n_active * W;
       if (e->stats.n_rounds > 50u * 1000u * 1000u) return e->fail(PM_E_CUDA, "pm_match: auction did not terminate");
     }
     if (eps == 1) break;
