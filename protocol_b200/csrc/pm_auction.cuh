@@ -14,8 +14,9 @@
 //
 // Rounds are cheap because every ask keeps a cache of its 32 best feasible workers (at the
 // prices of its last full scan) and the value theta that bounds every worker outside the cache:
-// prices only rise, so while the second-best cached value stays above theta the cached top-2 IS
-// the global top-2 (pm_auction_bid_cached: 32 gathers per ask); otherwise the ask rescans all
+// prices only rise, so while the cached best beats theta in (value, lowest index) order and the cached
+// second-best value is >= theta's, the cached top-2 IS the global top-2, ties included
+// (pm_auction_bid_cached: 32 gathers per ask); otherwise the ask rescans all
 // workers at the current prices in the same round (pm_auction_bid) — bids are bit-identical to a
 // full scan every round, which is what the sequential checker does.
 //
@@ -47,7 +48,8 @@ struct AuctionParams {
   long long* bid_max;          // [W] highest bid of the round (reset by the winner)
   uint32_t* winner;            // [W]
   uint32_t* cand;              // [T * 32] cached best feasible workers of each ask
-  long long* theta;            // [T] upper bound of every non-cached worker's value (INT64_MIN: cache is complete)
+  long long* theta;            // [T] (with theta_w) the best (value, lowest index) any NON-cached worker had at
+  uint32_t* theta_w;           //     scan time — an upper bound forever, prices only rise (INT64_MIN: cache complete)
   uint32_t* rescan;            // [T] asks whose cache could not decide this round
   uint32_t* n_rescan;
   const uint32_t* scan_list;   // asks pm_auction_bid scans (= rescan)
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
   long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
   uint32_t cw[4] = {kNone, kNone, kNone, kNone};
   long long dropped = kAucNeg;
+  uint32_t dropped_w = kNone;
 
   if (threadIdx.x == 0) mbar_init(&s.bar, 1);
   __syncthreads();
@@ -144,13 +147,13 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
           const long long v = -((long long)wr.price * p.scale) - s.price[i];
           const uint32_t w = w0 + i;                     // ascends per lane: strict '>' keeps ties in index order
           if (v > cv[3]) {
-            dropped = max(dropped, cv[3]);
+            if (cv[3] > dropped || (cv[3] == dropped && cw[3] < dropped_w)) { dropped = cv[3]; dropped_w = cw[3]; }
             cv[3] = v; cw[3] = w;
             if (cv[3] > cv[2]) { const long long tv = cv[2]; const uint32_t tw = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = tv; cw[3] = tw; }
             if (cv[2] > cv[1]) { const long long tv = cv[1]; const uint32_t tw = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = tv; cw[2] = tw; }
             if (cv[1] > cv[0]) { const long long tv = cv[0]; const uint32_t tw = cw[0]; cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = tv; cw[1] = tw; }
-          } else {
-            dropped = max(dropped, v);
+          } else if (v > dropped || (v == dropped && w < dropped_w)) {
+            dropped = v; dropped_w = w;
           }
         }
       }
@@ -174,12 +177,15 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
   long long next_v;
   uint32_t next_w;
   warp_argbest(cv[0], cw[0], &next_v, &next_w);       // the 33rd best candidate
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) dropped = max(dropped, __shfl_xor_sync(0xffffffffu, dropped, off));
-  const long long bound = max(next_v, dropped);
+  long long drop_v;
+  uint32_t drop_w;
+  warp_argbest(dropped, dropped_w, &drop_v, &drop_w); // the best worker no lane kept
+  const bool use_next = next_v > drop_v || (next_v == drop_v && next_w < drop_w);
+  const long long bound = use_next ? next_v : drop_v;
   p.cand[(size_t)t * kAucCache + lane] = mine;
   if (lane == 0) {
     p.theta[t] = (bound == kAucNeg) ? kThetaComplete : bound;
+    p.theta_w[t] = use_next ? next_w : drop_w;
     auction_place_bid(p, t, cap, b1, w1, b2);
   }
 }
@@ -206,8 +212,11 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionPara
     best = top2_merge(best, o);
   }
   if (lane == 0) {
-    // every worker outside the cache is worth at most theta (its value at scan time; prices only rise)
-    const bool decided = theta == kThetaComplete || (theta != kThetaInvalid && best.b2 > theta);
+    // every worker outside the cache ranks at or below (theta, theta_w) — its rank at scan time; prices only rise
+    const uint32_t theta_w = p.theta_w[t];
+    const bool decided = theta == kThetaComplete ||
+                         (theta != kThetaInvalid && best.b2 >= theta &&
+                          (best.b1 > theta || (best.b1 == theta && best.w1 < theta_w)));
     if (decided) auction_place_bid(p, t, p.price_cap[t], best.b1, best.w1, best.b2);
     else { p.bid_w[t] = kNone; p.rescan[atomicAdd(p.n_rescan, 1u)] = t; }
   }

@@ -117,7 +117,7 @@ struct pm_engine {
   // extension (auction) state
   DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
   DevBuf<long long> auc_price, auc_bid_p, auc_bid_max, auc_theta;
-  DevBuf<uint32_t> auc_cand, auc_rescan;
+  DevBuf<uint32_t> auc_cand, auc_rescan, auc_theta_w;
   bool have_caps = false;
   uint64_t auc_scale = 1, auc_eps_start = 1;
   uint32_t auc_eps_div = 4;
@@ -307,7 +307,7 @@ void pm_destroy(pm_engine* e) {
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
-  e->auc_theta.release(); e->auc_cand.release(); e->auc_rescan.release();
+  e->auc_theta.release(); e->auc_cand.release(); e->auc_rescan.release(); e->auc_theta_w.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
@@ -836,7 +836,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
   PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
-  PM_CUDA(e->auc_theta.ensure(T)); PM_CUDA(e->auc_cand.ensure((size_t)T * pm::kAucCache)); PM_CUDA(e->auc_rescan.ensure(T));
+  PM_CUDA(e->auc_theta.ensure(T)); PM_CUDA(e->auc_theta_w.ensure(T)); PM_CUDA(e->auc_cand.ensure((size_t)T * pm::kAucCache)); PM_CUDA(e->auc_rescan.ensure(T));
   PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(std::max(W, T)));
   PM_CUDA(e->group_ask.ensure((size_t)T + 1)); PM_CUDA(e->group_off.ensure((size_t)T + 2));
   PM_CUDA(e->ask_best.ensure(T)); PM_CUDA(e->ask_count.ensure(T)); PM_CUDA(e->first_ask.ensure(W));
@@ -852,7 +852,7 @@ static int match_auction_locked(pm_engine* e) {
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
   ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
-  ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.rescan = e->auc_rescan.p; ap.n_rescan = e->counters.p + 9;
+  ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p; ap.rescan = e->auc_rescan.p; ap.n_rescan = e->counters.p + 9;
   ap.scan_list = e->auc_rescan.p; ap.n_scan = 0;
   const size_t smem = sizeof(pm::AuctionStage);
   uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
