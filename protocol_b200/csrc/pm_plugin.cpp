@@ -131,7 +131,8 @@ struct pm_plugin {
   pm_plugin_policy policy{};
   pm_interner* interner = nullptr;
   std::string err;
-  std::mutex mu;
+  std::mutex mu;       // guards the tables below; heartbeat-side calls only ever wait for this one
+  std::mutex loop_mu;  // serialises management passes (the reference runs them in one tokio task)
 
   std::vector<Config> templates;  // sorted at seal (mod.rs:150-164)
   bool sealed = false;
@@ -642,89 +643,110 @@ int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_
 // try_form_new_groups (mod.rs:478-628): the evaluation and the allocation run on the GPU.
 int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   if (!p) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
   if (n_formed) *n_formed = 0;
-  if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
-  if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
-  const auto configs = p->available_configurations();
-
-  // node_store.get_nodes(): stable status-class sort (node_store.rs:195-206) = canonical order
-  const uint32_t W = (uint32_t)p->nodes.size();
-  std::vector<uint32_t> order(W);
-  for (uint32_t i = 0; i < W; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    return status_class(p->nodes[a].status) < status_class(p->nodes[b].status);
-  });
-  // address rank = BTreeSet<String> order (byte-lexicographic)
-  std::vector<uint32_t> by_addr(W), rank(W);
-  for (uint32_t i = 0; i < W; ++i) by_addr[i] = i;
-  std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return p->nodes[a].address < p->nodes[b].address; });
-  for (uint32_t i = 0; i < W; ++i) rank[by_addr[i]] = i;
-
-  std::vector<pm_worker_a> wa(W);
-  std::vector<pm_worker_b> wb(W);
-  std::vector<double> lat(W), lon(W);
-  std::vector<uint32_t> arank(W);
-  for (uint32_t i = 0; i < W; ++i) {
-    const NodeRec& n = p->nodes[order[i]];
-    wa[i] = n.a;
-    wb[i] = n.b;
-    uint32_t f = n.a.flags;
-    if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
-    if (n.has_p2p) f |= PM_W_P2P;                                        // :495
-    if (p->node_to_group.count(n.address)) f |= PM_W_ASSIGNED;           // :496
-    if (n.has_loc) f |= PM_W_HAS_LOC;
-    wa[i].flags = f;
-    lat[i] = n.lat;
-    lon[i] = n.lon;
-    arank[i] = rank[order[i]];
-  }
+  std::lock_guard<std::mutex> loop_lk(p->loop_mu);
+  // ---- phase 1 (tables locked): snapshot what the pass reads, like the reference's reads at loop start
+  uint32_t W = 0;
+  std::vector<pm_worker_a> wa;
+  std::vector<pm_worker_b> wb;
+  std::vector<double> lat, lon;
+  std::vector<uint32_t> arank;
+  std::vector<std::string> row_address, cfg_names;
   std::vector<pm_ask> asks;
   std::vector<pm_gpu_opt> opts;
-  for (const Config* c : configs) {
-    pm_ask a = c->ask;
-    a.opt_off = (uint32_t)opts.size();
-    a.min_group_size = c->min_group_size;
-    a.max_group_size = c->max_group_size;
-    opts.insert(opts.end(), c->opts.begin(), c->opts.end());
-    asks.push_back(a);
+  std::vector<uint32_t> bits_copy;
+  uint32_t npat = 0, nmod = 0, words = 1, mode = PM_MODE_FIRST_FIT;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
+    if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
+    const auto configs = p->available_configurations();
+    // node_store.get_nodes(): stable status-class sort (node_store.rs:195-206) = canonical order
+    W = (uint32_t)p->nodes.size();
+    std::vector<uint32_t> order(W);
+    for (uint32_t i = 0; i < W; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return status_class(p->nodes[a].status) < status_class(p->nodes[b].status);
+    });
+    // address rank = BTreeSet<String> order (byte-lexicographic)
+    std::vector<uint32_t> by_addr(W), rank(W);
+    for (uint32_t i = 0; i < W; ++i) by_addr[i] = i;
+    std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return p->nodes[a].address < p->nodes[b].address; });
+    for (uint32_t i = 0; i < W; ++i) rank[by_addr[i]] = i;
+    wa.resize(W); wb.resize(W); lat.resize(W); lon.resize(W); arank.resize(W); row_address.resize(W);
+    for (uint32_t i = 0; i < W; ++i) {
+      const NodeRec& n = p->nodes[order[i]];
+      wa[i] = n.a;
+      wb[i] = n.b;
+      uint32_t f = n.a.flags;
+      if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
+      if (n.has_p2p) f |= PM_W_P2P;                                        // :495
+      if (p->node_to_group.count(n.address)) f |= PM_W_ASSIGNED;           // :496
+      if (n.has_loc) f |= PM_W_HAS_LOC;
+      wa[i].flags = f;
+      lat[i] = n.lat;
+      lon[i] = n.lon;
+      arank[i] = rank[order[i]];
+      row_address[i] = n.address;
+    }
+    for (const Config* c : configs) {
+      pm_ask a = c->ask;
+      a.opt_off = (uint32_t)opts.size();
+      a.min_group_size = c->min_group_size;
+      a.max_group_size = c->max_group_size;
+      opts.insert(opts.end(), c->opts.begin(), c->opts.end());
+      asks.push_back(a);
+      cfg_names.push_back(c->name);
+    }
+    const uint32_t* bits = nullptr;
+    int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
+    if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
+    bits_copy.assign(bits, bits + (size_t)std::max<uint32_t>(npat, 1) * words);
+    mode = p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT;
   }
-  const uint32_t* bits = nullptr;
-  uint32_t npat = 0, nmod = 0, words = 1;
-  int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
-  if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
+  // ---- phase 2 (tables unlocked: heartbeats keep being served): the pass on the GPU
   auto chk = [&](int r, const char* what) {
     if (r != PM_OK) {
       const char* m = pm_last_error(p->engine);
+      std::lock_guard<std::mutex> lk(p->mu);
       p->err = std::string(what) + ": " + (m ? m : "");
     }
     return r;
   };
+  int rc;
   if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
-  if ((rc = chk(pm_set_model_table(p->engine, bits, npat, nmod, words), "pm_set_model_table"))) return rc;
+  if ((rc = chk(pm_set_model_table(p->engine, bits_copy.data(), npat, nmod, words), "pm_set_model_table"))) return rc;
   if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
   if ((rc = chk(pm_upsert_workers(p->engine, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
   if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
   if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
   if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;   // staging vectors are read asynchronously
-  const uint32_t mode = p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT;
   if ((rc = chk(pm_match(p->engine, mode), "pm_match"))) return rc;
   pm_result res{};
   if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
 
-  for (uint32_t g = 0; g < res.n_groups; ++g) {  // mod.rs:568-581
+  // ---- phase 3 (tables locked): publish the groups (create_group_atomically, mod.rs:299-322, 568-581)
+  std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t formed = 0;
+  for (uint32_t g = 0; g < res.n_groups; ++g) {
     Group grp;
+    grp.configuration_name = cfg_names[res.group_ask[g]];
+    grp.created_at_ms = (int64_t)std::time(nullptr) * 1000;
+    bool stale = false;   // a member was removed from the table while the pass ran
+    for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m) {
+      const std::string& addr = row_address[res.group_members[m]];
+      if (!p->node_index.count(addr) || p->node_to_group.count(addr)) stale = true;
+      grp.nodes.push_back(addr);
+    }
+    if (stale) continue;
     char idbuf[32];
     std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);  // format!("{:x}", ..)
     grp.id = idbuf;
-    grp.configuration_name = configs[res.group_ask[g]]->name;
-    grp.created_at_ms = (int64_t)std::time(nullptr) * 1000;
-    for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m)
-      grp.nodes.push_back(p->nodes[order[res.group_members[m]]].address);
     for (const auto& n : grp.nodes) p->node_to_group[n] = grp.id;
     p->groups.emplace(grp.id, std::move(grp));
+    ++formed;
   }
-  if (n_formed) *n_formed = res.n_groups;
+  if (n_formed) *n_formed = formed;
   return PM_OK;
 }
 
@@ -801,7 +823,8 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
 
 int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
   if (!p) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> loop_lk(p->loop_mu);
+  std::lock_guard<std::mutex> lk(p->mu);   // solo groups are few: the whole merge pass stays under the table lock
   if (n_merged) *n_merged = 0;
   if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: merging has no CPU path");
   auto solo_list = [&]() {
