@@ -40,6 +40,9 @@ WORKLOADS = {
     "cfg1": (1_000, 10_000, "uniform1", "1k asks x 10k workers, uniform single-GPU asks"),
     "cfg2": (100_000, 100_000, "mixed", "100k asks x 100k workers, mixed {1,2,4,8}-GPU asks"),
     "cfg3": (100_000, 1_000_000, "mixed", "100k asks x 1M workers, mixed asks (reference-mode columns)"),
+    # multi-GPU shapes of BASELINE configs[3]/[4] (workers sharded; run with --gpus 4 / --gpus 8)
+    "cfg4": (1_000_000, 250_000, "mixed", "1M asks x 250k workers per GPU (1M x 1M over 4 GPUs), mixed asks"),
+    "cfg5": (1_000_000, 1_000_000, "skewed", "1M asks x 1M workers per GPU (1M x 8M over 8 GPUs), 10% infeasible asks"),
 }
 
 

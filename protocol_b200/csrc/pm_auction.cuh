@@ -110,38 +110,59 @@ __device__ __forceinline__ uint32_t warp_argbest(long long v, uint32_t w, long l
 }
 
 // Full scan of every worker for the asks in scan_list: exact top-2 -> bid, and the ask's cache.
+// TPC asks per CTA share each staged worker stripe; an ask is scanned by 8/TPC warps whose
+// candidate lists are merged through shared memory (TPC = 8 for the big first round, TPC = 1 so a
+// handful of rescans is not one slow warp each).  Stripes are double-buffered: the bulk copies
+// of stripe k+1 are in flight while stripe k is evaluated.
+struct AuctionMerge {
+  long long v[kAucWarps][32];
+  uint32_t w[kAucWarps][32];
+  long long bound_v[kAucWarps];
+  uint32_t bound_w[kAucWarps];
+};
+
+template <int TPC>
 __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
+  constexpr int kWpt = kAucWarps / TPC;           // warps per ask
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  AuctionStage& s = *reinterpret_cast<AuctionStage*>(smem_raw);
+  AuctionStage* stage = reinterpret_cast<AuctionStage*>(smem_raw);            // [2]
+  AuctionMerge& mg = *reinterpret_cast<AuctionMerge*>(smem_raw + 2 * sizeof(AuctionStage));
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t slot = blockIdx.x * kAucWarps + warp;
+  const uint32_t slot = blockIdx.x * TPC + warp / kWpt;
+  const uint32_t sub = warp % kWpt;
   const bool live = slot < p.n_scan;
   const uint32_t t = live ? p.scan_list[slot] : 0u;
   const DevAsk ask = p.ev.asks[t];
   const uint32_t cap = p.price_cap[t];
-  // per lane: its 4 best (value, worker) in order, and the best value it did not keep
+  // per lane: its 4 best (value, worker) in order, and the best (value, worker) it did not keep
   long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
   uint32_t cw[4] = {kNone, kNone, kNone, kNone};
   long long dropped = kAucNeg;
   uint32_t dropped_w = kNone;
 
-  if (threadIdx.x == 0) mbar_init(&s.bar, 1);
+  if (threadIdx.x == 0) { mbar_init(&stage[0].bar, 1); mbar_init(&stage[1].bar, 1); }
   __syncthreads();
-  uint32_t phase = 0;
   const uint32_t W = p.ev.n_workers;
-  for (uint32_t w0 = 0; w0 < W; w0 += kAucStripe) {
+  const uint32_t n_stripes = (W + kAucStripe - 1) / kAucStripe;
+  auto issue = [&](uint32_t k) {
+    AuctionStage& s = stage[k & 1u];
+    const uint32_t w0 = k * kAucStripe;
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price[] is padded
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&s.bar, n * 32u + np * 8u);
-      bulk_g2s(s.a, p.ev.wa + w0, n * 16u, &s.bar);
-      bulk_g2s(s.b, p.ev.wb + w0, n * 16u, &s.bar);
-      bulk_g2s(s.price, p.price + w0, np * 8u, &s.bar);
-    }
-    mbar_wait(&s.bar, phase);
-    phase ^= 1u;
+    mbar_expect_tx(&s.bar, n * 32u + np * 8u);
+    bulk_g2s(s.a, p.ev.wa + w0, n * 16u, &s.bar);
+    bulk_g2s(s.b, p.ev.wb + w0, n * 16u, &s.bar);
+    bulk_g2s(s.price, p.price + w0, np * 8u, &s.bar);
+  };
+  if (threadIdx.x == 0 && n_stripes) issue(0);
+  for (uint32_t k = 0; k < n_stripes; ++k) {
+    if (threadIdx.x == 0 && k + 1 < n_stripes) issue(k + 1);   // buffer (k+1)&1 was released by the sync below
+    AuctionStage& s = stage[k & 1u];
+    mbar_wait(&s.bar, (k >> 1) & 1u);
+    const uint32_t w0 = k * kAucStripe;
+    const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     if (live) {
-      for (uint32_t i = lane; i < n; i += 32) {
+      for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
         if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
           const long long v = -((long long)wr.price * p.scale) - s.price[i];
@@ -158,11 +179,10 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
         }
       }
     }
-    __syncthreads();  // stripe fully consumed before the next bulk copy overwrites it
+    __syncthreads();  // stripe k fully consumed: its buffer may be refilled by issue(k + 2)
   }
-  if (!live) return;
   // 32 selection rounds over the warp's 128 candidates: lane r keeps the r-th best
-  long long b1 = kAucNeg, b2 = kAucNeg;
+  long long b1 = kAucNeg, b2 = kAucNeg, mine_v = kAucNeg;
   uint32_t w1 = kNone, mine = kNone;
 #pragma unroll 1
   for (int r = 0; r < kAucCache; ++r) {
@@ -171,21 +191,64 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
     const uint32_t win = warp_argbest(cv[0], cw[0], &bv, &bw);
     if (r == 0) { b1 = bv; w1 = bw; }
     if (r == 1) b2 = bv;
-    if ((int)lane == r) mine = (bv > kAucNeg) ? bw : kNone;
+    if ((int)lane == r) { mine = (bv > kAucNeg) ? bw : kNone; mine_v = bv; }
     if (lane == win) { cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = kAucNeg; cw[3] = kNone; }
   }
-  long long next_v;
-  uint32_t next_w;
-  warp_argbest(cv[0], cw[0], &next_v, &next_w);       // the 33rd best candidate
-  long long drop_v;
-  uint32_t drop_w;
+  long long next_v, drop_v;
+  uint32_t next_w, drop_w;
+  warp_argbest(cv[0], cw[0], &next_v, &next_w);       // the warp's 33rd best candidate
   warp_argbest(dropped, dropped_w, &drop_v, &drop_w); // the best worker no lane kept
   const bool use_next = next_v > drop_v || (next_v == drop_v && next_w < drop_w);
-  const long long bound = use_next ? next_v : drop_v;
+  long long bound_v = use_next ? next_v : drop_v;
+  uint32_t bound_w = use_next ? next_w : drop_w;
+
+  if (kWpt > 1) {
+    // merge the kWpt warps of the ask: warp `sub == 0` re-selects from kWpt sorted lists
+    mg.v[warp][lane] = mine_v;
+    mg.w[warp][lane] = mine;
+    if (lane == 0) { mg.bound_v[warp] = bound_v; mg.bound_w[warp] = bound_w; }
+    __syncthreads();
+    if (sub != 0) return;
+    long long lv[kWpt];
+    uint32_t lw[kWpt];
+#pragma unroll
+    for (int q = 0; q < kWpt; ++q) { lv[q] = mg.v[warp + q][lane]; lw[q] = mg.w[warp + q][lane]; }
+#pragma unroll
+    for (int i = 1; i < kWpt; ++i)      // sort the lane's kWpt entries by (value desc, worker asc)
+#pragma unroll
+      for (int j = i; j > 0; --j)
+        if (lv[j] > lv[j - 1] || (lv[j] == lv[j - 1] && lw[j] < lw[j - 1])) {
+          const long long tv = lv[j]; const uint32_t tw = lw[j];
+          lv[j] = lv[j - 1]; lw[j] = lw[j - 1]; lv[j - 1] = tv; lw[j - 1] = tw;
+        }
+    b1 = kAucNeg; b2 = kAucNeg; w1 = kNone; mine = kNone;
+#pragma unroll 1
+    for (int r = 0; r < kAucCache; ++r) {
+      long long bv;
+      uint32_t bw;
+      const uint32_t win = warp_argbest(lv[0], lw[0], &bv, &bw);
+      if (r == 0) { b1 = bv; w1 = bw; }
+      if (r == 1) b2 = bv;
+      if ((int)lane == r) mine = (bv > kAucNeg) ? bw : kNone;
+      if (lane == win) {
+#pragma unroll
+        for (int q = 0; q + 1 < kWpt; ++q) { lv[q] = lv[q + 1]; lw[q] = lw[q + 1]; }
+        lv[kWpt - 1] = kAucNeg; lw[kWpt - 1] = kNone;
+      }
+    }
+    warp_argbest(lv[0], lw[0], &bound_v, &bound_w);   // 33rd of the merged lists ...
+#pragma unroll
+    for (int q = 0; q < kWpt; ++q) {                  // ... against everything the warps left out
+      const long long qv = mg.bound_v[warp + q];
+      const uint32_t qw = mg.bound_w[warp + q];
+      if (qv > bound_v || (qv == bound_v && qw < bound_w)) { bound_v = qv; bound_w = qw; }
+    }
+  }
+  if (!live) return;
   p.cand[(size_t)t * kAucCache + lane] = mine;
   if (lane == 0) {
-    p.theta[t] = (bound == kAucNeg) ? kThetaComplete : bound;
-    p.theta_w[t] = use_next ? next_w : drop_w;
+    p.theta[t] = (bound_v == kAucNeg) ? kThetaComplete : bound_v;
+    p.theta_w[t] = bound_w;
     auction_place_bid(p, t, cap, b1, w1, b2);
   }
 }

@@ -854,7 +854,9 @@ static int match_auction_locked(pm_engine* e) {
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
   ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p; ap.rescan = e->auc_rescan.p; ap.n_rescan = e->counters.p + 9;
   ap.scan_list = e->auc_rescan.p; ap.n_scan = 0;
-  const size_t smem = sizeof(pm::AuctionStage);
+  const size_t smem = 2 * sizeof(pm::AuctionStage) + sizeof(pm::AuctionMerge);
+  PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_bid<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_bid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
   const uint32_t div = e->auc_eps_div < 2 ? 2 : e->auc_eps_div;
   for (;;) {  // eps phases: assignment cleared, prices kept
@@ -885,7 +887,8 @@ static int match_auction_locked(pm_engine* e) {
       const uint32_t n_scan = e->h_scalars.p[18];
       if (n_scan) {
         ap.n_scan = n_scan;
-        pm::pm_auction_bid<<<blocks_for(n_scan, pm::kAucWarps), pm::kAucThreads, smem, e->stream>>>(ap);
+        if (n_scan >= 8u * 296u) pm::pm_auction_bid<8><<<blocks_for(n_scan, 8), pm::kAucThreads, smem, e->stream>>>(ap);
+        else pm::pm_auction_bid<1><<<n_scan, pm::kAucThreads, smem, e->stream>>>(ap);
         PM_LAUNCH_CHECK("pm_auction_bid");
         e->stats.evals += (uint64_t)n_scan * W;
       }
