@@ -356,3 +356,45 @@ def test_extension_columns_are_neutral_in_reference_modes():
     for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_count"):
         assert np.array_equal(getattr(r0, f), getattr(r1, f)), f
     eng.close()
+
+
+def test_cfg3_100k_x_1m_properties():
+    """BASELINE configs[2] shape at full size (10^11 pairs: too many for an exhaustive CPU check) through
+    size-independent properties: materialised == fused bit for bit; every assignment is a compatible,
+    candidate pair (sampled against the oracle predicate); nobody is assigned twice; a worker's ask is the
+    FIRST compatible ask (sampled); the pass is idempotent once its groups are marked assigned."""
+    T, W = 100_000, 1_000_000
+    w, a, t = synth_tables(T, W, "mixed")
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match(abi.PM_MODE_FIRST_FIT | MAT)
+    r1 = eng.fetch()
+    assert r1.stats["evals"] == T * W and r1.stats["n_tiles"] > 50
+    eng.match(abi.PM_MODE_FIRST_FIT | FUSED)
+    r2 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_best", "ask_count"):
+        assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+    assigned = np.flatnonzero(r1.worker_ask != abi.PM_NONE)
+    assert len(np.unique(r1.group_members)) == len(r1.group_members) == len(assigned)
+    cand = (t["wa"]["flags"] & (abi.PM_W_HEALTHY | abi.PM_W_P2P | abi.PM_W_ASSIGNED)) == (abi.PM_W_HEALTHY | abi.PM_W_P2P)
+    assert cand[assigned].all()
+    rng = np.random.default_rng(0)
+    for wk in rng.choice(assigned, 300, replace=False):
+        tk = int(r1.worker_ask[wk])
+        assert orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][tk], t["opts"], t["bits"], t["words"])
+        for earlier in rng.integers(0, max(tk, 1), 5):            # no earlier ask accepts the worker
+            if earlier < tk:
+                assert not orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][int(earlier)], t["opts"], t["bits"], t["words"])
+    unassigned_cand = np.flatnonzero(cand & (r1.worker_ask == abi.PM_NONE))
+    for wk in rng.choice(unassigned_cand, 20, replace=False):     # left over => no ask at all accepts it
+        for tk in rng.integers(0, T, 50):
+            assert not orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][int(tk)], t["opts"], t["bits"], t["words"])
+    # per-ask counts add up: every candidate-compatible pair is counted once
+    band = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 500, 520, 0, W, threads=8)
+    assert np.array_equal(r1.ask_count[500:520], band["row_count"]) and np.array_equal(r1.ask_best[500:520], band["row_best"])
+    # idempotence: mark the formed groups' members assigned -> the next pass forms nothing
+    idx = assigned.astype(np.uint32)
+    eng.set_flags(idx, (t["wa"]["flags"][idx] | abi.PM_W_ASSIGNED).astype(np.uint32))
+    eng.match(abi.PM_MODE_FIRST_FIT | MAT)
+    assert eng.fetch().n_groups == 0
+    eng.close()
