@@ -219,7 +219,9 @@ enum pm_mode {
 };
 enum pm_path {
   PM_PATH_MATERIALIZED = 0,      /* build int64 cost tile in HBM, then argmin over it */
-  PM_PATH_FUSED        = 1u << 8 /* evaluate + reduce on chip, matrix never written   */
+  PM_PATH_FUSED        = 1u << 8,/* evaluate + reduce on chip, matrix never written   */
+  PM_NO_ASK_STATS      = 1u << 9 /* with PM_PATH_FUSED: skip ask_best / ask_count (the reference modes only
+                                    need the per-worker first feasible ask); they read INF / 0 then      */
 };
 
 typedef struct pm_stats {

@@ -512,13 +512,14 @@ static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, b
 #undef PM_BUILD_CASE
 }
 
-static void launch_fused(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, dim3 grid,
+static void launch_fused(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, bool stats, dim3 grid,
                          uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw) {
-#define PM_FUSED_CASE(B, F) pm::pm_fused_eval<B, F><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p)
+#define PM_FUSED_CASE(B, F, S) pm::pm_fused_eval<B, F, S><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->first_ask.p, e->ask_best.p, e->ask_count.p)
+  if (fast && !stats && bits_mode == 2) { PM_FUSED_CASE(2, true, false); return; }   // the lean common case
   if (fast) {
-    if (bits_mode == 2) PM_FUSED_CASE(2, true); else if (bits_mode == 1) PM_FUSED_CASE(1, true); else PM_FUSED_CASE(0, true);
+    if (bits_mode == 2) PM_FUSED_CASE(2, true, true); else if (bits_mode == 1) PM_FUSED_CASE(1, true, true); else PM_FUSED_CASE(0, true, true);
   } else {
-    if (bits_mode == 2) PM_FUSED_CASE(2, false); else if (bits_mode == 1) PM_FUSED_CASE(1, false); else PM_FUSED_CASE(0, false);
+    if (bits_mode == 2) PM_FUSED_CASE(2, false, true); else if (bits_mode == 1) PM_FUSED_CASE(1, false, true); else PM_FUSED_CASE(0, false, true);
   }
 #undef PM_FUSED_CASE
 }
@@ -599,7 +600,7 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
       for (uint32_t t0 = 0; t0 < T; t0 += rows_per_launch) {
         const uint32_t nt = std::min(rows_per_launch, T - t0);
         dim3 grid(blocks_for(nw, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
-        launch_fused(e, p, bits_mode, fast, grid, t0, nt, w0, nw);
+        launch_fused(e, p, bits_mode, fast, (mode & PM_NO_ASK_STATS) == 0, grid, t0, nt, w0, nw);
         PM_LAUNCH_CHECK("pm_fused_eval");
         ++e->stats.n_fused_launches;
       }

@@ -228,9 +228,9 @@ __device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalPara
 }
 
 // ------------------------------------------------------------------ build
-// grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 adjacent workers in
-// registers and walks the staged asks, emitting two 128-bit streaming stores per
-// row: a warp writes 1 KB contiguous, the CTA 8 KB contiguous per row.
+// grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 workers in registers and walks
+// the staged asks, emitting two 128-bit streaming stores per row: a warp writes 1 KB
+// contiguous (two fully coalesced 512-byte stores), the CTA 8 KB contiguous per row.
 template <int BITS, bool FAST, int MINB = 2>
 __global__ void __launch_bounds__(kEvalThreads, MINB)
 pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
@@ -238,14 +238,21 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
   __shared__ EvalStage s;
   const uint32_t r0 = blockIdx.y * kEvalRows;
   const uint32_t r1 = min(nt, r0 + (uint32_t)kEvalRows);
-  const uint32_t c = blockIdx.x * kEvalCols + threadIdx.x * kEvalWPT;  // column in tile
+  // A warp owns 128 consecutive columns; a lane owns the pairs (2l, 2l+1) and (64+2l, 64+2l+1), so each of
+  // its two 128-bit stores per row is part of a fully coalesced 512-byte warp store (4 whole lines).
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t cbase = blockIdx.x * kEvalCols + (threadIdx.x >> 5) * 128u + lane * 2u;
   WorkerReg w[kEvalWPT];
-  load_workers<kEvalWPT>(p, w0, nw, c, w);
-  const bool in_range = c < ld;   // ld is a multiple of 4: a thread's 4 columns are all in or all out
   uint32_t gw[kEvalWPT];
 #pragma unroll
-  for (int k = 0; k < kEvalWPT; ++k) gw[k] = w0 + c + k;
-  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + (in_range ? c : 0));
+  for (int k = 0; k < kEvalWPT; ++k) {
+    const uint32_t col = cbase + (k >> 1) * 64u + (k & 1);
+    gw[k] = w0 + col;
+    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+    else w[k] = null_worker();
+  }
+  const bool in0 = cbase < ld, in1 = cbase + 64u < ld;   // ld is a multiple of 16: a pair is all in or all out
+  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + (in0 ? cbase : 0));
   const size_t row_stride = ld / 2;   // in 16-byte units; rows are visited in increasing order
   for_each_staged_row(s, p, FAST, t0, r0, r1, [&](uint32_t, const DevAsk& a, uint32_t obegin, bool staged) {
     uint4 v0, v1;
@@ -266,10 +273,8 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
       v1.x = gw[2] | ~f[2]; v1.y = (w[2].price & f[2]) | (0x7FFFFFFFu & ~f[2]);
       v1.z = gw[3] | ~f[3]; v1.w = (w[3].price & f[3]) | (0x7FFFFFFFu & ~f[3]);
     }
-    if (in_range) {
-      __stcs(out, v0);
-      __stcs(out + 1, v1);
-    }
+    if (in0) __stcs(out, v0);
+    if (in1) __stcs(out + 32, v1);     // + 64 columns
     out += row_stride;
   });
 }
@@ -367,7 +372,9 @@ pm_argmin(const long long* __restrict__ cost, size_t ld, uint32_t nt, uint32_t t
 // leaves the SM: per-row results go through ballots (first-fit cost is the
 // worker index, so the row minimum is the lowest set bit), per-worker results
 // stay in registers.  Integer-issue-bound, not HBM-bound.
-template <int BITS, bool FAST>
+// STATS = false skips the per-ask (min, count) outputs — the reference modes only need the
+// per-worker first feasible ask — which removes the ballots from the inner loop.
+template <int BITS, bool FAST, bool STATS>
 __global__ void __launch_bounds__(kEvalThreads, 2)
 pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
               uint32_t* __restrict__ first_ask, long long* __restrict__ ask_best,
@@ -402,22 +409,26 @@ pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
       eval_row_global<kEvalWPT>(p, a, w, f);
     }
     const uint32_t t = t0 + r0 + r;
-    uint32_t cnt = 0, best = kNone;
 #pragma unroll
-    for (int k = 0; k < kEvalWPT; ++k) {
-      first[k] = min(first[k], t | ~f[k]);
-      const uint32_t b = __ballot_sync(0xffffffffu, f[k] != 0u);
-      cnt += (uint32_t)__popc(b);
-      if (b) best = min(best, ((uint32_t)__ffs(b) - 1u) * kEvalWPT + k);
-    }
-    if (cnt && lane == 0) {
-      atomicAdd(&s_cnt[r], cnt);
-      atomicMin(&s_best[r], warp_gw0 + best);
+    for (int k = 0; k < kEvalWPT; ++k) first[k] = min(first[k], t | ~f[k]);
+    if (STATS) {
+      uint32_t cnt = 0, best = kNone;
+#pragma unroll
+      for (int k = 0; k < kEvalWPT; ++k) {
+        const uint32_t b = __ballot_sync(0xffffffffu, f[k] != 0u);
+        cnt += (uint32_t)__popc(b);
+        if (b) best = min(best, ((uint32_t)__ffs(b) - 1u) * kEvalWPT + k);
+      }
+      if (cnt && lane == 0) {
+        atomicAdd(&s_cnt[r], cnt);
+        atomicMin(&s_best[r], warp_gw0 + best);
+      }
     }
   });
 #pragma unroll
   for (int k = 0; k < kEvalWPT; ++k)
     if (first[k] != kNone) atomicMin(first_ask + w0 + c + k, first[k]);
+  if (!STATS) return;
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < r1 - r0; i += kEvalThreads) {
     if (s_cnt[i]) {

@@ -398,3 +398,19 @@ def test_cfg3_100k_x_1m_properties():
     eng.match(abi.PM_MODE_FIRST_FIT | MAT)
     assert eng.fetch().n_groups == 0
     eng.close()
+
+
+def test_fused_lean_gives_the_same_groups():
+    """PM_NO_ASK_STATS: same assignment, per-ask statistics skipped."""
+    sizes = [(1, 1), (2, 2), (2, 4)]
+    w, a, t = synth_tables(500, 8000, "mixed", group_sizes=sizes)
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match(abi.PM_MODE_FIRST_FIT)
+    r1 = eng.fetch()
+    eng.match(abi.PM_MODE_FIRST_FIT | abi.PM_PATH_FUSED | abi.PM_NO_ASK_STATS)
+    r2 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members"):
+        assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+    assert (r2.ask_count == 0).all() and (r2.ask_best == abi.PM_COST_INF).all()
+    eng.close()
