@@ -353,3 +353,96 @@ def test_heartbeat_fast_path_is_constant_time(engine):
             assert sched.get_task_for_node(a)["name"] == "t1999"
     dt = time.perf_counter() - t0
     assert dt < 2.0, f"2000 heartbeats over 2000 tasks took {dt:.2f}s"
+
+
+# ------------------------------------------------------------------------------------------------
+# more scenarios of node_groups/tests.rs
+def test_group_formation_with_multiple_configs(engine):
+    """tests.rs:199-300: configs {2,2} and {1,1}; nodes 1+2 pair up, node 3 becomes a solo group."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config-s", 2, 2), NodeGroupConfiguration("test-config-xs", 1, 1)])
+    plugin.add_task(Task(allowed_topologies=["test-config-s", "test-config-xs"]))
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    plugin.try_form_new_groups()
+    plugin.add_node(OrchestratorNode(A3))
+    plugin.try_form_new_groups()
+    groups = plugin.get_all_groups()
+    assert len(groups) == 2
+    assert all(plugin.get_node_group(a) is not None for a in (A1, A2, A3))
+    assert plugin.get_node_group(A1)["configuration_name"] == "test-config-s"
+    assert plugin.get_node_group(A3)["configuration_name"] == "test-config-xs"
+
+
+def test_group_scheduling_without_tasks(engine):
+    """tests.rs:679-733: no task -> nothing is scheduled, before and after the group exists."""
+    plugin = make(engine, [NodeGroupConfiguration("test-config", 2, 5)])
+    sched = Scheduler(plugin)
+    plugin.enable_configuration("test-config")
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    assert sched.get_task_for_node(A1) is None
+    plugin.try_form_new_groups()
+    assert plugin.get_node_group(A1) is not None
+    assert sched.get_task_for_node(A1) is None
+
+
+def test_node_cannot_be_in_multiple_groups(engine):
+    """tests.rs:993-1212: repeated passes never put a node into a second group."""
+    plugin = make(engine, [NodeGroupConfiguration("pairs", 2, 2), NodeGroupConfiguration("solo", 1, 1)])
+    plugin.add_task(Task(allowed_topologies=["pairs", "solo"]))
+    addrs = [f"0x{i + 1}234567890123456789012345678901234567890" for i in range(5)]
+    for a in addrs:
+        plugin.add_node(OrchestratorNode(a))
+    assert plugin.try_form_new_groups() == 3                    # 2 + 2 + 1
+    before = {a: plugin.get_node_group(a)["id"] for a in addrs}
+    for _ in range(3):
+        assert plugin.try_form_new_groups() == 0                # everybody is already assigned (mod.rs:496)
+    assert {a: plugin.get_node_group(a)["id"] for a in addrs} == before
+    members = [n for g in plugin.get_all_groups() for n in g["nodes"]]
+    assert sorted(members) == sorted(addrs)
+
+
+def test_task_switching_policy(engine):
+    """tests.rs:2014-2168 through the merge pass: disabled -> no merge; prefer_larger_groups = false and
+    the solo group holds a task -> no merge; default policy -> merge."""
+    def setup(**kw):
+        plugin = make(engine, [NodeGroupConfiguration("test-config", 1, 3)], **kw)
+        plugin.add_task(Task(name="t", allowed_topologies=["test-config"]))
+        for a in (A1, A2):
+            plugin.add_node(OrchestratorNode(a))
+            assert plugin.try_form_new_groups() == 1
+        assert Scheduler(plugin).get_task_for_node(A1) is not None      # group of A1 now holds a task
+        return plugin
+
+    assert setup(task_switching_enabled=False).try_merge_solo_groups() == 0
+    assert setup(prefer_larger_groups=False).try_merge_solo_groups() == 0
+    assert setup().try_merge_solo_groups() == 1
+
+
+def test_task_assignment_during_merge(engine):
+    """tests.rs:2339-2470: the merged group gets a task that allows its configuration, never one that
+    is restricted to a different configuration."""
+    plugin = make(engine, [NodeGroupConfiguration("assign-config", 1, 2)])
+    good = Task(name="merge-task", created_at=1, allowed_topologies=["assign-config"])
+    bad = Task(name="incompatible-task", created_at=99, allowed_topologies=["different-config"])
+    plugin.add_task(good)
+    plugin.add_task(bad)
+    for a in (A1, A2):
+        plugin.add_node(OrchestratorNode(a))
+        assert plugin.try_form_new_groups() == 1
+    assert plugin.try_merge_solo_groups() == 1
+    g = plugin.get_node_group(A1)
+    assert g["nodes"] == [A1, A2] and g["task_id"] == good.id
+
+
+def test_edge_case_no_available_tasks(engine):
+    """tests.rs:2711-2782: merging works without any task; the merged group is idle."""
+    plugin = make(engine, [NodeGroupConfiguration("no-tasks-config", 1, 2)])
+    plugin.enable_configuration("no-tasks-config")
+    for a in (A1, A2):
+        plugin.add_node(OrchestratorNode(a))
+        assert plugin.try_form_new_groups() == 1
+    assert plugin.try_merge_solo_groups() == 1
+    g = plugin.get_node_group(A1)
+    assert g["nodes"] == [A1, A2] and g["task_id"] is None
+    assert Scheduler(plugin).get_task_for_node(A1) is None
