@@ -185,6 +185,7 @@ void* pm_alloc_pinned(size_t bytes);
 void  pm_free_pinned(void*);
 
 /* replaces the per-pass TaskStore/config reads (mod.rs:399-418)             */
+/* [opt_off, opt_off + n_opts) ranges may overlap or be shared between asks.  */
 int pm_set_asks(pm_engine*, const pm_ask* asks, uint32_t n_asks,
                 const pm_gpu_opt* opts, uint32_t n_opts);
 int pm_set_model_table(pm_engine*, const uint32_t* bits, uint32_t n_patterns,
@@ -228,7 +229,7 @@ typedef struct pm_stats {
   uint64_t evals;            /* predicate evaluations executed on the device        */
   uint64_t cost_bytes_written;
   uint64_t cost_bytes_read;
-  uint32_t n_tiles;
+  uint32_t n_tiles;          /* cost tiles; auction mode: class (re)scans           */
   uint32_t n_launches;       /* kernels of this library launched by the last match  */
   uint32_t n_bumped;         /* workers displaced by an under-filled tail group     */
   uint32_t n_rounds;         /* auction rounds (extension mode)                     */
@@ -237,9 +238,9 @@ typedef struct pm_stats {
   float ms_fused;
   float ms_resolve;
   float ms_total;
-  uint32_t n_build_launches;
+  uint32_t n_build_launches; /* auction mode: class pool refills                    */
   uint32_t n_argmin_launches;
-  uint32_t n_fused_launches;
+  uint32_t n_fused_launches; /* auction mode: per-ask fallback scans                */
   uint32_t reserved;
 } pm_stats;
 

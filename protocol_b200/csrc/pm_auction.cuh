@@ -2,7 +2,7 @@
 //
 // The reference orchestrator has no prices, caps, reputation or auction:
 // nothing here restates reference code, and parity for this mode is against the
-// builder's own sequential restatement (the auction checker of the test oracle) —
+// builder's own sequential restatement (the auction checker of the test suite) —
 // "self-oracle, parity unpinned by the reference".  The mode is inert unless
 // PM_MODE_AUCTION is requested; the reference modes never read ext_ask_price.
 //
@@ -12,18 +12,36 @@
 //   bid(t)        = price[w1] + (best - max(second, outside)) + eps    on the best worker w1
 //   a worker takes the highest bid (ties: lowest ask index), releasing its previous owner.
 //
-// Rounds are cheap because every ask keeps a cache of its 32 best feasible workers (at the
-// prices of its last full scan) and the value theta that bounds every worker outside the cache:
-// prices only rise, so while the cached best beats theta in (value, lowest index) order and the cached
-// second-best value is >= theta's, the cached top-2 IS the global top-2, ties included
-// (pm_auction_bid_cached: 32 gathers per ask); otherwise the ask rescans all
-// workers at the current prices in the same round (pm_auction_bid) — bids are bit-identical to a
-// full scan every round, which is what the sequential checker does.
+// What makes a round cheap (every bid stays bit-identical to a full scan of all workers by every
+// unassigned ask every round, which is what the sequential checker does):
 //
-// pm_auction_bid: one warp per unassigned ask; the CTA's 8 warps share stripes of the
-// worker table (planes A, B) and of the per-worker price vector, staged into shared
-// memory with 1-D TMA bulk copies; collisions are resolved by atomicMax on the bid and
-// atomicMin on the bidder (the claim), applied by the single winner of each worker.
+//  * ASK CLASSES.  value(t,w) does not depend on t; only feasibility does.  Asks with identical
+//    requirement rows form a class (found on the device: content hash, radix sort, adjacent
+//    compare — a hash collision can only split a class, never merge two).  A class keeps ONE cache
+//    of its 32 best compatible workers (cap ignored) and the bound (theta, theta_w): every
+//    compatible worker outside the cache ranked at or below it at scan time, and prices only
+//    rise, so it still does.
+//  * THE CAP IS THE OUTSIDE OPTION.  A worker with ask_price > cap[t] has value <= outside(t), so
+//    it can neither raise max(second, outside) nor beat a bid-worthy best: an ask's bid follows
+//    from the class cache as  w1 = best cached worker with ask_price <= cap,
+//    second = max(best cached value other than w1, outside)  whenever w1 beats (theta, theta_w)
+//    and theta <= max(that value, outside); it withdraws when nothing cached or bounded by theta
+//    can reach outside(t).  Anything else is "ambiguous": the class is rescanned once for all its
+//    asks (pm_auction_scan, class mode) and the ask bids again; an ask that is still ambiguous
+//    after a fresh class scan (a value tie exactly at outside) gets its own cap-filtered scan.
+//  * PRICE-SORTED WORKERS.  Scans walk a copy of the worker table sorted by (ask_price, index).
+//    value <= -(ask_price * S), so once every lane holds four candidates better than the stripe's
+//    last ask_price no later worker can enter the top 32 or the bound: the scan stops there
+//    (and, for a single ask, at its cap).
+//  * DEVICE-DRIVEN ROUNDS.  List lengths live in device memory; every kernel of a round is
+//    launched with a fixed grid and strides over its list, so the host launches rounds in batches
+//    and only polls the number of unassigned asks.
+//
+// pm_auction_scan: stripes of the sorted worker planes, their prices and original indices are
+// staged into shared memory with 1-D TMA bulk copies, double-buffered; 8 items share a stripe
+// (one warp each) when the list is long, otherwise the CTA's 8 warps split one item.
+// Collisions are resolved by atomicMax on the bid and atomicMin on the bidder (the claim),
+// applied by the single winner of each worker.
 #pragma once
 #include "pm_kernels.cuh"
 
@@ -31,70 +49,93 @@ namespace pm {
 
 constexpr int kAucThreads = 256;
 constexpr int kAucWarps = kAucThreads / 32;
-constexpr int kAucStripe = 1024;  // workers staged per step: 16 KB + 16 KB + 8 KB
+constexpr int kAucStripe = 1024;  // workers staged per step
+constexpr int kAucStages = 2;     // stripes in flight per CTA
 constexpr long long kAucNeg = (long long)(0x8000000000000000ull) / 4;
+constexpr int kAucCache = 32;
+constexpr int kAucPool = 1024;       // pool slots per class (4 per thread of the scanning CTA)
+constexpr int kAucPoolGood = 256;    // a class walk goes on until this many candidates beat every unseen worker ...
+constexpr int kAucPoolExtra = 8;     // ... or for this many stripes past the point where it could have stopped
+constexpr long long kThetaComplete = (long long)0x8000000000000000ull;   // the cache holds every compatible worker
+constexpr long long kThetaInvalid = 0x7FFFFFFFFFFFFFFFll;                // no cache yet
+
+// device-side control block of the round loop
+struct AuctionCtl {
+  uint32_t n_active;     // unassigned, not withdrawn asks of the current round
+  uint32_t n_next;       // ... being collected for the next one
+  uint32_t n_cls;        // classes to rescan this round
+  uint32_t n_retry;      // asks that bid again after the class rescans
+  uint32_t n_fallback;   // asks that need their own scan
+  uint32_t rounds;       // rounds in which at least one ask was active
+  unsigned long long evals;
+  unsigned long long n_class_scans, n_ask_scans, n_refills;
+};
 
 struct AuctionParams {
-  EvalParams ev;
+  EvalParams ev;               // original worker order (gathers); asks / options / model bits
+  const uint4* wa_s;           // worker planes sorted by (ask_price, index)
+  const uint4* wb_s;
+  const uint32_t* perm;        // [W] sorted position -> worker
+  const uint32_t* pos_of;      // [W] worker -> sorted position
+  long long* price_s;          // [W + 2] price mirror in sorted order
   const uint32_t* price_cap;   // [T]
   long long* price;            // [W] dual price of each worker
   uint32_t* owner;             // [W] ask currently holding the worker
   uint32_t* assigned;          // [T] worker held by the ask
   uint32_t* withdrawn;         // [T]
-  const uint32_t* active;      // [n_active] unassigned, not withdrawn asks
-  uint32_t n_active;
+  uint32_t* active;            // [T]
   uint32_t* bid_w;             // [T]
   long long* bid_p;            // [T]
   long long* bid_max;          // [W] highest bid of the round (reset by the winner)
   uint32_t* winner;            // [W]
-  uint32_t* cand;              // [T * 32] cached best feasible workers of each ask
-  long long* theta;            // [T] (with theta_w) the best (value, lowest index) any NON-cached worker had at
-  uint32_t* theta_w;           //     scan time — an upper bound forever, prices only rise (INT64_MIN: cache complete)
-  uint32_t* rescan;            // [T] asks whose cache could not decide this round
-  uint32_t* n_rescan;
-  const uint32_t* scan_list;   // asks pm_auction_bid scans (= rescan)
-  uint32_t n_scan;
+  const uint32_t* class_of;    // [T]
+  const uint32_t* class_rep;   // [C] lowest ask of the class
+  uint32_t* class_req;         // [C] round stamp of the last rescan request
+  uint32_t* cand;              // [C * 32] cached best compatible workers of each class
+  long long* theta;            // [C]
+  uint32_t* theta_w;           // [C]
+  uint32_t* pool;              // [C * kAucPool] candidates of the class's last walk
+  long long* pool_bound_v;     // [C] every compatible worker outside the pool ranks at or below this
+  uint32_t* pool_bound_w;      // [C]
+  uint32_t* class_list;        // [C]
+  uint32_t* retry;             // [T]
+  uint32_t* fallback;          // [T]
+  AuctionCtl* ctl;
   long long scale, eps;
+  uint32_t dbg;                // PM_TUNE_AUCTION: 1 = no early exit, 2 = every ask scans for itself
 };
-constexpr int kAucCache = 32;
-constexpr long long kThetaComplete = (long long)0x8000000000000000ull;
-constexpr long long kThetaInvalid = 0x7FFFFFFFFFFFFFFFll;
 
 struct __align__(128) AuctionStage {
   uint4 a[kAucStripe];
   uint4 b[kAucStripe];
   long long price[kAucStripe];
+  uint32_t perm[kAucStripe];
   uint64_t bar;
 };
 
-struct Top2 {
-  long long b1, b2;
-  uint32_t w1;
-};
-__device__ __forceinline__ Top2 top2_merge(const Top2& x, const Top2& y) {
-  Top2 r;
-  r.b1 = max(x.b1, y.b1);
-  r.w1 = (x.b1 > y.b1) ? x.w1 : (y.b1 > x.b1) ? y.w1 : min(x.w1, y.w1);
-  r.b2 = max(min(x.b1, y.b1), max(x.b2, y.b2));
-  return r;
+__device__ __forceinline__ bool auc_better(long long v1, uint32_t w1, long long v2, uint32_t w2) {
+  return v1 > v2 || (v1 == v2 && w1 < w2);
 }
 
+__device__ __forceinline__ void auction_withdraw(const AuctionParams& p, uint32_t t) {
+  p.withdrawn[t] = 1u;       // prices only rise: it can never come back
+  p.bid_w[t] = kNone;
+}
+__device__ __forceinline__ void auction_commit(const AuctionParams& p, uint32_t t, uint32_t w1, long long b1, long long second) {
+  const long long bid = p.price[w1] + (b1 - second) + p.eps;
+  p.bid_w[t] = w1;
+  p.bid_p[t] = bid;
+  atomicMax(p.bid_max + w1, bid);
+}
+// exact top-2 over the ask's feasible workers -> bid or withdrawal
 __device__ __forceinline__ void auction_place_bid(const AuctionParams& p, uint32_t t, uint32_t cap,
                                                   long long b1, uint32_t w1, long long b2) {
   const long long outside = -(((long long)cap + 1) * p.scale);
-  if (w1 == kNone || b1 < outside) {
-    p.withdrawn[t] = 1u;       // prices only rise: it can never come back
-    p.bid_w[t] = kNone;
-  } else {
-    const long long second = max(b2, outside);
-    const long long bid = p.price[w1] + (b1 - second) + p.eps;
-    p.bid_w[t] = w1;
-    p.bid_p[t] = bid;
-    atomicMax(p.bid_max + w1, bid);
-  }
+  if (w1 == kNone || b1 < outside) auction_withdraw(p, t);
+  else auction_commit(p, t, w1, b1, max(b2, outside));
 }
 
-// (value desc, worker asc) arg-max across the warp; returns the winning lane
+// (value desc, worker asc) arg-max across the warp; returns the winning lane (the same on every lane)
 __device__ __forceinline__ uint32_t warp_argbest(long long v, uint32_t w, long long* bv, uint32_t* bw) {
   uint32_t lane_id = threadIdx.x & 31u;
 #pragma unroll
@@ -102,216 +143,484 @@ __device__ __forceinline__ uint32_t warp_argbest(long long v, uint32_t w, long l
     const long long ov = __shfl_xor_sync(0xffffffffu, v, off);
     const uint32_t ow = __shfl_xor_sync(0xffffffffu, w, off);
     const uint32_t ol = __shfl_xor_sync(0xffffffffu, lane_id, off);
-    if (ov > v || (ov == v && ow < w)) { v = ov; w = ow; lane_id = ol; }
+    if (ov > v || (ov == v && (ow < w || (ow == w && ol < lane_id)))) { v = ov; w = ow; lane_id = ol; }
   }
   *bv = v;
   *bw = w;
   return lane_id;
 }
+__device__ __forceinline__ long long warp_max_i64(long long v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
 
-// Full scan of every worker for the asks in scan_list: exact top-2 -> bid, and the ask's cache.
-// TPC asks per CTA share each staged worker stripe; an ask is scanned by 8/TPC warps whose
-// candidate lists are merged through shared memory (TPC = 8 for the big first round, TPC = 1 so a
-// handful of rescans is not one slow warp each).  Stripes are double-buffered: the bulk copies
-// of stripe k+1 are in flight while stripe k is evaluated.
 struct AuctionMerge {
   long long v[kAucWarps][32];
   uint32_t w[kAucWarps][32];
   long long bound_v[kAucWarps];
   uint32_t bound_w[kAucWarps];
+  long long drop_v[kAucWarps];
+  uint32_t drop_w[kAucWarps];
+  uint32_t cnt[3];
+  uint32_t flag;
 };
 
-template <int TPC>
-__global__ void __launch_bounds__(kAucThreads) pm_auction_bid(AuctionParams p) {
-  constexpr int kWpt = kAucWarps / TPC;           // warps per ask
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  AuctionStage* stage = reinterpret_cast<AuctionStage*>(smem_raw);            // [2]
-  AuctionMerge& mg = *reinterpret_cast<AuctionMerge*>(smem_raw + 2 * sizeof(AuctionStage));
+struct AuctionPick {
+  uint32_t mine;            // lane r: the r-th best worker (kNone past the end)
+  long long b1, b2;         // best and second-best value
+  uint32_t w1;
+  long long bound_v;        // best (value, worker) among the candidates that are not in the top 32
+  uint32_t bound_w;
+  long long drop_v;         // best (value, worker) no lane kept at all
+  uint32_t drop_w;
+};
+
+__device__ __forceinline__ void auc_insert(long long (&cv)[4], uint32_t (&cw)[4], long long& dropped, uint32_t& dropped_w,
+                                           long long v, uint32_t w) {
+  if (auc_better(v, w, cv[3], cw[3])) {
+    if (auc_better(cv[3], cw[3], dropped, dropped_w)) { dropped = cv[3]; dropped_w = cw[3]; }
+    cv[3] = v; cw[3] = w;
+#pragma unroll
+    for (int j = 3; j > 0; --j)
+      if (auc_better(cv[j], cw[j], cv[j - 1], cw[j - 1])) {
+        const long long tv = cv[j - 1]; const uint32_t tw = cw[j - 1];
+        cv[j - 1] = cv[j]; cw[j - 1] = cw[j]; cv[j] = tv; cw[j] = tw;
+      }
+  } else if (auc_better(v, w, dropped, dropped_w)) {
+    dropped = v; dropped_w = w;
+  }
+}
+
+// Top 32 of an item's candidates (4 sorted per lane, kWpt warps per item) in (value desc, worker asc)
+// order, plus the bounds.  Consumes cv/cw.  With kWpt > 1 the result is valid in the item's warp 0 only and
+// every thread of the CTA must call (two barriers).
+template <int kWpt>
+__device__ __forceinline__ AuctionPick auction_select(long long (&cv)[4], uint32_t (&cw)[4], long long dropped, uint32_t dropped_w,
+                                                      AuctionMerge& mg) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t slot = blockIdx.x * TPC + warp / kWpt;
   const uint32_t sub = warp % kWpt;
-  const bool live = slot < p.n_scan;
-  const uint32_t t = live ? p.scan_list[slot] : 0u;
+  AuctionPick r;
+  r.b1 = kAucNeg; r.b2 = kAucNeg; r.w1 = kNone; r.mine = kNone;
+  long long mine_v = kAucNeg;
+  // 32 selection rounds over the warp's 128 candidates: lane i keeps the i-th best
+#pragma unroll 1
+  for (int i = 0; i < kAucCache; ++i) {
+    long long bv;
+    uint32_t bw;
+    const uint32_t win = warp_argbest(cv[0], cw[0], &bv, &bw);
+    if (i == 0) { r.b1 = bv; r.w1 = bw; }
+    if (i == 1) r.b2 = bv;
+    if ((int)lane == i) { r.mine = (bv > kAucNeg) ? bw : kNone; mine_v = bv; }
+    if (lane == win) { cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = kAucNeg; cw[3] = kNone; }
+  }
+  long long next_v;
+  uint32_t next_w;
+  warp_argbest(cv[0], cw[0], &next_v, &next_w);           // the warp's 33rd best candidate
+  warp_argbest(dropped, dropped_w, &r.drop_v, &r.drop_w); // the best worker no lane kept
+  const bool use_next = auc_better(next_v, next_w, r.drop_v, r.drop_w);
+  r.bound_v = use_next ? next_v : r.drop_v;
+  r.bound_w = use_next ? next_w : r.drop_w;
+  if (kWpt > 1) {
+    // merge the kWpt warps of the item: warp `sub == 0` re-selects from kWpt sorted lists
+    mg.v[warp][lane] = mine_v;
+    mg.w[warp][lane] = r.mine;
+    if (lane == 0) { mg.bound_v[warp] = r.bound_v; mg.bound_w[warp] = r.bound_w; mg.drop_v[warp] = r.drop_v; mg.drop_w[warp] = r.drop_w; }
+    __syncthreads();
+    if (sub == 0) {
+      long long lv[kWpt];
+      uint32_t lw[kWpt];
+#pragma unroll
+      for (int q = 0; q < kWpt; ++q) { lv[q] = mg.v[warp + q][lane]; lw[q] = mg.w[warp + q][lane]; }
+#pragma unroll
+      for (int i = 1; i < kWpt; ++i)      // sort the lane's kWpt entries by (value desc, worker asc)
+#pragma unroll
+        for (int j = i; j > 0; --j)
+          if (auc_better(lv[j], lw[j], lv[j - 1], lw[j - 1])) {
+            const long long tv = lv[j]; const uint32_t tw = lw[j];
+            lv[j] = lv[j - 1]; lw[j] = lw[j - 1]; lv[j - 1] = tv; lw[j - 1] = tw;
+          }
+      r.b1 = kAucNeg; r.b2 = kAucNeg; r.w1 = kNone; r.mine = kNone;
+#pragma unroll 1
+      for (int i = 0; i < kAucCache; ++i) {
+        long long bv;
+        uint32_t bw;
+        const uint32_t win = warp_argbest(lv[0], lw[0], &bv, &bw);
+        if (i == 0) { r.b1 = bv; r.w1 = bw; }
+        if (i == 1) r.b2 = bv;
+        if ((int)lane == i) r.mine = (bv > kAucNeg) ? bw : kNone;
+        if (lane == win) {
+#pragma unroll
+          for (int q = 0; q + 1 < kWpt; ++q) { lv[q] = lv[q + 1]; lw[q] = lw[q + 1]; }
+          lv[kWpt - 1] = kAucNeg; lw[kWpt - 1] = kNone;
+        }
+      }
+      warp_argbest(lv[0], lw[0], &r.bound_v, &r.bound_w);   // 33rd of the merged lists ...
+#pragma unroll
+      for (int q = 0; q < kWpt; ++q) {                      // ... against everything the warps left out
+        const long long qv = mg.bound_v[warp + q];
+        const uint32_t qw = mg.bound_w[warp + q];
+        if (auc_better(qv, qw, r.bound_v, r.bound_w)) { r.bound_v = qv; r.bound_w = qw; }
+        if (q > 0 && auc_better(mg.drop_v[warp + q], mg.drop_w[warp + q], r.drop_v, r.drop_w)) { r.drop_v = mg.drop_v[warp + q]; r.drop_w = mg.drop_w[warp + q]; }
+      }
+    }
+    __syncthreads();   // mg may be rewritten by the next select
+  }
+  return r;
+}
+
+// One scan item (a class, or a single ask in fallback mode) per 8/TPC warps.
+//
+// Class mode keeps, next to the 32-entry cache the asks bid from, a POOL: every candidate the lanes
+// held at the end of the class's last full scan (up to 1024 workers) and a bound on everything else.
+// A rescan request first re-ranks the pool at the current prices (a few gathers per thread); only when
+// the pool's best two no longer beat its bound does the class walk the price-sorted worker table again.
+template <int TPC>
+__device__ __forceinline__ void auction_scan_items(const AuctionParams& p, AuctionStage* stage, AuctionMerge& mg,
+                                                   uint32_t& phase_bits, uint32_t base, const uint32_t* __restrict__ list,
+                                                   uint32_t n_list, bool cls_mode) {
+  constexpr int kWpt = kAucWarps / TPC;           // warps per item
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t slot = base + warp / kWpt;
+  const uint32_t sub = warp % kWpt;
+  const uint32_t in_item = sub * 32u + lane;      // this thread's pool slot (4 workers)
+  const bool live = slot < n_list;
+  const uint32_t item = live ? list[slot] : 0u;
+  const uint32_t t = live ? (cls_mode ? p.class_rep[item] : item) : 0u;
   const DevAsk ask = p.ev.asks[t];
-  const uint32_t cap = p.price_cap[t];
+  const uint32_t cap = cls_mode ? 0xFFFFFFFFu : p.price_cap[t];
   // per lane: its 4 best (value, worker) in order, and the best (value, worker) it did not keep
   long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
   uint32_t cw[4] = {kNone, kNone, kNone, kNone};
   long long dropped = kAucNeg;
   uint32_t dropped_w = kNone;
-
-  if (threadIdx.x == 0) { mbar_init(&stage[0].bar, 1); mbar_init(&stage[1].bar, 1); }
+  if (threadIdx.x == 0) { mg.cnt[0] = 0; mg.cnt[1] = 0; mg.cnt[2] = 0; mg.flag = 0; }
   __syncthreads();
+
+  bool scan = live;       // this warp's item still needs the walk over the worker table
+  if (cls_mode) {
+    const long long pool_bound = live ? p.pool_bound_v[item] : kThetaInvalid;
+    const bool have_pool = live && pool_bound != kThetaInvalid && !(p.dbg & 8u);
+    if (have_pool) {
+      // the item's threads cover the pool's kAucPool / 4 slots (a single warp takes 8 slots per lane)
+      const uint4* pool = reinterpret_cast<const uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
+      for (uint32_t q = in_item; q < (uint32_t)(kAucPool / 4); q += kWpt * 32u) {
+        const uint4 e = pool[q];
+        const uint32_t pw[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
+      }
+      if (in_item == 0) {   // everything outside the pool
+        const uint32_t pbw = p.pool_bound_w[item];
+        if (auc_better(pool_bound, pbw, dropped, dropped_w)) { dropped = pool_bound; dropped_w = pbw; }
+      }
+    }
+    const AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+    bool refilled = false;
+    if (sub == 0) {
+      refilled = have_pool && !(p.dbg & 16u) && (r.bound_v == kAucNeg || (r.b2 >= r.bound_v && auc_better(r.b1, r.w1, r.bound_v, r.bound_w)));
+      if (refilled) {
+        p.cand[(size_t)item * kAucCache + lane] = r.mine;
+        if (lane == 0) {
+          p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
+          p.theta_w[item] = r.bound_w;
+          atomicAdd(&p.ctl->n_refills, 1ull);
+        }
+      }
+    }
+    if (kWpt > 1) {   // the item's other warps follow warp 0's verdict
+      if (sub == 0 && lane == 0) mg.flag = refilled ? 1u : 0u;
+      __syncthreads();
+      refilled = mg.flag != 0u;
+    }
+    scan = live && !refilled;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cv[j] = kAucNeg; cw[j] = kNone; }
+    dropped = kAucNeg; dropped_w = kNone;
+    if (!__syncthreads_or(scan)) return;   // (also: mg.flag may be rewritten)
+  }
+
   const uint32_t W = p.ev.n_workers;
   const uint32_t n_stripes = (W + kAucStripe - 1) / kAucStripe;
   auto issue = [&](uint32_t k) {
-    AuctionStage& s = stage[k & 1u];
+    AuctionStage& s = stage[k % kAucStages];
     const uint32_t w0 = k * kAucStripe;
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
-    const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price[] is padded
-    mbar_expect_tx(&s.bar, n * 32u + np * 8u);
-    bulk_g2s(s.a, p.ev.wa + w0, n * 16u, &s.bar);
-    bulk_g2s(s.b, p.ev.wb + w0, n * 16u, &s.bar);
-    bulk_g2s(s.price, p.price + w0, np * 8u, &s.bar);
+    const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price_s[] and perm[] are padded
+    const uint32_t nq = (n + 3u) & ~3u;
+    mbar_expect_tx(&s.bar, n * 32u + np * 8u + nq * 4u);
+    bulk_g2s(s.a, p.wa_s + w0, n * 16u, &s.bar);
+    bulk_g2s(s.b, p.wb_s + w0, n * 16u, &s.bar);
+    bulk_g2s(s.price, p.price_s + w0, np * 8u, &s.bar);
+    bulk_g2s(s.perm, p.perm + w0, nq * 4u, &s.bar);
   };
-  if (threadIdx.x == 0 && n_stripes) issue(0);
+  auto wait_stage = [&](uint32_t k) {
+    const uint32_t b = k % kAucStages;   // bit b of phase_bits = parity of the buffer's next completed phase
+    mbar_wait(&stage[b].bar, (phase_bits >> b) & 1u);
+    phase_bits ^= 1u << b;
+  };
+  uint32_t scanned = 0;
+  uint32_t first_good = kNone;   // first stripe after which 33 candidates beat every unseen worker
+  bool unseen = false;           // the walk stopped before the end of the table ...
+  long long unseen_u = kAucNeg;  // ... where every remaining worker has value <= unseen_u
+  if (threadIdx.x == 0)
+    for (uint32_t k = 0; k < (uint32_t)(kAucStages - 1) && k < n_stripes; ++k) issue(k);
   for (uint32_t k = 0; k < n_stripes; ++k) {
-    if (threadIdx.x == 0 && k + 1 < n_stripes) issue(k + 1);   // buffer (k+1)&1 was released by the sync below
-    AuctionStage& s = stage[k & 1u];
-    mbar_wait(&s.bar, (k >> 1) & 1u);
-    const uint32_t w0 = k * kAucStripe;
-    const uint32_t n = min((uint32_t)kAucStripe, W - w0);
-    if (live) {
+    // stripe k + kAucStages - 1 goes into the buffer stripe k - 1 used: released by the barrier that ended it
+    if (threadIdx.x == 0 && k + kAucStages - 1 < n_stripes) issue(k + kAucStages - 1);
+    AuctionStage& s = stage[k % kAucStages];
+    wait_stage(k);
+    const uint32_t n = min((uint32_t)kAucStripe, W - k * kAucStripe);
+    if (scan) {
+      scanned += n;
       for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
-        if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
-          const long long v = -((long long)wr.price * p.scale) - s.price[i];
-          const uint32_t w = w0 + i;                     // ascends per lane: strict '>' keeps ties in index order
-          if (v > cv[3]) {
-            if (cv[3] > dropped || (cv[3] == dropped && cw[3] < dropped_w)) { dropped = cv[3]; dropped_w = cw[3]; }
-            cv[3] = v; cw[3] = w;
-            if (cv[3] > cv[2]) { const long long tv = cv[2]; const uint32_t tw = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = tv; cw[3] = tw; }
-            if (cv[2] > cv[1]) { const long long tv = cv[1]; const uint32_t tw = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = tv; cw[2] = tw; }
-            if (cv[1] > cv[0]) { const long long tv = cv[0]; const uint32_t tw = cw[0]; cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = tv; cw[1] = tw; }
-          } else if (v > dropped || (v == dropped && w < dropped_w)) {
-            dropped = v; dropped_w = w;
-          }
-        }
+        if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words))
+          auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
       }
     }
-    __syncthreads();  // stripe k fully consumed: its buffer may be refilled by issue(k + 2)
+    // Every later worker has ask_price >= the stripe's last one, hence value <= U = -(last * S).  Once 33 of the
+    // item's kept candidates beat U strictly, at least one of them stays outside the 32-entry cache, so the bound
+    // (best candidate not cached) beats every unseen worker and the walk may stop; a class walks a little further
+    // to fill its pool, a single ask also stops at its cap.
+    const uint32_t last_price = s.b[n - 1].w;
+    const long long u = -((long long)last_price * p.scale);
+    uint32_t cnt = __popc(__ballot_sync(0xffffffffu, cv[0] > u)) + __popc(__ballot_sync(0xffffffffu, cv[1] > u)) +
+                   __popc(__ballot_sync(0xffffffffu, cv[2] > u)) + __popc(__ballot_sync(0xffffffffu, cv[3] > u));
+    if (kWpt > 1) {
+      if (lane == 0) atomicAdd(&mg.cnt[k % 3u], cnt);
+      if (threadIdx.x == 0) mg.cnt[(k + 1u) % 3u] = 0;
+      __syncthreads();
+      cnt = mg.cnt[k % 3u];
+    }
+    if (cnt > (uint32_t)kAucCache && first_good == kNone) first_good = k;
+    bool done = !scan || last_price > cap ||
+                (first_good != kNone && (!cls_mode || cnt > (uint32_t)kAucPoolGood || k - first_good >= (uint32_t)kAucPoolExtra));
+    if (p.dbg & 1u) done = false;
+    if (kWpt == 1) done = __syncthreads_and(done) != 0;
+    // (the barrier above also means: stripe k fully consumed, its buffer may be refilled)
+    if (done) {
+      if (k + 1 < n_stripes) { unseen = true; unseen_u = u; }
+      // the copies already in flight must land before the buffers are reused
+      for (uint32_t j = k + 1; j < k + kAucStages && j < n_stripes; ++j) wait_stage(j);
+      break;
+    }
   }
-  // 32 selection rounds over the warp's 128 candidates: lane r keeps the r-th best
-  long long b1 = kAucNeg, b2 = kAucNeg, mine_v = kAucNeg;
-  uint32_t w1 = kNone, mine = kNone;
-#pragma unroll 1
-  for (int r = 0; r < kAucCache; ++r) {
-    long long bv;
-    uint32_t bw;
-    const uint32_t win = warp_argbest(cv[0], cw[0], &bv, &bw);
-    if (r == 0) { b1 = bv; w1 = bw; }
-    if (r == 1) b2 = bv;
-    if ((int)lane == r) { mine = (bv > kAucNeg) ? bw : kNone; mine_v = bv; }
-    if (lane == win) { cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = kAucNeg; cw[3] = kNone; }
+  if (cls_mode && scan) {   // the new pool: what the lanes hold now
+    uint4* pool = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
+    pool[in_item] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    if (kWpt == 1)
+      for (uint32_t j = 32u + lane; j < (uint32_t)(kAucPool / 4); j += 32u) pool[j] = make_uint4(kNone, kNone, kNone, kNone);
   }
-  long long next_v, drop_v;
-  uint32_t next_w, drop_w;
-  warp_argbest(cv[0], cw[0], &next_v, &next_w);       // the warp's 33rd best candidate
-  warp_argbest(dropped, dropped_w, &drop_v, &drop_w); // the best worker no lane kept
-  const bool use_next = next_v > drop_v || (next_v == drop_v && next_w < drop_w);
-  long long bound_v = use_next ? next_v : drop_v;
-  uint32_t bound_w = use_next ? next_w : drop_w;
+  const AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+  if (scan && sub == 0) {
+    if (lane == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
+    if (cls_mode) {
+      p.cand[(size_t)item * kAucCache + lane] = r.mine;
+      if (lane == 0) {
+        p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
+        p.theta_w[item] = r.bound_w;
+        // outside the pool: what no lane kept, and the part of the table the walk did not reach
+        long long pb_v = r.drop_v;
+        uint32_t pb_w = r.drop_w;
+        if (unseen && auc_better(unseen_u, 0u, pb_v, pb_w)) { pb_v = unseen_u; pb_w = 0u; }
+        p.pool_bound_v[item] = (pb_v == kAucNeg) ? kThetaComplete : pb_v;
+        p.pool_bound_w[item] = pb_w;
+        atomicAdd(&p.ctl->n_class_scans, 1ull);
+      }
+    } else if (lane == 0) {
+      auction_place_bid(p, t, cap, r.b1, r.w1, r.b2);
+      atomicAdd(&p.ctl->n_ask_scans, 1ull);
+    }
+  }
+  __syncthreads();   // mg and the stage buffers are reused by the CTA's next item
+}
 
-  if (kWpt > 1) {
-    // merge the kWpt warps of the ask: warp `sub == 0` re-selects from kWpt sorted lists
-    mg.v[warp][lane] = mine_v;
-    mg.w[warp][lane] = mine;
-    if (lane == 0) { mg.bound_v[warp] = bound_v; mg.bound_w[warp] = bound_w; }
-    __syncthreads();
-    if (sub != 0) return;
-    long long lv[kWpt];
-    uint32_t lw[kWpt];
-#pragma unroll
-    for (int q = 0; q < kWpt; ++q) { lv[q] = mg.v[warp + q][lane]; lw[q] = mg.w[warp + q][lane]; }
-#pragma unroll
-    for (int i = 1; i < kWpt; ++i)      // sort the lane's kWpt entries by (value desc, worker asc)
-#pragma unroll
-      for (int j = i; j > 0; --j)
-        if (lv[j] > lv[j - 1] || (lv[j] == lv[j - 1] && lw[j] < lw[j - 1])) {
-          const long long tv = lv[j]; const uint32_t tw = lw[j];
-          lv[j] = lv[j - 1]; lw[j] = lw[j - 1]; lv[j - 1] = tv; lw[j - 1] = tw;
-        }
-    b1 = kAucNeg; b2 = kAucNeg; w1 = kNone; mine = kNone;
-#pragma unroll 1
-    for (int r = 0; r < kAucCache; ++r) {
-      long long bv;
-      uint32_t bw;
-      const uint32_t win = warp_argbest(lv[0], lw[0], &bv, &bw);
-      if (r == 0) { b1 = bv; w1 = bw; }
-      if (r == 1) b2 = bv;
-      if ((int)lane == r) mine = (bv > kAucNeg) ? bw : kNone;
-      if (lane == win) {
-#pragma unroll
-        for (int q = 0; q + 1 < kWpt; ++q) { lv[q] = lv[q + 1]; lw[q] = lw[q + 1]; }
-        lv[kWpt - 1] = kAucNeg; lw[kWpt - 1] = kNone;
-      }
-    }
-    warp_argbest(lv[0], lw[0], &bound_v, &bound_w);   // 33rd of the merged lists ...
-#pragma unroll
-    for (int q = 0; q < kWpt; ++q) {                  // ... against everything the warps left out
-      const long long qv = mg.bound_v[warp + q];
-      const uint32_t qw = mg.bound_w[warp + q];
-      if (qv > bound_v || (qv == bound_v && qw < bound_w)) { bound_v = qv; bound_w = qw; }
-    }
-  }
-  if (!live) return;
-  p.cand[(size_t)t * kAucCache + lane] = mine;
-  if (lane == 0) {
-    p.theta[t] = (bound_v == kAucNeg) ? kThetaComplete : bound_v;
-    p.theta_w[t] = bound_w;
-    auction_place_bid(p, t, cap, b1, w1, b2);
+__global__ void __launch_bounds__(kAucThreads) pm_auction_scan(AuctionParams p, int cls_mode) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AuctionStage* stage = reinterpret_cast<AuctionStage*>(smem_raw);            // [kAucStages]
+  AuctionMerge& mg = *reinterpret_cast<AuctionMerge*>(smem_raw + kAucStages * sizeof(AuctionStage));
+  const uint32_t n = cls_mode ? p.ctl->n_cls : p.ctl->n_fallback;
+  const uint32_t* list = cls_mode ? p.class_list : p.fallback;
+  if (blockIdx.x >= n) return;
+  if (threadIdx.x == 0)
+    for (int b = 0; b < kAucStages; ++b) mbar_init(&stage[b].bar, 1);
+  __syncthreads();
+  uint32_t phase_bits = 0u;
+  if (n >= 8u * gridDim.x) {
+    for (uint32_t base = blockIdx.x * 8u; base < n; base += gridDim.x * 8u)
+      auction_scan_items<8>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0);
+  } else {
+    for (uint32_t base = blockIdx.x; base < n; base += gridDim.x)
+      auction_scan_items<1>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0);
   }
 }
 
-// One round for an ask from its cache: 32 gathers instead of a scan of every worker.
-__global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionParams p) {
+// One round for an ask from its class cache: 32 gathers instead of a scan.
+// pass 0: the round's active asks; an undecided ask requests a rescan of its class and is retried.
+// pass 1: the retried asks after the class scans; still undecided -> its own scan.
+__global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionParams p, int pass) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t slot = blockIdx.x * kAucWarps + warp;
-  if (slot >= p.n_active) return;
-  const uint32_t t = p.active[slot];
-  const long long theta = p.theta[t];
-  const uint32_t w = p.cand[(size_t)t * kAucCache + lane];
-  Top2 best{kAucNeg, kAucNeg, kNone};
-  if (theta != kThetaInvalid && w != kNone) {
-    best.b1 = -((long long)p.ev.wb[w].w * p.scale) - p.price[w];
-    best.w1 = w;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    Top2 o;
-    o.b1 = __shfl_xor_sync(0xffffffffu, best.b1, off);
-    o.b2 = __shfl_xor_sync(0xffffffffu, best.b2, off);
-    o.w1 = __shfl_xor_sync(0xffffffffu, best.w1, off);
-    best = top2_merge(best, o);
-  }
-  if (lane == 0) {
-    // every worker outside the cache ranks at or below (theta, theta_w) — its rank at scan time; prices only rise
-    const uint32_t theta_w = p.theta_w[t];
-    const bool decided = theta == kThetaComplete ||
-                         (theta != kThetaInvalid && best.b2 >= theta &&
-                          (best.b1 > theta || (best.b1 == theta && best.w1 < theta_w)));
-    if (decided) auction_place_bid(p, t, p.price_cap[t], best.b1, best.w1, best.b2);
-    else { p.bid_w[t] = kNone; p.rescan[atomicAdd(p.n_rescan, 1u)] = t; }
+  const uint32_t n = pass ? p.ctl->n_retry : p.ctl->n_active;
+  const uint32_t* list = pass ? p.retry : p.active;
+  const uint32_t stamp = p.ctl->rounds + 1u;
+  for (uint32_t slot = blockIdx.x * kAucWarps + warp; slot < n; slot += gridDim.x * kAucWarps) {
+    const uint32_t t = list[slot];
+    const uint32_t c = p.class_of[t];
+    const long long theta = p.theta[c];
+    const uint32_t theta_w = p.theta_w[c];
+    const uint32_t cap = p.price_cap[t];
+    const long long outside = -(((long long)cap + 1) * p.scale);
+    const uint32_t w = (theta != kThetaInvalid) ? p.cand[(size_t)c * kAucCache + lane] : kNone;
+    long long v = kAucNeg;
+    bool feas = false;
+    if (w != kNone) {
+      const uint32_t ap = p.ev.wb[w].w;
+      v = -((long long)ap * p.scale) - p.price[w];
+      feas = ap <= cap;
+    }
+    long long bf;
+    uint32_t wf;
+    const uint32_t lf = warp_argbest(feas ? v : kAucNeg, feas ? w : kNone, &bf, &wf);
+    const bool has = wf != kNone;
+    const long long bx = warp_max_i64((has && lane == lf) ? kAucNeg : v);   // best cached value other than w1
+    if (lane == 0) {
+      // every compatible worker outside the cache ranks at or below (theta, theta_w); kThetaComplete is
+      // INT64_MIN (nothing outside), kThetaInvalid INT64_MAX (nothing known): both fall out of the compares
+      int verdict;   // 0 withdraw, 1 bid, 2 ambiguous
+      if (p.dbg & 2u) verdict = 2;
+      else if (has && auc_better(bf, wf, theta, theta_w)) {
+        if (bf < outside) verdict = 0;
+        else verdict = (theta <= max(bx, outside)) ? 1 : 2;
+      } else {
+        const long long ub = has ? max(bf, theta) : theta;
+        verdict = (ub < outside) ? 0 : 2;
+      }
+      if (verdict == 0) auction_withdraw(p, t);
+      else if (verdict == 1) auction_commit(p, t, wf, bf, max(bx, outside));
+      else {
+        p.bid_w[t] = kNone;
+        if (pass == 0) {
+          if (atomicExch(p.class_req + c, stamp) != stamp) p.class_list[atomicAdd(&p.ctl->n_cls, 1u)] = c;
+          p.retry[atomicAdd(&p.ctl->n_retry, 1u)] = t;
+        } else {
+          p.fallback[atomicAdd(&p.ctl->n_fallback, 1u)] = t;
+        }
+      }
+    }
   }
 }
 
 // the claim: among the highest bidders of a worker the lowest ask index wins
 __global__ void pm_auction_claim(AuctionParams p) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_active) return;
-  const uint32_t t = p.active[i], w = p.bid_w[t];
-  if (w != kNone && p.bid_p[t] == p.bid_max[w]) atomicMin(p.winner + w, t);
+  const uint32_t n = p.ctl->n_active;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = p.active[i], w = p.bid_w[t];
+    if (w != kNone && p.bid_p[t] == p.bid_max[w]) atomicMin(p.winner + w, t);
+  }
 }
 
 __global__ void pm_auction_apply(AuctionParams p) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_active) return;
-  const uint32_t t = p.active[i], w = p.bid_w[t];
-  if (w == kNone || p.winner[w] != t) return;
-  const uint32_t prev = p.owner[w];
-  if (prev != kNone) p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
-  p.owner[w] = t;
-  p.assigned[t] = w;
-  p.price[w] = p.bid_p[t];
-  p.bid_max[w] = kAucNeg;
-  p.winner[w] = kNone;
+  const uint32_t n = p.ctl->n_active;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = p.active[i], w = p.bid_w[t];
+    if (w == kNone || p.winner[w] != t) continue;
+    const uint32_t prev = p.owner[w];
+    if (prev != kNone) p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
+    p.owner[w] = t;
+    p.assigned[t] = w;
+    p.price[w] = p.bid_p[t];
+    p.price_s[p.pos_of[w]] = p.bid_p[t];
+    p.bid_max[w] = kAucNeg;
+    p.winner[w] = kNone;
+  }
 }
 
-__global__ void pm_auction_compact(const uint32_t* __restrict__ assigned, const uint32_t* __restrict__ withdrawn,
-                                   uint32_t n_asks, uint32_t* __restrict__ active, uint32_t* __restrict__ n_active) {
+// next round's active list
+__global__ void pm_auction_compact(AuctionParams p, uint32_t n_asks) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_asks) return;
-  if (assigned[t] == kNone && !withdrawn[t]) active[atomicAdd(n_active, 1u)] = t;
+  if (p.assigned[t] == kNone && !p.withdrawn[t]) p.active[atomicAdd(&p.ctl->n_next, 1u)] = t;
+}
+__global__ void pm_auction_advance(AuctionCtl* ctl, int first) {
+  if (!first && ctl->n_active) ++ctl->rounds;
+  ctl->n_active = ctl->n_next;
+  ctl->n_next = 0;
+  ctl->n_cls = 0;
+  ctl->n_retry = 0;
+  ctl->n_fallback = 0;
+}
+
+// ---- ask classes -----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t auc_mix(uint64_t h, uint32_t v) {
+  h ^= v;
+  h *= 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+__global__ void pm_auction_ask_hash(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts, uint32_t n_asks,
+                                    uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_asks) return;
+  const DevAsk a = asks[t];
+  uint64_t h = 0x243F6A8885A308D3ull;
+  h = auc_mix(h, a.need); h = auc_mix(h, a.n_opts); h = auc_mix(h, a.cpu_cores); h = auc_mix(h, a.ram_mb); h = auc_mix(h, a.storage_gb);
+  for (uint32_t o = 0; o < a.n_opts; ++o) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(opts + a.opt_off + o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h = auc_mix(h, q[j]);
+  }
+  key[t] = h;
+  idx[t] = t;
+}
+__device__ __forceinline__ bool auc_same_ask(const DevAsk* asks, const DevOpt* opts, uint32_t x, uint32_t y) {
+  const DevAsk a = asks[x], b = asks[y];
+  if (a.need != b.need || a.n_opts != b.n_opts || a.cpu_cores != b.cpu_cores || a.ram_mb != b.ram_mb ||
+      a.storage_gb != b.storage_gb)
+    return false;
+  for (uint32_t o = 0; o < a.n_opts; ++o) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(opts + a.opt_off + o);
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(opts + b.opt_off + o);
+    for (int j = 0; j < 8; ++j)
+      if (q[j] != r[j]) return false;
+  }
+  return true;
+}
+// flag[i] = 1 where the i-th ask in hash order starts a new class (content compared, not the hash)
+__global__ void pm_auction_class_flags(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts,
+                                       const uint32_t* __restrict__ sorted, uint32_t n_asks, uint32_t* __restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_asks) return;
+  flag[i] = (i == 0 || !auc_same_ask(asks, opts, sorted[i - 1], sorted[i])) ? 1u : 0u;
+}
+__global__ void pm_auction_class_assign(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ flag,
+                                        const uint32_t* __restrict__ incl, uint32_t n_asks, uint32_t* __restrict__ class_of,
+                                        uint32_t* __restrict__ class_rep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_asks) return;
+  const uint32_t c = incl[i] - 1u;
+  class_of[sorted[i]] = c;
+  if (flag[i]) class_rep[c] = sorted[i];   // stable sort: the lowest ask of the run
+}
+
+// ---- price-sorted worker copy ------------------------------------------------------------------
+__global__ void pm_auction_price_keys(const uint4* __restrict__ wb, uint32_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = wb[i].w;
+  idx[i] = i;
+}
+__global__ void pm_auction_gather_sorted(const uint4* __restrict__ wa, const uint4* __restrict__ wb,
+                                         const uint32_t* __restrict__ perm, const long long* __restrict__ price, uint32_t n,
+                                         uint4* __restrict__ wa_s, uint4* __restrict__ wb_s, uint32_t* __restrict__ pos_of,
+                                         long long* __restrict__ price_s) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t w = perm[i];
+  wa_s[i] = wa[w];
+  wb_s[i] = wb[w];
+  pos_of[w] = i;
+  price_s[i] = price[w];
 }
 
 // result in the engine's group form: one solo group per assigned ask, in ask order

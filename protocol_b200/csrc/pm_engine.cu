@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <string>
@@ -86,7 +87,7 @@ struct pm_engine {
   uint32_t max_pattern_row = 0;
   bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
   bool all_solo = true;  // every ask has min == max == 1
-  int tune_argmin = 0, tune_generic = 0, tune_build = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
+  int tune_argmin = 0, tune_generic = 0, tune_build = 0, tune_auction = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
   DevBuf<uint4> wa, wb;
   DevBuf<double> lat, lon;
   DevBuf<uint32_t> addr_rank;
@@ -117,7 +118,17 @@ struct pm_engine {
   // extension (auction) state
   DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
   DevBuf<long long> auc_price, auc_bid_p, auc_bid_max, auc_theta;
-  DevBuf<uint32_t> auc_cand, auc_rescan, auc_theta_w;
+  DevBuf<uint32_t> auc_cand, auc_theta_w, auc_pool, auc_pool_bound_w;
+  DevBuf<long long> auc_pool_bound_v;
+  DevBuf<uint32_t> auc_class_of, auc_class_rep, auc_class_req, auc_class_list, auc_retry, auc_fallback;
+  DevBuf<uint32_t> auc_perm, auc_pos_of, auc_key, auc_key_out, auc_idx, auc_sorted, auc_incl;
+  DevBuf<uint64_t> auc_hash, auc_hash_out;
+  DevBuf<uint4> auc_wa_s, auc_wb_s;
+  DevBuf<long long> auc_price_s;
+  DevBuf<pm::AuctionCtl> auc_ctl;
+  PinBuf<pm::AuctionCtl> h_ctl;
+  uint32_t auc_n_classes = 0;
+  bool auc_classes_valid = false;
   bool have_caps = false;
   uint64_t auc_scale = 1, auc_eps_start = 1;
   uint32_t auc_eps_div = 4;
@@ -271,6 +282,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   if (const char* t = std::getenv("PM_TUNE_ARGMIN")) e->tune_argmin = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_BUILD")) e->tune_build = std::atoi(t);
+  if (const char* t = std::getenv("PM_TUNE_AUCTION")) e->tune_auction = std::atoi(t);
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
     e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
@@ -307,7 +319,13 @@ void pm_destroy(pm_engine* e) {
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
-  e->auc_theta.release(); e->auc_cand.release(); e->auc_rescan.release(); e->auc_theta_w.release();
+  e->auc_theta.release(); e->auc_cand.release(); e->auc_theta_w.release();
+  e->auc_pool.release(); e->auc_pool_bound_w.release(); e->auc_pool_bound_v.release();
+  e->auc_class_of.release(); e->auc_class_rep.release(); e->auc_class_req.release(); e->auc_class_list.release();
+  e->auc_retry.release(); e->auc_fallback.release(); e->auc_perm.release(); e->auc_pos_of.release(); e->auc_key.release();
+  e->auc_key_out.release(); e->auc_idx.release(); e->auc_sorted.release(); e->auc_incl.release(); e->auc_hash.release();
+  e->auc_hash_out.release(); e->auc_wa_s.release(); e->auc_wb_s.release(); e->auc_price_s.release(); e->auc_ctl.release();
+  e->h_ctl.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
@@ -332,7 +350,13 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   PM_CUDA(e->raw_asks.ensure(n_asks)); PM_CUDA(e->raw_opts.ensure(n_opts));
   PM_CUDA(e->ask_counts.ensure((size_t)n_asks + 1)); PM_CUDA(e->ask_newoff.ensure((size_t)n_asks + 1));
   PM_CUDA(e->asks.ensure(n_asks)); PM_CUDA(e->amin.ensure(n_asks)); PM_CUDA(e->amax.ensure(n_asks));
-  PM_CUDA(e->opts.ensure(n_opts)); PM_CUDA(e->opts_fast.ensure(n_opts));
+  // asks may share or overlap option rows, so the converted table (one private range per ask) can be longer than
+  // the caller's: size it by the sum of the per-ask counts
+  uint64_t opt_rows = 0;
+  for (uint32_t i = 0; i < n_asks; ++i) opt_rows += asks[i].n_opts;
+  if (opt_rows >= (1ull << 31)) return e->fail(PM_E_INVALID, "pm_set_asks: too many option rows");
+  const size_t opt_cap = std::max<size_t>(n_opts, (size_t)opt_rows);
+  PM_CUDA(e->opts.ensure(opt_cap)); PM_CUDA(e->opts_fast.ensure(opt_cap));
   if (n_asks) PM_CUDA(cudaMemcpyAsync(e->raw_asks.p, asks, (size_t)n_asks * sizeof(pm_ask), cudaMemcpyHostToDevice, e->stream));
   if (n_opts) PM_CUDA(cudaMemcpyAsync(e->raw_opts.p, opts, (size_t)n_opts * sizeof(pm_gpu_opt), cudaMemcpyHostToDevice, e->stream));
   PM_CUDA(cudaMemsetAsync(e->counters.p + 12, 0, 8, e->stream));
@@ -366,6 +390,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   e->asks_small = (st & pm::kAskNotSmall) == 0;
   e->any_max_zero = (st & pm::kAskMaxZero) != 0;
   e->have_caps = false;
+  e->auc_classes_valid = false;
   e->have_asks = true;
   e->matched = e->local_done = false;
   return PM_OK;
@@ -815,6 +840,35 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
 }
 
 // ------------------------------------------------------------------ extension: auction
+// Ask classes for the auction: asks with identical requirement rows (pm_auction.cuh).
+static int auction_build_classes(pm_engine* e) {
+  const uint32_t T = e->n_asks;
+  e->auc_n_classes = 0;
+  PM_CUDA(e->auc_class_of.ensure(T)); PM_CUDA(e->auc_class_rep.ensure(T)); PM_CUDA(e->auc_hash.ensure(T));
+  PM_CUDA(e->auc_hash_out.ensure(T)); PM_CUDA(e->auc_idx.ensure(T)); PM_CUDA(e->auc_sorted.ensure(T));
+  PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_incl.ensure(T));
+  if (T == 0) { e->auc_classes_valid = true; return PM_OK; }
+  pm::pm_auction_ask_hash<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, T, e->auc_hash.p, e->auc_idx.p);
+  PM_LAUNCH_CHECK("pm_auction_ask_hash");
+  size_t tmp_sort = 0, tmp_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, e->auc_hash.p, e->auc_hash_out.p, e->auc_idx.p, e->auc_sorted.p, (int)T, 0, 64, e->stream);
+  cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, e->auc_flag.p, e->auc_incl.p, (int)T, e->stream);
+  size_t tmp = std::max(tmp_sort, tmp_scan);
+  PM_CUDA(e->cub_tmp.ensure(tmp));
+  PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_hash.p, e->auc_hash_out.p, e->auc_idx.p, e->auc_sorted.p, (int)T, 0, 64, e->stream));
+  pm::pm_auction_class_flags<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, e->auc_sorted.p, T, e->auc_flag.p);
+  PM_LAUNCH_CHECK("pm_auction_class_flags");
+  PM_CUDA(cub::DeviceScan::InclusiveSum(e->cub_tmp.p, tmp, e->auc_flag.p, e->auc_incl.p, (int)T, e->stream));
+  pm::pm_auction_class_assign<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->auc_sorted.p, e->auc_flag.p, e->auc_incl.p, T,
+                                                                          e->auc_class_of.p, e->auc_class_rep.p);
+  PM_LAUNCH_CHECK("pm_auction_class_assign");
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 16, e->auc_incl.p + (T - 1), 4, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  e->auc_n_classes = e->h_scalars.p[16];
+  e->auc_classes_valid = true;
+  return PM_OK;
+}
+
 static int match_auction_locked(pm_engine* e) {
   if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_match: worker and ask tables must be set first");
   if (!e->have_caps) return e->fail(PM_E_STATE, "pm_match: auction mode needs pm_set_ask_price_caps");
@@ -833,77 +887,136 @@ static int match_auction_locked(pm_engine* e) {
   e->ev_used = 0;
   if (e->cfg.flags & PM_CFG_TIMING) PM_CUDA(cudaEventRecord(e->ev0, e->stream));
   Timer tm(e, &e->stats.ms_fused);
+  if (!e->auc_classes_valid) {
+    const int rc = auction_build_classes(e);
+    if (rc != PM_OK) return rc;
+  }
+  const uint32_t C = e->auc_n_classes;
   PM_CUDA(e->auc_price.ensure((size_t)W + 2)); PM_CUDA(e->auc_owner.ensure(W)); PM_CUDA(e->auc_bid_max.ensure(W));
   PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
   PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
-  PM_CUDA(e->auc_theta.ensure(T)); PM_CUDA(e->auc_theta_w.ensure(T)); PM_CUDA(e->auc_cand.ensure((size_t)T * pm::kAucCache)); PM_CUDA(e->auc_rescan.ensure(T));
+  PM_CUDA(e->auc_theta.ensure(C)); PM_CUDA(e->auc_theta_w.ensure(C)); PM_CUDA(e->auc_cand.ensure((size_t)C * pm::kAucCache));
+  PM_CUDA(e->auc_pool.ensure((size_t)C * pm::kAucPool)); PM_CUDA(e->auc_pool_bound_v.ensure(C)); PM_CUDA(e->auc_pool_bound_w.ensure(C));
+  PM_CUDA(e->auc_class_req.ensure(C)); PM_CUDA(e->auc_class_list.ensure(C)); PM_CUDA(e->auc_retry.ensure(T)); PM_CUDA(e->auc_fallback.ensure(T));
+  PM_CUDA(e->auc_perm.ensure((size_t)W + 4)); PM_CUDA(e->auc_pos_of.ensure(W)); PM_CUDA(e->auc_key.ensure(W)); PM_CUDA(e->auc_key_out.ensure(W));
+  PM_CUDA(e->auc_idx.ensure(std::max(W, T))); PM_CUDA(e->auc_wa_s.ensure(W)); PM_CUDA(e->auc_wb_s.ensure(W)); PM_CUDA(e->auc_price_s.ensure((size_t)W + 2));
+  PM_CUDA(e->auc_ctl.ensure(1)); PM_CUDA(e->h_ctl.ensure(1));
   PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(std::max(W, T)));
   PM_CUDA(e->group_ask.ensure((size_t)T + 1)); PM_CUDA(e->group_off.ensure((size_t)T + 2));
   PM_CUDA(e->ask_best.ensure(T)); PM_CUDA(e->ask_count.ensure(T)); PM_CUDA(e->first_ask.ensure(W));
   PM_CUDA(cudaMemsetAsync(e->auc_price.p, 0, ((size_t)W + 2) * 8, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->auc_price_s.p, 0, ((size_t)W + 2) * 8, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->auc_ctl.p, 0, sizeof(pm::AuctionCtl), e->stream));
+  PM_CUDA(cudaMemsetAsync(e->auc_class_req.p, 0, (size_t)std::max<uint32_t>(C, 1) * 4, e->stream));
   if (W) {
     pm::pm_fill_i64<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->auc_bid_max.p, pm::kAucNeg, W);
     PM_LAUNCH_CHECK("pm_fill_i64");
+    // worker planes sorted by (ask_price, index): stable radix sort on the price
+    pm::pm_auction_price_keys<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wb.p, W, e->auc_key.p, e->auc_idx.p);
+    PM_LAUNCH_CHECK("pm_auction_price_keys");
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, e->auc_key.p, e->auc_key_out.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 32, e->stream);
+    PM_CUDA(e->cub_tmp.ensure(tmp));
+    PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_key.p, e->auc_key_out.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 32, e->stream));
+    pm::pm_auction_gather_sorted<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wa.p, e->wb.p, e->auc_perm.p, e->auc_price.p, W, e->auc_wa_s.p,
+                                                                            e->auc_wb_s.p, e->auc_pos_of.p, e->auc_price_s.p);
+    PM_LAUNCH_CHECK("pm_auction_gather_sorted");
   }
   PM_CUDA(cudaMemsetAsync(e->auc_winner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
 
   pm::AuctionParams ap;
   ap.ev = eval_params(e);
+  ap.wa_s = e->auc_wa_s.p; ap.wb_s = e->auc_wb_s.p; ap.perm = e->auc_perm.p; ap.pos_of = e->auc_pos_of.p; ap.price_s = e->auc_price_s.p;
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
   ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
-  ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p; ap.rescan = e->auc_rescan.p; ap.n_rescan = e->counters.p + 9;
-  ap.scan_list = e->auc_rescan.p; ap.n_scan = 0;
-  const size_t smem = 2 * sizeof(pm::AuctionStage) + sizeof(pm::AuctionMerge);
-  PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_bid<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_bid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ap.class_of = e->auc_class_of.p; ap.class_rep = e->auc_class_rep.p; ap.class_req = e->auc_class_req.p;
+  ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p;
+  ap.pool = e->auc_pool.p; ap.pool_bound_v = e->auc_pool_bound_v.p; ap.pool_bound_w = e->auc_pool_bound_w.p;
+  ap.class_list = e->auc_class_list.p; ap.retry = e->auc_retry.p; ap.fallback = e->auc_fallback.p; ap.ctl = e->auc_ctl.p;
+  ap.dbg = (uint32_t)e->tune_auction;
+  const size_t smem = pm::kAucStages * sizeof(pm::AuctionStage) + sizeof(pm::AuctionMerge);
+  PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // fixed grids: every kernel strides over a list whose length it reads from the control block
+  const unsigned g_scan = 296u;   // two CTAs per SM (shared memory)
+  const unsigned g_warp = std::max(1u, std::min(blocks_for(T, pm::kAucWarps), 1184u));
+  const unsigned g_thr = std::max(1u, std::min(blocks_for(T, 256), 592u));
+  const uint32_t kBatch = 32;  // rounds launched between polls of the control block
   uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
   const uint32_t div = e->auc_eps_div < 2 ? 2 : e->auc_eps_div;
-  for (;;) {  // eps phases: assignment cleared, prices kept
+  for (;;) {  // eps phases: assignment cleared, prices (and so the class caches' bounds) kept
     PM_CUDA(cudaMemsetAsync(e->auc_owner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->auc_assigned.p, 0xFF, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->auc_withdrawn.p, 0, (size_t)std::max<uint32_t>(T, 1) * 4, e->stream));
-    if (T) {  // no cache yet: theta = "invalid" sends every ask to a full scan in its first round
-      pm::pm_fill_i64<<<std::min(blocks_for(T, 256), 1184u), 256, 0, e->stream>>>(e->auc_theta.p, pm::kThetaInvalid, T);
+    if (C && eps == (e->auc_eps_start ? e->auc_eps_start : 1)) {  // no cache yet: "invalid" sends every class to a scan
+      pm::pm_fill_i64<<<std::min(blocks_for(C, 256), 1184u), 256, 0, e->stream>>>(e->auc_theta.p, pm::kThetaInvalid, C);
+      pm::pm_fill_i64<<<std::min(blocks_for(C, 256), 1184u), 256, 0, e->stream>>>(e->auc_pool_bound_v.p, pm::kThetaInvalid, C);
       PM_LAUNCH_CHECK("pm_fill_i64");
     }
     ap.eps = (long long)eps;
-    for (;;) {
-      PM_CUDA(cudaMemsetAsync(e->counters.p + 8, 0, 4, e->stream));
-      if (T) {
-        pm::pm_auction_compact<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->auc_assigned.p, e->auc_withdrawn.p, T, e->auc_active.p, e->counters.p + 8);
-        PM_LAUNCH_CHECK("pm_auction_compact");
-      }
-      PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 16, e->counters.p + 8, 4, cudaMemcpyDeviceToHost, e->stream));
-      PM_CUDA(cudaStreamSynchronize(e->stream));
-      const uint32_t n_active = e->h_scalars.p[16];
-      if (n_active == 0) break;
-      ap.n_active = n_active;
-      PM_CUDA(cudaMemsetAsync(e->counters.p + 9, 0, 4, e->stream));
-      pm::pm_auction_bid_cached<<<blocks_for(n_active, pm::kAucWarps), pm::kAucThreads, 0, e->stream>>>(ap);
-      PM_LAUNCH_CHECK("pm_auction_bid_cached");
-      PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 18, e->counters.p + 9, 4, cudaMemcpyDeviceToHost, e->stream));
-      PM_CUDA(cudaStreamSynchronize(e->stream));
-      const uint32_t n_scan = e->h_scalars.p[18];
-      if (n_scan) {
-        ap.n_scan = n_scan;
-        if (n_scan >= 8u * 296u) pm::pm_auction_bid<8><<<blocks_for(n_scan, 8), pm::kAucThreads, smem, e->stream>>>(ap);
-        else pm::pm_auction_bid<1><<<n_scan, pm::kAucThreads, smem, e->stream>>>(ap);
-        PM_LAUNCH_CHECK("pm_auction_bid");
-        e->stats.evals += (uint64_t)n_scan * W;
-      }
-      pm::pm_auction_claim<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
-      PM_LAUNCH_CHECK("pm_auction_claim");
-      pm::pm_auction_apply<<<blocks_for(n_active, 256), 256, 0, e->stream>>>(ap);
-      PM_LAUNCH_CHECK("pm_auction_apply");
-      ++e->stats.n_rounds;
-      ++e->stats.n_fused_launches;
-      if (e->stats.n_rounds > 50u * 1000u * 1000u) return e->fail(PM_E_CUDA, "pm_match: auction did not terminate");
+    if (T) {
+      pm::pm_auction_compact<<<blocks_for(T, 256), 256, 0, e->stream>>>(ap, T);
+      PM_LAUNCH_CHECK("pm_auction_compact");
     }
+    pm::pm_auction_advance<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, 1);
+    PM_LAUNCH_CHECK("pm_auction_advance");
+    auto launch_rounds = [&]() {
+      for (uint32_t r = 0; r < kBatch; ++r) {
+        pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 0);
+        pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 1);
+        pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 1);
+        pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 0);
+        pm::pm_auction_claim<<<g_thr, 256, 0, e->stream>>>(ap);
+        pm::pm_auction_apply<<<g_thr, 256, 0, e->stream>>>(ap);
+        pm::pm_auction_compact<<<blocks_for(T, 256), 256, 0, e->stream>>>(ap, T);
+        pm::pm_auction_advance<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, 0);
+      }
+    };
+    // a batch of rounds is one CUDA graph (the kernels are a few microseconds each: launch-bound otherwise);
+    // a stream that cannot be captured (the legacy default stream) gets plain launches
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    if (T && cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      launch_rounds();
+      if (cudaStreamEndCapture(e->stream, &graph) != cudaSuccess || cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        graph_exec = nullptr;
+      }
+    }
+    (void)cudaGetLastError();
+    int rc_rounds = PM_OK;
+    for (;;) {
+      cudaError_t ce = cudaMemcpyAsync(e->h_ctl.p, e->auc_ctl.p, sizeof(pm::AuctionCtl), cudaMemcpyDeviceToHost, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+      if (ce != cudaSuccess) { rc_rounds = e->fail(PM_E_CUDA, std::string("pm_match: auction rounds: ") + cudaGetErrorString(ce)); break; }
+      if (e->tune_auction & 4) {   // PM_TUNE_AUCTION=4: one line per batch of rounds
+        static thread_local double t_prev = 0;
+        timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+        std::fprintf(stderr, "auction batch: rounds=%u active=%u refills=%llu class_scans=%llu ask_scans=%llu evals=%llu dt_ms=%.2f\n", e->h_ctl.p->rounds,
+                     e->h_ctl.p->n_active, e->h_ctl.p->n_refills, e->h_ctl.p->n_class_scans, e->h_ctl.p->n_ask_scans, e->h_ctl.p->evals, t_prev ? now - t_prev : 0.0);
+        t_prev = now;
+      }
+      if (e->h_ctl.p->n_active == 0) break;
+      if (e->h_ctl.p->rounds > 50u * 1000u * 1000u) { rc_rounds = e->fail(PM_E_CUDA, "pm_match: auction did not terminate"); break; }
+      if (graph_exec) ce = cudaGraphLaunch(graph_exec, e->stream);
+      else { launch_rounds(); ce = cudaGetLastError(); }
+      if (ce != cudaSuccess) { rc_rounds = e->fail(PM_E_CUDA, std::string("pm_match: auction rounds: ") + cudaGetErrorString(ce)); break; }
+    }
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc_rounds != PM_OK) return rc_rounds;
     if (eps == 1) break;
     eps = std::max<uint64_t>(1, eps / div);
   }
+  e->stats.n_rounds = e->h_ctl.p->rounds;
+  e->stats.evals = e->h_ctl.p->evals;
+  e->stats.n_tiles = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_class_scans, 0xFFFFFFFFull);
+  e->stats.n_fused_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_ask_scans, 0xFFFFFFFFull);
+  e->stats.n_launches = e->h_ctl.p->rounds * 8u;
+  e->stats.n_build_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_refills, 0xFFFFFFFFull);
   tm.stop();
   Timer tr(e, &e->stats.ms_resolve);
   // result: one solo group per assigned ask, ask order

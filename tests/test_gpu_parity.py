@@ -301,6 +301,21 @@ def test_proximity_montreal_dallas_on_device():
     eng.close()
 
 
+def test_asks_sharing_option_rows():
+    """Several asks may point at the same option rows (identical requirements written once): the device
+    table gets one private range per ask, which can be longer than the caller's table."""
+    w, a, t = synth_tables(30, 4000, "mixed", group_sizes=[(1, 1), (1, 2), (2, 4)])
+    rng = np.random.default_rng(11)
+    idx = rng.permutation(np.repeat(np.arange(30), 25))
+    t["asks"] = np.ascontiguousarray(t["asks"][idx])
+    assert int(t["asks"]["n_opts"].sum()) > len(t["opts"])
+    for mode in (abi.PM_MODE_FIRST_FIT | MAT, abi.PM_MODE_FIRST_FIT | abi.PM_PATH_FUSED):
+        eng = Engine(cost_tile_bytes=8 << 20)
+        load_engine(eng, t)
+        check_against_oracle(eng, t, mode)
+        eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # NORTH-STAR EXTENSION (no reference counterpart): parity is against the builder's own sequential
 # auction — "self-oracle, parity unpinned by the reference" (SURVEY 0, 8c).
@@ -337,6 +352,58 @@ def test_extension_auction_matches_self_oracle(n_asks, n_workers, seed):
         assert t["wb"]["ext_ask_price"][wk] <= cap[tk]
         assert orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][tk], t["opts"], t["bits"], t["words"])
     eng.close()
+
+
+def _check_auction(t, cap, **params):
+    eng = Engine()
+    load_engine(eng, t)
+    eng.set_price_caps(cap)
+    if params:
+        eng.set_auction_params(**params)
+    eng.match(abi.PM_MODE_AUCTION)
+    res = eng.fetch()
+    want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap, **params)
+    got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
+    for g, (ask, members) in enumerate(res.groups()):
+        assert len(members) == 1
+        got[ask] = members[0]
+    assert np.array_equal(got, want)
+    assert res.stats["n_rounds"] == rounds
+    stats = res.stats
+    eng.close()
+    return got, stats
+
+
+@pytest.mark.parametrize("n_base,copies,n_workers,plo,phi,seed", [
+    (12, 40, 3000, 10, 14, 5),      # few classes, many identical bidders, almost every value tied
+    (40, 20, 5000, 10, 40, 6),
+    (25, 30, 20000, 5, 300, 7),     # 20 stripes: the price-sorted scan stops early
+    (3, 200, 2500, 7, 9, 8),        # caps straddle the whole price range: ties exactly at the outside option
+])
+def test_extension_auction_identical_bidders_and_ties(n_base, copies, n_workers, plo, phi, seed):
+    """Ask classes share one cache; the cap only enters through the outside option.  Duplicated asks with
+    different caps over a narrow integer price range hit every tie rule (equal values -> lowest worker,
+    equal bids -> lowest ask, value == outside) — assignments and round count must still equal the
+    sequential checker's, which scans every worker for every unassigned ask every round."""
+    w, a, t = synth_tables(n_base, n_workers, "mixed", seed_shift=seed)
+    rng = np.random.default_rng(seed)
+    idx = rng.permutation(np.repeat(np.arange(n_base), copies))
+    t["asks"] = np.ascontiguousarray(t["asks"][idx])     # duplicates share their option rows
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = rng.integers(plo, phi + 1, n_workers).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(max(plo - 2, 0), phi + 3, len(idx)).astype(np.uint32)
+    got, stats = _check_auction(t, cap)
+    # classes were scanned, not asks: at least one walk per distinct requirement row, far fewer than one per bid
+    n_classes = len({(int(r["flags"]), int(r["cpu_cores"]), int(r["ram_mb"]), int(r["storage_gb"]),
+                      t["opts"][r["opt_off"]:r["opt_off"] + r["n_opts"]].tobytes()) for r in t["asks"]})
+    assert n_classes <= stats["n_tiles"] <= n_classes * max(stats["n_rounds"], 1)
+
+
+@pytest.mark.parametrize("params", [dict(cost_scale=3), dict(cost_scale=4, eps_start=16, eps_div=4)])
+def test_extension_auction_scaled_costs_and_eps_phases(params):
+    t, cap = _auction_tables(300, 2500, 9)
+    _check_auction(t, cap, **params)
 
 
 def test_extension_columns_are_neutral_in_reference_modes():

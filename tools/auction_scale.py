@@ -21,5 +21,6 @@ for T, W in [(int(x.split("x")[0]), int(x.split("x")[1])) for x in sys.argv[1:]]
     res = eng.fetch()
     st = res.stats
     print({"T": T, "W": W, "wall_s": round(dt, 3), "rounds": st["n_rounds"], "evals": st["evals"],
-           "evals_per_s": st["evals"] / dt, "assigned": res.n_groups, "ms_bid_total": round(st["ms_fused"], 1)}, flush=True)
+           "class_scans": st["n_tiles"], "refills": st["n_build_launches"], "ask_scans": st["n_fused_launches"], "assigned": res.n_groups,
+           "ms_rounds": round(st["ms_fused"], 1)}, flush=True)
     eng.close()
