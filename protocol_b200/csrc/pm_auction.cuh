@@ -29,10 +29,15 @@
 //    can reach outside(t).  Anything else is "ambiguous": the class is rescanned once for all its
 //    asks (pm_auction_scan, class mode) and the ask bids again; an ask that is still ambiguous
 //    after a fresh class scan (a value tie exactly at outside) gets its own cap-filtered scan.
-//  * PRICE-SORTED WORKERS.  Scans walk a copy of the worker table sorted by (ask_price, index).
-//    value <= -(ask_price * S), so once every lane holds four candidates better than the stripe's
-//    last ask_price no later worker can enter the top 32 or the bound: the scan stops there
-//    (and, for a single ask, at its cap).
+//  * COST-SORTED WORKERS.  Scans walk a copy of the worker table sorted by (ask_price * S + price,
+//    index) as of the last sort (redone every few batches of rounds).  Prices only rise, so a
+//    worker's value is at most minus its sort key: once 33 kept candidates beat the key of the
+//    stripe's last worker no later worker can enter the top 32 or the bound, and the walk stops —
+//    after a stripe or two for most classes, because the workers whose prices were bid up have
+//    moved back in the order.
+//  * CLASS POOL.  The candidates the lanes held at the end of a walk (up to 1024) stay as the
+//    class's pool; a rescan request first re-ranks the pool at the current prices and walks the
+//    table only when the pool's best two no longer beat the bound on everything outside it.
 //  * DEVICE-DRIVEN ROUNDS.  List lengths live in device memory; every kernel of a round is
 //    launched with a fixed grid and strides over its list, so the host launches rounds in batches
 //    and only polls the number of unassigned asks.
@@ -73,11 +78,12 @@ struct AuctionCtl {
 
 struct AuctionParams {
   EvalParams ev;               // original worker order (gathers); asks / options / model bits
-  const uint4* wa_s;           // worker planes sorted by (ask_price, index)
+  const uint4* wa_s;           // worker planes sorted by (cost at the last sort, index)
   const uint4* wb_s;
   const uint32_t* perm;        // [W] sorted position -> worker
   const uint32_t* pos_of;      // [W] worker -> sorted position
   long long* price_s;          // [W + 2] price mirror in sorted order
+  const unsigned long long* csort_s;  // [W] the sort key: ask_price * S + price at the time of the last sort
   const uint32_t* price_cap;   // [T]
   long long* price;            // [W] dual price of each worker
   uint32_t* owner;             // [W] ask currently holding the worker
@@ -363,7 +369,8 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   uint32_t scanned = 0;
   uint32_t first_good = kNone;   // first stripe after which 33 candidates beat every unseen worker
   bool unseen = false;           // the walk stopped before the end of the table ...
-  long long unseen_u = kAucNeg;  // ... where every remaining worker has value <= unseen_u
+  long long unseen_u = kAucNeg;  // ... where every remaining worker ranks at or below (unseen_u, unseen_w)
+  uint32_t unseen_w = 0;
   if (threadIdx.x == 0)
     for (uint32_t k = 0; k < (uint32_t)(kAucStages - 1) && k < n_stripes; ++k) issue(k);
   for (uint32_t k = 0; k < n_stripes; ++k) {
@@ -380,14 +387,20 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
           auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
       }
     }
-    // Every later worker has ask_price >= the stripe's last one, hence value <= U = -(last * S).  Once 33 of the
-    // item's kept candidates beat U strictly, at least one of them stays outside the 32-entry cache, so the bound
-    // (best candidate not cached) beats every unseen worker and the walk may stop; a class walks a little further
-    // to fill its pool, a single ask also stops at its cap.
-    const uint32_t last_price = s.b[n - 1].w;
-    const long long u = -((long long)last_price * p.scale);
-    uint32_t cnt = __popc(__ballot_sync(0xffffffffu, cv[0] > u)) + __popc(__ballot_sync(0xffffffffu, cv[1] > u)) +
-                   __popc(__ballot_sync(0xffffffffu, cv[2] > u)) + __popc(__ballot_sync(0xffffffffu, cv[3] > u));
+    // The table is sorted by the cost ask_price * S + price each worker had at the last sort; prices only rise, so
+    // every later worker has value <= U = -(the stripe's last sort key).  Once 33 of the item's kept candidates beat the
+    // unseen workers, at least one of them stays outside the 32-entry cache, so the bound (best candidate not cached) beats
+    // every unseen worker and the walk may stop; a class walks a little further to fill its pool; a single ask also
+    // stops once the unseen workers cannot reach its outside option.
+    const long long u = -(long long)p.csort_s[k * kAucStripe + n - 1];
+    const bool past_cap = !cls_mode && u < -(((long long)cap + 1) * p.scale);
+    // ... and a later worker whose value still equals U has the same sort key as the stripe's last worker, hence a
+    // larger index: the unseen workers rank at or below (U, last index + 1) in (value desc, worker asc) order, which
+    // lets a walk stop inside a plateau of equal costs (where the whole bid-up mass of the market sits).
+    const uint32_t il = s.perm[n - 1];
+    auto beats = [&](long long v, uint32_t w) { return v > u || (v == u && w <= il); };
+    uint32_t cnt = __popc(__ballot_sync(0xffffffffu, beats(cv[0], cw[0]))) + __popc(__ballot_sync(0xffffffffu, beats(cv[1], cw[1]))) +
+                   __popc(__ballot_sync(0xffffffffu, beats(cv[2], cw[2]))) + __popc(__ballot_sync(0xffffffffu, beats(cv[3], cw[3])));
     if (kWpt > 1) {
       if (lane == 0) atomicAdd(&mg.cnt[k % 3u], cnt);
       if (threadIdx.x == 0) mg.cnt[(k + 1u) % 3u] = 0;
@@ -395,13 +408,13 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
       cnt = mg.cnt[k % 3u];
     }
     if (cnt > (uint32_t)kAucCache && first_good == kNone) first_good = k;
-    bool done = !scan || last_price > cap ||
+    bool done = !scan || past_cap ||
                 (first_good != kNone && (!cls_mode || cnt > (uint32_t)kAucPoolGood || k - first_good >= (uint32_t)kAucPoolExtra));
     if (p.dbg & 1u) done = false;
     if (kWpt == 1) done = __syncthreads_and(done) != 0;
     // (the barrier above also means: stripe k fully consumed, its buffer may be refilled)
     if (done) {
-      if (k + 1 < n_stripes) { unseen = true; unseen_u = u; }
+      if (k + 1 < n_stripes) { unseen = true; unseen_u = u; unseen_w = il + 1u; }
       // the copies already in flight must land before the buffers are reused
       for (uint32_t j = k + 1; j < k + kAucStages && j < n_stripes; ++j) wait_stage(j);
       break;
@@ -424,7 +437,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
         // outside the pool: what no lane kept, and the part of the table the walk did not reach
         long long pb_v = r.drop_v;
         uint32_t pb_w = r.drop_w;
-        if (unseen && auc_better(unseen_u, 0u, pb_v, pb_w)) { pb_v = unseen_u; pb_w = 0u; }
+        if (unseen && auc_better(unseen_u, unseen_w, pb_v, pb_w)) { pb_v = unseen_u; pb_w = unseen_w; }
         p.pool_bound_v[item] = (pb_v == kAucNeg) ? kThetaComplete : pb_v;
         p.pool_bound_w[item] = pb_w;
         atomicAdd(&p.ctl->n_class_scans, 1ull);
@@ -604,10 +617,11 @@ __global__ void pm_auction_class_assign(const uint32_t* __restrict__ sorted, con
 }
 
 // ---- price-sorted worker copy ------------------------------------------------------------------
-__global__ void pm_auction_price_keys(const uint4* __restrict__ wb, uint32_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
+__global__ void pm_auction_cost_keys(const uint4* __restrict__ wb, const long long* __restrict__ price, long long scale,
+                                     uint32_t n, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  key[i] = wb[i].w;
+  key[i] = (unsigned long long)((long long)wb[i].w * scale + price[i]);
   idx[i] = i;
 }
 __global__ void pm_auction_gather_sorted(const uint4* __restrict__ wa, const uint4* __restrict__ wb,

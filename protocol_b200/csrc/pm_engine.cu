@@ -121,8 +121,8 @@ struct pm_engine {
   DevBuf<uint32_t> auc_cand, auc_theta_w, auc_pool, auc_pool_bound_w;
   DevBuf<long long> auc_pool_bound_v;
   DevBuf<uint32_t> auc_class_of, auc_class_rep, auc_class_req, auc_class_list, auc_retry, auc_fallback;
-  DevBuf<uint32_t> auc_perm, auc_pos_of, auc_key, auc_key_out, auc_idx, auc_sorted, auc_incl;
-  DevBuf<uint64_t> auc_hash, auc_hash_out;
+  DevBuf<uint32_t> auc_perm, auc_pos_of, auc_idx, auc_sorted, auc_incl;
+  DevBuf<uint64_t> auc_hash, auc_hash_out, auc_ckey, auc_ckey_s;
   DevBuf<uint4> auc_wa_s, auc_wb_s;
   DevBuf<long long> auc_price_s;
   DevBuf<pm::AuctionCtl> auc_ctl;
@@ -320,10 +320,10 @@ void pm_destroy(pm_engine* e) {
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
   e->auc_theta.release(); e->auc_cand.release(); e->auc_theta_w.release();
-  e->auc_pool.release(); e->auc_pool_bound_w.release(); e->auc_pool_bound_v.release();
+  e->auc_pool.release(); e->auc_pool_bound_w.release(); e->auc_pool_bound_v.release(); e->auc_ckey.release(); e->auc_ckey_s.release();
   e->auc_class_of.release(); e->auc_class_rep.release(); e->auc_class_req.release(); e->auc_class_list.release();
-  e->auc_retry.release(); e->auc_fallback.release(); e->auc_perm.release(); e->auc_pos_of.release(); e->auc_key.release();
-  e->auc_key_out.release(); e->auc_idx.release(); e->auc_sorted.release(); e->auc_incl.release(); e->auc_hash.release();
+  e->auc_retry.release(); e->auc_fallback.release(); e->auc_perm.release(); e->auc_pos_of.release();
+  e->auc_idx.release(); e->auc_sorted.release(); e->auc_incl.release(); e->auc_hash.release();
   e->auc_hash_out.release(); e->auc_wa_s.release(); e->auc_wb_s.release(); e->auc_price_s.release(); e->auc_ctl.release();
   e->h_ctl.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
@@ -899,7 +899,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(e->auc_theta.ensure(C)); PM_CUDA(e->auc_theta_w.ensure(C)); PM_CUDA(e->auc_cand.ensure((size_t)C * pm::kAucCache));
   PM_CUDA(e->auc_pool.ensure((size_t)C * pm::kAucPool)); PM_CUDA(e->auc_pool_bound_v.ensure(C)); PM_CUDA(e->auc_pool_bound_w.ensure(C));
   PM_CUDA(e->auc_class_req.ensure(C)); PM_CUDA(e->auc_class_list.ensure(C)); PM_CUDA(e->auc_retry.ensure(T)); PM_CUDA(e->auc_fallback.ensure(T));
-  PM_CUDA(e->auc_perm.ensure((size_t)W + 4)); PM_CUDA(e->auc_pos_of.ensure(W)); PM_CUDA(e->auc_key.ensure(W)); PM_CUDA(e->auc_key_out.ensure(W));
+  PM_CUDA(e->auc_perm.ensure((size_t)W + 4)); PM_CUDA(e->auc_pos_of.ensure(W));
   PM_CUDA(e->auc_idx.ensure(std::max(W, T))); PM_CUDA(e->auc_wa_s.ensure(W)); PM_CUDA(e->auc_wb_s.ensure(W)); PM_CUDA(e->auc_price_s.ensure((size_t)W + 2));
   PM_CUDA(e->auc_ctl.ensure(1)); PM_CUDA(e->h_ctl.ensure(1));
   PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(std::max(W, T)));
@@ -909,25 +909,35 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(cudaMemsetAsync(e->auc_price_s.p, 0, ((size_t)W + 2) * 8, e->stream));
   PM_CUDA(cudaMemsetAsync(e->auc_ctl.p, 0, sizeof(pm::AuctionCtl), e->stream));
   PM_CUDA(cudaMemsetAsync(e->auc_class_req.p, 0, (size_t)std::max<uint32_t>(C, 1) * 4, e->stream));
+  PM_CUDA(e->auc_ckey.ensure(W)); PM_CUDA(e->auc_ckey_s.ensure(W));
   if (W) {
     pm::pm_fill_i64<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->auc_bid_max.p, pm::kAucNeg, W);
     PM_LAUNCH_CHECK("pm_fill_i64");
-    // worker planes sorted by (ask_price, index): stable radix sort on the price
-    pm::pm_auction_price_keys<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wb.p, W, e->auc_key.p, e->auc_idx.p);
-    PM_LAUNCH_CHECK("pm_auction_price_keys");
+  }
+  // worker planes sorted by (ask_price * S + price, index): stable radix sort; redone as prices move (below)
+  auto sort_workers = [&]() -> int {
+    if (!W) return PM_OK;
+    pm::pm_auction_cost_keys<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wb.p, e->auc_price.p, (long long)e->auc_scale, W, reinterpret_cast<unsigned long long*>(e->auc_ckey.p), e->auc_idx.p);
+    PM_LAUNCH_CHECK("pm_auction_cost_keys");
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, e->auc_key.p, e->auc_key_out.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 32, e->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, e->auc_ckey.p, e->auc_ckey_s.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 64, e->stream);
     PM_CUDA(e->cub_tmp.ensure(tmp));
-    PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_key.p, e->auc_key_out.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 32, e->stream));
+    PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_ckey.p, e->auc_ckey_s.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 64, e->stream));
     pm::pm_auction_gather_sorted<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wa.p, e->wb.p, e->auc_perm.p, e->auc_price.p, W, e->auc_wa_s.p,
                                                                             e->auc_wb_s.p, e->auc_pos_of.p, e->auc_price_s.p);
     PM_LAUNCH_CHECK("pm_auction_gather_sorted");
+    return PM_OK;
+  };
+  {
+    const int rc = sort_workers();
+    if (rc != PM_OK) return rc;
   }
   PM_CUDA(cudaMemsetAsync(e->auc_winner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
 
   pm::AuctionParams ap;
   ap.ev = eval_params(e);
   ap.wa_s = e->auc_wa_s.p; ap.wb_s = e->auc_wb_s.p; ap.perm = e->auc_perm.p; ap.pos_of = e->auc_pos_of.p; ap.price_s = e->auc_price_s.p;
+  ap.csort_s = reinterpret_cast<const unsigned long long*>(e->auc_ckey_s.p);
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
   ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
@@ -943,6 +953,7 @@ static int match_auction_locked(pm_engine* e) {
   const unsigned g_warp = std::max(1u, std::min(blocks_for(T, pm::kAucWarps), 1184u));
   const unsigned g_thr = std::max(1u, std::min(blocks_for(T, 256), 592u));
   const uint32_t kBatch = 32;  // rounds launched between polls of the control block
+  const uint32_t kResort = (e->tune_auction >> 8) ? (uint32_t)(e->tune_auction >> 8) : 4u;   // batches between re-sorts of the worker copy
   uint64_t eps = e->auc_eps_start ? e->auc_eps_start : 1;
   const uint32_t div = e->auc_eps_div < 2 ? 2 : e->auc_eps_div;
   for (;;) {  // eps phases: assignment cleared, prices (and so the class caches' bounds) kept
@@ -987,6 +998,7 @@ static int match_auction_locked(pm_engine* e) {
     }
     (void)cudaGetLastError();
     int rc_rounds = PM_OK;
+    uint32_t n_batches = 0;
     for (;;) {
       cudaError_t ce = cudaMemcpyAsync(e->h_ctl.p, e->auc_ctl.p, sizeof(pm::AuctionCtl), cudaMemcpyDeviceToHost, e->stream);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
@@ -1001,6 +1013,11 @@ static int match_auction_locked(pm_engine* e) {
       }
       if (e->h_ctl.p->n_active == 0) break;
       if (e->h_ctl.p->rounds > 50u * 1000u * 1000u) { rc_rounds = e->fail(PM_E_CUDA, "pm_match: auction did not terminate"); break; }
+      if (n_batches && n_batches % kResort == 0) {   // bid-up workers move back in the walk order
+        const int rc = sort_workers();
+        if (rc != PM_OK) { rc_rounds = rc; break; }
+      }
+      ++n_batches;
       if (graph_exec) ce = cudaGraphLaunch(graph_exec, e->stream);
       else { launch_rounds(); ce = cudaGetLastError(); }
       if (ce != cudaSuccess) { rc_rounds = e->fail(PM_E_CUDA, std::string("pm_match: auction rounds: ") + cudaGetErrorString(ce)); break; }

@@ -406,6 +406,36 @@ def test_extension_auction_scaled_costs_and_eps_phases(params):
     _check_auction(t, cap, **params)
 
 
+def test_extension_auction_cfg3_100k_x_1m_properties():
+    """BASELINE configs[2] names a price-capped auction at 100k asks x 1M workers.  The sequential checker cannot run at
+    this size (it scans every worker for every unassigned ask every round), so the full-size run is held to what can be
+    checked from the assignment alone: nobody is sold twice, every sale respects the cap and the requirements
+    (sampled against the oracle predicate), and the run terminates with far fewer table walks than bids."""
+    T, W = 100_000, 1_000_000
+    w, a, t = synth_tables(T, W, "mixed")
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = np.exp(np.log(10) + synth._unit(synth.SEED_EXT, W, 1) * np.log(200)).astype(np.uint32)
+    t["wb"] = wb
+    cap = np.exp(np.log(20) + synth._unit(synth.SEED_EXT, T, 2) * np.log(150)).astype(np.uint32)
+    eng = Engine()
+    load_engine(eng, t)
+    eng.set_price_caps(cap)
+    eng.match(abi.PM_MODE_AUCTION)
+    res = eng.fetch()
+    st = res.stats
+    ask_of_group = res.group_ask
+    sold = res.group_members
+    assert len(sold) == res.n_groups == len(ask_of_group) and res.n_groups > T // 2
+    assert len(np.unique(sold)) == len(sold) and len(np.unique(ask_of_group)) == len(ask_of_group)
+    assert np.all(wb["ext_ask_price"][sold] <= cap[ask_of_group])
+    rng = np.random.default_rng(3)
+    for g in rng.choice(res.n_groups, 300, replace=False):
+        tk, wk = int(ask_of_group[g]), int(sold[g])
+        assert orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][tk], t["opts"], t["bits"], t["words"])
+    assert st["n_rounds"] > 0 and st["n_tiles"] < 40 * st["n_rounds"]
+    eng.close()
+
+
 def test_extension_columns_are_neutral_in_reference_modes():
     """ext_ask_price only occupies the high word of the packed cost; groups do not depend on it."""
     w, a, t = synth_tables(200, 3000, "mixed")
