@@ -38,6 +38,9 @@
 //  * CLASS POOL.  The candidates the lanes held at the end of a walk (up to 1024) stay as the
 //    class's pool; a rescan request first re-ranks the pool at the current prices and walks the
 //    table only when the pool's best two no longer beat the bound on everything outside it.
+//  * SPLIT WALKS.  When a round has few walks (the long tail of an auction: a handful of scarce
+//    classes), each is split over up to 16 CTAs that take interleaved stripes; every part leaves
+//    its top 32 and one bound, and the part that arrives last (a ticket) merges them.
 //  * DEVICE-DRIVEN ROUNDS.  List lengths live in device memory; every kernel of a round is
 //    launched with a fixed grid and strides over its list, so the host launches rounds in batches
 //    and only polls the number of unassigned asks.
@@ -68,7 +71,8 @@ constexpr long long kThetaInvalid = 0x7FFFFFFFFFFFFFFFll;                // no c
 struct AuctionCtl {
   uint32_t n_active;     // unassigned, not withdrawn asks of the current round
   uint32_t n_next;       // ... being collected for the next one
-  uint32_t n_cls;        // classes to rescan this round
+  uint32_t n_cls;        // classes whose cache must be refreshed this round
+  uint32_t n_walk;       // ... of which the pool could not decide: they walk the worker table
   uint32_t n_retry;      // asks that bid again after the class rescans
   uint32_t n_fallback;   // asks that need their own scan
   uint32_t rounds;       // rounds in which at least one ask was active
@@ -104,6 +108,10 @@ struct AuctionParams {
   long long* pool_bound_v;     // [C] every compatible worker outside the pool ranks at or below this
   uint32_t* pool_bound_w;      // [C]
   uint32_t* class_list;        // [C]
+  uint32_t* walk_list;         // [C]
+  long long* split_bound_v;    // [grid * 16] per-part bounds of a walk split over several CTAs
+  uint32_t* split_bound_w;
+  uint32_t* split_ticket;      // [grid]
   uint32_t* retry;             // [T]
   uint32_t* fallback;          // [T]
   AuctionCtl* ctl;
@@ -284,7 +292,7 @@ __device__ __forceinline__ AuctionPick auction_select(long long (&cv)[4], uint32
 template <int TPC>
 __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, AuctionStage* stage, AuctionMerge& mg,
                                                    uint32_t& phase_bits, uint32_t base, const uint32_t* __restrict__ list,
-                                                   uint32_t n_list, bool cls_mode) {
+                                                   uint32_t n_list, bool cls_mode, uint32_t part, uint32_t G) {
   constexpr int kWpt = kAucWarps / TPC;           // warps per item
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t slot = base + warp / kWpt;
@@ -303,55 +311,15 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   if (threadIdx.x == 0) { mg.cnt[0] = 0; mg.cnt[1] = 0; mg.cnt[2] = 0; mg.flag = 0; }
   __syncthreads();
 
-  bool scan = live;       // this warp's item still needs the walk over the worker table
-  if (cls_mode) {
-    const long long pool_bound = live ? p.pool_bound_v[item] : kThetaInvalid;
-    const bool have_pool = live && pool_bound != kThetaInvalid && !(p.dbg & 8u);
-    if (have_pool) {
-      // the item's threads cover the pool's kAucPool / 4 slots (a single warp takes 8 slots per lane)
-      const uint4* pool = reinterpret_cast<const uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
-      for (uint32_t q = in_item; q < (uint32_t)(kAucPool / 4); q += kWpt * 32u) {
-        const uint4 e = pool[q];
-        const uint32_t pw[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
-      }
-      if (in_item == 0) {   // everything outside the pool
-        const uint32_t pbw = p.pool_bound_w[item];
-        if (auc_better(pool_bound, pbw, dropped, dropped_w)) { dropped = pool_bound; dropped_w = pbw; }
-      }
-    }
-    const AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
-    bool refilled = false;
-    if (sub == 0) {
-      refilled = have_pool && !(p.dbg & 16u) && (r.bound_v == kAucNeg || (r.b2 >= r.bound_v && auc_better(r.b1, r.w1, r.bound_v, r.bound_w)));
-      if (refilled) {
-        p.cand[(size_t)item * kAucCache + lane] = r.mine;
-        if (lane == 0) {
-          p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
-          p.theta_w[item] = r.bound_w;
-          atomicAdd(&p.ctl->n_refills, 1ull);
-        }
-      }
-    }
-    if (kWpt > 1) {   // the item's other warps follow warp 0's verdict
-      if (sub == 0 && lane == 0) mg.flag = refilled ? 1u : 0u;
-      __syncthreads();
-      refilled = mg.flag != 0u;
-    }
-    scan = live && !refilled;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { cv[j] = kAucNeg; cw[j] = kNone; }
-    dropped = kAucNeg; dropped_w = kNone;
-    if (!__syncthreads_or(scan)) return;   // (also: mg.flag may be rewritten)
-  }
+  const bool scan = live;
 
   const uint32_t W = p.ev.n_workers;
-  const uint32_t n_stripes = (W + kAucStripe - 1) / kAucStripe;
-  auto issue = [&](uint32_t k) {
-    AuctionStage& s = stage[k % kAucStages];
-    const uint32_t w0 = k * kAucStripe;
+  const uint32_t n_all = (W + kAucStripe - 1) / kAucStripe;
+  // a walk split over G CTAs: part `part` takes the stripes part, part + G, part + 2G, ...
+  const uint32_t n_stripes = n_all > part ? (n_all - part + G - 1u) / G : 0u;
+  auto issue = [&](uint32_t j) {
+    AuctionStage& s = stage[j % kAucStages];
+    const uint32_t w0 = (part + j * G) * kAucStripe;
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price_s[] and perm[] are padded
     const uint32_t nq = (n + 3u) & ~3u;
@@ -361,14 +329,14 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     bulk_g2s(s.price, p.price_s + w0, np * 8u, &s.bar);
     bulk_g2s(s.perm, p.perm + w0, nq * 4u, &s.bar);
   };
-  auto wait_stage = [&](uint32_t k) {
-    const uint32_t b = k % kAucStages;   // bit b of phase_bits = parity of the buffer's next completed phase
+  auto wait_stage = [&](uint32_t j) {
+    const uint32_t b = j % kAucStages;   // bit b of phase_bits = parity of the buffer's next completed phase
     mbar_wait(&stage[b].bar, (phase_bits >> b) & 1u);
     phase_bits ^= 1u << b;
   };
   uint32_t scanned = 0;
   uint32_t first_good = kNone;   // first stripe after which 33 candidates beat every unseen worker
-  bool unseen = false;           // the walk stopped before the end of the table ...
+  bool unseen = false;           // the walk stopped before the end of its stripes ...
   long long unseen_u = kAucNeg;  // ... where every remaining worker ranks at or below (unseen_u, unseen_w)
   uint32_t unseen_w = 0;
   if (threadIdx.x == 0)
@@ -378,7 +346,8 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     if (threadIdx.x == 0 && k + kAucStages - 1 < n_stripes) issue(k + kAucStages - 1);
     AuctionStage& s = stage[k % kAucStages];
     wait_stage(k);
-    const uint32_t n = min((uint32_t)kAucStripe, W - k * kAucStripe);
+    const uint32_t w0 = (part + k * G) * kAucStripe;
+    const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     if (scan) {
       scanned += n;
       for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
@@ -392,7 +361,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     // unseen workers, at least one of them stays outside the 32-entry cache, so the bound (best candidate not cached) beats
     // every unseen worker and the walk may stop; a class walks a little further to fill its pool; a single ask also
     // stops once the unseen workers cannot reach its outside option.
-    const long long u = -(long long)p.csort_s[k * kAucStripe + n - 1];
+    const long long u = -(long long)p.csort_s[w0 + n - 1];
     const bool past_cap = !cls_mode && u < -(((long long)cap + 1) * p.scale);
     // ... and a later worker whose value still equals U has the same sort key as the stripe's last worker, hence a
     // larger index: the unseen workers rank at or below (U, last index + 1) in (value desc, worker asc) order, which
@@ -420,24 +389,70 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
       break;
     }
   }
-  if (cls_mode && scan) {   // the new pool: what the lanes hold now
+  if (cls_mode && scan && G == 1u) {   // the new pool: what the lanes hold now
     uint4* pool = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
     pool[in_item] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     if (kWpt == 1)
       for (uint32_t j = 32u + lane; j < (uint32_t)(kAucPool / 4); j += 32u) pool[j] = make_uint4(kNone, kNone, kNone, kNone);
   }
-  const AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+  AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+  if (scan && sub == 0 && lane == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
+  long long pb_v = kAucNeg;   // outside the pool: what no lane kept, and the part of the table the walk did not reach
+  uint32_t pb_w = kNone;
+  if (kWpt > 1 && G > 1u) {
+    // Split walk: this part's top 32 become its slice of the pool, everything else it saw or skipped is summed up in
+    // one bound; the part that arrives last re-ranks the G slices into the class cache.
+    uint4* pool4 = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
+    if (sub == 0) {
+      p.pool[(size_t)item * kAucPool + part * 32u + lane] = r.mine;
+      if (lane == 0) {
+        long long bv = r.bound_v;
+        uint32_t bw = r.bound_w;
+        if (unseen && auc_better(unseen_u, unseen_w, bv, bw)) { bv = unseen_u; bw = unseen_w; }
+        p.split_bound_v[slot * 16u + part] = bv;
+        p.split_bound_w[slot * 16u + part] = bw;
+      }
+    }
+    {
+      const uint32_t j = G * 8u + threadIdx.x;   // the slots no slice uses
+      if (j < (uint32_t)(kAucPool / 4) && j % G == part) pool4[j] = make_uint4(kNone, kNone, kNone, kNone);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) mg.flag = (atomicAdd(p.split_ticket + slot, 1u) == G - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (mg.flag == 0u) return;   // uniform; the CTA has no further item in split mode
+    __threadfence();
+    long long bv = kAucNeg;
+    uint32_t bw = kNone;
+    if (sub == 0) {
+      if (lane < G) { bv = __ldcg(p.split_bound_v + slot * 16u + lane); bw = __ldcg(p.split_bound_w + slot * 16u + lane); }
+      warp_argbest(bv, bw, &pb_v, &pb_w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cv[j] = kAucNeg; cw[j] = kNone; }
+    dropped = kAucNeg; dropped_w = kNone;
+    {
+      const uint4 e = __ldcg(pool4 + in_item);
+      const uint32_t pw[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
+    }
+    if (in_item == 0) { dropped = pb_v; dropped_w = pb_w; }
+    r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+    if (threadIdx.x == 0) p.split_ticket[slot] = 0u;
+  } else if (scan && sub == 0) {
+    pb_v = r.drop_v;
+    pb_w = r.drop_w;
+    if (unseen && auc_better(unseen_u, unseen_w, pb_v, pb_w)) { pb_v = unseen_u; pb_w = unseen_w; }
+  }
   if (scan && sub == 0) {
-    if (lane == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
     if (cls_mode) {
       p.cand[(size_t)item * kAucCache + lane] = r.mine;
       if (lane == 0) {
         p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
         p.theta_w[item] = r.bound_w;
-        // outside the pool: what no lane kept, and the part of the table the walk did not reach
-        long long pb_v = r.drop_v;
-        uint32_t pb_w = r.drop_w;
-        if (unseen && auc_better(unseen_u, unseen_w, pb_v, pb_w)) { pb_v = unseen_u; pb_w = unseen_w; }
         p.pool_bound_v[item] = (pb_v == kAucNeg) ? kThetaComplete : pb_v;
         p.pool_bound_w[item] = pb_w;
         atomicAdd(&p.ctl->n_class_scans, 1ull);
@@ -450,23 +465,72 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   __syncthreads();   // mg and the stage buffers are reused by the CTA's next item
 }
 
+// Rescan requests first re-rank the class pool at the current prices (a few gathers per thread); the classes
+// whose pool cannot decide go on the walk list.
+__global__ void __launch_bounds__(kAucThreads) pm_auction_refill(AuctionParams p) {
+  __shared__ AuctionMerge mg;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t n = p.ctl->n_cls;
+  for (uint32_t slot = blockIdx.x; slot < n; slot += gridDim.x) {
+    const uint32_t item = p.class_list[slot];
+    const long long pool_bound = p.pool_bound_v[item];
+    if (pool_bound == kThetaInvalid || (p.dbg & 8u)) {   // no pool yet (uniform across the CTA)
+      if (threadIdx.x == 0) p.walk_list[atomicAdd(&p.ctl->n_walk, 1u)] = item;
+      continue;
+    }
+    long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
+    uint32_t cw[4] = {kNone, kNone, kNone, kNone};
+    long long dropped = kAucNeg;
+    uint32_t dropped_w = kNone;
+    const uint4 e = (reinterpret_cast<const uint4*>(p.pool) + (size_t)item * (kAucPool / 4))[threadIdx.x];
+    const uint32_t pw[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
+    if (threadIdx.x == 0) { dropped = pool_bound; dropped_w = p.pool_bound_w[item]; }   // everything outside the pool
+    const AuctionPick r = auction_select<kAucWarps>(cv, cw, dropped, dropped_w, mg);
+    if (warp == 0) {
+      const bool ok = !(p.dbg & 16u) && (r.bound_v == kAucNeg || (r.b2 >= r.bound_v && auc_better(r.b1, r.w1, r.bound_v, r.bound_w)));
+      if (ok) {
+        p.cand[(size_t)item * kAucCache + lane] = r.mine;
+        if (lane == 0) {
+          p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
+          p.theta_w[item] = r.bound_w;
+          atomicAdd(&p.ctl->n_refills, 1ull);
+        }
+      } else if (lane == 0) {
+        p.walk_list[atomicAdd(&p.ctl->n_walk, 1u)] = item;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kAucThreads) pm_auction_scan(AuctionParams p, int cls_mode) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AuctionStage* stage = reinterpret_cast<AuctionStage*>(smem_raw);            // [kAucStages]
   AuctionMerge& mg = *reinterpret_cast<AuctionMerge*>(smem_raw + kAucStages * sizeof(AuctionStage));
-  const uint32_t n = cls_mode ? p.ctl->n_cls : p.ctl->n_fallback;
-  const uint32_t* list = cls_mode ? p.class_list : p.fallback;
-  if (blockIdx.x >= n) return;
+  const uint32_t n = cls_mode ? p.ctl->n_walk : p.ctl->n_fallback;
+  const uint32_t* list = cls_mode ? p.walk_list : p.fallback;
+  // few class walks (the long tail of an auction): each is split over G CTAs, so that its latency, which is what a
+  // round then waits for, drops by G
+  uint32_t G = 1u;
+  if (cls_mode && n && 2u * n <= gridDim.x && !(p.dbg & 32u)) {
+    G = 16u;
+    while (n * G > gridDim.x) G >>= 1;
+  }
+  if (blockIdx.x >= n * G) return;
   if (threadIdx.x == 0)
     for (int b = 0; b < kAucStages; ++b) mbar_init(&stage[b].bar, 1);
   __syncthreads();
   uint32_t phase_bits = 0u;
-  if (n >= 8u * gridDim.x) {
+  if (G > 1u) {
+    auction_scan_items<1>(p, stage, mg, phase_bits, blockIdx.x / G, list, n, true, blockIdx.x % G, G);
+  } else if (n >= 8u * gridDim.x) {
     for (uint32_t base = blockIdx.x * 8u; base < n; base += gridDim.x * 8u)
-      auction_scan_items<8>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0);
+      auction_scan_items<8>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0, 0u, 1u);
   } else {
     for (uint32_t base = blockIdx.x; base < n; base += gridDim.x)
-      auction_scan_items<1>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0);
+      auction_scan_items<1>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0, 0u, 1u);
   }
 }
 
@@ -561,6 +625,7 @@ __global__ void pm_auction_advance(AuctionCtl* ctl, int first) {
   ctl->n_active = ctl->n_next;
   ctl->n_next = 0;
   ctl->n_cls = 0;
+  ctl->n_walk = 0;
   ctl->n_retry = 0;
   ctl->n_fallback = 0;
 }

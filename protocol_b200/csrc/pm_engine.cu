@@ -121,6 +121,8 @@ struct pm_engine {
   DevBuf<uint32_t> auc_cand, auc_theta_w, auc_pool, auc_pool_bound_w;
   DevBuf<long long> auc_pool_bound_v;
   DevBuf<uint32_t> auc_class_of, auc_class_rep, auc_class_req, auc_class_list, auc_retry, auc_fallback;
+  DevBuf<uint32_t> auc_walk_list, auc_split_w, auc_split_ticket;
+  DevBuf<long long> auc_split_v;
   DevBuf<uint32_t> auc_perm, auc_pos_of, auc_idx, auc_sorted, auc_incl;
   DevBuf<uint64_t> auc_hash, auc_hash_out, auc_ckey, auc_ckey_s;
   DevBuf<uint4> auc_wa_s, auc_wb_s;
@@ -320,6 +322,7 @@ void pm_destroy(pm_engine* e) {
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
   e->auc_theta.release(); e->auc_cand.release(); e->auc_theta_w.release();
+  e->auc_walk_list.release(); e->auc_split_w.release(); e->auc_split_ticket.release(); e->auc_split_v.release();
   e->auc_pool.release(); e->auc_pool_bound_w.release(); e->auc_pool_bound_v.release(); e->auc_ckey.release(); e->auc_ckey_s.release();
   e->auc_class_of.release(); e->auc_class_rep.release(); e->auc_class_req.release(); e->auc_class_list.release();
   e->auc_retry.release(); e->auc_fallback.release(); e->auc_perm.release(); e->auc_pos_of.release();
@@ -892,12 +895,16 @@ static int match_auction_locked(pm_engine* e) {
     if (rc != PM_OK) return rc;
   }
   const uint32_t C = e->auc_n_classes;
+  constexpr unsigned kScanGrid = 296u;   // two scanning CTAs per SM (shared memory)
   PM_CUDA(e->auc_price.ensure((size_t)W + 2)); PM_CUDA(e->auc_owner.ensure(W)); PM_CUDA(e->auc_bid_max.ensure(W));
   PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
   PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
   PM_CUDA(e->auc_theta.ensure(C)); PM_CUDA(e->auc_theta_w.ensure(C)); PM_CUDA(e->auc_cand.ensure((size_t)C * pm::kAucCache));
   PM_CUDA(e->auc_pool.ensure((size_t)C * pm::kAucPool)); PM_CUDA(e->auc_pool_bound_v.ensure(C)); PM_CUDA(e->auc_pool_bound_w.ensure(C));
+  PM_CUDA(e->auc_walk_list.ensure(C)); PM_CUDA(e->auc_split_v.ensure(kScanGrid * 16)); PM_CUDA(e->auc_split_w.ensure(kScanGrid * 16));
+  PM_CUDA(e->auc_split_ticket.ensure(kScanGrid));
+  PM_CUDA(cudaMemsetAsync(e->auc_split_ticket.p, 0, kScanGrid * 4, e->stream));
   PM_CUDA(e->auc_class_req.ensure(C)); PM_CUDA(e->auc_class_list.ensure(C)); PM_CUDA(e->auc_retry.ensure(T)); PM_CUDA(e->auc_fallback.ensure(T));
   PM_CUDA(e->auc_perm.ensure((size_t)W + 4)); PM_CUDA(e->auc_pos_of.ensure(W));
   PM_CUDA(e->auc_idx.ensure(std::max(W, T))); PM_CUDA(e->auc_wa_s.ensure(W)); PM_CUDA(e->auc_wb_s.ensure(W)); PM_CUDA(e->auc_price_s.ensure((size_t)W + 2));
@@ -944,12 +951,13 @@ static int match_auction_locked(pm_engine* e) {
   ap.class_of = e->auc_class_of.p; ap.class_rep = e->auc_class_rep.p; ap.class_req = e->auc_class_req.p;
   ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p;
   ap.pool = e->auc_pool.p; ap.pool_bound_v = e->auc_pool_bound_v.p; ap.pool_bound_w = e->auc_pool_bound_w.p;
+  ap.walk_list = e->auc_walk_list.p; ap.split_bound_v = e->auc_split_v.p; ap.split_bound_w = e->auc_split_w.p; ap.split_ticket = e->auc_split_ticket.p;
   ap.class_list = e->auc_class_list.p; ap.retry = e->auc_retry.p; ap.fallback = e->auc_fallback.p; ap.ctl = e->auc_ctl.p;
   ap.dbg = (uint32_t)e->tune_auction;
   const size_t smem = pm::kAucStages * sizeof(pm::AuctionStage) + sizeof(pm::AuctionMerge);
   PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // fixed grids: every kernel strides over a list whose length it reads from the control block
-  const unsigned g_scan = 296u;   // two CTAs per SM (shared memory)
+  const unsigned g_scan = kScanGrid;
   const unsigned g_warp = std::max(1u, std::min(blocks_for(T, pm::kAucWarps), 1184u));
   const unsigned g_thr = std::max(1u, std::min(blocks_for(T, 256), 592u));
   const uint32_t kBatch = 32;  // rounds launched between polls of the control block
@@ -975,6 +983,7 @@ static int match_auction_locked(pm_engine* e) {
     auto launch_rounds = [&]() {
       for (uint32_t r = 0; r < kBatch; ++r) {
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 0);
+        pm::pm_auction_refill<<<g_scan, pm::kAucThreads, 0, e->stream>>>(ap);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 1);
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 1);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 0);
@@ -1032,7 +1041,7 @@ static int match_auction_locked(pm_engine* e) {
   e->stats.evals = e->h_ctl.p->evals;
   e->stats.n_tiles = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_class_scans, 0xFFFFFFFFull);
   e->stats.n_fused_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_ask_scans, 0xFFFFFFFFull);
-  e->stats.n_launches = e->h_ctl.p->rounds * 8u;
+  e->stats.n_launches = e->h_ctl.p->rounds * 9u;
   e->stats.n_build_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_refills, 0xFFFFFFFFull);
   tm.stop();
   Timer tr(e, &e->stats.ms_resolve);

@@ -432,7 +432,7 @@ def test_extension_auction_cfg3_100k_x_1m_properties():
     for g in rng.choice(res.n_groups, 300, replace=False):
         tk, wk = int(ask_of_group[g]), int(sold[g])
         assert orc.soa_compatible(t["wa"][wk], t["wb"][wk], t["asks"][tk], t["opts"], t["bits"], t["words"])
-    assert st["n_rounds"] > 0 and st["n_tiles"] < 40 * st["n_rounds"]
+    assert st["n_rounds"] > 0 and st["n_tiles"] < 100 * st["n_rounds"]     # ~30 table walks per round, 12.4k classes
     eng.close()
 
 
