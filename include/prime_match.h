@@ -372,6 +372,11 @@ int pm_plugin_record_upload(pm_plugin*, const char* address, const char* group_i
 /* JSON out (NUL-terminated into buf): NodeGroup {"id","nodes","configuration_name","task_id"} or null */
 int pm_plugin_get_node_group(pm_plugin*, const char* address, char* buf, size_t len);
 int pm_plugin_get_all_groups(pm_plugin*, char* buf, size_t len);           /* sorted by id, mod.rs:1040 */
+/* get_group_by_id (mod.rs:1046-1055); validate_group_exists (:1067-1070) is `result != null`      */
+int pm_plugin_get_group_by_id(pm_plugin*, const char* group_id, char* buf, size_t len);
+/* handle_group_not_found (mod.rs:1073-1119): the task of a group that was dissolved under the scheduler goes
+ * to the first idle group in get_all_groups() order (SET NX); *reassigned = 1 when one took it      */
+int pm_plugin_handle_group_not_found(pm_plugin*, const char* group_id, const char* task_id, uint32_t* reassigned);
 /* Redis write-back in the reference's key formats (mod.rs:25-28,299-322,471-476), as a JSON array of
  * commands, so /groups, /nodes, storage routes and the metrics sync keep working unchanged.        */
 int pm_plugin_redis_writeback(pm_plugin*, char* buf, size_t len);

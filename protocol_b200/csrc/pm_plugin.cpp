@@ -944,6 +944,36 @@ int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
   return emit(p, out, buf, len);
 }
 
+// get_group_by_id (mod.rs:1046-1055): JSON NodeGroup or "null"
+int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, size_t len) {
+  if (!p || !group_id) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  std::string out = "null";
+  auto g = p->groups.find(group_id);
+  if (g != p->groups.end()) {
+    out.clear();
+    group_json(p, g->second, out);
+  }
+  return emit(p, out, buf, len);
+}
+
+// handle_group_not_found (mod.rs:1073-1119): walk get_all_groups() (id order); the first group without a
+// current task takes the orphaned one (assign_task_to_group = SET NX, mod.rs:471-476).  Finding none is not
+// an error (the reference logs a warning and returns Ok).
+int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const char* task_id, uint32_t* reassigned) {
+  if (!p || !group_id || !task_id) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (reassigned) *reassigned = 0;
+  for (const auto& kv : p->groups) {
+    if (p->current_group_task(kv.first)) continue;
+    if (p->group_task.count(kv.first)) continue;   // SET NX lost
+    p->group_task[kv.first] = task_id;
+    if (reassigned) *reassigned = 1;
+    break;
+  }
+  return PM_OK;
+}
+
 // The keys a drop-in must leave in Redis for /groups, /nodes, storage routes and the metrics sync to
 // keep working unchanged (mod.rs:25-28, 299-322, 471-476): a JSON array of commands
 //   ["SET","node_group:<id>","<NodeGroup json>"], ["SADD","orchestrator:groups_index","<id>"],

@@ -258,6 +258,20 @@ class NodeGroupsPlugin:
     def get_all_groups(self):
         return self._json(self._lib.pm_plugin_get_all_groups)
 
+    def get_group_by_id(self, group_id: str):
+        """mod.rs:1046-1055."""
+        return self._json(self._lib.pm_plugin_get_group_by_id, group_id.encode())
+
+    def validate_group_exists(self, group_id: str) -> bool:
+        """mod.rs:1067-1070."""
+        return self.get_group_by_id(group_id) is not None
+
+    def handle_group_not_found(self, group_id: str, task_id: str) -> bool:
+        """mod.rs:1073-1119: True when an idle group took the orphaned task."""
+        n = C.c_uint32()
+        self._check(self._lib.pm_plugin_handle_group_not_found(self._h, group_id.encode(), task_id.encode(), C.byref(n)))
+        return bool(n.value)
+
     def redis_writeback(self):
         """[[cmd, key, ...], ...] in the reference's key formats (mod.rs:25-28, 299-322)."""
         return self._json(self._lib.pm_plugin_redis_writeback, cap=1 << 24)

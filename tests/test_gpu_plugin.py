@@ -446,3 +446,60 @@ def test_edge_case_no_available_tasks(engine):
     g = plugin.get_node_group(A1)
     assert g["nodes"] == [A1, A2] and g["task_id"] is None
     assert Scheduler(plugin).get_task_for_node(A1) is None
+
+
+def test_group_formation_with_requirements_and_single_node(engine):
+    """tests.rs:303-385: a node without specs stays out of a configuration with requirements; one that meets
+    them forms the solo group."""
+    cfg = NodeGroupConfiguration("test-config-with-requirements", 1, 1, "gpu:count=8;gpu:model=RTX4090;")
+    plugin = make(engine, [cfg])
+    plugin.add_task(Task(allowed_topologies=[cfg.name]))
+    plugin.add_node(OrchestratorNode(A1))                    # compute_specs: None
+    plugin.try_form_new_groups()
+    assert plugin.get_node_group(A1) is None
+    plugin.add_node(OrchestratorNode(A2, compute_specs=RTX))
+    plugin.try_form_new_groups()
+    g = plugin.get_node_group(A2)
+    assert g is not None and g["nodes"] == [A2]
+    assert plugin.get_node_group(A1) is None
+
+
+def test_merge_solo_groups_with_active_tasks(engine):
+    """tests.rs:2171-2336: three nodes, a configuration of up to three, two tasks: everybody ends up grouped in at
+    most two groups (here: one group of three, the first-fit chunk by max_group_size), and a merge pass afterwards
+    leaves everybody grouped."""
+    plugin = make(engine, [NodeGroupConfiguration("merge-config", 1, 3)])
+    nodes = ["0x1111111111111111111111111111111111111111", "0x2222222222222222222222222222222222222222",
+             "0x3333333333333333333333333333333333333333"]
+    for a in nodes:
+        plugin.add_node(OrchestratorNode(a))
+    plugin.add_task(Task(allowed_topologies=["merge-config"]))
+    plugin.add_task(Task(allowed_topologies=["merge-config"]))
+    plugin.try_form_new_groups()
+    groups = [plugin.get_node_group(a) for a in nodes]
+    assert all(g is not None for g in groups)
+    assert {n for g in groups for n in g["nodes"]} == set(nodes)
+    assert len({g["id"] for g in groups}) == 1 and groups[0]["nodes"] == nodes
+    plugin.try_merge_solo_groups()                           # nothing solo is left; the pass must not disturb the group
+    assert [plugin.get_node_group(a) for a in nodes] == groups
+
+
+def test_scheduler_integration_with_dissolved_groups(engine):
+    """tests.rs:2783-2858: validate_group_exists, and handle_group_not_found when no other group can take the task."""
+    plugin = make(engine, [NodeGroupConfiguration("scheduler-test", 1, 2)])
+    node = "0x1111111111111111111111111111111111111111"
+    plugin.add_node(OrchestratorNode(node))
+    assert plugin.validate_group_exists("nonexistent-group") is False
+    plugin.enable_configuration("scheduler-test")
+    plugin.try_form_new_groups()
+    group = plugin.get_node_group(node)
+    assert group is not None
+    assert plugin.validate_group_exists(group["id"]) is True
+    assert plugin.get_group_by_id(group["id"]) == group
+    task = Task(allowed_topologies=["scheduler-test"])
+    plugin.add_task(task)
+    # the only group is idle: it takes the orphaned task (the reference only asserts that the call succeeds)
+    assert plugin.handle_group_not_found("dissolved-group", task.id) is True
+    assert plugin.get_node_group(node)["task_id"] == task.id
+    assert plugin.handle_group_not_found("dissolved-group", task.id) is False      # nobody idle any more
+    assert Scheduler(plugin).get_task_for_node(node)["id"] == task.id
