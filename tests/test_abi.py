@@ -51,3 +51,11 @@ def test_engine_fails_loudly_without_gpu():
         Engine()
     assert ei.value.status == abi.PM_E_NO_DEVICE
     assert "no CPU path" in str(ei.value) or "sm_100" in str(ei.value)
+
+
+def test_integration_doc_binds_every_export():
+    """INTEGRATION.md shows the reference-side (Rust) binding of the boundary: every exported entry point is named."""
+    import os
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    missing = [name for name in abi.EXPORTS if name not in doc]
+    assert not missing, missing
