@@ -27,6 +27,7 @@
 #include <set>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/prime_match.h"
@@ -77,6 +78,7 @@ struct NodeRec {
   pm_worker_b b{};
   bool has_loc = false;
   double lat = 0, lon = 0;
+  uint64_t sync_gen = 0;               // the discovery fetch that last touched the node (de-dup by id within a fetch)
 };
 
 struct Group {  // NodeGroup, mod.rs:63-69
@@ -170,6 +172,7 @@ struct pm_plugin {
   // (ip, port) -> number of Healthy nodes: replaces the per-node full scan of
   // count_healthy_nodes_with_same_endpoint (discovery/monitor.rs:218-234, Theta(N^2) per sync)
   std::unordered_map<std::string, uint32_t> healthy_at;
+  uint64_t sync_gen = 0;
 
   static std::string endpoint_key(const std::string& ip, uint16_t port) { return ip + ":" + std::to_string(port); }
   void index_remove(const NodeRec& n) {
@@ -369,24 +372,43 @@ int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status
 
 // DiscoveryMonitor::get_nodes -> sync_single_node_with_discovery (discovery/monitor.rs:236-435):
 // reconcile the validated nodes reported by the discovery service into the node table.
-int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
-                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
-  if (!p || (n && !dn)) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
-  if (n_new) *n_new = 0;
-  std::set<std::string> seen;  // "Remove duplicates based on node ID" (:203-210)
+}  // extern "C"
+
+// One fetch may be applied in several chunks (the JSON path releases the table lock between them, as the
+// reference awaits between nodes).  "Remove duplicates based on node ID" (:203-210): a node carries the number of
+// the fetch that last touched it; ids of this fetch that were not stored are kept in `unstored`.
+// The caller holds p->mu.
+struct ExistingView {   // the fields of the snapshot the reference keeps testing against
+  uint32_t status;
+  int64_t last_status_change_ms;
+  bool has_loc;
+};
+static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
+                                uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new, uint64_t gen,
+                                std::unordered_set<std::string>& unstored) {
+  std::string addr, ip, key;   // reused: no allocation per node once grown
   for (uint32_t i = 0; i < n; ++i) {
     const pm_discovery_node& d = dn[i];
     if (!d.node.address || !d.ip_address) return p->fail(PM_E_INVALID, "discovery node without id / ip");
     if (!d.is_validated) continue;                       // fetch keeps validated nodes only
-    if (!seen.insert(d.node.address).second) continue;
-    const std::string addr(d.node.address), ip(d.ip_address);
+    addr.assign(d.node.address);
+    ip.assign(d.ip_address);
     auto it = p->node_index.find(addr);
     const bool exists = it != p->node_index.end();
+    if (exists) {
+      NodeRec& e = p->nodes[it->second];
+      if (e.sync_gen == gen) continue;                   // a second entry with this id in the same fetch
+      e.sync_gen = gen;
+    } else if (!unstored.empty() && unstored.count(addr)) {
+      continue;
+    }
     // count_healthy_nodes_with_same_endpoint (:218-234) through the endpoint index
     uint32_t same = 0;
     {
-      auto h = p->healthy_at.find(pm_plugin::endpoint_key(ip, d.port));
+      key.assign(ip);
+      key += ':';
+      key += std::to_string(d.port);
+      auto h = p->healthy_at.find(key);
       if (h != p->healthy_at.end()) same = h->second;
       if (exists) {
         const NodeRec& e = p->nodes[it->second];
@@ -395,7 +417,7 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
     }
     if (exists) {
       NodeRec& node = p->nodes[it->second];
-      const NodeRec existing = node;                     // the snapshot the reference keeps testing against
+      const ExistingView existing{node.status, node.last_status_change_ms, node.has_loc};
       if (same > 0 && existing.status != kHealthy) {     // :254-268
         p->set_status(node, kDead, now_ms);
         continue;
@@ -408,7 +430,7 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
             existing.last_status_change_ms < 0 || (now_ms - existing.last_status_change_ms) > 5 * 60 * 1000;
         if (should_mark_inactive) p->set_status(node, d.is_provider_whitelisted ? kDead : kEjected, now_ms);
       }
-      if (existing.ip_address != ip) {                                                                   // :340-348
+      if (node.ip_address != ip) {                       // existing.ip_address: nothing above changes it     // :340-348
         p->index_remove(node);
         node.ip_address = ip;
         p->index_add(node);
@@ -433,7 +455,10 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
       }
       if (d.has_latest_balance && d.latest_balance_is_zero) p->set_status(node, kLowBalance, now_ms);    // :391-402
     } else {
-      if (same >= max_healthy_nodes_with_same_endpoint) continue;                                        // :405-415
+      if (same >= max_healthy_nodes_with_same_endpoint) {                                                // :405-415
+        unstored.insert(addr);
+        continue;
+      }
       NodeRec node;                                      // OrchestratorNode::from(DiscoveryNode), models/node.rs:46-66
       node.address = addr;
       node.ip_address = ip;
@@ -441,6 +466,7 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
       node.status = kDiscovered;
       node.has_p2p = false;                              // p2p_id: None until the first heartbeat
       node.first_seen_ms = now_ms;
+      node.sync_gen = gen;
       const uint32_t keep = PM_W_HAS_SPECS | PM_W_HAS_GPU | PM_W_HAS_GPU_COUNT | PM_W_HAS_GPU_MEM | PM_W_HAS_GPU_MODEL |
                             PM_W_HAS_CPU | PM_W_HAS_CPU_CORES | PM_W_HAS_RAM | PM_W_HAS_STORAGE;
       node.a.flags = d.node.spec_flags & keep;
@@ -460,6 +486,19 @@ int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t
   }
   return PM_OK;
 }
+
+extern "C" {
+
+int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
+                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
+  if (!p || (n && !dn)) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (n_new) *n_new = 0;
+  std::unordered_set<std::string> unstored;
+  return sync_discovery_chunk(p, dn, n, now_ms, max_healthy_nodes_with_same_endpoint, n_new, ++p->sync_gen, unstored);
+}
+
+}  // extern "C"
 
 namespace {
 
@@ -491,79 +530,274 @@ int64_t rfc3339_ms(const pmjson::Value* v) {
   return ms;
 }
 
+// One DiscoveryNode of the wire format, reduced to what the monitor reads (owning copies of the strings).
+struct DiscRec {
+  std::string id, ip, model;
+  uint32_t port = 0, flags = 0, gpu_count = 0, gpu_mem_mb = 0, cpu_cores = 0, ram_mb = 0, storage_gb = 0;
+  bool has_loc = false, validated = false, active = false, whitelisted = false, blacklisted = false;
+  bool has_balance = false, balance_zero = false;
+  double lat = 0, lon = 0;
+  int64_t last_updated_ms = -1;
+};
+
+struct KeyView {   // an object key, compared in place
+  const char* p;
+  size_t n;
+  bool operator==(const char* s) const { return std::strlen(s) == n && std::memcmp(p, s, n) == 0; }
+};
+
+// Walks the object at the cursor (after its '{'): `on_key(key)` must consume the value and returns false on malformed
+// input.  Returns false on malformed JSON.
+template <class F>
+bool walk_object(pmjson::Parser& ps, std::string& scratch, F&& on_key) {
+  if (ps.consume('}')) return true;
+  for (;;) {
+    KeyView k;
+    if (!ps.read_key(&scratch, &k.p, &k.n) || !ps.consume(':')) return false;
+    if (!on_key(k)) return false;
+    if (ps.consume(',')) continue;
+    return ps.consume('}');
+  }
+}
+
+// compute_specs (shared/src/models/node.rs:128-178): typed read, unknown members (gpu.indices, cpu.model, storage_path ...)
+// are skipped in place.  Anything but an object (null) means "no specs".  First occurrence of a key counts.
+bool read_specs(pmjson::Parser& ps, DiscRec& d, uint32_t* flags, std::string& key, pmjson::Value& tmp) {
+  if (ps.peek() != '{') return ps.skip_value(2);
+  ps.consume('{');
+  uint32_t f = PM_W_HAS_SPECS, seen = 0;
+  const bool ok = walk_object(ps, key, [&](const KeyView& k) {
+    if (k == "gpu" && !(seen & 1u)) {
+      seen |= 1u;
+      if (ps.peek() != '{') return ps.skip_value(3);
+      ps.consume('{');
+      f |= PM_W_HAS_GPU;
+      uint32_t gseen = 0;
+      std::string gkey;
+      return walk_object(ps, gkey, [&](const KeyView& g) {
+        if (g == "count" && !(gseen & 1u)) { gseen |= 1u; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (json_u32(&tmp, &d.gpu_count)) f |= PM_W_HAS_GPU_COUNT; return true; }
+        if (g == "memory_mb" && !(gseen & 2u)) { gseen |= 2u; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (json_u32(&tmp, &d.gpu_mem_mb)) f |= PM_W_HAS_GPU_MEM; return true; }
+        if (g == "model" && !(gseen & 4u)) {
+          gseen |= 4u;
+          tmp = pmjson::Value();
+          if (!ps.read_value(&tmp)) return false;
+          if (tmp.kind == pmjson::Value::String) { f |= PM_W_HAS_GPU_MODEL; d.model = std::move(tmp.str); }
+          return true;
+        }
+        return ps.skip_value(4);
+      });
+    }
+    if (k == "cpu" && !(seen & 2u)) {
+      seen |= 2u;
+      if (ps.peek() != '{') return ps.skip_value(3);
+      ps.consume('{');
+      f |= PM_W_HAS_CPU;
+      bool cseen = false;
+      std::string ckey;
+      return walk_object(ps, ckey, [&](const KeyView& c) {
+        if (c == "cores" && !cseen) { cseen = true; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (json_u32(&tmp, &d.cpu_cores)) f |= PM_W_HAS_CPU_CORES; return true; }
+        return ps.skip_value(4);
+      });
+    }
+    if (k == "ram_mb" && !(seen & 4u)) { seen |= 4u; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (json_u32(&tmp, &d.ram_mb)) f |= PM_W_HAS_RAM; return true; }
+    if (k == "storage_gb" && !(seen & 8u)) { seen |= 8u; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (json_u32(&tmp, &d.storage_gb)) f |= PM_W_HAS_STORAGE; return true; }
+    return ps.skip_value(3);
+  });
+  *flags = f;
+  return ok;
+}
+
+// location (node.rs:25-44): latitude and longitude must both be numbers
+bool read_location(pmjson::Parser& ps, DiscRec& d, std::string& key, pmjson::Value& tmp) {
+  if (ps.peek() != '{') return ps.skip_value(2);
+  ps.consume('{');
+  bool have_la = false, have_lo = false, seen_la = false, seen_lo = false;
+  double la = 0, lo = 0;
+  const bool ok = walk_object(ps, key, [&](const KeyView& k) {
+    if (k == "latitude" && !seen_la) { seen_la = true; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (tmp.kind == pmjson::Value::Number) { have_la = true; la = tmp.num; } return true; }
+    if (k == "longitude" && !seen_lo) { seen_lo = true; tmp = pmjson::Value(); if (!ps.read_value(&tmp)) return false; if (tmp.kind == pmjson::Value::Number) { have_lo = true; lo = tmp.num; } return true; }
+    return ps.skip_value(3);
+  });
+  if (ok && have_la && have_lo) { d.has_loc = true; d.lat = la; d.lon = lo; }
+  return ok;
+}
+
+// Reads one node object at the parser's cursor.  Only the fields the monitor uses are materialised;
+// everything else is skipped without building it.  Duplicate keys: the first occurrence counts.
+bool read_discovery_node(pmjson::Parser& ps, DiscRec* out, std::string* err) {
+  enum { kId, kIp, kPort, kSpecs, kLoc, kValidated, kActive, kWhitelisted, kBlacklisted, kLastUpdated, kBalance, kNumKeys };
+  static const char* const kNames[kNumKeys] = {"id", "ip_address", "port", "compute_specs", "location", "is_validated", "is_active",
+                                               "is_provider_whitelisted", "is_blacklisted", "last_updated", "latest_balance"};
+  auto bad = [&]() {
+    *err = "discovery JSON: " + (ps.error().empty() ? std::string("invalid JSON") : ps.error());
+    return false;
+  };
+  DiscRec& d = *out;
+  d = DiscRec();
+  if (ps.peek() != '{') {   // an element that is not an object has no id
+    if (!ps.skip_value(2)) return bad();
+    *err = "discovery JSON: node without id / ip_address";
+    return false;
+  }
+  ps.consume('{');
+  pmjson::Value vals[kNumKeys];   // scalars only (compute_specs and location are read in place)
+  pmjson::Value tmp;
+  uint32_t have = 0, flags = 0;
+  std::string key, sub;
+  const bool ok = walk_object(ps, key, [&](const KeyView& k) {
+    int j = -1;
+    for (int q = 0; q < kNumKeys; ++q)
+      if (!(have & (1u << q)) && k == kNames[q]) { j = q; break; }
+    if (j < 0) return ps.skip_value(2);
+    have |= 1u << j;
+    if (j == kSpecs) return read_specs(ps, d, &flags, sub, tmp);
+    if (j == kLoc) return read_location(ps, d, sub, tmp);
+    return ps.read_value(&vals[j]);
+  });
+  if (!ok) return bad();
+  auto get = [&](int k) -> pmjson::Value* { return (have & (1u << k)) ? &vals[k] : nullptr; };
+  pmjson::Value* id = get(kId);
+  pmjson::Value* ip = get(kIp);
+  if (!id || id->kind != pmjson::Value::String || !ip || ip->kind != pmjson::Value::String) {
+    *err = "discovery JSON: node without id / ip_address";
+    return false;
+  }
+  d.id = std::move(id->str);
+  d.ip = std::move(ip->str);
+  json_u32(get(kPort), &d.port);
+  d.port &= 0xFFFFu;
+  d.flags = flags;
+  d.validated = json_bool(get(kValidated), false);
+  d.active = json_bool(get(kActive), false);
+  d.whitelisted = json_bool(get(kWhitelisted), false);   // #[serde(default)]
+  d.blacklisted = json_bool(get(kBlacklisted), false);
+  d.last_updated_ms = rfc3339_ms(get(kLastUpdated));
+  const pmjson::Value* bal = get(kBalance);                // Option<U256>
+  if (bal && !bal->is_null()) {
+    d.has_balance = true;
+    const std::string& t = bal->str;   // decimal, hex quantity ("0x0") or a JSON number
+    bool zero = !t.empty();
+    for (size_t k = (t.rfind("0x", 0) == 0 ? 2 : 0); k < t.size(); ++k)
+      if (t[k] != '0') zero = false;
+    d.balance_zero = zero;
+  }
+  return true;
+}
+
+// streams the elements of the array at the cursor into `recs`
+bool read_discovery_array(pmjson::Parser& ps, std::vector<DiscRec>* recs, std::string* err) {
+  if (!ps.consume('[')) { *err = "discovery JSON: no node array"; return false; }
+  if (ps.consume(']')) return true;
+  for (;;) {
+    recs->emplace_back();
+    if (!read_discovery_node(ps, &recs->back(), err)) return false;
+    if (ps.consume(',')) continue;
+    if (ps.consume(']')) return true;
+    *err = "discovery JSON: invalid JSON";
+    return false;
+  }
+}
+
 }  // namespace
+
+extern "C" {
 
 // The discovery service's wire format: `{"success":true,"data":[DiscoveryNode,...]}` (or a bare
 // array), DiscoveryNode = flattened Node + flags (shared/src/models/node.rs:10-23, 552-570).
+// (f-1) ingest: the body is read in one streaming pass — no document tree, unknown fields skipped in place —
+// into compact records (nothing is applied if the body does not parse, like `response.json()` failing in the
+// reference), which then go through the monitor's per-node logic in chunks, the table lock released in between.
 int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, int64_t now_ms,
                                   uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
   if (!p || !json) return PM_E_INVALID;
-  pmjson::Value root;
+  if (n_new) *n_new = 0;
+  std::vector<DiscRec> recs;
+  recs.reserve(len / 384 + 1);   // a node of the wire format is several hundred bytes
   std::string err;
-  if (!pmjson::Parser(json, len).parse(&root, &err)) return p->fail(PM_E_PARSE, "discovery JSON: " + err);
-  const pmjson::Value* list = &root;
-  if (root.kind == pmjson::Value::Object) list = root.get("data");
-  if (!list || list->kind != pmjson::Value::Array) return p->fail(PM_E_PARSE, "discovery JSON: no node array");
-  std::vector<pm_discovery_node> nodes(list->arr.size());
-  for (size_t i = 0; i < list->arr.size(); ++i) {
-    const pmjson::Value& n = list->arr[i];
-    pm_discovery_node& d = nodes[i];
-    std::memset(&d, 0, sizeof d);
-    const pmjson::Value* id = n.get("id");
-    const pmjson::Value* ip = n.get("ip_address");
-    if (!id || id->kind != pmjson::Value::String || !ip || ip->kind != pmjson::Value::String)
-      return p->fail(PM_E_PARSE, "discovery JSON: node without id / ip_address");
-    d.node.address = id->str.c_str();
-    d.ip_address = ip->str.c_str();
-    uint32_t port = 0;
-    json_u32(n.get("port"), &port);
-    d.port = (uint16_t)port;
-    uint32_t f = 0;
-    const pmjson::Value* specs = n.get("compute_specs");
-    if (specs && specs->kind == pmjson::Value::Object) {
-      f |= PM_W_HAS_SPECS;
-      const pmjson::Value* gpu = specs->get("gpu");
-      if (gpu && gpu->kind == pmjson::Value::Object) {
-        f |= PM_W_HAS_GPU;
-        if (json_u32(gpu->get("count"), &d.node.gpu_count)) f |= PM_W_HAS_GPU_COUNT;
-        if (json_u32(gpu->get("memory_mb"), &d.node.gpu_mem_mb)) f |= PM_W_HAS_GPU_MEM;
-        const pmjson::Value* model = gpu->get("model");
-        if (model && model->kind == pmjson::Value::String) { f |= PM_W_HAS_GPU_MODEL; d.node.gpu_model = model->str.c_str(); }
+  {
+    pmjson::Parser ps(json, len);
+    bool ok = true, found = false;
+    const char c = ps.peek();
+    if (c == '[') {
+      found = true;
+      ok = read_discovery_array(ps, &recs, &err);
+    } else if (c == '{') {
+      ps.consume('{');
+      if (!ps.consume('}')) {
+        std::string key;
+        for (;;) {
+          if (!ps.read_string(&key) || !ps.consume(':')) { ok = false; break; }
+          if (key == "data" && !found) {
+            found = true;
+            if (ps.peek() != '[') { ok = false; err = "discovery JSON: no node array"; break; }
+            if (!read_discovery_array(ps, &recs, &err)) { ok = false; break; }
+          } else if (!ps.skip_value(1)) {
+            ok = false;
+            break;
+          }
+          if (ps.consume(',')) continue;
+          if (ps.consume('}')) break;
+          ok = false;
+          break;
+        }
       }
-      const pmjson::Value* cpu = specs->get("cpu");
-      if (cpu && cpu->kind == pmjson::Value::Object) {
-        f |= PM_W_HAS_CPU;
-        if (json_u32(cpu->get("cores"), &d.node.cpu_cores)) f |= PM_W_HAS_CPU_CORES;
-      }
-      if (json_u32(specs->get("ram_mb"), &d.node.ram_mb)) f |= PM_W_HAS_RAM;
-      if (json_u32(specs->get("storage_gb"), &d.node.storage_gb)) f |= PM_W_HAS_STORAGE;
+    } else {
+      ok = ps.skip_value();   // a scalar document: well-formed or not, it holds no node array
+      if (ok && ps.at_end()) err = "discovery JSON: no node array";
+      if (ok && !ps.at_end()) err = "discovery JSON: trailing characters after JSON value";
+      ok = false;
     }
-    d.node.spec_flags = f;
-    const pmjson::Value* loc = n.get("location");
-    if (loc && loc->kind == pmjson::Value::Object) {
-      const pmjson::Value *la = loc->get("latitude"), *lo = loc->get("longitude");
-      if (la && lo && la->kind == pmjson::Value::Number && lo->kind == pmjson::Value::Number) {
-        d.node.has_location = 1;
-        d.node.lat = la->num;
-        d.node.lon = lo->num;
-      }
-    }
-    d.is_validated = json_bool(n.get("is_validated"), false);
-    d.is_active = json_bool(n.get("is_active"), false);
-    d.is_provider_whitelisted = json_bool(n.get("is_provider_whitelisted"), false);   // #[serde(default)]
-    d.is_blacklisted = json_bool(n.get("is_blacklisted"), false);
-    d.last_updated_ms = rfc3339_ms(n.get("last_updated"));
-    const pmjson::Value* bal = n.get("latest_balance");                                 // Option<U256>
-    if (bal && !bal->is_null()) {
-      d.has_latest_balance = 1;
-      const std::string& t = bal->str;   // decimal, hex quantity ("0x0") or a JSON number
-      bool zero = !t.empty();
-      for (size_t k = (t.rfind("0x", 0) == 0 ? 2 : 0); k < t.size(); ++k)
-        if (t[k] != '0') zero = false;
-      d.latest_balance_is_zero = zero;
+    if (ok && !ps.at_end()) { ok = false; err = "discovery JSON: trailing characters after JSON value"; }
+    if (ok && !found) { ok = false; err = "discovery JSON: no node array"; }
+    if (!ok) {
+      std::lock_guard<std::mutex> lk(p->mu);
+      return p->fail(PM_E_PARSE, err.empty() ? (ps.error().empty() ? "discovery JSON: invalid JSON" : "discovery JSON: " + ps.error()) : err);
     }
   }
-  return pm_plugin_sync_discovery(p, nodes.data(), (uint32_t)nodes.size(), now_ms, max_healthy_nodes_with_same_endpoint, n_new);
+  std::unordered_set<std::string> unstored;
+  uint64_t gen;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    gen = ++p->sync_gen;
+    if (p->node_index.empty()) {   // first fetch: no rehashing or table moves while the chunks go in
+      p->node_index.reserve(recs.size());
+      p->nodes.reserve(recs.size());
+    }
+  }
+  constexpr size_t kChunk = 8192;
+  std::vector<pm_discovery_node> nodes(std::min(recs.size(), kChunk));
+  for (size_t base = 0; base < recs.size(); base += kChunk) {
+    const size_t n = std::min(kChunk, recs.size() - base);
+    for (size_t i = 0; i < n; ++i) {
+      const DiscRec& r = recs[base + i];
+      pm_discovery_node& d = nodes[i];
+      std::memset(&d, 0, sizeof d);
+      d.node.address = r.id.c_str();
+      d.ip_address = r.ip.c_str();
+      d.port = (uint16_t)r.port;
+      d.node.spec_flags = r.flags;
+      d.node.gpu_count = r.gpu_count;
+      d.node.gpu_mem_mb = r.gpu_mem_mb;
+      d.node.gpu_model = (r.flags & PM_W_HAS_GPU_MODEL) ? r.model.c_str() : nullptr;
+      d.node.cpu_cores = r.cpu_cores;
+      d.node.ram_mb = r.ram_mb;
+      d.node.storage_gb = r.storage_gb;
+      d.node.has_location = r.has_loc;
+      d.node.lat = r.lat;
+      d.node.lon = r.lon;
+      d.is_validated = r.validated;
+      d.is_active = r.active;
+      d.is_provider_whitelisted = r.whitelisted;
+      d.is_blacklisted = r.blacklisted;
+      d.last_updated_ms = r.last_updated_ms;
+      d.has_latest_balance = r.has_balance;
+      d.latest_balance_is_zero = r.balance_zero;
+    }
+    std::lock_guard<std::mutex> lk(p->mu);
+    const int rc = sync_discovery_chunk(p, nodes.data(), (uint32_t)n, now_ms, max_healthy_nodes_with_same_endpoint, n_new, gen, unstored);
+    if (rc != PM_OK) return rc;
+  }
+  return PM_OK;
 }
 
 // node as the /nodes route would show it (fields on this path): JSON or null

@@ -130,3 +130,86 @@ def test_sync_from_discovery_wire_format():
         with pytest.raises(PrimeMatchError) as e:
             plugin.sync_discovery_json(bad, NOW)
         assert e.value.status == abi.PM_E_PARSE
+
+
+def _wire(node_id, ip="10.0.0.1", port=8080, **extra):
+    d = {"id": node_id, "provider_address": node_id, "ip_address": ip, "port": port, "compute_pool_id": 1,
+         "compute_specs": {"gpu": {"count": 8, "model": "NVIDIA H100", "memory_mb": 80000, "indices": [0, 1, [2, {"x": "]}\\\""}]]},
+                           "cpu": {"cores": 64, "model": "x\\\"y"}, "ram_mb": 1024, "storage_gb": 10, "storage_path": "/var/{lib}"},
+         "is_validated": True, "is_active": True, "is_provider_whitelisted": True, "is_blacklisted": False,
+         "location": {"latitude": 45.5, "longitude": -73.5, "city": "Montr\u00e9al"}}
+    d.update(extra)
+    return d
+
+
+def test_streaming_reader_skips_what_it_does_not_need():
+    """The body is read in one streaming pass: members the monitor does not use (nested, with quotes, braces and
+    escapes inside strings) are skipped in place, 'data' need not come first, and a key written with an escape
+    still matches."""
+    import json
+
+    body = json.dumps({"meta": {"pages": [1, 2, {"next": None}], "note": "a \"quoted\" } ] string"}, "success": True,
+                       "data": [_wire(A1), _wire(A3, ip="10.0.0.3")], "trailer": [[[]]]})
+    body = body.replace('"id": "' + A1, '"i\\u0064": "' + A1)        # "i\u0064" == "id"
+    plugin = NodeGroupsPlugin([])
+    assert plugin.sync_discovery_json("  \n" + body + " \t\n", NOW) == 2
+    n1 = plugin.get_node(A1)
+    assert n1["ip_address"] == "10.0.0.1" and n1["has_location"] and n1["has_compute_specs"] and n1["ram_mb"] == 1024
+    assert plugin.get_node(A3)["ip_address"] == "10.0.0.3"
+
+
+def test_streaming_reader_field_rules():
+    """First occurrence of a duplicated key counts (as `Value::get` did); wrongly typed members are absent, not errors:
+    a string port is 0, a string latitude means no location, compute_specs: null means no specs."""
+    import json
+
+    a = json.dumps(_wire(A1, port="8080", location={"latitude": "45.5", "longitude": -73.5}, compute_specs=None))
+    a = a[:-1] + ', "ip_address": "9.9.9.9", "is_validated": false}'      # later duplicates are ignored
+    b = json.dumps(_wire(A2, latest_balance="0x0000"))
+    plugin = NodeGroupsPlugin([])
+    assert plugin.sync_discovery_json('{"data": [' + a + "," + b + '], "data": [{"broken": 1}]}', NOW) == 2
+    n1 = plugin.get_node(A1)
+    assert n1["ip_address"] == "10.0.0.1" and n1["port"] == 0 and not n1["has_location"] and not n1["has_compute_specs"]
+    assert plugin.get_node(A2)["status"] == "Discovered"
+    assert plugin.sync_discovery_json("[" + b + "]", NOW + 1000) == 0      # zero balance applies to the existing node
+    assert plugin.get_node(A2)["status"] == "LowBalance"
+
+
+def test_malformed_body_applies_nothing():
+    """`response.json()` failing in the reference means the fetch does nothing: a body that breaks after ten thousand
+    good nodes (inside a member that is only skipped) leaves the table untouched."""
+    import json
+
+    import pytest
+
+    from protocol_b200 import abi
+    from protocol_b200._lib import PrimeMatchError
+
+    good = ",".join(json.dumps(_wire(f"0x{i:040x}", ip=f"10.{i >> 8}.{i & 255}.1")) for i in range(1, 10001))
+    plugin = NodeGroupsPlugin([])
+    for bad_tail in (', {"id": "x", "ip_address": "y", "junk": [1, 2}]', ', 7]', ', {"id": "x"}]', "]]", ", {\"id\": \"x\", \"ip_address\": \"y\", \"s\": \"\\q\"}]"):
+        with pytest.raises(PrimeMatchError) as e:
+            plugin.sync_discovery_json("[" + good + bad_tail, NOW)
+        assert e.value.status == abi.PM_E_PARSE
+        assert plugin.get_node(f"0x{1:040x}") is None
+    assert plugin.sync_discovery_json("[" + good + "]", NOW) == 10000
+
+
+def test_duplicate_ids_across_chunks_and_unstored_nodes():
+    """'Remove duplicates based on node ID' (monitor.rs:203-210) holds across the chunks the body is applied in
+    (8192 nodes each), and for an id that was not stored the first time (endpoint already taken by a healthy node)."""
+    import json
+
+    plugin = NodeGroupsPlugin([])
+    plugin.add_node(OrchestratorNode(A1, status=NodeStatus.Healthy, compute_specs=SPECS, ip_address="10.9.9.9", port=1))
+    ids = [f"0x{i:040x}" for i in range(100, 9100)]
+    nodes = [_wire(a, ip=f"10.{(i >> 8) & 255}.{i & 255}.7") for i, a in enumerate(ids)]
+    blocked = "0x" + "b" * 40
+    nodes.insert(5, _wire(blocked, ip="10.9.9.9", port=1))                 # same endpoint as the healthy A1: not stored
+    nodes.append(_wire(ids[0], ip="1.1.1.1"))                              # duplicate of the first id, 9000 nodes later
+    nodes.append(_wire(blocked, ip="10.9.9.10", port=2))                   # duplicate of the unstored id: still skipped
+    assert plugin.sync_discovery_json(json.dumps(nodes), NOW) == len(ids)
+    assert plugin.get_node(ids[0])["ip_address"] == "10.0.0.7"
+    assert plugin.get_node(blocked) is None
+    # the next fetch is a new one: the id is free again
+    assert plugin.sync_discovery_json(json.dumps([_wire(blocked, ip="10.9.9.10", port=2)]), NOW + 1000) == 1
