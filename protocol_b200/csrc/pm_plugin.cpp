@@ -144,11 +144,14 @@ struct pm_plugin {
   std::unordered_map<std::string, size_t> node_index;
 
   std::vector<TaskRec> tasks;  // RPUSH order (task_store.rs:41)
+  std::unordered_map<std::string, size_t> task_pos;   // id -> first position in `tasks` (a heartbeat resolves its claim in O(1))
   // heartbeat fast path: the reference re-reads and re-filters every task on every
   // heartbeat (scheduler/mod.rs:27, scheduler_impl.rs:42-61: O(T*K) string compares); here the
   // task a fresh group of a configuration would claim is cached until the task list changes
   std::unordered_map<std::string, std::string> claim_cache;  // configuration name -> task id ("" = none)
   bool claim_cache_valid = false;
+  bool newest_valid = false;   // NewestTaskPlugin's choice, valid until the task list changes
+  size_t newest_pos = 0;
   const TaskRec* task_for_configuration(const std::string& configuration_name) {
     if (!claim_cache_valid) {
       claim_cache.clear();
@@ -210,9 +213,12 @@ struct pm_plugin {
     return v;
   }
   const TaskRec* find_task(const std::string& id) const {
-    for (const auto& t : tasks)
-      if (t.id == id) return &t;
-    return nullptr;
+    auto it = task_pos.find(id);
+    return it == task_pos.end() ? nullptr : &tasks[it->second];
+  }
+  void reindex_tasks() {
+    task_pos.clear();
+    for (size_t i = 0; i < tasks.size(); ++i) task_pos.emplace(tasks[i].id, i);   // first occurrence of an id counts
   }
 
   std::vector<const Config*> available_configurations() const {  // mod.rs:399-418
@@ -845,8 +851,10 @@ int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
   // on_task_created: enable the configuration of every allowed topology (mod.rs:1224-1243)
   if (t.scheduling == 3)
     for (const auto& topo : t.topologies) p->available.insert(topo);
+  p->task_pos.emplace(t.id, p->tasks.size());
   p->tasks.push_back(std::move(t));
   p->claim_cache_valid = false;
+  p->newest_valid = false;
   return PM_OK;
 }
 
@@ -857,7 +865,9 @@ int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_
   if (it == p->tasks.end()) return PM_OK;
   TaskRec gone = *it;
   p->tasks.erase(it);
+  p->reindex_tasks();
   p->claim_cache_valid = false;
+  p->newest_valid = false;
   // dissolve every group working on the task (mod.rs:1259-1291)
   std::vector<std::string> doomed;
   for (const auto& kv : p->group_task)
@@ -1385,10 +1395,16 @@ int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf,
   if (!p->templates.empty()) {  // plugin chain = [NodeGroupsPlugin]
     have = node_groups_filter(p, addr, &e);
   } else if (!p->tasks.empty()) {  // Scheduler::new pushes NewestTaskPlugin when no plugin is configured
-    const auto tasks = p->all_tasks();
-    const TaskRec* chosen = tasks[0];
-    for (const TaskRec* t : tasks)
-      if (t->created_at >= chosen->created_at) chosen = t;  // max_by_key: last maximum
+    // max_by_key over get_all_tasks() (stable sort, created_at desc) = the LAST task of the newest timestamp in
+    // store order; cached until the task list changes
+    if (!p->newest_valid) {
+      size_t best = 0;
+      for (size_t i = 1; i < p->tasks.size(); ++i)
+        if (p->tasks[i].created_at >= p->tasks[best].created_at) best = i;
+      p->newest_pos = best;
+      p->newest_valid = true;
+    }
+    const TaskRec* chosen = &p->tasks[p->newest_pos];
     e.task = chosen;
     e.env = chosen->env; e.has_env = chosen->has_env;
     e.cmd = chosen->cmd; e.has_cmd = chosen->has_cmd;

@@ -84,3 +84,27 @@ def test_group_formation_has_no_cpu_path():
     with pytest.raises(PrimeMatchError) as e:
         plugin.try_form_new_groups()
     assert e.value.status == abi.PM_E_NO_DEVICE
+
+
+def test_newest_task_choice_is_cached_until_the_task_list_changes():
+    """NewestTaskPlugin (newest_task/mod.rs:8-19) = max_by_key over the created_at-desc list: the LAST task of the
+    newest timestamp in store order.  The choice is cached per task-list version; adds and deletes refresh it."""
+    plugin = NodeGroupsPlugin([])
+    sched = Scheduler(plugin)
+    tasks = [Task(name=f"t{i}", created_at=c) for i, c in enumerate([5, 9, 9, 3])]
+    for t in tasks:
+        plugin.add_task(t)
+    assert sched.get_task_for_node(ZERO)["name"] == "t2"
+    assert sched.get_task_for_node(ONES)["name"] == "t2"
+    plugin.delete_task(tasks[2].id)
+    assert sched.get_task_for_node(ZERO)["name"] == "t1"
+    t4 = Task(name="t4", created_at=9)
+    plugin.add_task(t4)
+    assert sched.get_task_for_node(ZERO)["name"] == "t4"
+    plugin.delete_task(tasks[1].id)
+    plugin.delete_task(tasks[0].id)
+    assert sched.get_task_for_node(ZERO)["name"] == "t4"
+    plugin.delete_task(t4.id)
+    assert sched.get_task_for_node(ZERO)["name"] == "t3"
+    plugin.delete_task(tasks[3].id)
+    assert sched.get_task_for_node(ZERO) is None

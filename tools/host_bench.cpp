@@ -4,7 +4,7 @@
 //   the management pass            -> pm_plugin_try_form_new_groups (host snapshot + GPU pass + publish)
 // Build:  g++ -O2 -std=c++17 tools/host_bench.cpp -Iinclude -Lprotocol_b200 -lprime_match -lpthread
 //             -Wl,-rpath,$PWD/protocol_b200 -o /tmp/pm_host_bench
-// Run:    /tmp/pm_host_bench [n_nodes=1000000] [n_tasks=2000]
+// Run:    /tmp/pm_host_bench [n_nodes=1000000] [n_tasks=2000] [noconfig]
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -48,8 +48,11 @@ int main(int argc, char** argv) {
     engine = nullptr;
   }
   CHECK(pm_plugin_create(engine, nullptr, &plugin));
-  CHECK(pm_plugin_add_config(plugin, "pair-h100", 2, 2, "gpu:count=8;gpu:model=H100"));
-  CHECK(pm_plugin_add_config(plugin, "solo", 1, 1, nullptr));
+  const bool no_configs = argc > 3 && std::strcmp(argv[3], "noconfig") == 0;   // Scheduler with the default NewestTaskPlugin
+  if (!no_configs) {
+    CHECK(pm_plugin_add_config(plugin, "pair-h100", 2, 2, "gpu:count=8;gpu:model=H100"));
+    CHECK(pm_plugin_add_config(plugin, "solo", 1, 1, nullptr));
+  }
   CHECK(pm_plugin_seal_configs(plugin));
   std::vector<std::string> addrs(N);
   for (uint32_t i = 0; i < N; ++i) addrs[i] = addr_of(i);
@@ -123,7 +126,7 @@ int main(int argc, char** argv) {
 
   // ---- the management pass ---------------------------------------------------------------------------
   uint32_t n_formed = 0;
-  if (engine) {
+  if (engine && !no_configs) {
     t0 = now_s();
     CHECK(pm_plugin_try_form_new_groups(plugin, &n_formed));
     dt = now_s() - t0;
