@@ -18,6 +18,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <queue>
 
 namespace {
 
@@ -860,6 +861,103 @@ orc_groups* orc_soa_form_groups(const pm_worker_a* a, const pm_worker_b* b, uint
         pos += take;
         n_taken_here += take;
         if (take == 0) break;  // :606 no progress
+      }
+    } else if (proximity == 2 && std::all_of(compat.begin(), compat.end(), [&](u32 w) {
+                 return !(a[w].flags & PM_W_HAS_LOC) || std::fabs(lat[w]) <= 90.0;   // the bound needs real latitudes
+               })) {
+      // Same groups as the branch below (tested against it), without re-sorting every remaining worker for every
+      // group: haversine distance >= R * |delta latitude| (a >= sin^2(dlat/2) in calculate_distance), so the located
+      // workers are kept in latitude order and a group looks outward from its seed only while that lower bound can
+      // still beat its current k-th nearest.  Plan for the device-side sweep; here it makes the
+      // checker usable at swarm scale.
+      const size_t K = compat.size();
+      std::vector<char> alive(K, 1);
+      std::vector<u32> by_lat;                      // compat indices of located workers, by (latitude, canonical position)
+      for (u32 i = 0; i < K; ++i)
+        if (a[compat[i]].flags & PM_W_HAS_LOC) by_lat.push_back(i);
+      std::sort(by_lat.begin(), by_lat.end(), [&](u32 x, u32 y) {
+        const double lx = lat[compat[x]], ly = lat[compat[y]];
+        return lx < ly || (lx == ly && x < y);
+      });
+      const u32 NONE = 0xFFFFFFFFu;
+      std::vector<u32> lat_pos(K, NONE), prv(by_lat.size()), nxt(by_lat.size());
+      for (u32 r = 0; r < by_lat.size(); ++r) {
+        lat_pos[by_lat[r]] = r;
+        prv[r] = r ? r - 1 : NONE;
+        nxt[r] = r + 1 < by_lat.size() ? r + 1 : NONE;
+      }
+      auto unlink = [&](u32 i) {                    // compat index i leaves the alive sets
+        alive[i] = 0;
+        const u32 r = lat_pos[i];
+        if (r == NONE) return;
+        if (prv[r] != NONE) nxt[prv[r]] = nxt[r];
+        if (nxt[r] != NONE) prv[nxt[r]] = prv[r];
+      };
+      size_t n_alive = K, n_alive_loc = by_lat.size(), ploc = 0, pany = 0;
+      const double kRadsPerDeg = 3.14159265358979323846264338327950288 / 180.0;
+      for (;;) {
+        if (remaining.size() - n_taken_here < mn) break;
+        if (n_alive < mn) break;
+        std::vector<u32> mem;                       // compat indices
+        if (n_alive) {
+          u32 seed;
+          if (n_alive_loc) {
+            while (!(alive[ploc] && lat_pos[ploc] != NONE)) ++ploc;
+            seed = u32(ploc);
+          } else {
+            while (!alive[pany]) ++pany;
+            seed = u32(pany);
+          }
+          const size_t want = std::min<u64>(mx ? mx - 1 : 0, n_alive - 1);
+          if (1 + want < mn) break;                 // mem.size() < min: nothing is taken
+          mem.push_back(seed);
+          if (want && lat_pos[seed] != NONE) {
+            typedef std::pair<double, u32> DI;      // (distance, canonical position): max-heap keeps the `want` smallest
+            std::priority_queue<DI> heap;
+            const double slat = lat[compat[seed]];
+            u32 lo = prv[lat_pos[seed]], hi = nxt[lat_pos[seed]];
+            auto consider = [&](u32 r) -> bool {    // false: this side cannot improve the result any more
+              const u32 i = by_lat[r];
+              const double dl = std::fabs(lat[compat[i]] - slat) * kRadsPerDeg;
+              const double lb = 6371.0 * dl * (1.0 - 1e-9) - 1e-9;
+              if (heap.size() == want && lb > heap.top().first) return false;
+              const DI cand(soa_distance(lat, lon, compat[seed], compat[i]), i);
+              if (heap.size() < want) heap.push(cand);
+              else if (cand < heap.top()) { heap.pop(); heap.push(cand); }
+              return true;
+            };
+            while (lo != NONE || hi != NONE) {
+              bool take_lo;
+              if (lo == NONE) take_lo = false;
+              else if (hi == NONE) take_lo = true;
+              else take_lo = (slat - lat[compat[by_lat[lo]]]) <= (lat[compat[by_lat[hi]]] - slat);
+              if (take_lo) { if (consider(lo)) lo = prv[lo]; else lo = NONE; }
+              else { if (consider(hi)) hi = nxt[hi]; else hi = NONE; }
+            }
+            std::vector<DI> picked;
+            while (!heap.empty()) { picked.push_back(heap.top()); heap.pop(); }
+            for (size_t q = picked.size(); q-- > 0;) mem.push_back(picked[q].second);
+          }
+          // distance f64::MAX (no location), or a seed without location: the next ones in canonical order
+          for (size_t q = pany; mem.size() < 1 + want && q < K; ++q) {
+            if (!alive[q] || q == seed) continue;
+            if (lat_pos[seed] != NONE && lat_pos[q] != NONE) continue;   // located ones were ranked by distance above
+            mem.push_back(u32(q));
+          }
+        }
+        if (mem.size() < mn) break;
+        std::vector<u32> workers;
+        for (u32 i : mem) {
+          if (lat_pos[i] != NONE) --n_alive_loc;
+          --n_alive;
+          unlink(i);
+          taken[compat[i]] = 1;
+          workers.push_back(compat[i]);
+        }
+        const size_t took = workers.size();
+        emit(ci, workers);
+        n_taken_here += took;
+        if (took == 0) break;
       }
     } else {
       std::vector<u32> list = compat;  // still-available compatible, canonical order

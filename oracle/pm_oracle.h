@@ -150,7 +150,7 @@ orc_groups* orc_soa_form_groups(const pm_worker_a* a, const pm_worker_b* b, uint
                                 const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
                                 const uint32_t* model_bits, uint32_t words,
                                 const uint32_t* addr_rank, const double* lat, const double* lon,
-                                int proximity);
+                                int proximity /* 0 first fit, 1 the reference's proximity loop, 2 same result with latitude pruning */);
 
 /* Full evaluation of the sub-matrix asks[t0,t1) x workers[w0,w1) over `threads`
  * host threads: cost[t][w] = compat && candidate ? (price<<32 | w) : INF with

@@ -306,6 +306,7 @@ def soa_compatible(a_row, b_row, ask_row, opts, bits, words) -> bool:
 
 
 def soa_form_groups(a, b, asks, opts, bits, words, addr_rank=None, lat=None, lon=None, proximity=False) -> Groups:
+    """proximity: False (first fit), True (the reference's loop restated) or "banded" (same groups, latitude-pruned)."""
     a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
     asks = np.ascontiguousarray(asks); opts = np.ascontiguousarray(opts)
     bits = np.ascontiguousarray(bits, dtype=np.uint32)
@@ -316,7 +317,8 @@ def soa_form_groups(a, b, asks, opts, bits, words, addr_rank=None, lat=None, lon
                                    opts.ctypes.data, bits.ctypes.data, words,
                                    ar.ctypes.data if ar is not None else None,
                                    la.ctypes.data if la is not None else None,
-                                   lo.ctypes.data if lo is not None else None, 1 if proximity else 0)
+                                   lo.ctypes.data if lo is not None else None,
+                                   2 if proximity == "banded" else (1 if proximity else 0))
     return Groups(h)
 
 

@@ -261,3 +261,32 @@ def test_merge_chunks_and_leftovers():
     assert [(c, sorted(m)) for c, m in g.as_list()] == [(0, [0, 1, 2]), (0, [3, 4, 5])]   # the 7th stays solo
     g = orc.merge_solo_groups(nodes, solos, [("upto4", 1, 4, None)], proximity=False)
     assert [sorted(m) for _, m in g.as_list()] == [[0, 1, 2, 3], [4, 5, 6]]
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24])
+@pytest.mark.parametrize("where", ["cities", "scattered", "one_point"])
+def test_latitude_pruned_proximity_equals_the_restated_loop(seed, where):
+    """The checker's fast proximity mode (latitude-ordered candidates, a group looks outward from its seed only while
+    R * |delta latitude| can still beat its k-th nearest) forms exactly the groups of the reference's loop restated
+    literally (distances to every remaining worker, stable sort): same groups, creation order and members — with
+    every worker of a city on one coordinate (all ties: canonical position decides), with scattered coordinates, and
+    with everybody on one point; unlocated workers and degenerate sizes included."""
+    sizes_ = [(1, 1), (2, 2), (2, 4), (3, 3), (1, 3), (4, 8), (0, 2), (0, 0), (2, 5)]
+    w = synth.make_workers(3000, seed=seed, with_addresses=True)
+    a = synth.make_asks(50, "mixed", seed=seed + 1, group_sizes=sizes_)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    rng = np.random.default_rng(seed)
+    lat, lon = w.lat.copy(), w.lon.copy()
+    if where == "scattered":
+        lat = lat + rng.normal(0, 3.0, len(lat)).clip(-20, 20)
+        lon = lon + rng.normal(0, 5.0, len(lon))
+        lat[rng.random(len(lat)) < 0.05] = 48.8566                     # and a cluster of exact latitude ties
+    elif where == "one_point":
+        lat[:] = 45.5
+        lon[:] = -73.5
+    args = (w.a, w.b, a.asks, a.opts, bits, words)
+    want = orc.soa_form_groups(*args, addr_rank=w.addr_rank, lat=lat, lon=lon, proximity=True)
+    got = orc.soa_form_groups(*args, addr_rank=w.addr_rank, lat=lat, lon=lon, proximity="banded")
+    assert np.array_equal(want.cfg, got.cfg) and np.array_equal(want.off, got.off)
+    assert np.array_equal(want.members, got.members)
+    assert len(want) > 50
