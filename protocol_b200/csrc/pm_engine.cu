@@ -23,6 +23,7 @@
 
 #include "pm_kernels.cuh"
 #include "pm_proximity.cuh"
+#include "pm_proximity_band.cuh"
 #include "pm_auction.cuh"
 
 struct pm_engine;
@@ -87,7 +88,7 @@ struct pm_engine {
   uint32_t max_pattern_row = 0;
   bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
   bool all_solo = true;  // every ask has min == max == 1
-  int tune_argmin = 0, tune_generic = 0, tune_build = 0, tune_auction = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
+  int tune_argmin = 0, tune_generic = 0, tune_build = 0, tune_auction = 0, tune_prox = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
   DevBuf<uint4> wa, wb;
   DevBuf<double> lat, lon;
   DevBuf<uint32_t> addr_rank;
@@ -113,7 +114,8 @@ struct pm_engine {
   DevBuf<uint32_t> base_len, xhead, xnext, xcount, popped, counters;  // counters: [0]=any_bad [1]=n_bumped
   DevBuf<unsigned char> cub_tmp;
   DevBuf<uint32_t> prox_list, prox_xs, members_raw;
-  DevBuf<double> prox_dist;
+  DevBuf<double> prox_dist, prox_lat_key;
+  DevBuf<uint32_t> prox_lat_ord, prox_rank_of;
   bool any_max_zero = false;
   // extension (auction) state
   DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
@@ -285,6 +287,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_BUILD")) e->tune_build = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_AUCTION")) e->tune_auction = std::atoi(t);
+  if (const char* t = std::getenv("PM_TUNE_PROX")) e->tune_prox = std::atoi(t);   // 1: latitude-banded sweep (experimental)
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
     e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
@@ -318,6 +321,7 @@ void pm_destroy(pm_engine* e) {
   e->base_len.release(); e->xhead.release(); e->xnext.release(); e->xcount.release();
   e->popped.release(); e->counters.release(); e->cub_tmp.release();
   e->prox_list.release(); e->prox_xs.release(); e->members_raw.release(); e->prox_dist.release();
+  e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
@@ -742,6 +746,13 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = e->counters.p + 4;
     pp.group_cap = cap;
     if (merge_mode) pm::pm_merge_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
+    else if (e->tune_prox & 1) {   // experimental: same groups from a latitude-ordered view (pm_proximity_band.cuh)
+      PM_CUDA(e->prox_lat_key.ensure(P)); PM_CUDA(e->prox_lat_ord.ensure(P)); PM_CUDA(e->prox_rank_of.ensure(W));
+      pm::BandParams bp;
+      bp.p = pp;
+      bp.lat_key = e->prox_lat_key.p; bp.lat_ord = e->prox_lat_ord.p; bp.rank_of = e->prox_rank_of.p;
+      pm::pm_proximity_sweep_banded<<<1, pm::kProxThreads, 0, e->stream>>>(bp);
+    }
     else pm::pm_proximity_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
     PM_LAUNCH_CHECK("pm_proximity_sweep");
     PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 8, e->counters.p + 4, 16, cudaMemcpyDeviceToHost, e->stream));
