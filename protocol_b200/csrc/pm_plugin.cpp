@@ -825,7 +825,14 @@ int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len)
     out += ",\"last_status_change_ms\":" + (n.last_status_change_ms < 0 ? std::string("null") : std::to_string(n.last_status_change_ms));
     out += std::string(",\"has_location\":") + (n.has_loc ? "true" : "false");
     out += std::string(",\"has_compute_specs\":") + ((n.a.flags & PM_W_HAS_SPECS) ? "true" : "false");
-    out += ",\"ram_mb\":" + std::to_string(n.b.ram_mb) + "}";
+    out += ",\"ram_mb\":" + std::to_string(n.b.ram_mb);
+    // the SoA row the engine will see (presence bits of include/prime_match.h, interned model id)
+    out += ",\"spec_flags\":" + std::to_string(n.a.flags) + ",\"gpu_count\":" + std::to_string(n.a.gpu_count);
+    out += ",\"gpu_mem_mb\":" + std::to_string(n.a.gpu_mem_mb) + ",\"model_id\":" + std::to_string(n.a.model_id);
+    out += ",\"cpu_cores\":" + std::to_string(n.b.cpu_cores) + ",\"storage_gb\":" + std::to_string(n.b.storage_gb);
+    char ll[96];
+    std::snprintf(ll, sizeof ll, ",\"lat\":%.17g,\"lon\":%.17g}", n.has_loc ? n.lat : 0.0, n.has_loc ? n.lon : 0.0);
+    out += ll;
   }
   if (!buf || len < out.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
   std::memcpy(buf, out.c_str(), out.size() + 1);

@@ -213,3 +213,66 @@ def test_duplicate_ids_across_chunks_and_unstored_nodes():
     assert plugin.get_node(blocked) is None
     # the next fetch is a new one: the id is free again
     assert plugin.sync_discovery_json(json.dumps([_wire(blocked, ip="10.9.9.10", port=2)]), NOW + 1000) == 1
+
+
+def test_json_and_struct_ingest_agree_on_random_fetches():
+    """Differential property: the same fetch given as C structs (pm_plugin_sync_discovery) and as the discovery
+    service's JSON body (pm_plugin_sync_discovery_json, with members the monitor does not read mixed in) leaves the
+    same node table — presence bits, interned model, location, status — over several rounds of random changes."""
+    import json
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from protocol_b200.plugin import GpuSpecs
+
+    models = [None, "NVIDIA H100 80GB HBM3", "NVIDIA GeForce RTX 4090", "A100", "weird \"quoted\" \\ model"]
+    gpu = st.one_of(st.none(), st.builds(GpuSpecs, count=st.one_of(st.none(), st.integers(0, 16)), model=st.sampled_from(models),
+                                         memory_mb=st.one_of(st.none(), st.integers(0, 200_000))))
+    specs = st.one_of(st.none(), st.builds(ComputeSpecs, gpu=gpu, cpu_cores=st.one_of(st.none(), st.integers(0, 256)),
+                                           cpu_present=st.one_of(st.none(), st.booleans()),
+                                           ram_mb=st.one_of(st.none(), st.integers(0, 2**32 - 1)),
+                                           storage_gb=st.one_of(st.none(), st.integers(0, 100_000))))
+    node = st.builds(DiscoveryNode, id=st.sampled_from([f"0x{i:040x}" for i in range(1, 9)]),
+                     ip_address=st.sampled_from(["10.0.0.1", "10.0.0.2", "192.168.100.200"]), port=st.integers(0, 65535),
+                     compute_specs=specs, is_validated=st.booleans(), is_active=st.booleans(), is_provider_whitelisted=st.booleans(),
+                     is_blacklisted=st.booleans(), last_updated_ms=st.one_of(st.none(), st.integers(NOW - 10**6, NOW + 10**6)),
+                     location=st.one_of(st.none(), st.tuples(st.floats(-90, 90), st.floats(-180, 180))),
+                     latest_balance=st.one_of(st.none(), st.sampled_from([0, 1, 10**18])))
+
+    def wire(n):
+        d = {"id": n.id, "provider_address": n.id, "ip_address": n.ip_address, "port": n.port, "compute_pool_id": 7,
+             "extra": {"nested": [1, {"deep": "]}"}], "s": "a\\\"b"}, "is_validated": n.is_validated, "is_active": n.is_active,
+             "is_provider_whitelisted": n.is_provider_whitelisted, "is_blacklisted": n.is_blacklisted}
+        s = n.compute_specs
+        if s is None:
+            d["compute_specs"] = None
+        else:
+            cpu_present = s.cpu_present if s.cpu_present is not None else s.cpu_cores is not None
+            d["compute_specs"] = {
+                "gpu": None if s.gpu is None else {"count": s.gpu.count, "model": s.gpu.model, "memory_mb": s.gpu.memory_mb, "indices": [0, 1]},
+                "cpu": {"cores": s.cpu_cores, "model": "cpu"} if cpu_present else None,
+                "ram_mb": s.ram_mb, "storage_gb": s.storage_gb, "storage_path": "/x"}
+        if n.last_updated_ms is not None:
+            ms = n.last_updated_ms
+            import datetime
+            d["last_updated"] = datetime.datetime.fromtimestamp(ms / 1000, datetime.timezone.utc).strftime("%Y-%m-%dT%H:%M:%S.") + f"{ms % 1000:03d}Z"
+        if n.location is not None:
+            d["location"] = {"latitude": n.location[0], "longitude": n.location[1], "city": None}
+        if n.latest_balance is not None:
+            d["latest_balance"] = hex(n.latest_balance) if n.latest_balance % 2 == 0 else str(n.latest_balance)
+        return d
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.lists(node, max_size=12), min_size=1, max_size=4))
+    def check(fetches):
+        a, b = NodeGroupsPlugin([]), NodeGroupsPlugin([])
+        for r, fetch in enumerate(fetches):
+            now = NOW + r * 400_000
+            na = a.sync_discovery(fetch, now)
+            nb = b.sync_discovery_json(json.dumps({"success": True, "data": [wire(n) for n in fetch]}), now)
+            assert na == nb
+            for i in range(1, 9):
+                assert a.get_node(f"0x{i:040x}") == b.get_node(f"0x{i:040x}")
+
+    check()
