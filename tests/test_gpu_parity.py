@@ -284,6 +284,23 @@ def test_proximity_groups_general(sizes):
     eng.close()
 
 
+def test_proximity_groups_at_100k_workers():
+    """The default policy at the size of profiles/r01_modes.txt (2000 configurations x 100k workers, mixed group sizes,
+    10 815 groups): groups, creation order and members equal the checker's.  The checker runs its latitude-pruned
+    mode here (0.07 s instead of 7.9 s), which tests/test_oracle_groups.py proves equal to the literal loop."""
+    sizes = [(1, 1), (2, 2), (2, 4), (3, 3), (4, 8), (1, 3)]
+    w, a, t = synth_tables(2000, 100_000, "mixed", group_sizes=sizes)
+    eng = Engine()
+    load_engine(eng, t, locations=True)
+    eng.match(abi.PM_MODE_PROXIMITY)
+    res = eng.fetch()
+    og = orc.soa_form_groups(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], lat=t["lat"], lon=t["lon"],
+                             proximity="banded")
+    assert groups_equal(res, og), f"groups differ: engine {res.n_groups} vs checker {len(og)}"
+    assert res.n_groups == 10815
+    eng.close()
+
+
 @pytest.mark.skipif(__import__("os").environ.get("PM_TEST_EXPERIMENTAL") != "1",
                     reason="experimental latitude-banded sweep (PM_TUNE_PROX=1): run with PM_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("n_asks,n_workers,where", [(120, 4000, "cities"), (120, 4000, "scattered"), (50, 3000, "one_point"),
