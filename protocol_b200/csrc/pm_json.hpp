@@ -5,8 +5,6 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <memory>
 #include <string>
 #include <vector>
 

@@ -34,7 +34,6 @@ struct BandShared {
   ProxShared base;
   uint32_t red_p[32];
   uint32_t cnt;        // window fill / member slots
-  uint32_t flag;
 };
 
 constexpr double kBandMax = 1.7976931348623157e308;
