@@ -377,6 +377,12 @@ int pm_plugin_get_group_by_id(pm_plugin*, const char* group_id, char* buf, size_
 /* handle_group_not_found (mod.rs:1073-1119): the task of a group that was dissolved under the scheduler goes
  * to the first idle group in get_all_groups() order (SET NX); *reassigned = 1 when one took it      */
 int pm_plugin_handle_group_not_found(pm_plugin*, const char* group_id, const char* task_id, uint32_t* reassigned);
+/* The inverse of pm_plugin_redis_writeback, for start-up: a group read back from the reference's keys
+ * (`node_group:<id>` JSON + `group_task:<id>`) is put into the tables as it is.  nodes come in the stored
+ * (BTreeSet) order; task_id NULL = no claim; created_at_ms < 0 = now.  PM_E_STATE when the id exists or a node is
+ * already in a group.  The group id counter moves past ids of the engine's own form (lower-case hex).        */
+int pm_plugin_restore_group(pm_plugin*, const char* id, const char* configuration_name, const char* const* nodes,
+                            uint32_t n_nodes, const char* task_id, int64_t created_at_ms);
 /* Redis write-back in the reference's key formats (mod.rs:25-28,299-322,471-476), as a JSON array of
  * commands, so /groups, /nodes, storage routes and the metrics sync keep working unchanged.        */
 int pm_plugin_redis_writeback(pm_plugin*, char* buf, size_t len);

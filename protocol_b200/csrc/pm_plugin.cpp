@@ -25,6 +25,7 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -133,7 +134,7 @@ struct pm_plugin {
   pm_plugin_policy policy{};
   pm_interner* interner = nullptr;
   std::string err;
-  std::mutex mu;       // guards the tables below; heartbeat-side calls only ever wait for this one
+  std::shared_mutex mu;  // guards the tables below: exclusive for every update, shared for the read-only heartbeat path
   std::mutex loop_mu;  // serialises management passes (the reference runs them in one tokio task)
 
   std::vector<Config> templates;  // sorted at seal (mod.rs:150-164)
@@ -276,7 +277,7 @@ const char* pm_plugin_last_error(const pm_plugin* p) { return p ? p->err.c_str()
 int pm_plugin_add_config(pm_plugin* p, const char* name, uint32_t min_group_size, uint32_t max_group_size,
                          const char* requirements) {
   if (!p || !name) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   if (p->sealed) return p->fail(PM_E_STATE, "configurations are sealed");
   for (const auto& c : p->templates)
     if (c.name == name) return p->fail(PM_E_INVALID, "Configuration names must be unique");       // mod.rs:142-144
@@ -302,7 +303,7 @@ int pm_plugin_add_config(pm_plugin* p, const char* name, uint32_t min_group_size
 
 int pm_plugin_seal_configs(pm_plugin* p) {
   if (!p) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   const uint32_t n = (uint32_t)p->templates.size();
   std::vector<uint32_t> mn(n), perm(n);
   std::vector<uint8_t> hr(n);
@@ -323,7 +324,7 @@ int pm_plugin_seal_configs(pm_plugin* p) {
 
 int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) {  // mod.rs:1328-1346
   if (!p || !name) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   if (enable) p->available.insert(name);
   else p->available.erase(name);
   return PM_OK;
@@ -331,7 +332,7 @@ int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) {
 
 int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
   if (!p || !d || !d->address) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   NodeRec* r;
   auto it = p->node_index.find(d->address);
   if (it == p->node_index.end()) {
@@ -369,7 +370,7 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
 // StatusUpdatePlugin::handle_status_change (plugins/mod.rs:23-34 -> status_update_impl.rs:8-39)
 int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status) {
   if (!p || !address) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   if (it == p->node_index.end()) return p->fail(PM_E_INVALID, "unknown node");
   p->set_status(p->nodes[it->second], status, (int64_t)std::time(nullptr) * 1000);
@@ -498,7 +499,7 @@ extern "C" {
 int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
                              uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
   if (!p || (n && !dn)) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   if (n_new) *n_new = 0;
   std::unordered_set<std::string> unstored;
   return sync_discovery_chunk(p, dn, n, now_ms, max_healthy_nodes_with_same_endpoint, n_new, ++p->sync_gen, unstored);
@@ -756,14 +757,14 @@ int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, in
     if (ok && !ps.at_end()) { ok = false; err = "discovery JSON: trailing characters after JSON value"; }
     if (ok && !found) { ok = false; err = "discovery JSON: no node array"; }
     if (!ok) {
-      std::lock_guard<std::mutex> lk(p->mu);
+      std::lock_guard<std::shared_mutex> lk(p->mu);
       return p->fail(PM_E_PARSE, err.empty() ? (ps.error().empty() ? "discovery JSON: invalid JSON" : "discovery JSON: " + ps.error()) : err);
     }
   }
   std::unordered_set<std::string> unstored;
   uint64_t gen;
   {
-    std::lock_guard<std::mutex> lk(p->mu);
+    std::lock_guard<std::shared_mutex> lk(p->mu);
     gen = ++p->sync_gen;
     if (p->node_index.empty()) {   // first fetch: no rehashing or table moves while the chunks go in
       p->node_index.reserve(recs.size());
@@ -799,7 +800,7 @@ int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, in
       d.has_latest_balance = r.has_balance;
       d.latest_balance_is_zero = r.balance_zero;
     }
-    std::lock_guard<std::mutex> lk(p->mu);
+    std::lock_guard<std::shared_mutex> lk(p->mu);
     const int rc = sync_discovery_chunk(p, nodes.data(), (uint32_t)n, now_ms, max_healthy_nodes_with_same_endpoint, n_new, gen, unstored);
     if (rc != PM_OK) return rc;
   }
@@ -809,7 +810,7 @@ int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, in
 // node as the /nodes route would show it (fields on this path): JSON or null
 int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len) {
   if (!p || !address) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   std::string out = "null";
   if (it != p->node_index.end()) {
@@ -841,7 +842,7 @@ int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len)
 
 int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
   if (!p || !d || !d->id) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   TaskRec t;
   t.id = d->id;
   t.name = d->name ? d->name : "";
@@ -867,7 +868,7 @@ int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
 
 int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_task + on_task_deleted
   if (!p || !id) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = std::find_if(p->tasks.begin(), p->tasks.end(), [&](const TaskRec& t) { return t.id == id; });
   if (it == p->tasks.end()) return PM_OK;
   TaskRec gone = *it;
@@ -908,7 +909,7 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   std::vector<uint32_t> bits_copy;
   uint32_t npat = 0, nmod = 0, words = 1, mode = PM_MODE_FIRST_FIT;
   {
-    std::lock_guard<std::mutex> lk(p->mu);
+    std::lock_guard<std::shared_mutex> lk(p->mu);
     if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
     if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
     const auto configs = p->available_configurations();
@@ -959,7 +960,7 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   auto chk = [&](int r, const char* what) {
     if (r != PM_OK) {
       const char* m = pm_last_error(p->engine);
-      std::lock_guard<std::mutex> lk(p->mu);
+      std::lock_guard<std::shared_mutex> lk(p->mu);
       p->err = std::string(what) + ": " + (m ? m : "");
     }
     return r;
@@ -977,7 +978,7 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
 
   // ---- phase 3 (tables locked): publish the groups (create_group_atomically, mod.rs:299-322, 568-581)
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   uint32_t formed = 0;
   for (uint32_t g = 0; g < res.n_groups; ++g) {
     Group grp;
@@ -1075,7 +1076,7 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
 int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::mutex> loop_lk(p->loop_mu);
-  std::lock_guard<std::mutex> lk(p->mu);   // solo groups are few: the whole merge pass stays under the table lock
+  std::lock_guard<std::shared_mutex> lk(p->mu);   // solo groups are few: the whole merge pass stays under the table lock
   if (n_merged) *n_merged = 0;
   if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: merging has no CPU path");
   auto solo_list = [&]() {
@@ -1159,7 +1160,7 @@ static int emit(pm_plugin* p, const std::string& s, char* buf, size_t len) {
 // the key the storage route writes per requested upload (consumed by scheduler_impl.rs:131-157)
 int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group_id, const char* file_name) {
   if (!p || !address || !group_id || !file_name) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   p->upload_keys.insert(std::string("upload:") + address + ":" + group_id + ":" + file_name);
   return PM_OK;
 }
@@ -1167,7 +1168,7 @@ int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group
 // get_node_group (mod.rs:324-337): JSON NodeGroup or "null"
 int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_t len) {
   if (!p || !address) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "null";
   auto it = p->node_to_group.find(address);
   if (it != p->node_to_group.end()) {
@@ -1183,7 +1184,7 @@ int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_
 // get_all_groups (mod.rs:1006-1044): sorted by id
 int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
   if (!p) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "[";
   bool first = true;
   for (const auto& kv : p->groups) {
@@ -1198,7 +1199,7 @@ int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
 // get_group_by_id (mod.rs:1046-1055): JSON NodeGroup or "null"
 int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, size_t len) {
   if (!p || !group_id) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "null";
   auto g = p->groups.find(group_id);
   if (g != p->groups.end()) {
@@ -1213,7 +1214,7 @@ int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, siz
 // an error (the reference logs a warning and returns Ok).
 int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const char* task_id, uint32_t* reassigned) {
   if (!p || !group_id || !task_id) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   if (reassigned) *reassigned = 0;
   for (const auto& kv : p->groups) {
     if (p->current_group_task(kv.first)) continue;
@@ -1225,6 +1226,41 @@ int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const c
   return PM_OK;
 }
 
+// Start-up: a group as the reference stored it (create_group_atomically, mod.rs:299-322) goes back into the tables.
+int pm_plugin_restore_group(pm_plugin* p, const char* id, const char* configuration_name, const char* const* nodes,
+                            uint32_t n_nodes, const char* task_id, int64_t created_at_ms) {
+  if (!p || !id || !*id || !configuration_name || (n_nodes && !nodes)) return PM_E_INVALID;
+  std::lock_guard<std::shared_mutex> lk(p->mu);
+  if (p->groups.count(id)) return p->fail(PM_E_STATE, std::string("pm_plugin_restore_group: group exists: ") + id);
+  Group g;
+  g.id = id;
+  g.configuration_name = configuration_name;
+  g.created_at_ms = created_at_ms < 0 ? (int64_t)std::time(nullptr) * 1000 : created_at_ms;
+  for (uint32_t i = 0; i < n_nodes; ++i) {
+    if (!nodes[i]) return p->fail(PM_E_INVALID, "pm_plugin_restore_group: null node");
+    if (p->node_to_group.count(nodes[i])) return p->fail(PM_E_STATE, std::string("pm_plugin_restore_group: node already grouped: ") + nodes[i]);
+    g.nodes.emplace_back(nodes[i]);
+  }
+  for (size_t i = 0; i < g.nodes.size(); ++i)
+    for (size_t j = i + 1; j < g.nodes.size(); ++j)
+      if (g.nodes[i] == g.nodes[j]) return p->fail(PM_E_INVALID, "pm_plugin_restore_group: node listed twice");
+  // ids this library makes are format!("{:x}", counter): keep the counter ahead of any such id
+  {
+    unsigned long long v = 0;
+    bool hex = g.id.size() <= 16;
+    for (char ch : g.id) {
+      if (ch >= '0' && ch <= '9') v = (v << 4) | (unsigned)(ch - '0');
+      else if (ch >= 'a' && ch <= 'f') v = (v << 4) | (unsigned)(ch - 'a' + 10);
+      else { hex = false; break; }
+    }
+    if (hex && v >= p->next_group_id) p->next_group_id = v + 1;
+  }
+  for (const auto& n : g.nodes) p->node_to_group[n] = g.id;
+  if (task_id && *task_id) p->group_task[g.id] = task_id;
+  p->groups.emplace(g.id, std::move(g));
+  return PM_OK;
+}
+
 // The keys a drop-in must leave in Redis for /groups, /nodes, storage routes and the metrics sync to
 // keep working unchanged (mod.rs:25-28, 299-322, 471-476): a JSON array of commands
 //   ["SET","node_group:<id>","<NodeGroup json>"], ["SADD","orchestrator:groups_index","<id>"],
@@ -1232,7 +1268,7 @@ int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const c
 //   ["SADD","available_node_group_configs","<name>"].
 int pm_plugin_redis_writeback(pm_plugin* p, char* buf, size_t len) {
   if (!p) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "[";
   bool first = true;
   auto cmd = [&](std::initializer_list<std::string> parts) {
@@ -1292,27 +1328,40 @@ struct Expanded {
   bool has_env = false, has_cmd = false, has_mounts = false;
 };
 
-// NodeGroupsPlugin::filter_tasks, scheduler_impl.rs:11-210.  Returns false for "no task".
-bool node_groups_filter(pm_plugin* p, const std::string& addr, Expanded* out) {
+enum FilterResult { kNoTask = 0, kHasTask = 1, kNeedsUpdate = 2 };
+
+// NodeGroupsPlugin::filter_tasks, scheduler_impl.rs:11-210.
+// read_only (the caller holds the table lock shared): nothing is written; a heartbeat whose answer would need a write
+// — claiming a task for an idle group (SET NX), dropping a claim on a deleted task — reports kNeedsUpdate and is
+// served again under the exclusive lock.  A group that holds a live claim (the steady state) never needs one.
+FilterResult node_groups_filter(pm_plugin* p, const std::string& addr, Expanded* out, bool read_only) {
   auto ng = p->node_to_group.find(addr);
-  if (ng == p->node_to_group.end()) return false;            // "Node is not in a group, skipping all tasks"
+  if (ng == p->node_to_group.end()) return kNoTask;          // "Node is not in a group, skipping all tasks"
   auto git = p->groups.find(ng->second);
-  if (git == p->groups.end()) return false;
+  if (git == p->groups.end()) return kNoTask;
   const Group& group = git->second;
   auto pos = std::find(group.nodes.begin(), group.nodes.end(), addr);  // get_idx_in_group, mod.rs:424-434
-  if (pos == group.nodes.end()) return false;
+  if (pos == group.nodes.end()) return kNoTask;
   const size_t idx = size_t(pos - group.nodes.begin());
 
-  const TaskRec* current = p->current_group_task(group.id);
-  if (!current) {
-    if (p->tasks.empty()) return false;
-    // reference: filter by allowed_topologies then IteratorRandom::choose (scheduler_impl.rs:42-70);
-    // determinised to the NewestTask rule (max_by_key over the desc-sorted list = LAST maximum)
-    const TaskRec* chosen = p->task_for_configuration(group.configuration_name);
-    if (!chosen) return false;
-    if (!p->group_task.count(group.id)) p->group_task[group.id] = chosen->id;   // SET NX, mod.rs:471-476
+  const TaskRec* current = nullptr;
+  if (read_only) {
+    auto claim = p->group_task.find(group.id);
+    if (claim == p->group_task.end()) return p->tasks.empty() ? kNoTask : kNeedsUpdate;
+    current = p->find_task(claim->second);
+    if (!current) return kNeedsUpdate;                       // stale claim: collected under the exclusive lock
+  } else {
     current = p->current_group_task(group.id);
-    if (!current) return false;
+    if (!current) {
+      if (p->tasks.empty()) return kNoTask;
+      // reference: filter by allowed_topologies then IteratorRandom::choose (scheduler_impl.rs:42-70);
+      // determinised to the NewestTask rule (max_by_key over the desc-sorted list = LAST maximum)
+      const TaskRec* chosen = p->task_for_configuration(group.configuration_name);
+      if (!chosen) return kNoTask;
+      if (!p->group_task.count(group.id)) p->group_task[group.id] = chosen->id;   // SET NX, mod.rs:471-476
+      current = p->current_group_task(group.id);
+      if (!current) return kNoTask;
+    }
   }
 
   const std::string idx_s = std::to_string(idx), size_s = std::to_string(group.nodes.size());
@@ -1349,7 +1398,7 @@ bool node_groups_filter(pm_plugin* p, const std::string& addr, Expanded* out) {
   out->has_mounts = current->has_mounts;
   for (const auto& m : current->mounts)
     out->mounts.emplace_back(replace_all(m.first, "${GROUP_ID}", group.id), replace_all(m.second, "${GROUP_ID}", group.id));
-  return true;
+  return kHasTask;
 }
 
 void task_json(const Expanded& e, std::string& out) {
@@ -1393,18 +1442,18 @@ void task_json(const Expanded& e, std::string& out) {
 
 // Scheduler::get_task_for_node (scheduler/mod.rs:26-74).  Writes the heartbeat payload
 // {"current_task": Task|null} (crates/shared/src/models/heartbeat.rs:7-22).
-int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) {
-  if (!p || !address) return PM_E_INVALID;
-  std::lock_guard<std::mutex> lk(p->mu);
-  const std::string addr(address);
+// builds {"current_task": ...} for one heartbeat.  Returns kNeedsUpdate only when read_only.
+static FilterResult heartbeat_answer(pm_plugin* p, const std::string& addr, bool read_only, std::string* out_json) {
   Expanded e;
-  bool have = false;
+  FilterResult have = kNoTask;
   if (!p->templates.empty()) {  // plugin chain = [NodeGroupsPlugin]
-    have = node_groups_filter(p, addr, &e);
+    have = node_groups_filter(p, addr, &e, read_only);
+    if (have == kNeedsUpdate) return have;
   } else if (!p->tasks.empty()) {  // Scheduler::new pushes NewestTaskPlugin when no plugin is configured
     // max_by_key over get_all_tasks() (stable sort, created_at desc) = the LAST task of the newest timestamp in
     // store order; cached until the task list changes
     if (!p->newest_valid) {
+      if (read_only) return kNeedsUpdate;
       size_t best = 0;
       for (size_t i = 1; i < p->tasks.size(); ++i)
         if (p->tasks[i].created_at >= p->tasks[best].created_at) best = i;
@@ -1416,12 +1465,13 @@ int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf,
     e.env = chosen->env; e.has_env = chosen->has_env;
     e.cmd = chosen->cmd; e.has_cmd = chosen->has_cmd;
     e.mounts = chosen->mounts; e.has_mounts = chosen->has_mounts;
-    have = true;
+    have = kHasTask;
   }
-  std::string out = "{\"current_task\":";
-  if (!have) {
+  std::string& out = *out_json;
+  out = "{\"current_task\":";
+  if (have == kNoTask) {
     out += "null}";
-    return emit(p, out, buf, len);
+    return kNoTask;
   }
   // scheduler/mod.rs:34-70: ${TASK_ID}, ${NODE_ADDRESS} (+ ${TIMESTAMP} in volume mounts)
   const std::string& tid = e.task->id;
@@ -1437,6 +1487,25 @@ int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf,
   }
   task_json(e, out);
   out += '}';
+  return kHasTask;
+}
+
+// Heartbeats take the table lock SHARED and answer from what is there (group, claim, task); only a heartbeat that has
+// to write — the first one of an idle group, a claim on a deleted task, a cold NewestTask cache — repeats under the
+// exclusive lock.  Every table update elsewhere in this file is exclusive.
+int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) {
+  if (!p || !address) return PM_E_INVALID;
+  const std::string addr(address);
+  std::string out;
+  {
+    std::shared_lock<std::shared_mutex> rd(p->mu);
+    if (heartbeat_answer(p, addr, /*read_only=*/true, &out) != kNeedsUpdate && buf && len >= out.size() + 1) {
+      std::memcpy(buf, out.c_str(), out.size() + 1);
+      return PM_OK;
+    }
+  }
+  std::lock_guard<std::shared_mutex> lk(p->mu);
+  heartbeat_answer(p, addr, /*read_only=*/false, &out);
   return emit(p, out, buf, len);
 }
 

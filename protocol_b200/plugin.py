@@ -272,6 +272,13 @@ class NodeGroupsPlugin:
         self._check(self._lib.pm_plugin_handle_group_not_found(self._h, group_id.encode(), task_id.encode(), C.byref(n)))
         return bool(n.value)
 
+    def restore_group(self, group_id: str, configuration_name: str, nodes, task_id: str | None = None,
+                      created_at_ms: int = -1):
+        """A NodeGroup read back from Redis at start-up (node_group:<id>, group_task:<id>)."""
+        arr = (C.c_char_p * max(len(nodes), 1))(*[n.encode() for n in nodes])
+        self._check(self._lib.pm_plugin_restore_group(self._h, group_id.encode(), configuration_name.encode(), arr, len(nodes),
+                                                      _b(task_id), created_at_ms))
+
     def redis_writeback(self):
         """[[cmd, key, ...], ...] in the reference's key formats (mod.rs:25-28, 299-322)."""
         return self._json(self._lib.pm_plugin_redis_writeback, cap=1 << 24)

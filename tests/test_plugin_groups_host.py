@@ -1,0 +1,173 @@
+"""The host mirror once groups exist — on the CPU: groups are put in with pm_plugin_restore_group (the start-up path:
+what the reference left in Redis) instead of being formed on the GPU, and the scheduler / observer / recovery paths of
+node_groups (scheduler_impl.rs:11-210, status_update_impl.rs:8-39, mod.rs:1046-1119, 1224-1325, 1423-1487) run
+against them.  The same scenarios run with GPU-formed groups in test_gpu_plugin.py."""
+import json
+import threading
+
+import pytest
+
+from protocol_b200 import abi
+from protocol_b200._lib import PrimeMatchError
+from protocol_b200.plugin import NodeGroupConfiguration, NodeGroupsPlugin, NodeStatus, OrchestratorNode, Scheduler, Task
+
+A1 = "0x1234567890123456789012345678901234567890"
+A2 = "0x2234567890123456789012345678901234567890"
+A3 = "0x3234567890123456789012345678901234567890"
+
+
+def make(configs, **kw):
+    return NodeGroupsPlugin(configs, **kw)
+
+
+def test_restored_group_is_scheduled_like_a_formed_one():
+    """tests.rs:509-676 with the group restored: same task for both members, GROUP_INDEX by BTreeSet order, variables."""
+    plugin = make([NodeGroupConfiguration("test-config", 2, 2)])
+    sched = Scheduler(plugin)
+    plugin.add_node(OrchestratorNode(A1, p2p_id="p2p-1"))
+    plugin.add_node(OrchestratorNode(A2, p2p_id="p2p-2"))
+    env = {"LOCAL_RANK": "0", "RANK": "${GROUP_INDEX}", "WORLD_SIZE": "${GROUP_SIZE}", "GROUP_ID": "${GROUP_ID}",
+           "NEXT": "${NEXT_P2P_ADDRESS}", "TOTAL_UPLOAD_COUNT": "${TOTAL_UPLOAD_COUNT}", "LAST_FILE_IDX": "${LAST_FILE_IDX}"}
+    task = Task(image="prime-vllm", name="test-task", env_vars=env, cmd=["run", "--rank", "${GROUP_INDEX}.${GROUP_SIZE}"],
+                allowed_topologies=["test-config"])
+    plugin.add_task(task)
+    assert sched.get_task_for_node(A1) is None                          # not in a group yet
+    plugin.restore_group("2a", "test-config", [A1, A2])
+    g = plugin.get_node_group(A2)
+    assert g == {"id": "2a", "nodes": [A1, A2], "configuration_name": "test-config", "task_id": None}
+    plugin.record_upload(A1, "2a", "f0")
+    plugin.record_upload(A1, "2a", "f1")
+    t1, t2 = sched.get_task_for_node(A1), sched.get_task_for_node(A2)
+    assert t1["id"] == t2["id"] == task.id
+    e1, e2 = t1["env_vars"], t2["env_vars"]
+    assert (e1["GROUP_INDEX"], e1["RANK"], e1["WORLD_SIZE"], e1["GROUP_ID"], e1["NEXT"]) == ("0", "0", "2", "2a", "p2p-2")
+    assert (e2["GROUP_INDEX"], e2["RANK"], e2["WORLD_SIZE"], e2["GROUP_ID"], e2["NEXT"]) == ("1", "1", "2", "2a", "p2p-1")
+    assert (e1["TOTAL_UPLOAD_COUNT"], e1["LAST_FILE_IDX"]) == ("2", "1") and (e2["TOTAL_UPLOAD_COUNT"], e2["LAST_FILE_IDX"]) == ("0", "0")
+    assert t1["cmd"] == ["run", "--rank", "0.2"] and t2["cmd"] == ["run", "--rank", "1.2"]
+    assert plugin.get_node_group(A1)["task_id"] == task.id              # the claim (SET NX) is on the group now
+
+
+def test_restore_validates_and_keeps_the_id_counter_ahead():
+    plugin = make([NodeGroupConfiguration("c", 1, 2)])
+    for a in (A1, A2, A3):
+        plugin.add_node(OrchestratorNode(a))
+    plugin.restore_group("ff", "c", [A1], task_id="some-task-that-no-longer-exists")
+    with pytest.raises(PrimeMatchError) as e:
+        plugin.restore_group("ff", "c", [A2])                           # id taken
+    assert e.value.status == abi.PM_E_STATE
+    with pytest.raises(PrimeMatchError) as e:
+        plugin.restore_group("100", "c", [A1])                          # node already grouped
+    assert e.value.status == abi.PM_E_STATE
+    with pytest.raises(PrimeMatchError):
+        plugin.restore_group("101", "c", [A2, A2])
+    plugin.restore_group("not-hex-id", "c", [A2, A3], created_at_ms=1_700_000_000_250)
+    assert [g["id"] for g in plugin.get_all_groups()] == ["ff", "not-hex-id"]
+    # a claim on a task that is gone is dropped at the first look (get_current_group_task, mod.rs:436-469)
+    assert Scheduler(plugin).get_task_for_node(A1) is None
+    assert plugin.get_node_group(A1)["task_id"] is None
+    cmds = plugin.redis_writeback()
+    stored = json.loads({(c[0], c[1]): c[2:] for c in cmds}[("SET", "node_group:not-hex-id")][0])
+    assert stored["nodes"] == [A2, A3] and stored["created_at"] == "2023-11-14T22:13:20.250Z"
+
+
+def test_writeback_then_restore_round_trip():
+    """What pm_plugin_redis_writeback emits is what a fresh plugin needs at start-up."""
+    src = make([NodeGroupConfiguration("c2", 2, 2), NodeGroupConfiguration("c1", 1, 1)])
+    for a in (A1, A2, A3):
+        src.add_node(OrchestratorNode(a))
+    task = Task(allowed_topologies=["c2", "c1"])
+    src.add_task(task)
+    src.restore_group("1", "c2", [A1, A2], task_id=task.id)
+    src.restore_group("2", "c1", [A3])
+    cmds = src.redis_writeback()
+    dst = make([NodeGroupConfiguration("c2", 2, 2), NodeGroupConfiguration("c1", 1, 1)])
+    for a in (A1, A2, A3):
+        dst.add_node(OrchestratorNode(a))
+    dst.add_task(task)
+    claims = {c[1].split(":", 1)[1]: c[2] for c in cmds if c[0] == "SET" and c[1].startswith("group_task:")}
+    for c in cmds:
+        if c[0] == "SET" and c[1].startswith("node_group:"):
+            g = json.loads(c[2])
+            dst.restore_group(g["id"], g["configuration_name"], g["nodes"], task_id=claims.get(g["id"]))
+    assert dst.get_all_groups() == src.get_all_groups()
+    assert sorted(map(tuple, dst.redis_writeback())) == sorted(map(tuple, cmds))
+
+
+def test_dissolution_paths_on_restored_groups():
+    """handle_status_change (status_update_impl.rs:8-39) and on_task_deleted (mod.rs:1259-1320)."""
+    plugin = make([NodeGroupConfiguration("c", 2, 2)])
+    for a in (A1, A2):
+        plugin.add_node(OrchestratorNode(a))
+    task = Task(allowed_topologies=["c"])
+    plugin.add_task(task)
+    plugin.restore_group("1", "c", [A1, A2])
+    assert Scheduler(plugin).get_task_for_node(A1)["id"] == task.id
+    plugin.update_node_status(A1, NodeStatus.Dead)
+    assert plugin.get_node_group(A1) is None and plugin.get_node_group(A2) is None and plugin.get_all_groups() == []
+    plugin.update_node_status(A1, NodeStatus.Healthy)
+    plugin.restore_group("2", "c", [A1, A2])
+    assert Scheduler(plugin).get_task_for_node(A2)["id"] == task.id
+    plugin.delete_task(task.id)                                          # the group working on it goes with it
+    assert plugin.get_all_groups() == []
+
+
+def test_group_recovery_entry_points_on_restored_groups():
+    """get_group_by_id / validate_group_exists / handle_group_not_found (mod.rs:1046-1119)."""
+    plugin = make([NodeGroupConfiguration("c", 1, 1)])
+    for a in (A1, A2):
+        plugin.add_node(OrchestratorNode(a))
+    busy, idle = Task(name="busy", allowed_topologies=["c"]), Task(name="orphan", allowed_topologies=["c"])
+    plugin.add_task(busy)
+    plugin.add_task(idle)
+    plugin.restore_group("1", "c", [A1], task_id=busy.id)
+    plugin.restore_group("2", "c", [A2])
+    assert plugin.validate_group_exists("1") and not plugin.validate_group_exists("3")
+    assert plugin.get_group_by_id("2")["nodes"] == [A2]
+    assert plugin.handle_group_not_found("gone", idle.id) is True        # group 1 is busy, group 2 takes it
+    assert plugin.get_group_by_id("2")["task_id"] == idle.id and plugin.get_group_by_id("1")["task_id"] == busy.id
+    assert plugin.handle_group_not_found("gone", idle.id) is False
+
+
+def test_concurrent_heartbeats_and_table_updates():
+    """Heartbeats from several threads while tasks and statuses change: every answer is a consistent one (the group's
+    claim or none), nothing crashes, and the tables end in the expected state."""
+    plugin = make([NodeGroupConfiguration("c", 1, 1)])
+    sched = Scheduler(plugin)
+    addrs = [f"0x{i + 1:040x}" for i in range(64)]
+    for i, a in enumerate(addrs):
+        plugin.add_node(OrchestratorNode(a))
+        plugin.restore_group(f"{i + 1:x}", "c", [a])
+    tasks = [Task(name=f"t{i}", created_at=i, allowed_topologies=["c"]) for i in range(50)]
+    for t in tasks:
+        plugin.add_task(t)
+    names = {t.name for t in tasks} | {"late"}
+    errors, stop = [], threading.Event()
+
+    def beat(offset):
+        try:
+            i = offset
+            while not stop.is_set():
+                got = sched.get_task_for_node(addrs[i % len(addrs)])
+                if got is not None and got["name"] not in names:
+                    errors.append(got)
+                i += 7
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=beat, args=(k,)) for k in range(6)]
+    for th in threads:
+        th.start()
+    late = Task(name="late", created_at=999, allowed_topologies=["c"])
+    plugin.add_task(late)
+    for t in tasks[:25]:
+        plugin.delete_task(t.id)                                         # groups that claimed them dissolve
+    for a in addrs[:8]:
+        plugin.update_node_status(a, NodeStatus.Dead)
+    stop.set()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
+    for a in addrs[:8]:
+        assert plugin.get_node_group(a) is None
+    for g in plugin.get_all_groups():
+        assert g["task_id"] is None or g["task_id"] in {t.id for t in tasks[25:]} | {late.id}

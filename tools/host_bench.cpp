@@ -137,9 +137,21 @@ int main(int argc, char** argv) {
     std::printf("try_form_new_groups (steady state: everybody grouped) groups_formed=%u  %.3f s\n", n_formed, dt);
   }
 
+  if (!engine && !no_configs) {   // no GPU here: groups come in the way they do at start-up, from the stored state
+    t0 = now_s();
+    for (uint32_t i = 0; i < N; ++i) {
+      char gid[24];
+      std::snprintf(gid, sizeof gid, "%x", i + 1);
+      const char* members[1] = {addrs[i].c_str()};
+      CHECK(pm_plugin_restore_group(plugin, gid, "solo", members, 1, nullptr, -1));
+    }
+    dt = now_s() - t0;
+    std::printf("restore_group       groups=%u  %.3f s  %.3g groups/s\n", N, dt, N / dt);
+  }
+
   // ---- (f-2) heartbeats ------------------------------------------------------------------------------
   const uint32_t H = N < 1000000u ? N : 1000000u;
-  for (int threads : {1, 8}) {
+  for (int threads : {1, 1, 2, 4, 8}) {
     std::atomic<uint64_t> with_task{0};
     std::atomic<int> bad{0};
     t0 = now_s();
