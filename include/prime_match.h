@@ -377,6 +377,11 @@ int pm_plugin_get_group_by_id(pm_plugin*, const char* group_id, char* buf, size_
 /* handle_group_not_found (mod.rs:1073-1119): the task of a group that was dissolved under the scheduler goes
  * to the first idle group in get_all_groups() order (SET NX); *reassigned = 1 when one took it      */
 int pm_plugin_handle_group_not_found(pm_plugin*, const char* group_id, const char* task_id, uint32_t* reassigned);
+/* The node table as the engine's SoA tables, exactly what a management pass uploads: rows in
+ * node_store.get_nodes() order (stable status-class sort, node_store.rs:195-206), candidate flags (PM_W_HEALTHY / P2P /
+ * ASSIGNED, mod.rs:492-497), locations, BTreeSet<String> address ranks.  Any array may be NULL; capacity in rows.    */
+int pm_plugin_export_tables(pm_plugin*, pm_worker_a* a, pm_worker_b* b, double* lat, double* lon, uint32_t* addr_rank,
+                            uint32_t capacity, uint32_t* n_rows);
 /* The inverse of pm_plugin_redis_writeback, for start-up: a group read back from the reference's keys
  * (`node_group:<id>` JSON + `group_task:<id>`) is put into the tables as it is.  nodes come in the stored
  * (BTreeSet) order; task_id NULL = no claim; created_at_ms < 0 = now.  PM_E_STATE when the id exists or a node is

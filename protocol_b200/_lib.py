@@ -85,6 +85,7 @@ def load() -> C.CDLL:
         "pm_plugin_get_all_groups": (i32, [vp, C.c_char_p, sz]),
         "pm_plugin_get_group_by_id": (i32, [vp, cp, C.c_char_p, sz]),
         "pm_plugin_handle_group_not_found": (i32, [vp, cp, cp, P(u32)]),
+        "pm_plugin_export_tables": (i32, [vp, vp, vp, vp, vp, vp, u32, P(u32)]),
         "pm_plugin_restore_group": (i32, [vp, cp, cp, P(C.c_char_p), u32, cp, C.c_int64]),
         "pm_plugin_redis_writeback": (i32, [vp, C.c_char_p, sz]),
         "pm_scheduler_get_task_for_node": (i32, [vp, cp, C.c_char_p, sz]),

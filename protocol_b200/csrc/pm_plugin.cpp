@@ -80,6 +80,7 @@ struct NodeRec {
   bool has_loc = false;
   double lat = 0, lon = 0;
   uint64_t sync_gen = 0;               // the discovery fetch that last touched the node (de-dup by id within a fetch)
+  bool grouped = false;                // mirrors node_to_group.count(address): read by the table snapshot
 };
 
 struct Group {  // NodeGroup, mod.rs:63-69
@@ -177,6 +178,10 @@ struct pm_plugin {
   // count_healthy_nodes_with_same_endpoint (discovery/monitor.rs:218-234, Theta(N^2) per sync)
   std::unordered_map<std::string, uint32_t> healthy_at;
   uint64_t sync_gen = 0;
+  // BTreeSet<String> rank of every node's address: addresses never change and nodes are only appended, so the ranks
+  // are recomputed only when the table has grown since the last management pass
+  std::vector<uint32_t> addr_rank_cache;
+  size_t addr_rank_n = 0;
 
   static std::string endpoint_key(const std::string& ip, uint16_t port) { return ip + ":" + std::to_string(port); }
   void index_remove(const NodeRec& n) {
@@ -230,10 +235,22 @@ struct pm_plugin {
     return v;
   }
 
+  // node_to_group with the per-node mirror bit kept in step
+  void map_node(const std::string& addr, const std::string& gid) {
+    node_to_group[addr] = gid;
+    auto it = node_index.find(addr);
+    if (it != node_index.end()) nodes[it->second].grouped = true;
+  }
+  void unmap_node(const std::string& addr) {
+    node_to_group.erase(addr);
+    auto it = node_index.find(addr);
+    if (it != node_index.end()) nodes[it->second].grouped = false;
+  }
+
   void dissolve(const std::string& group_id) {  // mod.rs:1423-1487
     auto it = groups.find(group_id);
     if (it == groups.end()) return;
-    for (const auto& n : it->second.nodes) node_to_group.erase(n);
+    for (const auto& n : it->second.nodes) unmap_node(n);
     group_task.erase(group_id);
     groups.erase(it);
   }
@@ -340,6 +357,7 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
     p->nodes.emplace_back();
     r = &p->nodes.back();
     r->address = d->address;
+    r->grouped = p->node_to_group.count(r->address) != 0;   // a restored group may name a node before it is stored
   } else {
     r = &p->nodes[it->second];
   }
@@ -486,6 +504,7 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
       node.has_loc = d.node.has_location != 0;
       node.lat = d.node.lat;
       node.lon = d.node.lon;
+      node.grouped = p->node_to_group.count(addr) != 0;
       p->node_index.emplace(addr, p->nodes.size());
       p->nodes.push_back(std::move(node));
       if (n_new) ++*n_new;
@@ -892,6 +911,73 @@ int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_
   return PM_OK;
 }
 
+}  // extern "C"
+
+// The node table as the engine's SoA tables (ingest -> columnar): rows in the canonical order of
+// node_store.get_nodes() (stable status-class sort, node_store.rs:195-206), the candidate flags of mod.rs:492-497,
+// locations, and every row's BTreeSet<String> address rank.  The caller holds the table lock exclusively.
+struct TableSnapshot {
+  std::vector<pm_worker_a> wa;
+  std::vector<pm_worker_b> wb;
+  std::vector<double> lat, lon;
+  std::vector<uint32_t> arank;
+  std::vector<uint32_t> row_node;   // row -> index in pm_plugin::nodes (stable: nodes are never removed)
+};
+static void build_table_snapshot(pm_plugin* p, TableSnapshot* s) {
+  const uint32_t W = (uint32_t)p->nodes.size();
+  if (p->addr_rank_n != W) {
+    std::vector<uint32_t> by_addr(W);
+    for (uint32_t i = 0; i < W; ++i) by_addr[i] = i;
+    std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return p->nodes[a].address < p->nodes[b].address; });
+    p->addr_rank_cache.resize(W);
+    for (uint32_t i = 0; i < W; ++i) p->addr_rank_cache[by_addr[i]] = i;
+    p->addr_rank_n = W;
+  }
+  // stable sort by status class = four buckets filled in table order
+  uint32_t start[5] = {0, 0, 0, 0, 0};
+  for (uint32_t i = 0; i < W; ++i) ++start[status_class(p->nodes[i].status) + 1];
+  for (int c = 0; c < 4; ++c) start[c + 1] += start[c];
+  s->wa.resize(W); s->wb.resize(W); s->lat.resize(W); s->lon.resize(W); s->arank.resize(W); s->row_node.resize(W);
+  for (uint32_t i = 0; i < W; ++i) {
+    const NodeRec& n = p->nodes[i];
+    const uint32_t r = start[status_class(n.status)]++;
+    s->wa[r] = n.a;
+    s->wb[r] = n.b;
+    uint32_t f = n.a.flags;
+    if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
+    if (n.has_p2p) f |= PM_W_P2P;                                        // :495
+    if (n.grouped) f |= PM_W_ASSIGNED;                                   // :496 (get_node_group is Some)
+    if (n.has_loc) f |= PM_W_HAS_LOC;
+    s->wa[r].flags = f;
+    s->lat[r] = n.lat;
+    s->lon[r] = n.lon;
+    s->arank[r] = p->addr_rank_cache[i];
+    s->row_node[r] = i;
+  }
+}
+
+extern "C" {
+
+// The SoA tables a management pass would upload, for callers that keep their own device copy and for inspection.
+// Arrays may be NULL (skipped); capacity is in rows; *n_rows receives the row count (PM_E_NOMEM when it does not fit).
+int pm_plugin_export_tables(pm_plugin* p, pm_worker_a* a, pm_worker_b* b, double* lat, double* lon, uint32_t* addr_rank,
+                            uint32_t capacity, uint32_t* n_rows) {
+  if (!p) return PM_E_INVALID;
+  std::lock_guard<std::shared_mutex> lk(p->mu);
+  const uint32_t W = (uint32_t)p->nodes.size();
+  if (n_rows) *n_rows = W;
+  if ((a || b || lat || lon || addr_rank) && capacity < W) return p->fail(PM_E_NOMEM, "pm_plugin_export_tables: capacity too small");
+  if (!(a || b || lat || lon || addr_rank)) return PM_OK;
+  TableSnapshot s;
+  build_table_snapshot(p, &s);
+  if (a && W) std::memcpy(a, s.wa.data(), (size_t)W * sizeof(pm_worker_a));
+  if (b && W) std::memcpy(b, s.wb.data(), (size_t)W * sizeof(pm_worker_b));
+  if (lat && W) std::memcpy(lat, s.lat.data(), (size_t)W * sizeof(double));
+  if (lon && W) std::memcpy(lon, s.lon.data(), (size_t)W * sizeof(double));
+  if (addr_rank && W) std::memcpy(addr_rank, s.arank.data(), (size_t)W * sizeof(uint32_t));
+  return PM_OK;
+}
+
 // try_form_new_groups (mod.rs:478-628): the evaluation and the allocation run on the GPU.
 int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   if (!p) return PM_E_INVALID;
@@ -899,11 +985,8 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   std::lock_guard<std::mutex> loop_lk(p->loop_mu);
   // ---- phase 1 (tables locked): snapshot what the pass reads, like the reference's reads at loop start
   uint32_t W = 0;
-  std::vector<pm_worker_a> wa;
-  std::vector<pm_worker_b> wb;
-  std::vector<double> lat, lon;
-  std::vector<uint32_t> arank;
-  std::vector<std::string> row_address, cfg_names;
+  TableSnapshot snap;
+  std::vector<std::string> cfg_names;
   std::vector<pm_ask> asks;
   std::vector<pm_gpu_opt> opts;
   std::vector<uint32_t> bits_copy;
@@ -913,34 +996,8 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
     if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
     if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
     const auto configs = p->available_configurations();
-    // node_store.get_nodes(): stable status-class sort (node_store.rs:195-206) = canonical order
-    W = (uint32_t)p->nodes.size();
-    std::vector<uint32_t> order(W);
-    for (uint32_t i = 0; i < W; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-      return status_class(p->nodes[a].status) < status_class(p->nodes[b].status);
-    });
-    // address rank = BTreeSet<String> order (byte-lexicographic)
-    std::vector<uint32_t> by_addr(W), rank(W);
-    for (uint32_t i = 0; i < W; ++i) by_addr[i] = i;
-    std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return p->nodes[a].address < p->nodes[b].address; });
-    for (uint32_t i = 0; i < W; ++i) rank[by_addr[i]] = i;
-    wa.resize(W); wb.resize(W); lat.resize(W); lon.resize(W); arank.resize(W); row_address.resize(W);
-    for (uint32_t i = 0; i < W; ++i) {
-      const NodeRec& n = p->nodes[order[i]];
-      wa[i] = n.a;
-      wb[i] = n.b;
-      uint32_t f = n.a.flags;
-      if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
-      if (n.has_p2p) f |= PM_W_P2P;                                        // :495
-      if (p->node_to_group.count(n.address)) f |= PM_W_ASSIGNED;           // :496
-      if (n.has_loc) f |= PM_W_HAS_LOC;
-      wa[i].flags = f;
-      lat[i] = n.lat;
-      lon[i] = n.lon;
-      arank[i] = rank[order[i]];
-      row_address[i] = n.address;
-    }
+    build_table_snapshot(p, &snap);
+    W = (uint32_t)snap.wa.size();
     for (const Config* c : configs) {
       pm_ask a = c->ask;
       a.opt_off = (uint32_t)opts.size();
@@ -969,9 +1026,9 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
   if ((rc = chk(pm_set_model_table(p->engine, bits_copy.data(), npat, nmod, words), "pm_set_model_table"))) return rc;
   if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
-  if ((rc = chk(pm_upsert_workers(p->engine, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
-  if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
-  if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
+  if ((rc = chk(pm_upsert_workers(p->engine, snap.wa.data(), snap.wb.data(), 0, W), "pm_upsert_workers"))) return rc;
+  if ((rc = chk(pm_set_worker_locations(p->engine, snap.lat.data(), snap.lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
+  if ((rc = chk(pm_set_worker_addr_rank(p->engine, snap.arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
   if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;   // staging vectors are read asynchronously
   if ((rc = chk(pm_match(p->engine, mode), "pm_match"))) return rc;
   pm_result res{};
@@ -986,15 +1043,15 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
     grp.created_at_ms = (int64_t)std::time(nullptr) * 1000;
     bool stale = false;   // a member was removed from the table while the pass ran
     for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m) {
-      const std::string& addr = row_address[res.group_members[m]];
-      if (!p->node_index.count(addr) || p->node_to_group.count(addr)) stale = true;
+      const std::string& addr = p->nodes[snap.row_node[res.group_members[m]]].address;   // nodes are never removed
+      if (p->node_to_group.count(addr)) stale = true;
       grp.nodes.push_back(addr);
     }
     if (stale) continue;
     char idbuf[32];
     std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);  // format!("{:x}", ..)
     grp.id = idbuf;
-    for (const auto& n : grp.nodes) p->node_to_group[n] = grp.id;
+    for (const auto& n : grp.nodes) p->map_node(n, grp.id);
     p->groups.emplace(grp.id, std::move(grp));
     ++formed;
   }
@@ -1102,7 +1159,7 @@ int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
     // find_best_task_for_group (mod.rs:1122-1189), determinised to the NewestTask rule
     const TaskRec* chosen = p->task_for_configuration(cfg->name);
     for (const auto& gid : ids) p->dissolve(gid);
-    for (const auto& n : merged.nodes) p->node_to_group[n] = merged.id;
+    for (const auto& n : merged.nodes) p->map_node(n, merged.id);
     if (chosen) p->group_task[merged.id] = chosen->id;              // SET NX on a fresh key
     p->groups.emplace(merged.id, std::move(merged));
     if (n_merged) ++*n_merged;
@@ -1255,7 +1312,7 @@ int pm_plugin_restore_group(pm_plugin* p, const char* id, const char* configurat
     }
     if (hex && v >= p->next_group_id) p->next_group_id = v + 1;
   }
-  for (const auto& n : g.nodes) p->node_to_group[n] = g.id;
+  for (const auto& n : g.nodes) p->map_node(n, g.id);
   if (task_id && *task_id) p->group_task[g.id] = task_id;
   p->groups.emplace(g.id, std::move(g));
   return PM_OK;

@@ -272,6 +272,20 @@ class NodeGroupsPlugin:
         self._check(self._lib.pm_plugin_handle_group_not_found(self._h, group_id.encode(), task_id.encode(), C.byref(n)))
         return bool(n.value)
 
+    def export_tables(self):
+        """The SoA tables a management pass uploads: dict(a, b, lat, lon, addr_rank) of numpy arrays, canonical row order."""
+        import numpy as np
+
+        n = C.c_uint32()
+        self._check(self._lib.pm_plugin_export_tables(self._h, None, None, None, None, None, 0, C.byref(n)))
+        w = n.value
+        a = np.zeros(w, dtype=abi.WORKER_A)
+        b = np.zeros(w, dtype=abi.WORKER_B)
+        lat, lon, rank = np.zeros(w), np.zeros(w), np.zeros(w, dtype=np.uint32)
+        self._check(self._lib.pm_plugin_export_tables(self._h, a.ctypes.data, b.ctypes.data, lat.ctypes.data, lon.ctypes.data,
+                                                      rank.ctypes.data, w, C.byref(n)))
+        return dict(a=a, b=b, lat=lat, lon=lon, addr_rank=rank)
+
     def restore_group(self, group_id: str, configuration_name: str, nodes, task_id: str | None = None,
                       created_at_ms: int = -1):
         """A NodeGroup read back from Redis at start-up (node_group:<id>, group_task:<id>)."""

@@ -171,3 +171,88 @@ def test_concurrent_heartbeats_and_table_updates():
         assert plugin.get_node_group(a) is None
     for g in plugin.get_all_groups():
         assert g["task_id"] is None or g["task_id"] in {t.id for t in tasks[25:]} | {late.id}
+
+
+def test_export_tables_is_the_snapshot_a_management_pass_uploads():
+    """SURVEY 8 A21 / 8f-1, ingest -> columnar: rows in node_store.get_nodes() order (stable status-class sort:
+    Healthy, Discovered, the rest, Dead), candidate flags of mod.rs:492-497, locations, BTreeSet<String> address ranks;
+    the cached ranks follow the table when it grows."""
+    import numpy as np
+
+    from protocol_b200.plugin import ComputeSpecs, GpuSpecs
+
+    rng = np.random.default_rng(5)
+    plugin = make([NodeGroupConfiguration("c", 1, 2)])
+    statuses = [NodeStatus.Healthy, NodeStatus.Discovered, NodeStatus.Dead, NodeStatus.Unhealthy, NodeStatus.WaitingForHeartbeat,
+                NodeStatus.Ejected, NodeStatus.LowBalance]
+    nodes = []
+
+    def add(n):
+        for _ in range(n):
+            addr = "0x" + "".join(rng.choice(list("0123456789abcdefABCDEF"), 40))
+            st = statuses[int(rng.integers(len(statuses)))]
+            node = OrchestratorNode(addr, status=st, p2p_id=None if rng.random() < 0.3 else "p",
+                                    compute_specs=ComputeSpecs(gpu=GpuSpecs(count=int(rng.integers(1, 9)), model="H100", memory_mb=80000),
+                                                               ram_mb=int(rng.integers(1, 10**6))) if rng.random() < 0.8 else None,
+                                    location=(float(rng.uniform(-60, 60)), float(rng.uniform(-170, 170))) if rng.random() < 0.6 else None)
+            plugin.add_node(node)
+            nodes.append(node)
+
+    def check():
+        t = plugin.export_tables()
+        cls = {NodeStatus.Healthy: 0, NodeStatus.Discovered: 1, NodeStatus.Dead: 3}
+        order = sorted(range(len(nodes)), key=lambda i: cls.get(nodes[i].status, 2))          # stable
+        by_addr = sorted(range(len(nodes)), key=lambda i: nodes[i].address.encode())             # byte-lexicographic
+        rank = {i: r for r, i in enumerate(by_addr)}
+        grouped = {n for g in plugin.get_all_groups() for n in g["nodes"]}
+        assert len(t["a"]) == len(nodes)
+        for row, i in enumerate(order):
+            n, f = nodes[i], int(t["a"]["flags"][row])
+            assert bool(f & abi.PM_W_HEALTHY) == (n.status == NodeStatus.Healthy)
+            assert bool(f & abi.PM_W_P2P) == (n.p2p_id is not None)
+            assert bool(f & abi.PM_W_ASSIGNED) == (n.address in grouped)
+            assert bool(f & abi.PM_W_HAS_LOC) == (n.location is not None)
+            assert bool(f & abi.PM_W_HAS_SPECS) == (n.compute_specs is not None)
+            if n.compute_specs is not None:
+                assert int(t["a"]["gpu_count"][row]) == n.compute_specs.gpu.count and int(t["b"]["ram_mb"][row]) == n.compute_specs.ram_mb
+            if n.location is not None:
+                assert (t["lat"][row], t["lon"][row]) == n.location
+            assert int(t["addr_rank"][row]) == rank[i]
+
+    add(300)
+    healthy = [n.address for n in nodes if n.status == NodeStatus.Healthy]
+    plugin.restore_group("1", "c", healthy[:2])
+    plugin.restore_group("2", "c", healthy[2:3])
+    check()
+    add(150)                                                             # the rank cache is for 300 rows: it must follow
+    check()
+    plugin.update_node_status(nodes[0].address, NodeStatus.Dead)         # a status change moves a row, not a rank
+    nodes[0].status = NodeStatus.Dead
+    check()
+
+
+def test_assigned_flag_follows_every_membership_change():
+    """The PM_W_ASSIGNED bit of the exported table (mod.rs:496: get_node_group is Some) through restore, dissolution by
+    status change and by task deletion, and a group restored before its node is stored."""
+    plugin = make([NodeGroupConfiguration("c", 1, 2)])
+
+    def assigned():
+        t = plugin.export_tables()
+        rows = sorted(range(len(t["a"])), key=lambda r: int(t["addr_rank"][r]))      # address order
+        return [bool(int(t["a"]["flags"][r]) & abi.PM_W_ASSIGNED) for r in rows]
+
+    plugin.add_node(OrchestratorNode(A1))
+    plugin.add_node(OrchestratorNode(A2))
+    assert assigned() == [False, False]
+    plugin.restore_group("1", "c", [A1, A3])                              # A3 is not stored yet
+    assert assigned() == [True, False]
+    plugin.add_node(OrchestratorNode(A3))
+    assert assigned() == [True, False, True]
+    plugin.update_node_status(A3, NodeStatus.Dead)                        # dissolves group 1
+    assert assigned() == [False, False, False]
+    task = Task(allowed_topologies=["c"])
+    plugin.add_task(task)
+    plugin.restore_group("2", "c", [A2], task_id=task.id)
+    assert assigned() == [False, True, False]
+    plugin.delete_task(task.id)                                           # the group working on it goes
+    assert assigned() == [False, False, False]

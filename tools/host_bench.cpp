@@ -149,6 +149,22 @@ int main(int argc, char** argv) {
     std::printf("restore_group       groups=%u  %.3f s  %.3g groups/s\n", N, dt, N / dt);
   }
 
+  // ---- ingest -> columnar: the SoA snapshot a management pass uploads -------------------------------
+  {
+    std::vector<pm_worker_a> ta(N);
+    std::vector<pm_worker_b> tb(N);
+    std::vector<double> tlat(N), tlon(N);
+    std::vector<uint32_t> trank(N);
+    uint32_t rows = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      t0 = now_s();
+      CHECK(pm_plugin_export_tables(plugin, ta.data(), tb.data(), tlat.data(), tlon.data(), trank.data(), N, &rows));
+      dt = now_s() - t0;
+      std::printf("export_tables       rows=%u  %.3f s  %.3g rows/s  (%s)\n", rows, dt, rows / dt,
+                  rep ? "address ranks cached" : "first: address ranks sorted");
+    }
+  }
+
   // ---- (f-2) heartbeats ------------------------------------------------------------------------------
   const uint32_t H = N < 1000000u ? N : 1000000u;
   for (int threads : {1, 1, 2, 4, 8}) {
