@@ -1,0 +1,227 @@
+"""The class-cache auction of protocol_b200/csrc/pm_auction.cuh restated in Python and held against the sequential
+checker (orc_soa_auction: every unassigned ask scans every worker every round): ask classes sharing one 32-entry cache
+and bound, the price cap folded into the outside option, the pool of candidates kept from the last table walk and
+re-ranked before any new walk, walks over a cost-sorted worker order (re-sorted every few rounds) that stop once enough
+kept candidates beat the composite bound on the unseen part, and the per-ask scan when a value ties exactly with the
+outside option.  Same assignments and the same number of rounds, on tie-heavy inputs.  This guards the ALGORITHM (the
+exactness argument of DESIGN.md 4); the GPU tests guard the kernels."""
+import numpy as np
+import pytest
+
+from oracle import pm_oracle as orc
+from protocol_b200 import synth
+
+NEG = -(1 << 61)                  # "no value" (kAucNeg)
+INVALID = (1 << 63) - 1           # no cache yet (kThetaInvalid)
+COMPLETE = -(1 << 63)             # the cache / pool holds every compatible worker (kThetaComplete)
+NONE = 0xFFFFFFFF
+
+
+def better(v1, w1, v2, w2):
+    """(value desc, worker asc) order."""
+    return v1 > v2 or (v1 == v2 and w1 < w2)
+
+
+def bmax(a, b):
+    return a if better(a[0], a[1], b[0], b[1]) else b
+
+
+def auction_class_algorithm(t, cap, S=1, eps=1, K=32, stripe=1024, lanes=256, resort_every=5):
+    """Returns (ask -> worker, rounds, counters).  `stripe` workers per walk step, `lanes` threads per scanning CTA
+    (4 kept candidates each), the worker order re-sorted every `resort_every` rounds."""
+    asks, T, W = t["asks"], len(t["asks"]), len(t["wa"])
+    # classes: asks with identical requirement rows
+    keys, reps, class_of = {}, [], np.zeros(T, int)
+    for i in range(T):
+        r = asks[i]
+        key = (int(r["flags"]), int(r["cpu_cores"]), int(r["ram_mb"]), int(r["storage_gb"]),
+               t["opts"][r["opt_off"]:r["opt_off"] + r["n_opts"]].tobytes())
+        if key not in keys:
+            keys[key] = len(reps)
+            reps.append(i)
+        class_of[i] = keys[key]
+    C = len(reps)
+    ev = orc.soa_eval_matrix(t["wa"], t["wb"], np.ascontiguousarray(asks[reps]), t["opts"], t["bits"], t["words"], 0, C, 0, W,
+                             threads=4, want_cost=True)
+    compat = ev["cost"] != np.iinfo(np.int64).max
+    ap = t["wb"]["ext_ask_price"].astype(np.int64)
+    perm = np.lexsort((np.arange(W), ap))                     # walk order: (cost at the last sort, worker)
+    order = {"perm": perm, "key": ap[perm] * S}
+    price = np.zeros(W, np.int64)
+    owner = np.full(W, NONE, np.int64)
+    assigned = np.full(T, NONE, np.int64)
+    withdrawn = np.zeros(T, bool)
+    cand = [[] for _ in range(C)]                             # the 32-entry cache of each class ...
+    theta = [(INVALID, NONE)] * C                             # ... and the bound on everything outside it
+    pool = [None] * C                                         # what the lanes held after the class's last walk ...
+    pool_bound = [(INVALID, NONE)] * C                        # ... and the bound on everything outside the pool
+    count = dict(full=0, refill=0, fb=0)
+
+    def value(w):
+        return int(-(ap[w] * S) - price[w])
+
+    def select(lists, dropped):
+        """top K of the kept candidates, best two values, and the best (value, worker) left out"""
+        kept = sorted((e for lane in lists for e in lane), key=lambda e: (-e[0], e[1]))
+        top = kept[:K]
+        bound = kept[K] if len(kept) > K else (NEG, NONE)
+        bound = bmax(bound, dropped)
+        b1 = top[0] if top else (NEG, NONE)
+        b2 = top[1][0] if len(top) > 1 else NEG
+        return top, b1, b2, bound
+
+    def store_cache(c, top, bound):
+        cand[c] = [e[1] for e in top]
+        theta[c] = (COMPLETE, NONE) if bound[0] == NEG else bound
+
+    def class_refresh(c):
+        # 1. re-rank the pool at the current prices; good enough while its best two beat its bound
+        if pool_bound[c][0] != INVALID:
+            lists = [[(value(w), int(w)) for w in lane] for lane in pool[c]]
+            outside = pool_bound[c] if pool_bound[c][0] != COMPLETE else (NEG, NONE)
+            top, b1, b2, bound = select(lists, outside)
+            if bound[0] == NEG or (b2 >= bound[0] and better(b1[0], b1[1], bound[0], bound[1])):
+                store_cache(c, top, bound)
+                count["refill"] += 1
+                return
+        # 2. walk the cost-sorted table: each lane keeps its 4 best and remembers the best it dropped
+        count["full"] += 1
+        lists = [[] for _ in range(lanes)]
+        dropped = [(NEG, NONE)] * lanes
+        unseen, first_good = None, None
+        n_stripes = (W + stripe - 1) // stripe
+        for k in range(n_stripes):
+            n = min(stripe, W - k * stripe)
+            for i in range(n):
+                w = order["perm"][k * stripe + i]
+                if not compat[c, w]:
+                    continue
+                lane = i % lanes
+                lists[lane].append((value(w), int(w)))
+                lists[lane].sort(key=lambda e: (-e[0], e[1]))
+                if len(lists[lane]) > 4:
+                    dropped[lane] = bmax(dropped[lane], lists[lane].pop())
+            # every later worker ranks at or below (-key_last, worker_last + 1): prices only rise
+            u, last = -int(order["key"][k * stripe + n - 1]), int(order["perm"][k * stripe + n - 1])
+            beating = sum(1 for lane in lists for e in lane if e[0] > u or (e[0] == u and e[1] <= last))
+            if beating > K and first_good is None:
+                first_good = k
+            if first_good is not None and (beating > 256 or k - first_good >= 8):
+                if k + 1 < n_stripes:
+                    unseen = (u, last + 1)
+                break
+        pool[c] = [[e[1] for e in lane] for lane in lists]
+        best_dropped = (NEG, NONE)
+        for d in dropped:
+            best_dropped = bmax(best_dropped, d)
+        top, b1, b2, bound = select(lists, best_dropped)
+        store_cache(c, top, bound)
+        outside = best_dropped if unseen is None else bmax(best_dropped, unseen)
+        pool_bound[c] = (COMPLETE, NONE) if outside[0] == NEG else outside
+
+    def decide(tk):
+        """0 withdraw, 1 bid (worker, best, second), 2 the class cache cannot tell"""
+        c, out = class_of[tk], -((int(cap[tk]) + 1) * S)
+        th, thw = theta[c]
+        if th == INVALID:
+            return 2, None
+        entries = [(value(w), int(w)) for w in cand[c]]
+        affordable = [e for e in entries if ap[e[1]] <= cap[tk]]
+        if affordable:
+            bf, wf = max(affordable, key=lambda e: (e[0], -e[1]))
+            if better(bf, wf, th, thw):
+                if bf < out:
+                    return 0, None
+                others = [e[0] for e in entries if e[1] != wf]
+                bx = max(others) if others else NEG
+                return (1, (wf, bf, max(bx, out))) if th <= max(bx, out) else (2, None)
+            upper = max(bf, th)
+        else:
+            upper = th
+        return (0, None) if upper < out else (2, None)
+
+    rounds = 0
+    while True:
+        active = [i for i in range(T) if assigned[i] == NONE and not withdrawn[i]]
+        if not active:
+            break
+        if rounds and rounds % resort_every == 0:             # bid-up workers move back in the walk order
+            key = ap * S + price
+            perm = np.lexsort((np.arange(W), key))
+            order["perm"], order["key"] = perm, key[perm]
+        rounds += 1
+        bid_w, bid_p = {}, {}
+
+        def place(tk, verdict, d):
+            if verdict == 0:
+                withdrawn[tk] = True
+            else:
+                bid_w[tk] = d[0]
+                bid_p[tk] = int(price[d[0]]) + (d[1] - d[2]) + eps
+
+        retry, requested = [], set()
+        for tk in active:                                     # pass 0: from the class caches as they are
+            verdict, d = decide(tk)
+            if verdict == 2:
+                retry.append(tk)
+                requested.add(class_of[tk])
+            else:
+                place(tk, verdict, d)
+        for c in requested:
+            class_refresh(c)
+        for tk in retry:                                      # pass 1: after the refreshes
+            verdict, d = decide(tk)
+            if verdict != 2:
+                place(tk, verdict, d)
+                continue
+            count["fb"] += 1                                  # a tie exactly at the outside option: the ask's own scan
+            c, out = class_of[tk], -((int(cap[tk]) + 1) * S)
+            ws = np.flatnonzero(compat[c] & (ap <= cap[tk]))
+            if len(ws) == 0:
+                withdrawn[tk] = True
+                continue
+            v = -(ap[ws] * S) - price[ws]
+            by_value = np.lexsort((ws, -v))
+            ws, v = ws[by_value], v[by_value]
+            if v[0] < out:
+                withdrawn[tk] = True
+                continue
+            second = max(int(v[1]) if len(ws) > 1 else NEG, out)
+            place(tk, 1, (int(ws[0]), int(v[0]), second))
+        winner = {}                                           # highest bid, ties to the lowest ask
+        for tk in sorted(bid_w):
+            w = bid_w[tk]
+            if w not in winner or bid_p[tk] > bid_p[winner[w]]:
+                winner[w] = tk
+        for w, tk in winner.items():
+            if owner[w] != NONE:
+                assigned[owner[w]] = NONE
+            owner[w], assigned[tk], price[w] = tk, w, bid_p[tk]
+    return assigned.astype(np.uint32), rounds, count
+
+
+def _tables(n_base, copies, n_workers, plo, phi, seed):
+    w = synth.make_workers(n_workers, seed=synth.SEED_WORKERS + seed)
+    a = synth.make_asks(n_base, "mixed", seed=synth.SEED_ASKS + seed)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    rng = np.random.default_rng(seed)
+    idx = rng.permutation(np.repeat(np.arange(n_base), copies))
+    wb = w.b.copy()
+    wb["ext_ask_price"] = rng.integers(plo, phi + 1, n_workers).astype(np.uint32)
+    t = dict(asks=np.ascontiguousarray(a.asks[idx]), opts=a.opts, wa=w.a, wb=wb, bits=bits, words=words)
+    cap = rng.integers(max(plo - 2, 0), phi + 3, len(idx)).astype(np.uint32)
+    return t, cap
+
+
+@pytest.mark.parametrize("n_base,copies,n_workers,plo,phi,seed", [
+    (8, 30, 1500, 10, 14, 5),       # few classes, many identical bidders, almost every value tied
+    (20, 12, 2500, 10, 40, 6),
+    (3, 80, 1200, 7, 9, 8),         # caps straddle the whole price range: ties exactly at the outside option
+])
+@pytest.mark.parametrize("stripe,lanes", [(1024, 256), (64, 16)], ids=["kernel_shape", "tiny_stripes"])
+def test_class_cache_auction_equals_the_sequential_checker(n_base, copies, n_workers, plo, phi, seed, stripe, lanes):
+    t, cap = _tables(n_base, copies, n_workers, plo, phi, seed)
+    want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap)
+    got, r, st = auction_class_algorithm(t, cap, stripe=stripe, lanes=lanes, resort_every=7)
+    assert np.array_equal(got, want) and r == rounds
+    assert st["full"] >= 1 and st["refill"] >= 1          # both refresh paths ran
