@@ -241,7 +241,8 @@ typedef struct pm_stats {
   uint32_t n_build_launches; /* auction mode: class pool refills                    */
   uint32_t n_argmin_launches;
   uint32_t n_fused_launches; /* auction mode: per-ask fallback scans                */
-  uint32_t reserved;
+  float    ms_exchange;      /* sharded pass: pack + all-gather + fold, on the engine stream */
+  uint64_t exchange_bytes;   /* bytes this rank received in the exchange            */
 } pm_stats;
 
 typedef struct pm_result {
@@ -279,10 +280,51 @@ enum pm_buffer {
   PM_BUF_ASK_BEST         = 1,  /* int64 [n_asks] packed row argmin (allreduce MIN)          */
   PM_BUF_ASK_COUNT        = 2   /* uint32[n_asks] (allreduce SUM)                            */
 };
+/* Re-target the engine at the range [first, first+count) of the worker table (count 0 = to the end). */
+int pm_set_shard(pm_engine*, uint32_t first, uint32_t count);
 int pm_match_local(pm_engine*, uint32_t mode);    /* evaluation over this shard only */
 int pm_match_finish(pm_engine*, uint32_t mode);   /* resolution sweep over the global arrays */
 int pm_device_buffer(pm_engine*, uint32_t which, void** dev_ptr, size_t* bytes);
 int pm_stream_sync(pm_engine*);
+
+/* ------------------------------------------------------------------------ */
+/* Multi-GPU inside the engine (SURVEY 8b "multi-GPU is inside the engine", 8e).  */
+/* The path shards by workers: every GPU evaluates all asks against an equal     */
+/* contiguous share of the canonical worker order; ONE packed all-gather per     */
+/* pass (NCCL over NVLink, resolved at run time) carries {per-ask (min cost,     */
+/* argmin) + feasible count, per-worker first feasible ask}; every GPU then runs */
+/* the same O(W+T) resolution sweep on identical arrays.  With a communicator    */
+/* attached pm_match does all of it; the shard is the rank's share.              */
+/* ------------------------------------------------------------------------ */
+typedef struct pm_comm pm_comm;
+#define PM_COMM_ID_BYTES 128
+/* one process per GPU: rank 0 makes the id, the host hands it to every rank (any transport) */
+int  pm_comm_unique_id(uint8_t id_out[PM_COMM_ID_BYTES]);
+int  pm_comm_create(const uint8_t unique_id[PM_COMM_ID_BYTES], uint32_t n_ranks, uint32_t rank, int32_t device,
+                    pm_comm** out);
+void pm_comm_destroy(pm_comm*);
+int  pm_attach_comm(pm_engine*, pm_comm*);   /* NULL detaches; the communicator must outlive the engine's use of it */
+
+/* One process, several GPUs — the form the orchestrator's single management loop                          */
+/* (crates/orchestrator/src/main.rs:283-289, mod.rs:180-203) calls: table calls go to every device,        */
+/* pm_multi_match is one sharded pass, the result is read from device 0.  cfg->device/shard/stream ignored. */
+typedef struct pm_multi pm_multi;
+int         pm_multi_create(const pm_cfg* cfg, const int32_t* devices, uint32_t n_devices, pm_multi** out);
+void        pm_multi_destroy(pm_multi*);
+uint32_t    pm_multi_size(const pm_multi*);
+pm_engine*  pm_multi_engine(pm_multi*, uint32_t i);   /* per-device access (stats, auction params, ...) */
+const char* pm_multi_last_error(const pm_multi*);
+int pm_multi_set_asks(pm_multi*, const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts, uint32_t n_opts);
+int pm_multi_set_model_table(pm_multi*, const uint32_t* bits, uint32_t n_patterns, uint32_t n_models,
+                             uint32_t words_per_pattern);
+int pm_multi_set_worker_count(pm_multi*, uint32_t n_workers);
+int pm_multi_upsert_workers(pm_multi*, const pm_worker_a* a, const pm_worker_b* b, uint32_t first, uint32_t n);
+int pm_multi_set_worker_locations(pm_multi*, const double* lat, const double* lon, uint32_t first, uint32_t n);
+int pm_multi_set_worker_addr_rank(pm_multi*, const uint32_t* rank, uint32_t first, uint32_t n);
+int pm_multi_set_flags(pm_multi*, const uint32_t* idx, const uint32_t* flags, uint32_t n);
+int pm_multi_sync(pm_multi*);
+int pm_multi_match(pm_multi*, uint32_t mode);
+int pm_multi_fetch_result(pm_multi*, pm_result* out);
 
 uint32_t pm_abi_version(void);
 

@@ -65,6 +65,26 @@ def load() -> C.CDLL:
         "pm_match_finish": (i32, [vp, u32]),
         "pm_device_buffer": (i32, [vp, u32, P(vp), P(sz)]),
         "pm_stream_sync": (i32, [vp]),
+        "pm_set_shard": (i32, [vp, u32, u32]),
+        "pm_comm_unique_id": (i32, [vp]),
+        "pm_comm_create": (i32, [vp, u32, u32, C.c_int32, P(vp)]),
+        "pm_comm_destroy": (None, [vp]),
+        "pm_attach_comm": (i32, [vp, vp]),
+        "pm_multi_create": (i32, [P(abi.PmCfg), P(C.c_int32), u32, P(vp)]),
+        "pm_multi_destroy": (None, [vp]),
+        "pm_multi_size": (u32, [vp]),
+        "pm_multi_engine": (vp, [vp, u32]),
+        "pm_multi_last_error": (cp, [vp]),
+        "pm_multi_set_asks": (i32, [vp, vp, u32, vp, u32]),
+        "pm_multi_set_model_table": (i32, [vp, vp, u32, u32, u32]),
+        "pm_multi_set_worker_count": (i32, [vp, u32]),
+        "pm_multi_upsert_workers": (i32, [vp, vp, vp, u32, u32]),
+        "pm_multi_set_worker_locations": (i32, [vp, vp, vp, u32, u32]),
+        "pm_multi_set_worker_addr_rank": (i32, [vp, vp, u32, u32]),
+        "pm_multi_set_flags": (i32, [vp, vp, vp, u32]),
+        "pm_multi_sync": (i32, [vp]),
+        "pm_multi_match": (i32, [vp, u32]),
+        "pm_multi_fetch_result": (i32, [vp, P(abi.PmResult)]),
         "pm_plugin_create": (i32, [vp, P(abi.PmPluginPolicy), P(vp)]),
         "pm_plugin_destroy": (None, [vp]),
         "pm_plugin_last_error": (cp, [vp]),

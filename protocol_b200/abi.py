@@ -9,6 +9,7 @@ PM_ABI_VERSION = 1
 PM_NONE = 0xFFFFFFFF
 PM_COST_INF = 0x7FFFFFFFFFFFFFFF
 
+PM_COMM_ID_BYTES = 128
 PM_OK, PM_E_INVALID, PM_E_CUDA, PM_E_NO_DEVICE = 0, -1, -2, -3
 PM_E_STATE, PM_E_NOMEM, PM_E_UNSUPPORTED, PM_E_PARSE = -4, -5, -6, -7
 
@@ -85,7 +86,7 @@ class PmStats(C.Structure):
         ("n_tiles", C.c_uint32), ("n_launches", C.c_uint32), ("n_bumped", C.c_uint32), ("n_rounds", C.c_uint32),
         ("ms_build", C.c_float), ("ms_argmin", C.c_float), ("ms_fused", C.c_float), ("ms_resolve", C.c_float),
         ("ms_total", C.c_float), ("n_build_launches", C.c_uint32), ("n_argmin_launches", C.c_uint32),
-        ("n_fused_launches", C.c_uint32), ("reserved", C.c_uint32),
+        ("n_fused_launches", C.c_uint32), ("ms_exchange", C.c_float), ("exchange_bytes", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -112,7 +113,12 @@ EXPORTS = [
     "pm_set_worker_locations", "pm_set_worker_addr_rank", "pm_set_flags",
     "pm_set_ask_price_caps", "pm_set_auction_params",
     "pm_match", "pm_fetch_result", "pm_get_stats", "pm_build_cost_tile",
-    "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync",
+    "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync", "pm_set_shard",
+    "pm_comm_unique_id", "pm_comm_create", "pm_comm_destroy", "pm_attach_comm",
+    "pm_multi_create", "pm_multi_destroy", "pm_multi_size", "pm_multi_engine", "pm_multi_last_error",
+    "pm_multi_set_asks", "pm_multi_set_model_table", "pm_multi_set_worker_count", "pm_multi_upsert_workers",
+    "pm_multi_set_worker_locations", "pm_multi_set_worker_addr_rank", "pm_multi_set_flags", "pm_multi_sync",
+    "pm_multi_match", "pm_multi_fetch_result",
     "pm_plugin_create", "pm_plugin_destroy", "pm_plugin_last_error", "pm_plugin_add_config", "pm_plugin_seal_configs",
     "pm_plugin_enable_configuration", "pm_plugin_upsert_node", "pm_plugin_set_node_status", "pm_plugin_sync_discovery", "pm_plugin_sync_discovery_json", "pm_plugin_get_node", "pm_plugin_add_task",
     "pm_plugin_delete_task", "pm_plugin_record_upload", "pm_plugin_try_form_new_groups", "pm_plugin_try_merge_solo_groups", "pm_plugin_get_node_group", "pm_plugin_get_all_groups", "pm_plugin_get_group_by_id", "pm_plugin_handle_group_not_found", "pm_plugin_restore_group", "pm_plugin_export_tables", "pm_plugin_redis_writeback",

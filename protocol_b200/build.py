@@ -14,12 +14,12 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libprime_match.so")
 SOURCES = [os.path.join(HERE, "csrc", "pm_engine.cu"), os.path.join(HERE, "csrc", "pm_host.cpp"),
            os.path.join(HERE, "csrc", "pm_plugin.cpp")]
-DEPS = SOURCES + [
-    os.path.join(HERE, "csrc", "pm_kernels.cuh"),
-    os.path.join(HERE, "csrc", "pm_device.cuh"),
-    os.path.join(HERE, "csrc", "pm_proximity.cuh"),
-    os.path.join(ROOT, "include", "prime_match.h"),
-]
+# every header under csrc/ and include/ is a dependency: a stale .so on the GPU box would silently run old kernels
+DEPS = SOURCES + sorted(
+    os.path.join(d, f)
+    for d in (os.path.join(HERE, "csrc"), os.path.join(ROOT, "include"))
+    for f in os.listdir(d) if f.endswith((".cuh", ".hpp", ".h"))
+)
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

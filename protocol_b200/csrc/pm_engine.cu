@@ -11,7 +11,11 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is resolved at run time (nccl_api below), never linked
+
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,8 +23,10 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "pm_guard.hpp"
 #include "pm_kernels.cuh"
 #include "pm_proximity.cuh"
 #include "pm_proximity_band.cuh"
@@ -73,7 +79,44 @@ template <class T> struct PinBuf {
 
 inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// NCCL is plumbing for the one exchange of a sharded pass.  It is looked up at run time so that the library loads
+// (and every single-GPU path works) on hosts without it: first among the symbols already in the process (a host that
+// has NCCL loaded, e.g. through torch, shares its copy), then by soname.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclCommAbort) CommAbort = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+  std::string err;
+};
+const NcclApi& nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void* h = dlsym(RTLD_DEFAULT, "ncclAllGather") ? RTLD_DEFAULT : nullptr;
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { a.err = "NCCL not found (libnccl.so.2): multi-GPU matching needs it"; return a; }
+#define PM_NCCL_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name)); if (!a.name) { a.err = "libnccl: missing nccl" #name; return a; }
+    PM_NCCL_SYM(GetUniqueId) PM_NCCL_SYM(CommInitRank) PM_NCCL_SYM(CommInitAll) PM_NCCL_SYM(CommDestroy)
+    PM_NCCL_SYM(CommAbort) PM_NCCL_SYM(AllGather) PM_NCCL_SYM(GetErrorString)
+#undef PM_NCCL_SYM
+    a.ok = true;
+    return a;
+  }();
+  return api;
+}
+
 }  // namespace
+
+struct pm_comm {
+  ncclComm_t nccl = nullptr;
+  uint32_t n_ranks = 1, rank = 0;
+  int device = 0;
+};
 
 struct pm_engine {
   pm_cfg cfg{};
@@ -144,6 +187,24 @@ struct pm_engine {
   PinBuf<long long> r_ask_best;
   uint32_t n_groups = 0, n_assigned = 0;
   bool matched = false, local_done = false;
+
+  // multi-GPU: the communicator this engine exchanges through (not owned), and the packed exchange buffers
+  pm_comm* comm = nullptr;
+  DevBuf<unsigned char> xchg_send, xchg_recv;
+
+  // The contiguous canonical-order range of workers this engine evaluates: the whole table, the range fixed by
+  // pm_cfg / pm_set_shard, or — with a communicator attached — the rank's equal share.
+  void shard(uint32_t* w0, uint32_t* nw) const {
+    const uint32_t W = n_workers;
+    if (comm) {
+      const uint32_t per = (uint32_t)(((uint64_t)W + comm->n_ranks - 1) / comm->n_ranks);
+      *w0 = (uint32_t)std::min<uint64_t>((uint64_t)comm->rank * per, W);
+      *nw = std::min(per, W - *w0);
+    } else {
+      *w0 = cfg.shard_first;
+      *nw = cfg.shard_count ? cfg.shard_count : (W > *w0 ? W - *w0 : 0);
+    }
+  }
 
   pm_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -251,7 +312,7 @@ void pm_free_pinned(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-int pm_create(const pm_cfg* cfg, pm_engine** out) {
+int pm_create(const pm_cfg* cfg, pm_engine** out) try {
   if (!cfg || !out) {
     g_create_error = "pm_create: null argument";
     return PM_E_INVALID;
@@ -305,7 +366,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) {
   }
   *out = e;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 void pm_destroy(pm_engine* e) {
   if (!e) return;
@@ -335,6 +396,7 @@ void pm_destroy(pm_engine* e) {
   e->h_ctl.release();
   e->worker_group.release(); e->worker_ask.release(); e->group_ask.release();
   e->group_off.release(); e->members.release(); e->h_scalars.release();
+  e->xchg_send.release(); e->xchg_recv.release();
   e->r_worker_group.release(); e->r_worker_ask.release(); e->r_group_ask.release();
   e->r_group_off.release(); e->r_members.release(); e->r_ask_count.release(); e->r_ask_best.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -347,7 +409,7 @@ void pm_destroy(pm_engine* e) {
 const char* pm_last_error(const pm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
 int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
-                uint32_t n_opts) {
+                uint32_t n_opts) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if ((n_asks && !asks) || (n_opts && !opts)) return e->fail(PM_E_INVALID, "pm_set_asks: null table");
@@ -401,10 +463,10 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   e->have_asks = true;
   e->matched = e->local_done = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, uint32_t n_models,
-                       uint32_t words) {
+                       uint32_t words) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (words == 0) words = 1;
@@ -423,9 +485,9 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
   e->have_bits = true;
   e->matched = e->local_done = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_set_worker_count(pm_engine* e, uint32_t n_workers) {
+int pm_set_worker_count(pm_engine* e, uint32_t n_workers) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   PM_CUDA(cudaSetDevice(e->device));
@@ -442,10 +504,10 @@ int pm_set_worker_count(pm_engine* e, uint32_t n_workers) {
   e->have_loc = e->have_rank = false;
   e->matched = e->local_done = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, uint32_t first,
-                      uint32_t n) {
+                      uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_upsert_workers: call pm_set_worker_count first");
@@ -459,10 +521,10 @@ int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, 
   e->workers_checked = false;
   e->matched = e->local_done = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 int pm_set_worker_locations(pm_engine* e, const double* lat, const double* lon, uint32_t first,
-                            uint32_t n) {
+                            uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_locations: no worker table");
@@ -476,9 +538,9 @@ int pm_set_worker_locations(pm_engine* e, const double* lat, const double* lon, 
   }
   e->have_loc = true;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, uint32_t n) {
+int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_addr_rank: no worker table");
@@ -488,9 +550,9 @@ int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, 
   if (n) PM_CUDA(cudaMemcpyAsync(e->addr_rank.p + first, rank, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   e->have_rank = true;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint32_t n) {
+int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_flags: no worker table");
@@ -506,7 +568,7 @@ int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint3
   e->workers_checked = false;
   e->matched = e->local_done = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // ------------------------------------------------------------------ evaluation
 // Fast predicate only when both tables fit its operand limits; decided per match.
@@ -593,8 +655,8 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
   }
   PM_CUDA(cudaSetDevice(e->device));
   const uint32_t W = e->n_workers, T = e->n_asks;
-  const uint32_t w0 = e->cfg.shard_first;
-  const uint32_t nw = e->cfg.shard_count ? e->cfg.shard_count : (W > w0 ? W - w0 : 0);
+  uint32_t w0 = 0, nw = 0;
+  e->shard(&w0, &nw);
   if ((uint64_t)w0 + nw > W) return e->fail(PM_E_INVALID, "pm_match: shard range exceeds the worker table");
   if (!e->have_bits) {  // tables without any model clause: a one-row all-ones table
     PM_CUDA(e->bits.ensure(1));
@@ -696,6 +758,9 @@ static int sort_and_scan(pm_engine* e, uint32_t n_bins, uint32_t shift) {
   return PM_OK;
 }
 
+// The O(W + T) resolution sweep.  Everything between the sort and the last kernel stays on the device (counts are
+// read through device pointers, tables are sized for the worst case), so a pass has exactly ONE host synchronisation:
+// the one at the end that brings back {groups, members, bumped} (and resolves the event timers).
 static int match_finish_locked(pm_engine* e, uint32_t mode) {
   if (!e->local_done) return e->fail(PM_E_STATE, "pm_match_finish: pm_match_local has not run");
   PM_CUDA(cudaSetDevice(e->device));
@@ -712,13 +777,14 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   PM_CUDA(e->seg_start.ensure((size_t)n_bins + 1)); PM_CUDA(e->ngroups.ensure((size_t)n_bins + 1));
   PM_CUDA(e->group_base.ensure((size_t)n_bins + 1));
   PM_CUDA(e->worker_group.ensure(W)); PM_CUDA(e->worker_ask.ensure(W)); PM_CUDA(e->members.ensure(W));
-  PM_CUDA(cudaMemsetAsync(e->counters.p, 0, 16 * 4, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->counters.p, 0, 12 * 4, e->stream));   // [12..13] belong to pm_set_asks
   if (W) {
     pm::pm_iota_u32<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->iota.p, W);
     PM_LAUNCH_CHECK("pm_iota_u32");
   }
   int rc = sort_and_scan(e, n_bins, shift);
   if (rc != PM_OK) return rc;
+  uint32_t* const scal = e->counters.p + 8;   // device mailbox {groups, members, bumped, overflow}
 
   if (prox_general) {
     // sequential-per-group nearest-neighbour formation (pm_proximity.cuh)
@@ -735,7 +801,6 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     PM_CUDA(cudaMemsetAsync(e->xcount.p, 0, (size_t)T * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
     PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
-    PM_CUDA(cudaMemsetAsync(e->counters.p + 4, 0, 4 * 4, e->stream));
     pm::ProxParams pp;
     pp.ev = eval_params(e);
     pp.lat = e->lat.p; pp.lon = e->lon.p;
@@ -743,7 +808,7 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     pp.xhead = e->xhead.p; pp.xnext = e->xnext.p; pp.xcount = e->xcount.p; pp.amin = e->amin.p; pp.amax = e->amax.p;
     pp.list = e->prox_list.p; pp.xs = e->prox_xs.p; pp.dist = e->prox_dist.p; pp.popped = e->popped.p;
     pp.worker_group = e->worker_group.p; pp.worker_ask = e->worker_ask.p; pp.group_ask = e->group_ask.p;
-    pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = e->counters.p + 4;
+    pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = scal;   // {G, M, bumped, overflow}
     pp.group_cap = cap;
     if (merge_mode) pm::pm_merge_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
     else if (e->tune_prox & 1) {   // experimental: same groups from a latitude-ordered view (pm_proximity_band.cuh)
@@ -755,35 +820,16 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     }
     else pm::pm_proximity_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
     PM_LAUNCH_CHECK("pm_proximity_sweep");
-    PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 8, e->counters.p + 4, 16, cudaMemcpyDeviceToHost, e->stream));
-    PM_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->h_scalars.p[11]) return e->fail(PM_E_CUDA, "pm_match: proximity group table overflow");
-    const uint32_t G = e->h_scalars.p[8], M = e->h_scalars.p[9];
-    e->stats.n_bumped = e->h_scalars.p[10];
-    e->n_groups = G;
-    e->n_assigned = M;
-    if (M) {
-      pm::pm_order_members<<<blocks_for(M, 256), 256, 0, e->stream>>>(
-          e->members_raw.p, M, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
+    if (W) {
+      pm::pm_order_members<<<blocks_for(W, 256), 256, 0, e->stream>>>(
+          e->members_raw.p, scal + 1, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
       PM_LAUNCH_CHECK("pm_order_members");
     }
-    tm.stop();
-    if (e->cfg.flags & PM_CFG_TIMING) {
-      PM_CUDA(cudaEventRecord(e->ev1, e->stream));
-      PM_CUDA(cudaEventSynchronize(e->ev1));
-      PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
-      e->resolve_timers();
-    }
-    e->matched = true;
-    return PM_OK;
-  }
-
-  if (shift == 0 && T && !e->all_solo) {
-    pm::pm_check_tails<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, T, e->counters.p);
-    PM_LAUNCH_CHECK("pm_check_tails");
-    PM_CUDA(cudaMemcpyAsync(e->h_scalars.p, e->counters.p, 4, cudaMemcpyDeviceToHost, e->stream));
-    PM_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->h_scalars.p[0]) {
+  } else {
+    if (shift == 0 && T && !e->all_solo) {
+      // under-filled tails: flagged on the device; the single-CTA sweep returns at once when there is none
+      pm::pm_check_tails<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, T, e->counters.p);
+      PM_LAUNCH_CHECK("pm_check_tails");
       PM_CUDA(e->base_len.ensure(T)); PM_CUDA(e->xhead.ensure(T)); PM_CUDA(e->xcount.ensure(T));
       PM_CUDA(e->xnext.ensure(W)); PM_CUDA(e->popped.ensure(W));
       PM_CUDA(cudaMemcpyAsync(e->base_len.p, e->hist.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -794,58 +840,59 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
       sp.cur = e->first_ask.p; sp.base_len = e->base_len.p; sp.seg_start = e->seg_start.p;
       sp.order = e->order.p; sp.xhead = e->xhead.p; sp.xnext = e->xnext.p; sp.xcount = e->xcount.p;
       sp.amin = e->amin.p; sp.amax = e->amax.p; sp.popped = e->popped.p; sp.n_bumped = e->counters.p + 1;
+      sp.any_bad = e->counters.p;
       pm::pm_sweep<<<1, 1024, 0, e->stream>>>(sp);
       PM_LAUNCH_CHECK("pm_sweep");
-      rc = sort_and_scan(e, n_bins, shift);
+      rc = sort_and_scan(e, n_bins, shift);   // owners may have moved
       if (rc != PM_OK) return rc;
     }
-  }
 
-  if (n_bins) {
-    pm::pm_count_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, n_bins, shift, e->ngroups.p);
-    PM_LAUNCH_CHECK("pm_count_groups");
-  }
-  PM_CUDA(cudaMemsetAsync(e->ngroups.p + n_bins, 0, 4, e->stream));
-  {
-    size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream);
-    PM_CUDA(e->cub_tmp.ensure(tmp));
-    PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream));
-  }
-  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 1, e->group_base.p + n_bins, 4, cudaMemcpyDeviceToHost, e->stream));
-  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 2, e->seg_start.p + n_bins, 4, cudaMemcpyDeviceToHost, e->stream));
-  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 3, e->counters.p + 1, 4, cudaMemcpyDeviceToHost, e->stream));
-  PM_CUDA(cudaStreamSynchronize(e->stream));
-  const uint32_t G = e->h_scalars.p[1], n_assigned = e->h_scalars.p[2];
-  e->stats.n_bumped = e->h_scalars.p[3];
-  e->n_groups = G;
-  e->n_assigned = n_assigned;
-
-  PM_CUDA(e->group_ask.ensure((size_t)G + 1));
-  PM_CUDA(e->group_off.ensure((size_t)G + 1));
-  PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
-  PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
-  if (n_assigned) {
-    pm::pm_emit_workers<<<blocks_for(n_assigned, 256), 256, 0, e->stream>>>(
-        e->keys_sorted.p, e->order.p, n_assigned, e->hist.p, e->seg_start.p, e->group_base.p, e->amin.p,
-        e->amax.p, shift, e->worker_group.p, e->worker_ask.p, e->group_ask.p, e->group_off.p);
-    PM_LAUNCH_CHECK("pm_emit_workers");
-  }
-  if (n_bins && !e->all_solo) {
-    pm::pm_emit_empty_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(
-        e->hist.p, e->seg_start.p, e->group_base.p, e->ngroups.p, e->amin.p, n_bins, shift, e->group_ask.p, e->group_off.p);
-    PM_LAUNCH_CHECK("pm_emit_empty_groups");
-  }
-  PM_CUDA(cudaMemcpyAsync(e->group_off.p + G, &e->h_scalars.p[2], 4, cudaMemcpyHostToDevice, e->stream));
-  if (n_assigned) {
-    pm::pm_order_members<<<blocks_for(n_assigned, 256), 256, 0, e->stream>>>(
-        e->order.p, n_assigned, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
-    PM_LAUNCH_CHECK("pm_order_members");
+    if (n_bins) {
+      pm::pm_count_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(e->hist.p, e->amin.p, e->amax.p, n_bins, shift, e->ngroups.p);
+      PM_LAUNCH_CHECK("pm_count_groups");
+    }
+    PM_CUDA(cudaMemsetAsync(e->ngroups.p + n_bins, 0, 4, e->stream));
+    {
+      size_t tmp = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream);
+      PM_CUDA(e->cub_tmp.ensure(tmp));
+      PM_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp, e->ngroups.p, e->group_base.p, (int)(n_bins + 1), e->stream));
+    }
+    // groups <= members + one empty group per bin; sized for that so the count never has to visit the host first
+    const size_t gcap = (size_t)W + n_bins + 1;
+    PM_CUDA(e->group_ask.ensure(gcap + 1));
+    PM_CUDA(e->group_off.ensure(gcap + 1));
+    const uint32_t* n_assigned_dev = e->seg_start.p + n_bins;
+    PM_CUDA(cudaMemsetAsync(e->worker_group.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->worker_ask.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
+    if (W) {
+      pm::pm_emit_workers<<<blocks_for(W, 256), 256, 0, e->stream>>>(
+          e->keys_sorted.p, e->order.p, n_assigned_dev, e->hist.p, e->seg_start.p, e->group_base.p, e->amin.p,
+          e->amax.p, shift, e->worker_group.p, e->worker_ask.p, e->group_ask.p, e->group_off.p);
+      PM_LAUNCH_CHECK("pm_emit_workers");
+    }
+    if (n_bins && !e->all_solo) {
+      pm::pm_emit_empty_groups<<<blocks_for(n_bins, 256), 256, 0, e->stream>>>(
+          e->hist.p, e->seg_start.p, e->group_base.p, e->ngroups.p, e->amin.p, n_bins, shift, e->group_ask.p, e->group_off.p);
+      PM_LAUNCH_CHECK("pm_emit_empty_groups");
+    }
+    pm::pm_close_groups<<<1, 1, 0, e->stream>>>(e->group_base.p + n_bins, n_assigned_dev, e->counters.p + 1, e->group_off.p, scal);
+    PM_LAUNCH_CHECK("pm_close_groups");
+    if (W) {
+      pm::pm_order_members<<<blocks_for(W, 256), 256, 0, e->stream>>>(
+          e->order.p, n_assigned_dev, e->worker_group.p, e->group_off.p, e->have_rank ? e->addr_rank.p : nullptr, e->members.p);
+      PM_LAUNCH_CHECK("pm_order_members");
+    }
   }
   tm.stop();
+  PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 8, scal, 16, cudaMemcpyDeviceToHost, e->stream));
+  if (e->cfg.flags & PM_CFG_TIMING) PM_CUDA(cudaEventRecord(e->ev1, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));   // the pass's one host synchronisation
+  if (prox_general && e->h_scalars.p[11]) return e->fail(PM_E_CUDA, "pm_match: proximity group table overflow");
+  e->n_groups = e->h_scalars.p[8];
+  e->n_assigned = e->h_scalars.p[9];
+  e->stats.n_bumped = e->h_scalars.p[10];
   if (e->cfg.flags & PM_CFG_TIMING) {
-    PM_CUDA(cudaEventRecord(e->ev1, e->stream));
-    PM_CUDA(cudaEventSynchronize(e->ev1));
     PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
     e->resolve_timers();
   }
@@ -888,7 +935,7 @@ static int match_auction_locked(pm_engine* e) {
   if (!e->have_caps) return e->fail(PM_E_STATE, "pm_match: auction mode needs pm_set_ask_price_caps");
   if (e->max_pattern_row > e->n_patterns || (e->max_pattern_row && !e->have_bits))
     return e->fail(PM_E_STATE, "pm_match: an ask references a model pattern missing from the model table");
-  if (e->cfg.shard_count) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is single-GPU");
+  if (e->cfg.shard_count || e->comm) return e->fail(PM_E_UNSUPPORTED, "pm_match: auction mode is single-GPU");
   PM_CUDA(cudaSetDevice(e->device));
   const uint32_t W = e->n_workers, T = e->n_asks;
   if (!e->have_bits) {
@@ -1091,7 +1138,7 @@ static int match_auction_locked(pm_engine* e) {
   return PM_OK;
 }
 
-int pm_set_ask_price_caps(pm_engine* e, const uint32_t* price_cap, uint32_t n_asks) {
+int pm_set_ask_price_caps(pm_engine* e, const uint32_t* price_cap, uint32_t n_asks) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_asks || n_asks != e->n_asks) return e->fail(PM_E_INVALID, "pm_set_ask_price_caps: one cap per ask, after pm_set_asks");
@@ -1101,38 +1148,132 @@ int pm_set_ask_price_caps(pm_engine* e, const uint32_t* price_cap, uint32_t n_as
   PM_CUDA(cudaStreamSynchronize(e->stream));
   e->have_caps = true;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_set_auction_params(pm_engine* e, uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div) {
+int pm_set_auction_params(pm_engine* e, uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   e->auc_scale = cost_scale ? cost_scale : 1;
   e->auc_eps_start = eps_start ? eps_start : 1;
   e->auc_eps_div = eps_div < 2 ? 2 : eps_div;
   return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+// The one data-path exchange of a sharded pass: every rank packs {per-ask (min cost, argmin) and feasible
+// count over its workers, first feasible ask of its own workers} into one buffer, ONE all-gather over NVLink moves
+// them, and every rank folds the contributions into the same global arrays.  Enqueued on the engine's stream: no host
+// synchronisation, nothing but NCCL's kernel between the evaluation and the resolution sweep.
+static int exchange_locked(pm_engine* e) {
+  const NcclApi& nccl = nccl_api();
+  if (!nccl.ok) return e->fail(PM_E_UNSUPPORTED, nccl.err);
+  const uint32_t W = e->n_workers, T = e->n_asks, n = e->comm->n_ranks;
+  uint32_t w0 = 0, nw = 0;
+  e->shard(&w0, &nw);
+  const uint32_t per = (uint32_t)(((uint64_t)W + n - 1) / n);
+  const size_t stride = (((size_t)T * 12 + (size_t)per * 4) + 15) & ~(size_t)15;
+  PM_CUDA(e->xchg_send.ensure(stride));
+  PM_CUDA(e->xchg_recv.ensure(stride * n));
+  Timer tm(e, &e->stats.ms_exchange);
+  const size_t work = std::max<size_t>(std::max<size_t>(T, W), 1);
+  pm::pm_xchg_pack<<<std::min(blocks_for(work, 256), 1184u), 256, 0, e->stream>>>(e->first_ask.p + w0, nw, per, e->ask_best.p, e->ask_count.p, T,
+                                                                                  e->xchg_send.p);
+  PM_LAUNCH_CHECK("pm_xchg_pack");
+  const ncclResult_t nr = nccl.AllGather(e->xchg_send.p, e->xchg_recv.p, stride, ncclUint8, e->comm->nccl, e->stream);
+  if (nr != ncclSuccess) return e->fail(PM_E_CUDA, std::string("ncclAllGather: ") + nccl.GetErrorString(nr));
+  pm::pm_xchg_unpack<<<std::min(blocks_for(work, 256), 1184u), 256, 0, e->stream>>>(e->xchg_recv.p, n, stride, std::max(per, 1u), W, T, e->first_ask.p,
+                                                                                    e->ask_best.p, e->ask_count.p);
+  PM_LAUNCH_CHECK("pm_xchg_unpack");
+  tm.stop();
+  e->stats.exchange_bytes = (uint64_t)stride * n;
+  return PM_OK;
 }
 
-int pm_match_local(pm_engine* e, uint32_t mode) {
+int pm_match_local(pm_engine* e, uint32_t mode) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if ((mode & 0xFFu) == PM_MODE_AUCTION) return e->fail(PM_E_UNSUPPORTED, "pm_match_local: auction mode is single-GPU (use pm_match)");
   return match_local_locked(e, mode);
-}
-int pm_match_finish(pm_engine* e, uint32_t mode) {
+} catch (...) { return pm_guard_rc(); }
+int pm_match_finish(pm_engine* e, uint32_t mode) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   return match_finish_locked(e, mode);
-}
-int pm_match(pm_engine* e, uint32_t mode) {
+} catch (...) { return pm_guard_rc(); }
+int pm_match(pm_engine* e, uint32_t mode) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if ((mode & 0xFFu) == PM_MODE_AUCTION) return match_auction_locked(e);
   int rc = match_local_locked(e, mode);
   if (rc != PM_OK) return rc;
+  if (e->comm && e->comm->n_ranks > 1) {
+    rc = exchange_locked(e);
+    if (rc != PM_OK) return rc;
+  }
   return match_finish_locked(e, mode);
+} catch (...) { return pm_guard_rc(); }
+
+int pm_set_shard(pm_engine* e, uint32_t first, uint32_t count) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->cfg.shard_first = first;
+  e->cfg.shard_count = count;
+  e->matched = e->local_done = false;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+// ------------------------------------------------------------------ communicators
+int pm_comm_unique_id(uint8_t* id_out) try {
+  if (!id_out) return PM_E_INVALID;
+  const NcclApi& nccl = nccl_api();
+  if (!nccl.ok) { g_create_error = nccl.err; return PM_E_UNSUPPORTED; }
+  static_assert(sizeof(ncclUniqueId) == PM_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  const ncclResult_t nr = nccl.GetUniqueId(&id);
+  if (nr != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + nccl.GetErrorString(nr); return PM_E_CUDA; }
+  std::memcpy(id_out, &id, sizeof id);
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+int pm_comm_create(const uint8_t* unique_id, uint32_t n_ranks, uint32_t rank, int32_t device, pm_comm** out) try {
+  if (!unique_id || !out || n_ranks == 0 || rank >= n_ranks) return PM_E_INVALID;
+  *out = nullptr;
+  const NcclApi& nccl = nccl_api();
+  if (!nccl.ok) { g_create_error = nccl.err; return PM_E_UNSUPPORTED; }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); g_create_error = "pm_comm_create: bad device"; return PM_E_INVALID; }
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof id);
+  pm_comm* c = new pm_comm;
+  c->n_ranks = n_ranks; c->rank = rank; c->device = device;
+  const ncclResult_t nr = nccl.CommInitRank(&c->nccl, (int)n_ranks, id, (int)rank);
+  if (nr != ncclSuccess) {
+    g_create_error = std::string("ncclCommInitRank: ") + nccl.GetErrorString(nr);
+    delete c;
+    return PM_E_CUDA;
+  }
+  *out = c;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+void pm_comm_destroy(pm_comm* c) {
+  if (!c) return;
+  if (c->nccl && nccl_api().ok) {
+    cudaSetDevice(c->device);
+    nccl_api().CommDestroy(c->nccl);
+  }
+  delete c;
 }
 
-int pm_fetch_result(pm_engine* e, pm_result* out) {
+int pm_attach_comm(pm_engine* e, pm_comm* c) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (c && c->device != e->device) return e->fail(PM_E_INVALID, "pm_attach_comm: communicator and engine are on different devices");
+  e->comm = c;
+  e->matched = e->local_done = false;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+
+int pm_fetch_result(pm_engine* e, pm_result* out) try {
   if (!e || !out) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->matched) return e->fail(PM_E_STATE, "pm_fetch_result: no completed match");
@@ -1159,9 +1300,9 @@ int pm_fetch_result(pm_engine* e, pm_result* out) {
   out->ask_best = (const int64_t*)e->r_ask_best.p; out->ask_count = e->r_ask_count.p;
   out->stats = e->stats;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out) {
+int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out) try {
   if (!e || !host_out) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_workers || !e->have_asks) return e->fail(PM_E_STATE, "pm_build_cost_tile: tables not set");
@@ -1169,8 +1310,9 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
     return e->fail(PM_E_STATE, "pm_build_cost_tile: model table missing");
   if ((uint64_t)t0 + nt > e->n_asks || nt == 0) return e->fail(PM_E_INVALID, "pm_build_cost_tile: ask range");
   PM_CUDA(cudaSetDevice(e->device));
-  const uint32_t W = e->n_workers, w0 = e->cfg.shard_first;
-  const uint32_t nw = e->cfg.shard_count ? e->cfg.shard_count : (W > w0 ? W - w0 : 0);
+  const uint32_t W = e->n_workers;
+  uint32_t w0 = 0, nw = 0;
+  e->shard(&w0, &nw);
   if (nw == 0 || (uint64_t)w0 + nw > W) return e->fail(PM_E_INVALID, "pm_build_cost_tile: empty worker range");
   if (!e->have_bits) {
     PM_CUDA(e->bits.ensure(1));
@@ -1196,15 +1338,15 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
                             cudaMemcpyDeviceToHost, e->stream));
   PM_CUDA(cudaStreamSynchronize(e->stream));
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_get_stats(const pm_engine* e, pm_stats* out) {
+int pm_get_stats(const pm_engine* e, pm_stats* out) try {
   if (!e || !out) return PM_E_INVALID;
   *out = e->stats;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_device_buffer(pm_engine* e, uint32_t which, void** dev_ptr, size_t* bytes) {
+int pm_device_buffer(pm_engine* e, uint32_t which, void** dev_ptr, size_t* bytes) try {
   if (!e || !dev_ptr || !bytes) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
   switch (which) {
@@ -1215,13 +1357,148 @@ int pm_device_buffer(pm_engine* e, uint32_t which, void** dev_ptr, size_t* bytes
   }
   if (!*dev_ptr) return e->fail(PM_E_STATE, "pm_device_buffer: buffer not allocated yet (run pm_match_local)");
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_stream_sync(pm_engine* e) {
+int pm_stream_sync(pm_engine* e) try {
   if (!e) return PM_E_INVALID;
   PM_CUDA(cudaSetDevice(e->device));
   PM_CUDA(cudaStreamSynchronize(e->stream));
   return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+// ------------------------------------------------------------------ one process, several GPUs
+// The orchestrator is one process with one management loop (reference crates/orchestrator/src/main.rs:283-289), so
+// the multi-GPU form it can call is this one: N engines, one per device, each with the full (small) tables and an
+// equal share of the canonical worker order; communicators from ncclCommInitAll; a pass = every device evaluates its
+// share, one all-gather, every device runs the same resolution sweep (engine 0's result is the result).
+struct pm_multi {
+  std::vector<pm_engine*> engines;
+  std::vector<pm_comm*> comms;
+  std::string err;
+};
+
+void pm_multi_destroy(pm_multi* m) {
+  if (!m) return;
+  for (pm_engine* e : m->engines) pm_destroy(e);
+  for (pm_comm* c : m->comms) pm_comm_destroy(c);
+  delete m;
 }
+
+int pm_multi_create(const pm_cfg* cfg, const int32_t* devices, uint32_t n, pm_multi** out) try {
+  if (!cfg || !devices || !out || n == 0) return PM_E_INVALID;
+  *out = nullptr;
+  pm_multi* m = new pm_multi;
+  for (uint32_t i = 0; i < n; ++i) {
+    pm_cfg c = *cfg;
+    c.device = devices[i];
+    c.shard_first = c.shard_count = 0;
+    c.stream = nullptr;   // one private stream per device
+    pm_engine* e = nullptr;
+    const int rc = pm_create(&c, &e);
+    if (rc != PM_OK) { pm_multi_destroy(m); return rc; }
+    m->engines.push_back(e);
+  }
+  if (n > 1) {
+    const NcclApi& nccl = nccl_api();
+    if (!nccl.ok) { g_create_error = nccl.err; pm_multi_destroy(m); return PM_E_UNSUPPORTED; }
+    std::vector<ncclComm_t> raw(n, nullptr);
+    std::vector<int> devs(devices, devices + n);
+    const ncclResult_t nr = nccl.CommInitAll(raw.data(), (int)n, devs.data());
+    if (nr != ncclSuccess) {
+      g_create_error = std::string("ncclCommInitAll: ") + nccl.GetErrorString(nr);
+      pm_multi_destroy(m);
+      return PM_E_CUDA;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      pm_comm* c = new pm_comm;
+      c->nccl = raw[i]; c->n_ranks = n; c->rank = i; c->device = devices[i];
+      m->comms.push_back(c);
+      m->engines[i]->comm = c;
+    }
+  }
+  *out = m;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+uint32_t pm_multi_size(const pm_multi* m) { return m ? (uint32_t)m->engines.size() : 0u; }
+pm_engine* pm_multi_engine(pm_multi* m, uint32_t i) { return (m && i < m->engines.size()) ? m->engines[i] : nullptr; }
+const char* pm_multi_last_error(const pm_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+#define PM_MULTI_EACH(call)                                      \
+  do {                                                           \
+    if (!m) return PM_E_INVALID;                                 \
+    for (pm_engine* e : m->engines) {                            \
+      const int rc_ = (call);                                    \
+      if (rc_ != PM_OK) { m->err = pm_last_error(e); return rc_; } \
+    }                                                            \
+    return PM_OK;                                                \
+  } while (0)
+
+int pm_multi_set_asks(pm_multi* m, const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts, uint32_t n_opts) try {
+  PM_MULTI_EACH(pm_set_asks(e, asks, n_asks, opts, n_opts));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_set_model_table(pm_multi* m, const uint32_t* bits, uint32_t n_patterns, uint32_t n_models, uint32_t words) try {
+  PM_MULTI_EACH(pm_set_model_table(e, bits, n_patterns, n_models, words));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_set_worker_count(pm_multi* m, uint32_t n_workers) try {
+  PM_MULTI_EACH(pm_set_worker_count(e, n_workers));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_upsert_workers(pm_multi* m, const pm_worker_a* a, const pm_worker_b* b, uint32_t first, uint32_t n) try {
+  PM_MULTI_EACH(pm_upsert_workers(e, a, b, first, n));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_set_worker_locations(pm_multi* m, const double* lat, const double* lon, uint32_t first, uint32_t n) try {
+  PM_MULTI_EACH(pm_set_worker_locations(e, lat, lon, first, n));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_set_worker_addr_rank(pm_multi* m, const uint32_t* rank, uint32_t first, uint32_t n) try {
+  PM_MULTI_EACH(pm_set_worker_addr_rank(e, rank, first, n));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_set_flags(pm_multi* m, const uint32_t* idx, const uint32_t* flags, uint32_t n) try {
+  PM_MULTI_EACH(pm_set_flags(e, idx, flags, n));
+} catch (...) { return pm_guard_rc(); }
+int pm_multi_sync(pm_multi* m) try {
+  PM_MULTI_EACH(pm_stream_sync(e));
+} catch (...) { return pm_guard_rc(); }
+#undef PM_MULTI_EACH
+
+int pm_multi_match(pm_multi* m, uint32_t mode) try {
+  if (!m) return PM_E_INVALID;
+  const size_t n = m->engines.size();
+  if (n == 1) {
+    const int rc = pm_match(m->engines[0], mode);
+    if (rc != PM_OK) m->err = pm_last_error(m->engines[0]);
+    return rc;
+  }
+  // a rank that fails before the collective would leave the others waiting in it: check what can be checked first,
+  // and abort every communicator if a rank still fails on the way
+  for (pm_engine* e : m->engines) {
+    if (!e->have_workers || !e->have_asks) { m->err = "pm_multi_match: worker and ask tables must be set first"; return PM_E_STATE; }
+    if (e->n_workers != m->engines[0]->n_workers || e->n_asks != m->engines[0]->n_asks) {
+      m->err = "pm_multi_match: engines hold different tables";
+      return PM_E_STATE;
+    }
+  }
+  std::vector<int> rcs(n, PM_OK);
+  std::atomic<bool> aborted{false};
+  std::vector<std::thread> threads;
+  for (size_t i = 0; i < n; ++i) {
+    threads.emplace_back([&, i] {
+      rcs[i] = pm_match(m->engines[i], mode);
+      if (rcs[i] != PM_OK && !aborted.exchange(true) && nccl_api().ok)
+        for (pm_comm* c : m->comms)
+          if (c->nccl) { nccl_api().CommAbort(c->nccl); c->nccl = nullptr; }
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (size_t i = 0; i < n; ++i)
+    if (rcs[i] != PM_OK) { m->err = pm_last_error(m->engines[i]); return rcs[i]; }
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+int pm_multi_fetch_result(pm_multi* m, pm_result* out) try {
+  if (!m || m->engines.empty()) return PM_E_INVALID;
+  const int rc = pm_fetch_result(m->engines[0], out);
+  if (rc != PM_OK) m->err = pm_last_error(m->engines[0]);
+  return rc;
+} catch (...) { return pm_guard_rc(); }
 
 }  // extern "C"

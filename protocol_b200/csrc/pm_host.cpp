@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/prime_match.h"
+#include "pm_guard.hpp"
 
 namespace {
 
@@ -80,7 +81,7 @@ uint32_t pm_abi_version(void) { return PM_ABI_VERSION; }
 pm_interner* pm_interner_create(void) { return new (std::nothrow) pm_interner; }
 void pm_interner_destroy(pm_interner* in) { delete in; }
 
-uint32_t pm_intern_model(pm_interner* in, const char* spec_model) {
+uint32_t pm_intern_model(pm_interner* in, const char* spec_model) try {
   if (!in || !spec_model) return PM_NONE;
   std::string key(spec_model);
   auto it = in->model_ids.find(key);
@@ -93,9 +94,9 @@ uint32_t pm_intern_model(pm_interner* in, const char* spec_model) {
   in->model_ids.emplace(std::move(key), id);
   in->dirty = true;
   return id;
-}
+} catch (...) { return PM_NONE; }
 
-uint32_t pm_intern_pattern(pm_interner* in, const char* req_model) {
+uint32_t pm_intern_pattern(pm_interner* in, const char* req_model) try {
   if (!in || !req_model) return PM_NONE;
   std::string key(req_model);
   auto it = in->pattern_ids.find(key);
@@ -117,10 +118,10 @@ uint32_t pm_intern_pattern(pm_interner* in, const char* req_model) {
   in->pattern_ids.emplace(std::move(key), id);
   in->dirty = true;
   return id;
-}
+} catch (...) { return PM_NONE; }
 
 int pm_interner_table(pm_interner* in, const uint32_t** bits, uint32_t* n_patterns,
-                      uint32_t* n_models, uint32_t* words_per_pattern) {
+                      uint32_t* n_models, uint32_t* words_per_pattern) try {
   if (!in) return PM_E_INVALID;
   if (in->dirty) {
     const uint32_t nm = uint32_t(in->models.size()), np = uint32_t(in->patterns.size());
@@ -137,7 +138,7 @@ int pm_interner_table(pm_interner* in, const uint32_t** bits, uint32_t* n_patter
   if (n_models) *n_models = uint32_t(in->models.size());
   if (words_per_pattern) *words_per_pattern = in->words;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // ---- ComputeRequirements::from_str (node.rs:180-374) ------------------------
 namespace {
@@ -160,7 +161,7 @@ int fail(char* err, size_t n, const std::string& msg) {
 }  // namespace
 
 int pm_parse_requirements(const char* s, pm_interner* interner, pm_ask* ask, pm_gpu_opt* opts,
-                          uint32_t max_opts, uint32_t* n_opts_out, char* err, size_t err_len) {
+                          uint32_t max_opts, uint32_t* n_opts_out, char* err, size_t err_len) try {
   if (!s || !ask) return PM_E_INVALID;
   std::vector<pm_gpu_opt> done;
   pm_gpu_opt cur{};
@@ -270,11 +271,11 @@ int pm_parse_requirements(const char* s, pm_interner* interner, pm_ask* ask, pm_
   ask->ram_mb = ram;
   ask->storage_gb = storage;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // mod.rs:150-164
 int pm_sort_configs(const uint32_t* min_group_size, const uint8_t* has_requirements, uint32_t n,
-                    uint32_t* perm_out) {
+                    uint32_t* perm_out) try {
   if ((n && (!min_group_size || !has_requirements)) || !perm_out) return PM_E_INVALID;
   std::vector<uint32_t> p(n);
   for (uint32_t i = 0; i < n; ++i) p[i] = i;
@@ -284,6 +285,6 @@ int pm_sort_configs(const uint32_t* min_group_size, const uint8_t* has_requireme
   });
   std::copy(p.begin(), p.end(), perm_out);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 }  // extern "C"

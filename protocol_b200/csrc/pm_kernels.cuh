@@ -611,6 +611,7 @@ struct SweepParams {
   const uint32_t* amax;
   uint32_t* popped;          // [W] scratch
   uint32_t* n_bumped;
+  const uint32_t* any_bad;   // written by pm_check_tails: 0 = no configuration has an under-filled tail, nothing to do
 };
 
 // Sequential-in-priority sweep (single CTA): configurations are final in
@@ -619,6 +620,7 @@ struct SweepParams {
 // front, mod.rs:554-561) to their next feasible configuration.
 __global__ void __launch_bounds__(1024) pm_sweep(SweepParams p) {
   __shared__ uint32_t s_first_bad, s_npop;
+  if (*p.any_bad == 0u) return;   // the common case costs one launch, not a host round trip
   const uint32_t T = p.ev.n_asks;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   uint32_t c_lo = 0;
@@ -717,7 +719,7 @@ __global__ void pm_count_groups(const uint32_t* __restrict__ hist, const uint32_
 // group table.  Positions past the formed groups of a bin (an unformed tail can
 // only exist if the sweep was skipped by the caller) stay unassigned.
 __global__ void pm_emit_workers(const uint32_t* __restrict__ keys_sorted,
-                                const uint32_t* __restrict__ order, uint32_t n_assigned,
+                                const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_assigned_dev,
                                 const uint32_t* __restrict__ hist,
                                 const uint32_t* __restrict__ seg_start,
                                 const uint32_t* __restrict__ group_base,
@@ -726,7 +728,7 @@ __global__ void pm_emit_workers(const uint32_t* __restrict__ keys_sorted,
                                 uint32_t* __restrict__ worker_ask, uint32_t* __restrict__ group_ask,
                                 uint32_t* __restrict__ group_off) {
   uint32_t pidx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pidx >= n_assigned) return;
+  if (pidx >= *n_assigned_dev) return;   // launched over all workers: no host read of the count
   const uint32_t b = keys_sorted[pidx], c = b >> shift, w = order[pidx];
   const uint32_t mx = amax[c], K = hist[b], r = pidx - seg_start[b];
   if (mx == 0) return;
@@ -760,13 +762,13 @@ __global__ void pm_emit_empty_groups(const uint32_t* __restrict__ hist,
 
 // members of a group in BTreeSet<String> order (mod.rs:63-69): position = number
 // of members whose address rank is smaller.
-__global__ void pm_order_members(const uint32_t* __restrict__ order, uint32_t n_assigned,
+__global__ void pm_order_members(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_assigned_dev,
                                  const uint32_t* __restrict__ worker_group,
                                  const uint32_t* __restrict__ group_off,
                                  const uint32_t* __restrict__ addr_rank,
                                  uint32_t* __restrict__ members) {
   uint32_t pidx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pidx >= n_assigned) return;
+  if (pidx >= *n_assigned_dev) return;
   const uint32_t w = order[pidx];
   const uint32_t g = worker_group[w];
   if (g == kNone) { members[pidx] = w; return; }
@@ -779,6 +781,61 @@ __global__ void pm_order_members(const uint32_t* __restrict__ order, uint32_t n_
     pos += ((addr_rank ? addr_rank[o] : o) < mine) ? 1u : 0u;
   }
   members[gs + pos] = w;
+}
+
+// The CSR end marker group_off[G] and the pass's scalars {G, members, bumped}, written on the device so the
+// resolution chain needs no host round trip before its last kernel.
+__global__ void pm_close_groups(const uint32_t* __restrict__ n_groups_dev, const uint32_t* __restrict__ n_assigned_dev,
+                                const uint32_t* __restrict__ n_bumped_dev, uint32_t* __restrict__ group_off,
+                                uint32_t* __restrict__ scalars) {
+  const uint32_t G = *n_groups_dev, M = *n_assigned_dev;
+  group_off[G] = M;
+  scalars[0] = G;
+  scalars[1] = M;
+  scalars[2] = *n_bumped_dev;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange
+// One rank's contribution to the single collective of a sharded pass, packed into one buffer:
+//   [ ask_best int64[T] | ask_count u32[T] | first_ask of the rank's own worker range u32[per] ]
+// (`per` = ceil(W / ranks): every rank sends the same size; the last rank's tail is padding.)
+__global__ void pm_xchg_pack(const uint32_t* __restrict__ first_ask_shard, uint32_t nw, uint32_t per,
+                             const long long* __restrict__ ask_best, const uint32_t* __restrict__ ask_count, uint32_t T,
+                             unsigned char* __restrict__ send) {
+  long long* s_best = reinterpret_cast<long long*>(send);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(send + (size_t)T * 8);
+  uint32_t* s_first = s_cnt + T;
+  const size_t n = (size_t)max(T, per);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < T) { s_best[i] = ask_best[i]; s_cnt[i] = ask_count[i]; }
+    if (i < per) s_first[i] = i < nw ? first_ask_shard[i] : kNone;
+  }
+}
+
+// After the all-gather: every rank folds the `ranks` contributions into the same global arrays — per ask the
+// packed (cost, worker) minimum and the feasible-count sum, per worker the first feasible ask from its owner.
+__global__ void pm_xchg_unpack(const unsigned char* __restrict__ recv, uint32_t ranks, size_t stride, uint32_t per,
+                               uint32_t W, uint32_t T, uint32_t* __restrict__ first_ask,
+                               long long* __restrict__ ask_best, uint32_t* __restrict__ ask_count) {
+  const size_t n = (size_t)max(T, W);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < T) {
+      long long best = kInf;
+      uint32_t cnt = 0;
+      for (uint32_t r = 0; r < ranks; ++r) {
+        const unsigned char* base = recv + (size_t)r * stride;
+        best = min(best, reinterpret_cast<const long long*>(base)[i]);
+        cnt += reinterpret_cast<const uint32_t*>(base + (size_t)T * 8)[i];
+      }
+      ask_best[i] = best;
+      ask_count[i] = cnt;
+    }
+    if (i < W) {
+      const uint32_t r = (uint32_t)(i / per);
+      const uint32_t* f = reinterpret_cast<const uint32_t*>(recv + (size_t)r * stride + (size_t)T * 12);
+      first_ask[i] = f[i - (size_t)r * per];
+    }
+  }
 }
 
 }  // namespace pm

@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "../../include/prime_match.h"
+#include "pm_guard.hpp"
 #include "pm_json.hpp"
 
 namespace {
@@ -178,6 +179,7 @@ struct pm_plugin {
   // count_healthy_nodes_with_same_endpoint (discovery/monitor.rs:218-234, Theta(N^2) per sync)
   std::unordered_map<std::string, uint32_t> healthy_at;
   uint64_t sync_gen = 0;
+  uint64_t sync_skipped = 0;   // discovery entries without id / ip, skipped (the reference logs them)
   // BTreeSet<String> rank of every node's address: addresses never change and nodes are only appended, so the ranks
   // are recomputed only when the table has grown since the last management pass
   std::vector<uint32_t> addr_rank_cache;
@@ -267,7 +269,7 @@ struct pm_plugin {
 
 extern "C" {
 
-int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugin** out) {
+int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugin** out) try {
   if (!out) return PM_E_INVALID;
   pm_plugin* p = new (std::nothrow) pm_plugin;
   if (!p) return PM_E_NOMEM;
@@ -281,7 +283,7 @@ int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugi
   p->interner = pm_interner_create();
   *out = p;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 void pm_plugin_destroy(pm_plugin* p) {
   if (!p) return;
@@ -292,7 +294,7 @@ void pm_plugin_destroy(pm_plugin* p) {
 const char* pm_plugin_last_error(const pm_plugin* p) { return p ? p->err.c_str() : ""; }
 
 int pm_plugin_add_config(pm_plugin* p, const char* name, uint32_t min_group_size, uint32_t max_group_size,
-                         const char* requirements) {
+                         const char* requirements) try {
   if (!p || !name) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   if (p->sealed) return p->fail(PM_E_STATE, "configurations are sealed");
@@ -316,9 +318,9 @@ int pm_plugin_add_config(pm_plugin* p, const char* name, uint32_t min_group_size
   c.ask.max_group_size = max_group_size;
   p->templates.push_back(std::move(c));
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_plugin_seal_configs(pm_plugin* p) {
+int pm_plugin_seal_configs(pm_plugin* p) try {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   const uint32_t n = (uint32_t)p->templates.size();
@@ -337,17 +339,17 @@ int pm_plugin_seal_configs(pm_plugin* p) {
   }
   p->sealed = true;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) {  // mod.rs:1328-1346
+int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) try {  // mod.rs:1328-1346
   if (!p || !name) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   if (enable) p->available.insert(name);
   else p->available.erase(name);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
+int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) try {
   if (!p || !d || !d->address) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   NodeRec* r;
@@ -383,17 +385,17 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) {
   r->lon = d->lon;
   p->index_add(*r);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // StatusUpdatePlugin::handle_status_change (plugins/mod.rs:23-34 -> status_update_impl.rs:8-39)
-int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status) {
+int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status) try {
   if (!p || !address) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   if (it == p->node_index.end()) return p->fail(PM_E_INVALID, "unknown node");
   p->set_status(p->nodes[it->second], status, (int64_t)std::time(nullptr) * 1000);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // DiscoveryMonitor::get_nodes -> sync_single_node_with_discovery (discovery/monitor.rs:236-435):
 // reconcile the validated nodes reported by the discovery service into the node table.
@@ -414,7 +416,8 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
   std::string addr, ip, key;   // reused: no allocation per node once grown
   for (uint32_t i = 0; i < n; ++i) {
     const pm_discovery_node& d = dn[i];
-    if (!d.node.address || !d.ip_address) return p->fail(PM_E_INVALID, "discovery node without id / ip");
+    // a node the monitor cannot use is logged and skipped; the rest of the fetch still applies (monitor.rs:425-429)
+    if (!d.node.address || !d.ip_address) { ++p->sync_skipped; continue; }
     if (!d.is_validated) continue;                       // fetch keeps validated nodes only
     addr.assign(d.node.address);
     ip.assign(d.ip_address);
@@ -516,13 +519,13 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
 extern "C" {
 
 int pm_plugin_sync_discovery(pm_plugin* p, const pm_discovery_node* dn, uint32_t n, int64_t now_ms,
-                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
+                             uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) try {
   if (!p || (n && !dn)) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   if (n_new) *n_new = 0;
   std::unordered_set<std::string> unstored;
   return sync_discovery_chunk(p, dn, n, now_ms, max_healthy_nodes_with_same_endpoint, n_new, ++p->sync_gen, unstored);
-}
+} catch (...) { return pm_guard_rc(); }
 
 }  // extern "C"
 
@@ -530,6 +533,7 @@ namespace {
 
 bool json_u32(const pmjson::Value* v, uint32_t* out) {   // Option<u32>
   if (!v || v->kind != pmjson::Value::Number || v->num < 0 || v->num > 4294967295.0) return false;
+  if (v->num != (double)(uint32_t)v->num) return false;   // 1.5 is not a u32 (serde rejects it; here the field reads as None)
   *out = (uint32_t)v->num;
   return true;
 }
@@ -734,7 +738,7 @@ extern "C" {
 // into compact records (nothing is applied if the body does not parse, like `response.json()` failing in the
 // reference), which then go through the monitor's per-node logic in chunks, the table lock released in between.
 int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, int64_t now_ms,
-                                  uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) {
+                                  uint32_t max_healthy_nodes_with_same_endpoint, uint32_t* n_new) try {
   if (!p || !json) return PM_E_INVALID;
   if (n_new) *n_new = 0;
   std::vector<DiscRec> recs;
@@ -824,10 +828,10 @@ int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, in
     if (rc != PM_OK) return rc;
   }
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // node as the /nodes route would show it (fields on this path): JSON or null
-int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len) {
+int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
@@ -857,9 +861,9 @@ int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len)
   if (!buf || len < out.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
   std::memcpy(buf, out.c_str(), out.size() + 1);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
+int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) try {
   if (!p || !d || !d->id) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   TaskRec t;
@@ -883,9 +887,9 @@ int pm_plugin_add_task(pm_plugin* p, const pm_task_desc* d) {
   p->claim_cache_valid = false;
   p->newest_valid = false;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
-int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_task + on_task_deleted
+int pm_plugin_delete_task(pm_plugin* p, const char* id) try {  // TaskStore::delete_task + on_task_deleted
   if (!p || !id) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = std::find_if(p->tasks.begin(), p->tasks.end(), [&](const TaskRec& t) { return t.id == id; });
@@ -909,7 +913,7 @@ int pm_plugin_delete_task(pm_plugin* p, const char* id) {  // TaskStore::delete_
       if (!remaining) p->available.erase(topo);
     }
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 }  // extern "C"
 
@@ -961,7 +965,7 @@ extern "C" {
 // The SoA tables a management pass would upload, for callers that keep their own device copy and for inspection.
 // Arrays may be NULL (skipped); capacity is in rows; *n_rows receives the row count (PM_E_NOMEM when it does not fit).
 int pm_plugin_export_tables(pm_plugin* p, pm_worker_a* a, pm_worker_b* b, double* lat, double* lon, uint32_t* addr_rank,
-                            uint32_t capacity, uint32_t* n_rows) {
+                            uint32_t capacity, uint32_t* n_rows) try {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   const uint32_t W = (uint32_t)p->nodes.size();
@@ -976,10 +980,10 @@ int pm_plugin_export_tables(pm_plugin* p, pm_worker_a* a, pm_worker_b* b, double
   if (lon && W) std::memcpy(lon, s.lon.data(), (size_t)W * sizeof(double));
   if (addr_rank && W) std::memcpy(addr_rank, s.arank.data(), (size_t)W * sizeof(uint32_t));
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // try_form_new_groups (mod.rs:478-628): the evaluation and the allocation run on the GPU.
-int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
+int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) try {
   if (!p) return PM_E_INVALID;
   if (n_formed) *n_formed = 0;
   std::lock_guard<std::mutex> loop_lk(p->loop_mu);
@@ -1057,13 +1061,25 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) {
   }
   if (n_formed) *n_formed = formed;
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // try_merge_solo_groups (mod.rs:631-971).  Compatibility of the solo groups' nodes with each
 // configuration, and the batch selection, run on the engine over a temporary table that holds only
 // those nodes in get_all_groups() order (sorted by id, mod.rs:1040).
-static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, const std::vector<std::string>& solo_ids,
+static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, const std::vector<std::string>& all_solo_ids,
                       std::vector<std::pair<const Config*, std::vector<std::string>>>* merged /* (config, solo group ids) */) {
+  // A solo group whose node is not in the node table (a group restored from the stored keys before its node was
+  // synced) is compatible with nothing: find_compatible_solo_groups looks the node up and takes a miss as
+  // `false` (mod.rs:733-741, node_specs.get(..).unwrap_or(false)).  It stays out of the engine's table.
+  std::vector<std::string> solo_ids;
+  solo_ids.reserve(all_solo_ids.size());
+  for (const auto& gid : all_solo_ids) {
+    const auto g = p->groups.find(gid);
+    if (g == p->groups.end() || g->second.nodes.empty()) continue;
+    if (p->node_index.find(g->second.nodes[0]) == p->node_index.end()) continue;
+    solo_ids.push_back(gid);
+  }
+  if (solo_ids.size() < 2) return PM_OK;
   const uint32_t W = (uint32_t)solo_ids.size();
   std::vector<pm_worker_a> wa(W);
   std::vector<pm_worker_b> wb(W);
@@ -1130,7 +1146,7 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
   return PM_OK;
 }
 
-int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
+int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) try {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::mutex> loop_lk(p->loop_mu);
   std::lock_guard<std::shared_mutex> lk(p->mu);   // solo groups are few: the whole merge pass stays under the table lock
@@ -1189,7 +1205,7 @@ int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) {
     }
   }
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 static void group_json(const pm_plugin* p, const Group& g, std::string& out) {
   out += "{\"id\":";
@@ -1215,15 +1231,15 @@ static int emit(pm_plugin* p, const std::string& s, char* buf, size_t len) {
 }
 
 // the key the storage route writes per requested upload (consumed by scheduler_impl.rs:131-157)
-int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group_id, const char* file_name) {
+int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group_id, const char* file_name) try {
   if (!p || !address || !group_id || !file_name) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   p->upload_keys.insert(std::string("upload:") + address + ":" + group_id + ":" + file_name);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // get_node_group (mod.rs:324-337): JSON NodeGroup or "null"
-int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_t len) {
+int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "null";
@@ -1236,10 +1252,10 @@ int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_
     }
   }
   return emit(p, out, buf, len);
-}
+} catch (...) { return pm_guard_rc(); }
 
 // get_all_groups (mod.rs:1006-1044): sorted by id
-int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
+int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) try {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "[";
@@ -1251,10 +1267,10 @@ int pm_plugin_get_all_groups(pm_plugin* p, char* buf, size_t len) {
   }
   out += ']';
   return emit(p, out, buf, len);
-}
+} catch (...) { return pm_guard_rc(); }
 
 // get_group_by_id (mod.rs:1046-1055): JSON NodeGroup or "null"
-int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, size_t len) {
+int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, size_t len) try {
   if (!p || !group_id) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "null";
@@ -1264,12 +1280,12 @@ int pm_plugin_get_group_by_id(pm_plugin* p, const char* group_id, char* buf, siz
     group_json(p, g->second, out);
   }
   return emit(p, out, buf, len);
-}
+} catch (...) { return pm_guard_rc(); }
 
 // handle_group_not_found (mod.rs:1073-1119): walk get_all_groups() (id order); the first group without a
 // current task takes the orphaned one (assign_task_to_group = SET NX, mod.rs:471-476).  Finding none is not
 // an error (the reference logs a warning and returns Ok).
-int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const char* task_id, uint32_t* reassigned) {
+int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const char* task_id, uint32_t* reassigned) try {
   if (!p || !group_id || !task_id) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   if (reassigned) *reassigned = 0;
@@ -1281,11 +1297,11 @@ int pm_plugin_handle_group_not_found(pm_plugin* p, const char* group_id, const c
     break;
   }
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // Start-up: a group as the reference stored it (create_group_atomically, mod.rs:299-322) goes back into the tables.
 int pm_plugin_restore_group(pm_plugin* p, const char* id, const char* configuration_name, const char* const* nodes,
-                            uint32_t n_nodes, const char* task_id, int64_t created_at_ms) {
+                            uint32_t n_nodes, const char* task_id, int64_t created_at_ms) try {
   if (!p || !id || !*id || !configuration_name || (n_nodes && !nodes)) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   if (p->groups.count(id)) return p->fail(PM_E_STATE, std::string("pm_plugin_restore_group: group exists: ") + id);
@@ -1316,14 +1332,14 @@ int pm_plugin_restore_group(pm_plugin* p, const char* id, const char* configurat
   if (task_id && *task_id) p->group_task[g.id] = task_id;
   p->groups.emplace(g.id, std::move(g));
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 // The keys a drop-in must leave in Redis for /groups, /nodes, storage routes and the metrics sync to
 // keep working unchanged (mod.rs:25-28, 299-322, 471-476): a JSON array of commands
 //   ["SET","node_group:<id>","<NodeGroup json>"], ["SADD","orchestrator:groups_index","<id>"],
 //   ["HSET","node_to_group","<node>","<id>"], ["SET","group_task:<id>","<task id>"],
 //   ["SADD","available_node_group_configs","<name>"].
-int pm_plugin_redis_writeback(pm_plugin* p, char* buf, size_t len) {
+int pm_plugin_redis_writeback(pm_plugin* p, char* buf, size_t len) try {
   if (!p) return PM_E_INVALID;
   std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "[";
@@ -1374,7 +1390,7 @@ int pm_plugin_redis_writeback(pm_plugin* p, char* buf, size_t len) {
   if (!buf || len < out.size() + 1) return p->fail(PM_E_NOMEM, "output buffer too small");
   std::memcpy(buf, out.c_str(), out.size() + 1);
   return PM_OK;
-}
+} catch (...) { return pm_guard_rc(); }
 
 namespace {
 
@@ -1404,7 +1420,16 @@ FilterResult node_groups_filter(pm_plugin* p, const std::string& addr, Expanded*
   const TaskRec* current = nullptr;
   if (read_only) {
     auto claim = p->group_task.find(group.id);
-    if (claim == p->group_task.end()) return p->tasks.empty() ? kNoTask : kNeedsUpdate;
+    if (claim == p->group_task.end()) {
+      if (p->tasks.empty()) return kNoTask;
+      // an idle group with no applicable task (allowed_topologies excludes its configuration) writes nothing either:
+      // answer from the cached choice under the shared lock, escalate only when a claim would be written
+      if (p->claim_cache_valid) {
+        auto cc = p->claim_cache.find(group.configuration_name);
+        if (cc != p->claim_cache.end() && cc->second.empty()) return kNoTask;
+      }
+      return kNeedsUpdate;
+    }
     current = p->find_task(claim->second);
     if (!current) return kNeedsUpdate;                       // stale claim: collected under the exclusive lock
   } else {
@@ -1550,7 +1575,7 @@ static FilterResult heartbeat_answer(pm_plugin* p, const std::string& addr, bool
 // Heartbeats take the table lock SHARED and answer from what is there (group, claim, task); only a heartbeat that has
 // to write — the first one of an idle group, a claim on a deleted task, a cold NewestTask cache — repeats under the
 // exclusive lock.  Every table update elsewhere in this file is exclusive.
-int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) {
+int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
   const std::string addr(address);
   std::string out;
@@ -1564,6 +1589,6 @@ int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf,
   std::lock_guard<std::shared_mutex> lk(p->mu);
   heartbeat_answer(p, addr, /*read_only=*/false, &out);
   return emit(p, out, buf, len);
-}
+} catch (...) { return pm_guard_rc(); }
 
 }  // extern "C"

@@ -224,23 +224,138 @@ class Engine:
     def fetch(self, copy: bool = True) -> MatchResult:
         r = abi.PmResult()
         self._check(self._lib.pm_fetch_result(self._h, C.byref(r)))
+        return _result_views(r, copy)
 
-        def view(ptr, n, dt):
-            if n == 0:
-                return np.zeros(0, dtype=dt)
-            arr = np.ctypeslib.as_array(ptr, shape=(n,))
-            return arr.copy() if copy else arr
+    # ---- multi-GPU, one process per GPU -------------------------
+    def set_shard(self, first: int, count: int):
+        self._check(self._lib.pm_set_shard(self._h, first, count))
 
-        return MatchResult(
-            worker_group=view(r.worker_group, r.n_workers, np.uint32),
-            worker_ask=view(r.worker_ask, r.n_workers, np.uint32),
-            group_ask=view(r.group_ask, r.n_groups, np.uint32),
-            group_off=view(r.group_off, r.n_groups + 1, np.uint32),
-            group_members=view(r.group_members, r.n_members, np.uint32),
-            ask_best=view(r.ask_best, r.n_asks, np.int64),
-            ask_count=view(r.ask_count, r.n_asks, np.uint32),
-            stats=r.stats.as_dict(),
-        )
+    def attach_comm(self, comm: "Comm | None"):
+        """With a communicator attached, match() evaluates this rank's share of the workers, exchanges once
+        (one packed all-gather inside the library) and runs the replicated resolution sweep."""
+        self._check(self._lib.pm_attach_comm(self._h, comm._h if comm is not None else None))
+        self._comm = comm   # keep it alive
+
+
+def _result_views(r: "abi.PmResult", copy: bool) -> MatchResult:
+    def view(ptr, n, dt):
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        arr = np.ctypeslib.as_array(ptr, shape=(n,))
+        return arr.copy() if copy else arr
+
+    return MatchResult(
+        worker_group=view(r.worker_group, r.n_workers, np.uint32),
+        worker_ask=view(r.worker_ask, r.n_workers, np.uint32),
+        group_ask=view(r.group_ask, r.n_groups, np.uint32),
+        group_off=view(r.group_off, r.n_groups + 1, np.uint32),
+        group_members=view(r.group_members, r.n_members, np.uint32),
+        ask_best=view(r.ask_best, r.n_asks, np.int64),
+        ask_count=view(r.ask_count, r.n_asks, np.uint32),
+        stats=r.stats.as_dict(),
+    )
+
+
+class Comm:
+    """pm_comm: this rank's end of the communicator the sharded pass exchanges through (NCCL inside the library)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * abi.PM_COMM_ID_BYTES)()
+        lib = load()
+        rc = lib.pm_comm_unique_id(buf)
+        if rc != abi.PM_OK:
+            raise PrimeMatchError(rc, (lib.pm_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def __init__(self, unique_id: bytes, n_ranks: int, rank: int, device: int):
+        self._lib = load()
+        assert len(unique_id) == abi.PM_COMM_ID_BYTES
+        buf = (C.c_uint8 * abi.PM_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        rc = self._lib.pm_comm_create(buf, n_ranks, rank, device, C.byref(h))
+        if rc != abi.PM_OK:
+            raise PrimeMatchError(rc, (self._lib.pm_last_error(None) or b"").decode())
+        self._h = h
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pm_comm_destroy(self._h)
+            self._h = None
+
+
+class MultiEngine:
+    """pm_multi: one process driving several GPUs (the form the orchestrator's single management loop calls)."""
+
+    def __init__(self, devices, cost_tile_bytes: int = 0, timing: bool = False):
+        self._lib = load()
+        cfg = abi.PmCfg(abi.PM_ABI_VERSION, 0, abi.PM_CFG_TIMING if timing else 0, 0, cost_tile_bytes, 0, 0, None)
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.pm_multi_create(C.byref(cfg), devs, len(devices), C.byref(h))
+        if rc != abi.PM_OK:
+            raise PrimeMatchError(rc, (self._lib.pm_multi_last_error(None) or b"").decode())
+        self._h = h
+        self.n = len(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != abi.PM_OK:
+            raise PrimeMatchError(rc, (self._lib.pm_multi_last_error(self._h) or b"").decode())
+
+    def set_asks(self, asks, opts):
+        asks = np.ascontiguousarray(asks, dtype=abi.ASK)
+        opts = np.ascontiguousarray(opts, dtype=abi.GPU_OPT)
+        self._check(self._lib.pm_multi_set_asks(self._h, _ptr(asks), len(asks), _ptr(opts), len(opts)))
+
+    def set_model_table(self, bits, n_patterns, n_models, words):
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        self._check(self._lib.pm_multi_set_model_table(self._h, _ptr(bits), n_patterns, n_models, words))
+
+    def set_workers(self, a, b):
+        a = np.ascontiguousarray(a, dtype=abi.WORKER_A)
+        b = np.ascontiguousarray(b, dtype=abi.WORKER_B)
+        self._check(self._lib.pm_multi_set_worker_count(self._h, len(a)))
+        self._check(self._lib.pm_multi_upsert_workers(self._h, _ptr(a), _ptr(b), 0, len(a)))
+        self._check(self._lib.pm_multi_sync(self._h))
+
+    def set_locations(self, lat, lon):
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        self._check(self._lib.pm_multi_set_worker_locations(self._h, _ptr(lat), _ptr(lon), 0, len(lat)))
+        self._check(self._lib.pm_multi_sync(self._h))
+
+    def set_addr_rank(self, rank):
+        rank = np.ascontiguousarray(rank, dtype=np.uint32)
+        self._check(self._lib.pm_multi_set_worker_addr_rank(self._h, _ptr(rank), 0, len(rank)))
+        self._check(self._lib.pm_multi_sync(self._h))
+
+    def match(self, mode: int = abi.PM_MODE_FIRST_FIT):
+        self._check(self._lib.pm_multi_match(self._h, mode))
+
+    def fetch(self, copy: bool = True) -> MatchResult:
+        r = abi.PmResult()
+        self._check(self._lib.pm_multi_fetch_result(self._h, C.byref(r)))
+        return _result_views(r, copy)
+
+    def stats(self, i: int = 0) -> dict:
+        st = abi.PmStats()
+        e = self._lib.pm_multi_engine(self._h, i)
+        rc = self._lib.pm_get_stats(e, C.byref(st))
+        if rc != abi.PM_OK:
+            raise PrimeMatchError(rc, "pm_get_stats")
+        return st.as_dict()
 
 
 def pinned_empty(n: int, dtype) -> np.ndarray:

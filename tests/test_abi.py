@@ -31,7 +31,7 @@ def test_abi_version_and_struct_sizes():
     assert lib.pm_abi_version() == abi.PM_ABI_VERSION
     assert C.sizeof(abi.PmAsk) == 32 and C.sizeof(abi.PmGpuOpt) == 32
     assert C.sizeof(abi.PmCfg) == 40
-    assert C.sizeof(abi.PmStats) == 80
+    assert C.sizeof(abi.PmStats) == 88
 
 
 def test_product_does_not_reference_the_oracle():
