@@ -1047,7 +1047,8 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b, const p
         // (ng/mod.rs:555-556): its row of the cost matrix is masked
         if (ask.max_group_size != 0 && soa_candidate(a[w].flags) &&
             orc_soa_compatible(&a[w], &b[w], &ask, opts, model_bits, words)) {
-          cost = int64_t(w);
+          // packed cost = price << 32 | worker; the price is the extension column (0 in the reference's own modes)
+          cost = (int64_t(b[w].ext_ask_price) << 32) | int64_t(w);
           ++count;
           if (cf && (*cf)[c] == PM_NONE) (*cf)[c] = t0 + r;
         }
@@ -1069,6 +1070,46 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b, const p
   return u64(nt) * nw;
 }
 
+
+// The acceptance table the engine is handed, computed here from the strings with the reference's own clause
+// (model_matches = node.rs:463-484), so tests do not have to trust the product's interner for it.
+void orc_model_table(const char* const* models, uint32_t n_models, const char* const* patterns,
+                     uint32_t n_patterns, uint32_t words, uint32_t threads, uint32_t* bits_out) {
+  if (threads == 0) threads = 1;
+  for (size_t i = 0; i < size_t(n_patterns) * words; ++i) bits_out[i] = 0;
+  auto work = [&](u32 tid) {
+    for (u32 p = tid; p < n_patterns; p += threads)
+      for (u32 m = 0; m < n_models; ++m)
+        if (model_matches(models[m], patterns[p])) bits_out[size_t(p) * words + (m >> 5)] |= 1u << (m & 31);
+  };
+  std::vector<std::thread> pool;
+  for (u32 t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+}
+
+// First configuration (priority order) a worker is a compatible candidate of, PM_NONE if none — per worker, with
+// early exit, workers split over threads.  With only solo configurations (min == max == 1) try_form_new_groups
+// gives every remaining compatible node its own group at the first configuration that accepts it (mod.rs:505-609),
+// so this IS the allocation there; it lets tests reach ask counts where the per-configuration loop is too slow.
+void orc_soa_first_feasible(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                            const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                            const uint32_t* model_bits, uint32_t words, uint32_t threads, uint32_t* first_out) {
+  if (threads == 0) threads = 1;
+  auto work = [&](u32 tid) {
+    for (u32 w = tid; w < n_workers; w += threads) {
+      u32 f = PM_NONE;
+      if (soa_candidate(a[w].flags))
+        for (u32 t = 0; t < n_asks; ++t)
+          if (asks[t].max_group_size != 0 && orc_soa_compatible(&a[w], &b[w], &asks[t], opts, model_bits, words)) { f = t; break; }
+      first_out[w] = f;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (u32 t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+}
 
 // EXTENSION, self-oracle (see pm_oracle.h): synchronous forward auction, sequentially.
 uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,

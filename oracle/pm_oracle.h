@@ -154,7 +154,7 @@ orc_groups* orc_soa_form_groups(const pm_worker_a* a, const pm_worker_b* b, uint
 
 /* Full evaluation of the sub-matrix asks[t0,t1) x workers[w0,w1) over `threads`
  * host threads: cost[t][w] = compat && candidate ? (price<<32 | w) : INF with
- * price = 0 (reference modes); rows of asks with max_group_size == 0 are all INF
+ * price = pm_worker_b.ext_ask_price (0 in the reference's own modes); rows of asks with max_group_size == 0 are all INF
  * (such a configuration never takes a worker).  Any out pointer may be NULL.
  *   cost_out      [(t1-t0) * (w1-w0)] row-major
  *   row_best_out  [t1-t0] min over w      row_count_out [t1-t0] #feasible
@@ -166,6 +166,16 @@ uint64_t orc_soa_eval_matrix(const pm_worker_a* a, const pm_worker_b* b,
                              uint32_t t0, uint32_t t1, uint32_t w0, uint32_t w1,
                              uint32_t threads, int64_t* cost_out, int64_t* row_best_out,
                              uint32_t* row_count_out, uint32_t* col_first_out);
+
+/* The (pattern x model) acceptance bit table from the strings, with the reference's model clause
+ * (GpuSpecs::meets, node.rs:463-484): bits_out[p * words + (m >> 5)] bit (m & 31).               */
+void orc_model_table(const char* const* models, uint32_t n_models, const char* const* patterns,
+                     uint32_t n_patterns, uint32_t words, uint32_t threads, uint32_t* bits_out);
+/* First configuration (priority order) whose compat filter + candidate filter accept the worker, or
+ * PM_NONE.  For solo configurations this is the worker's group (mod.rs:505-609).                 */
+void orc_soa_first_feasible(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                            const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                            const uint32_t* model_bits, uint32_t words, uint32_t threads, uint32_t* first_out);
 
 /* ---- north-star EXTENSION: price-capped auction.  SELF-ORACLE: the reference has no
  * prices, caps or auction; parity for this mode is UNPINNED BY THE REFERENCE.

@@ -88,6 +88,8 @@ def load() -> C.CDLL:
         "orc_soa_compatible": (i32, [vp, vp, vp, vp, vp, u32]),
         "orc_soa_form_groups": (vp, [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, i32]),
         "orc_soa_auction": (u32, [vp, vp, u32, vp, u32, vp, vp, u32, vp, C.c_uint64, C.c_uint64, u32, vp, vp]),
+        "orc_model_table": (None, [P(cp), u32, P(cp), u32, u32, u32, vp]),
+        "orc_soa_first_feasible": (None, [vp, vp, u32, vp, u32, vp, vp, u32, u32, vp]),
         "orc_soa_eval_matrix": (C.c_uint64, [vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -338,6 +340,27 @@ def soa_eval_matrix(a, b, asks, opts, bits, words, t0, t1, w0, w1, threads=1,
         cost.ctypes.data if cost is not None else None, rb.ctypes.data if rb is not None else None,
         rc.ctypes.data if rc is not None else None, cf.ctypes.data if cf is not None else None)
     return {"evals": int(evals), "cost": cost, "row_best": rb, "row_count": rc, "col_first": cf}
+
+
+def model_table(model_strings, pattern_strings, threads=8):
+    """(bits, n_patterns, n_models, words) in pm_set_model_table's layout, from the oracle's own model clause."""
+    nm, npat = len(model_strings), len(pattern_strings)
+    words = max((nm + 31) // 32, 1)
+    bits = np.zeros(max(npat, 1) * words, dtype=np.uint32)
+    ms = (C.c_char_p * max(nm, 1))(*[m.encode() for m in model_strings])
+    ps = (C.c_char_p * max(npat, 1))(*[p.encode() for p in pattern_strings])
+    load().orc_model_table(ms, nm, ps, npat, words, threads, bits.ctypes.data)
+    return bits, npat, nm, words
+
+
+def soa_first_feasible(a, b, asks, opts, bits, words, threads=8):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    asks = np.ascontiguousarray(asks); opts = np.ascontiguousarray(opts)
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    out = np.empty(len(a), dtype=np.uint32)
+    load().orc_soa_first_feasible(a.ctypes.data, b.ctypes.data, len(a), asks.ctypes.data, len(asks), opts.ctypes.data,
+                                  bits.ctypes.data, words, threads, out.ctypes.data)
+    return out
 
 
 def soa_auction(a, b, asks, opts, bits, words, price_cap, cost_scale=1, eps_start=1, eps_div=4):

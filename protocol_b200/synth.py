@@ -97,14 +97,52 @@ class Workers:
         return len(self.a)
 
 
+def zipf_levels(seed: int, n: int, stream: int, s: float = 1.1, levels: int = 1024) -> np.ndarray:
+    """Zipf(s) over `levels` price levels: level k (1-based) with probability ~ k^-s."""
+    p = np.arange(1, levels + 1, dtype=np.float64) ** (-s)
+    cdf = np.cumsum(p / p.sum())
+    return (np.minimum(np.searchsorted(cdf, _unit(seed, n, stream), side="right"), levels - 1) + 1).astype(np.uint32)
+
+
+def wide_model_catalogue(n_models: int):
+    """A permissionless pool's model strings: free-form NVML names (node.rs:463-484 normalises and substring-matches
+    them), far more than 32 distinct ones.  The 16 catalogue entries come first (ids stay valid), then variants."""
+    out = list(MODEL_CATALOGUE)
+    fam = ["NVIDIA H100", "NVIDIA A100", "NVIDIA GeForce RTX 4090", "NVIDIA RTX A6000", "Tesla V100", "NVIDIA L40S",
+           "AMD Instinct MI300X", "NVIDIA H200", "NVIDIA GeForce RTX 3090", "NVIDIA B200", "Quadro RTX 8000"]
+    mem = [80000, 40000, 24564, 49140, 32768, 46068, 192000, 141000, 24576, 183000, 49152]
+    suffix = ["", " PCIe", " SXM", " NVL", "-SXM4", " 80GB HBM3", " Ti"]
+    seen = {m for m, _ in out}
+    i = 0
+    while len(out) < n_models:
+        f = i % len(fam)
+        k = i // len(fam)
+        name = fam[f] + suffix[k % len(suffix)] + (f" rev{k // len(suffix)}" if k >= len(suffix) else "")
+        i += 1
+        if name in seen:
+            continue
+        seen.add(name)
+        out.append((name, mem[f]))
+    return out[:n_models]
+
+
 def make_workers(n: int, seed: int = SEED_WORKERS, with_addresses: bool = False,
-                 healthy_frac: float = 0.90) -> Workers:
+                 healthy_frac: float = 0.90, price: str | None = None, catalogue=None) -> Workers:
+    """price: None (0: the reference has no prices), 'loguniform' (cfg3: 10..2000) or 'zipf' (cfg5: Zipf(1.1) over
+    1024 levels) for the extension column; catalogue: [(model string, memory_mb)], default the 16-entry one."""
+    catalogue = MODEL_CATALOGUE if catalogue is None else catalogue
     a = np.zeros(n, dtype=abi.WORKER_A)
     b = np.zeros(n, dtype=abi.WORKER_B)
     a["gpu_count"] = _choice(seed, n, 1, [1, 2, 4, 8], [0.40, 0.25, 0.20, 0.15])
-    model = _choice(seed, n, 2, np.arange(len(MODEL_CATALOGUE)))
+    model = _choice(seed, n, 2, np.arange(len(catalogue)))
     a["model_id"] = model
-    a["gpu_mem_mb"] = np.array([m for _, m in MODEL_CATALOGUE], dtype=np.uint32)[model]
+    a["gpu_mem_mb"] = np.array([m for _, m in catalogue], dtype=np.uint32)[model]
+    if price == "loguniform":
+        b["ext_ask_price"] = np.exp(np.log(10) + _unit(SEED_EXT, n, 1) * np.log(200)).astype(np.uint32)
+    elif price == "zipf":
+        b["ext_ask_price"] = zipf_levels(SEED_EXT, n, 2)
+    elif price is not None:
+        raise ValueError(price)
     b["cpu_cores"] = _choice(seed, n, 3, [8, 16, 32, 64, 128])
     b["ram_mb"] = _choice(seed, n, 4, [32000, 64000, 128000, 256000, 512000, 1024000])
     b["storage_gb"] = _choice(seed, n, 5, [250, 500, 1000, 2000, 4000, 8000])
@@ -135,7 +173,7 @@ def make_workers(n: int, seed: int = SEED_WORKERS, with_addresses: bool = False,
     # non-healthy rows spread over the other NodeStatus ordinals
     other = _choice(seed, n, 12, [0, 1, 3, 4, 5, 6, 7])
     status = np.where(healthy, 2, other).astype(np.uint32)
-    w = Workers(a=a, b=b, lat=lat, lon=lon, model_strings=[m for m, _ in MODEL_CATALOGUE], status=status)
+    w = Workers(a=a, b=b, lat=lat, lon=lon, model_strings=[m for m, _ in catalogue], status=status)
     if with_addresses:
         h1 = splitmix64(seed, n, 13)
         h2 = splitmix64(seed, n, 14)

@@ -558,3 +558,69 @@ def test_fused_lean_gives_the_same_groups():
         assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
     assert (r2.ask_count == 0).all() and (r2.ask_best == abi.PM_COST_INF).all()
     eng.close()
+
+
+def skewed_tables(T, W, seed_shift=0):
+    """BASELINE configs[3]/[4] columns: mixed asks with 10 % made infeasible (gpu:count = 3), worker
+    ask prices Zipf(1.1) over 1024 levels in the extension column (the high word of the packed cost)."""
+    w = synth.make_workers(W, seed=synth.SEED_WORKERS + seed_shift, price="zipf")
+    a = synth.make_asks(T, "skewed", seed=synth.SEED_ASKS + seed_shift)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    return w, a, dict(asks=a.asks, opts=a.opts, wa=w.a, wb=w.b, bits=bits, n_patterns=npat, n_models=nmod,
+                      words=words, lat=w.lat, lon=w.lon)
+
+
+def test_one_million_asks_full_groups_at_20k_workers():
+    """T = 1M (BASELINE configs[3]/[4] ask count), Zipf prices, 10 % infeasible asks, against the oracle's
+    per-configuration loop (orc_soa_form_groups) — complete group table, both evaluation paths."""
+    T, W = 1_000_000, 20_000
+    w, a, t = skewed_tables(T, W, seed_shift=41)
+    og = orc.soa_form_groups(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"])
+    eng = Engine(cost_tile_bytes=1 << 30)
+    load_engine(eng, t)
+    for path in (MAT, FUSED, FUSED | abi.PM_NO_ASK_STATS):
+        eng.match(abi.PM_MODE_FIRST_FIT | path)
+        res = eng.fetch()
+        assert groups_equal(res, og)
+    eng.close()
+
+
+def test_cfg4_shape_one_million_asks_x_250k_workers():
+    """The per-GPU shape of BASELINE configs[3] (1M asks x 1M workers over 4 GPUs): every worker's configuration
+    against the oracle's first-feasible search (with solo configurations that IS try_form_new_groups' allocation,
+    mod.rs:505-609), sampled rows of the per-ask (min cost, argmin) and counts with prices in the cost's high word,
+    every infeasible ask empty, group table consistent with the per-worker view."""
+    import os
+    T, W = 1_000_000, 250_000
+    w, a, t = skewed_tables(T, W)
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match(abi.PM_MODE_FIRST_FIT | MAT)
+    r1 = eng.fetch()
+    assert r1.stats["evals"] == T * W
+    threads = max(1, len(os.sched_getaffinity(0)))
+    first = orc.soa_first_feasible(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], threads=threads)
+    assert np.array_equal(r1.worker_ask, first)
+    # groups: one per assigned worker, creation order = (configuration, canonical worker order)
+    assigned = np.flatnonzero(first != abi.PM_NONE)
+    order = assigned[np.argsort(first[assigned], kind="stable")]
+    assert r1.n_groups == len(order) and np.array_equal(r1.group_members, order.astype(np.uint32))
+    assert np.array_equal(r1.group_ask, first[order]) and np.array_equal(r1.group_off, np.arange(len(order) + 1, dtype=np.uint32))
+    assert np.array_equal(r1.worker_group[order], np.arange(len(order), dtype=np.uint32))
+    # infeasible asks (gpu:count = 3 on every option) see nobody
+    infeasible = np.flatnonzero(np.minimum.reduceat((a.opts["count"] == 3).astype(np.uint8), a.asks["opt_off"].astype(np.int64)) == 1)
+    assert 0.08 * T < len(infeasible) < 0.12 * T
+    assert (r1.ask_count[infeasible] == 0).all() and (r1.ask_best[infeasible] == abi.PM_COST_INF).all()
+    # sampled rows, prices included: argmin is the cheapest compatible candidate, lowest index on ties
+    rng = np.random.default_rng(4)
+    for t0 in rng.integers(0, T - 16, 12):
+        band = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], int(t0), int(t0) + 16, 0, W, threads=threads)
+        assert np.array_equal(r1.ask_count[t0:t0 + 16], band["row_count"]) and np.array_equal(r1.ask_best[t0:t0 + 16], band["row_best"])
+    feasible_best = r1.ask_best[r1.ask_best != abi.PM_COST_INF]
+    assert ((feasible_best >> 32) >= 1).all() and ((feasible_best >> 32) <= 1024).all()
+    # the other paths agree bit for bit
+    eng.match(abi.PM_MODE_FIRST_FIT | FUSED)
+    r2 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_count"):
+        assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+    eng.close()
