@@ -30,6 +30,7 @@
 #include "pm_kernels.cuh"
 #include "pm_proximity.cuh"
 #include "pm_proximity_band.cuh"
+#include "pm_proximity_grid.cuh"
 #include "pm_auction.cuh"
 
 struct pm_engine;
@@ -159,6 +160,9 @@ struct pm_engine {
   DevBuf<uint32_t> prox_list, prox_xs, members_raw;
   DevBuf<double> prox_dist, prox_lat_key;
   DevBuf<uint32_t> prox_lat_ord, prox_rank_of;
+  DevBuf<double> pg_part_d;
+  DevBuf<uint32_t> pg_part_i, pg_cta_cnt, pg_ctl;
+  int coop_blocks = -1;   // co-resident CTAs of pm_proximity_grid on this device (0: cooperative launch unavailable)
   bool any_max_zero = false;
   // extension (auction) state
   DevBuf<uint32_t> price_cap, auc_owner, auc_assigned, auc_withdrawn, auc_active, auc_bid_w, auc_winner, auc_flag, auc_gidx;
@@ -348,7 +352,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) try {
   if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_BUILD")) e->tune_build = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_AUCTION")) e->tune_auction = std::atoi(t);
-  if (const char* t = std::getenv("PM_TUNE_PROX")) e->tune_prox = std::atoi(t);   // 1: latitude-banded sweep (experimental)
+  if (const char* t = std::getenv("PM_TUNE_PROX")) e->tune_prox = std::atoi(t);   // 0: all-SM cooperative sweep; 2: single-CTA sweep; 1: latitude-banded single-CTA sweep (experimental)
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
     e->stream = (cudaStream_t)cfg->stream;  // caller's stream (e.g. torch's current stream)
@@ -383,6 +387,7 @@ void pm_destroy(pm_engine* e) {
   e->popped.release(); e->counters.release(); e->cub_tmp.release();
   e->prox_list.release(); e->prox_xs.release(); e->members_raw.release(); e->prox_dist.release();
   e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
+  e->pg_part_d.release(); e->pg_part_i.release(); e->pg_cta_cnt.release(); e->pg_ctl.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
@@ -810,7 +815,30 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
     pp.worker_group = e->worker_group.p; pp.worker_ask = e->worker_ask.p; pp.group_ask = e->group_ask.p;
     pp.group_off = e->group_off.p; pp.members = e->members_raw.p; pp.out_counts = scal;   // {G, M, bumped, overflow}
     pp.group_cap = cap;
+    if (e->coop_blocks < 0) {   // once per engine: can the whole-chip sweep be launched cooperatively, and how wide?
+      int coop = 0, per_sm = 0, sms = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+      if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::pm_proximity_grid, pm::kPgThreads, 0) == cudaSuccess)
+        e->coop_blocks = per_sm * sms;
+      else
+        e->coop_blocks = 0;
+      (void)cudaGetLastError();
+    }
     if (merge_mode) pm::pm_merge_sweep<<<1, pm::kProxThreads, 0, e->stream>>>(pp);
+    else if (e->tune_prox == 0 && e->coop_blocks > 0) {
+      // all SMs: one grid barrier per group instead of one CTA doing everything (pm_proximity_grid.cuh)
+      const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)e->coop_blocks, blocks_for(std::max<uint32_t>(W, 1), pm::kPgThreads)));
+      PM_CUDA(e->pg_part_d.ensure((size_t)2 * grid * pm::kPgTopK)); PM_CUDA(e->pg_part_i.ensure((size_t)2 * grid * pm::kPgTopK));
+      PM_CUDA(e->pg_cta_cnt.ensure((size_t)2 * grid)); PM_CUDA(e->pg_ctl.ensure(4));
+      PM_CUDA(cudaMemsetAsync(e->pg_ctl.p, 0, 16, e->stream));
+      pm::GridProxParams gp;
+      gp.p = pp;
+      gp.part_d = e->pg_part_d.p; gp.part_i = e->pg_part_i.p; gp.cta_cnt = e->pg_cta_cnt.p; gp.gctl = e->pg_ctl.p;
+      gp.n_workers = W;
+      void* args[] = {&gp};
+      PM_CUDA(cudaLaunchCooperativeKernel((const void*)pm::pm_proximity_grid, dim3(grid), dim3(pm::kPgThreads), args, 0, e->stream));
+    }
     else if (e->tune_prox & 1) {   // experimental: same groups from a latitude-ordered view (pm_proximity_band.cuh)
       PM_CUDA(e->prox_lat_key.ensure(P)); PM_CUDA(e->prox_lat_ord.ensure(P)); PM_CUDA(e->prox_rank_of.ensure(W));
       pm::BandParams bp;

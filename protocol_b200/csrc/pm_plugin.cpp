@@ -1015,7 +1015,9 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) try {
     int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
     if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
     bits_copy.assign(bits, bits + (size_t)std::max<uint32_t>(npat, 1) * words);
-    mode = p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT;
+    // the pass needs the per-worker first feasible configuration only: evaluate and reduce on chip, skip the per-ask
+    // statistics (same groups as the materialised pass, ~20 MB of DRAM traffic instead of 16 B per pair)
+    mode = (p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS;
   }
   // ---- phase 2 (tables unlocked: heartbeats keep being served): the pass on the GPU
   auto chk = [&](int r, const char* what) {
@@ -1135,7 +1137,7 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
   if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
   if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
   if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;
-  if ((rc = chk(pm_match(p->engine, prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT), "pm_match"))) return rc;
+  if ((rc = chk(pm_match(p->engine, (prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS), "pm_match"))) return rc;
   pm_result res{};
   if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
   for (uint32_t g = 0; g < res.n_groups; ++g) {

@@ -1,0 +1,531 @@
+// pm_proximity_grid.cuh — proximity group formation on ALL SMs (cooperative launch).
+//
+// Reference: NodeGroupsPlugin::try_form_new_groups with ProximityOptimizationPolicy{enabled:true} — the reference's
+// DEFAULT policy (crates/orchestrator/src/plugins/node_groups/mod.rs:85-89), proximity branch :524-552,
+// calculate_distance :218-231, sort_nodes_by_proximity :234-255 — run every 10 s by the management loop (:180-203).
+//
+// The loop is sequential per group by construction: a group's seed is the first remaining located node in canonical
+// order, its members are the max-1 nearest remaining nodes, and the next group depends on who was removed.
+// pm_proximity_sweep (pm_proximity.cuh) runs that loop in ONE CTA: every group costs a distance pass and max-1
+// arg-mins over all remaining candidates of the configuration — 40 s for 250k candidates / 125k pair groups.
+// Here the per-group work is spread over the whole chip and a group costs ONE grid barrier:
+//
+//   every thread of the grid owns a strided slice of the configuration's candidate list; per group
+//     1. every CTA finds the seed by itself (same data, same answer — no exchange),
+//     2. owners compute haversine(seed, candidate) for their live candidates and the CTA selects its k best
+//        by (distance, list position) — k = max-1, in chunks of kPgTopK,
+//     3. the per-CTA partial lists go to global memory, ONE grid.sync(),
+//     4. every CTA merges all partials to the same k winners and marks them taken in its view of the list
+//        (all CTAs write the same bits); CTA 0 also writes the group tables.
+//   Rule that keeps the redundant control flow identical on every CTA: the list is only modified right after a grid
+//   barrier, and only by decisions every CTA took from data that was complete before that barrier.
+//
+// Configurations of solo groups (max == 1) need no loop at all: located candidates first, then the others, each its
+// own group (the seed rule, mod.rs:526-530) — an ordered partition, two barriers.  A configuration's candidate list
+// is the sorted base segment merged with the workers handed down by earlier configurations; a long hand-down
+// (e.g. the 750k workers a pair configuration leaves to the solo one) is rebuilt by an ordered compaction of
+// {w : cur[w] == c} over the whole table instead of walking the linked list.
+//
+// Results are bit-identical to pm_proximity_sweep and to the oracle (tests/test_gpu_parity.py, test_gpu_proximity.py);
+// the single-CTA kernel stays as the fallback when a cooperative launch is not possible.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "pm_proximity.cuh"
+
+namespace pm {
+
+namespace cg = cooperative_groups;
+
+constexpr int kPgThreads = 512;
+constexpr int kPgWarps = kPgThreads / 32;
+constexpr uint32_t kPgTopK = 16;        // neighbours selected per grid barrier (larger groups take several)
+constexpr uint32_t kPgXsSmem = 128;     // hand-downs up to this long are walked and sorted in shared memory
+constexpr double kPgMax = 1.7976931348623157e308;   // f64::MAX: distance of a candidate without location
+
+struct GridProxParams {
+  ProxParams p;
+  double* part_d;        // [2][grid][kPgTopK] per-CTA partial selections, double-buffered by pass parity
+  uint32_t* part_i;      // [2][grid][kPgTopK]
+  uint32_t* cta_cnt;     // [2 * grid] per-CTA counts for the ordered compactions
+  uint32_t* gctl;        // [4] [0] leftover count
+  uint32_t n_workers;
+};
+
+struct PgShared {
+  uint32_t u[8];
+  uint32_t warp_cnt[kPgWarps];
+  uint32_t warp_cnt2[kPgWarps];
+  double red_d[kPgWarps];
+  uint32_t red_i[kPgWarps];
+  uint32_t picks[kPgThreads];     // positions chosen in the current pass (<= kPgTopK, or a chunk of list-order picks)
+  uint32_t xs[kPgXsSmem];
+};
+
+__device__ __forceinline__ uint32_t pg_ld(const uint32_t* p) { return __ldcg(p); }
+
+// smallest position >= start whose entry satisfies (e & mask) == want, or n.  Uniform over the CTA and — because every
+// CTA reads the same list — over the grid.
+__device__ __forceinline__ uint32_t pg_find_first(PgShared& sh, const uint32_t* list, uint32_t n, uint32_t start,
+                                                  uint32_t mask, uint32_t want) {
+  for (uint32_t base = start; base < n; base += kPgThreads) {
+    if (threadIdx.x == 0) sh.u[7] = kNone;
+    __syncthreads();
+    const uint32_t i = base + threadIdx.x;
+    if (i < n && (pg_ld(list + i) & mask) == want) atomicMin(&sh.u[7], i);
+    __syncthreads();
+    const uint32_t f = sh.u[7];
+    __syncthreads();
+    if (f != kNone) return f;
+  }
+  return n;
+}
+
+// lexicographic (distance, position) minimum over the CTA; kNone when no thread has a candidate.  Uniform result in
+// *out_d / return value.
+__device__ __forceinline__ uint32_t pg_block_argmin(PgShared& sh, double bd, uint32_t bi, double* out_d) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (oi != kNone && (bi == kNone || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh.red_d[warp] = bd; sh.red_i[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bd = lane < (uint32_t)kPgWarps ? sh.red_d[lane] : kPgMax;
+    bi = lane < (uint32_t)kPgWarps ? sh.red_i[lane] : kNone;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (oi != kNone && (bi == kNone || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+    }
+    if (lane == 0) { sh.red_d[0] = bd; sh.u[6] = bi; }
+  }
+  __syncthreads();
+  const uint32_t r = sh.u[6];
+  *out_d = sh.red_d[0];
+  __syncthreads();
+  return r;
+}
+
+// exclusive rank of this thread's flag inside the CTA and the CTA total
+__device__ __forceinline__ uint32_t pg_block_rank(PgShared& sh, bool flag, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t b = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) sh.warp_cnt[warp] = (uint32_t)__popc(b);
+  __syncthreads();
+  uint32_t before = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < kPgWarps; ++q) {
+    const uint32_t v = sh.warp_cnt[q];
+    if ((uint32_t)q < warp) before += v;
+    tot += v;
+  }
+  __syncthreads();
+  *total = tot;
+  return before + (uint32_t)__popc(b & ((1u << lane) - 1u));
+}
+
+// two flags ranked in one pass (located / not located)
+__device__ __forceinline__ void pg_block_rank2(PgShared& sh, bool f0, bool f1, uint32_t* r0, uint32_t* r1,
+                                               uint32_t* t0, uint32_t* t1) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+  if (lane == 0) { sh.warp_cnt[warp] = (uint32_t)__popc(b0); sh.warp_cnt2[warp] = (uint32_t)__popc(b1); }
+  __syncthreads();
+  uint32_t bef0 = 0, bef1 = 0, tot0 = 0, tot1 = 0;
+#pragma unroll
+  for (int q = 0; q < kPgWarps; ++q) {
+    const uint32_t v0 = sh.warp_cnt[q], v1 = sh.warp_cnt2[q];
+    if ((uint32_t)q < warp) { bef0 += v0; bef1 += v1; }
+    tot0 += v0; tot1 += v1;
+  }
+  __syncthreads();
+  const uint32_t below = (1u << lane) - 1u;
+  *r0 = bef0 + (uint32_t)__popc(b0 & below);
+  *r1 = bef1 + (uint32_t)__popc(b1 & below);
+  *t0 = tot0;
+  *t1 = tot1;
+}
+
+// sum over the CTA
+__device__ __forceinline__ uint32_t pg_block_sum(PgShared& sh, uint32_t v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) sh.warp_cnt[warp] = v;
+  __syncthreads();
+  uint32_t tot = 0;
+#pragma unroll
+  for (int q = 0; q < kPgWarps; ++q) tot += sh.warp_cnt[q];
+  __syncthreads();
+  return tot;
+}
+
+// sum of cnt[0 .. upto) and of cnt[0 .. all), both CTA-uniform
+__device__ __forceinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* cnt, uint32_t upto, uint32_t all,
+                                                  uint32_t* before, uint32_t* total) {
+  uint32_t a = 0, t = 0;
+  for (uint32_t b = threadIdx.x; b < all; b += kPgThreads) {
+    const uint32_t v = pg_ld(cnt + b);
+    if (b < upto) a += v;
+    t += v;
+  }
+  *before = pg_block_sum(sh, a);
+  *total = pg_block_sum(sh, t);
+}
+
+__global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams gp) {
+  __shared__ PgShared sh;
+  cg::grid_group grid = cg::this_grid();
+  const ProxParams& p = gp.p;
+  const uint32_t T = p.ev.n_asks, W = gp.n_workers;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t cta = blockIdx.x, ncta = gridDim.x;
+  const uint32_t gtid = cta * kPgThreads + tid, nthr = ncta * kPgThreads;
+  const bool lead = cta == 0;   // the CTA that writes the group tables
+  uint32_t g = 0, mpos = 0, c_lo = 0, parity = 0;
+  bool overflow = false;
+
+  while (c_lo < T && !overflow) {
+    // ---- next configuration that has members (or produces the empty group of min_group_size == 0)
+    if (tid == 0) sh.u[0] = kNone;
+    __syncthreads();
+    {
+      const uint32_t cc = c_lo + tid;
+      if (cc < T && (pg_ld(p.base_len + cc) + pg_ld(p.xcount + cc) != 0u || p.amin[cc] == 0u)) atomicMin(&sh.u[0], cc);
+    }
+    __syncthreads();
+    const uint32_t c = sh.u[0];
+    __syncthreads();
+    if (c == kNone) { c_lo += kPgThreads; continue; }
+    const uint32_t mn = p.amin[c], mx = p.amax[c];
+    const uint32_t bl = pg_ld(p.base_len + c), xc = pg_ld(p.xcount + c);
+    const uint32_t n = bl + xc;
+    const uint32_t* base = p.order + p.seg_start[c];
+
+    // ---- the configuration's candidate list in canonical order, located candidates tagged
+    if (xc <= kPgXsSmem) {
+      // short hand-down: every CTA walks and sorts it by itself in shared memory, then the merge is spread over the grid
+      if (xc) {
+        if (tid == 0) {
+          uint32_t j = 0;
+          for (uint32_t x = pg_ld(p.xhead + c); x != kNone && j < kPgXsSmem; x = pg_ld(p.xnext + x)) sh.xs[j++] = x;
+        }
+        for (uint32_t j = xc + tid; j < kPgXsSmem; j += kPgThreads) sh.xs[j] = kNone;
+        __syncthreads();
+        for (uint32_t k = 2; k <= kPgXsSmem; k <<= 1)
+          for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (tid < kPgXsSmem) {
+              const uint32_t i = tid, l = i ^ j;
+              if (l > i) {
+                const uint32_t a = sh.xs[i], b = sh.xs[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { sh.xs[i] = b; sh.xs[l] = a; }
+              }
+            }
+            __syncthreads();
+          }
+      }
+      for (uint32_t i = gtid; i < bl; i += nthr) {
+        const uint32_t w = base[i];
+        p.list[i + lower_bound_u32(sh.xs, xc, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+      }
+      for (uint32_t j = gtid; j < xc; j += nthr) {
+        const uint32_t w = sh.xs[j];
+        p.list[j + lower_bound_u32(base, bl, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+      }
+    } else {
+      // long hand-down: the list is {w : cur[w] == c} in index order — an ordered compaction over the whole table
+      const uint32_t chunk = ((W + ncta - 1) / ncta + kPgThreads - 1) / kPgThreads * kPgThreads;
+      const uint32_t w_lo = min(W, cta * chunk), w_hi = min(W, w_lo + chunk);
+      uint32_t mine = 0;
+      for (uint32_t w = w_lo + tid; w < w_hi; w += kPgThreads) mine += pg_ld(p.cur + w) == c ? 1u : 0u;
+      const uint32_t cnt = pg_block_sum(sh, mine);
+      if (tid == 0) gp.cta_cnt[cta] = cnt;
+      __threadfence();
+      grid.sync();
+      uint32_t off = 0, tot = 0;
+      pg_prefix_of_ctas(sh, gp.cta_cnt, cta, ncta, &off, &tot);
+      for (uint32_t w0 = w_lo; w0 < w_hi; w0 += kPgThreads) {
+        const uint32_t w = w0 + tid;
+        const bool f = w < w_hi && pg_ld(p.cur + w) == c;
+        uint32_t tile = 0;
+        const uint32_t r = pg_block_rank(sh, f, &tile);
+        if (f) p.list[off + r] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+        off += tile;
+      }
+    }
+    __threadfence();
+    grid.sync();
+
+    if (mx == 1u) {
+      // ---- solo groups: located candidates first, then the others, each its own group (mod.rs:526-530)
+      const uint32_t chunk = ((n + ncta - 1) / ncta + kPgThreads - 1) / kPgThreads * kPgThreads;
+      const uint32_t i_lo = min(n, cta * chunk), i_hi = min(n, i_lo + chunk);
+      const uint32_t extra = mn == 0u ? 1u : 0u;                       // the trailing empty group (:564,:606)
+      if ((uint64_t)g + n + extra > (uint64_t)p.group_cap) {
+        overflow = true;
+      } else {
+        uint32_t mine = 0;
+        for (uint32_t i = i_lo + tid; i < i_hi; i += kPgThreads) mine += (pg_ld(p.list + i) & kLocBit) ? 1u : 0u;
+        const uint32_t cnt = pg_block_sum(sh, mine);
+        if (tid == 0) gp.cta_cnt[ncta + cta] = cnt;
+        __threadfence();
+        grid.sync();
+        uint32_t loc_before = 0, n_loc = 0;
+        pg_prefix_of_ctas(sh, gp.cta_cnt + ncta, cta, ncta, &loc_before, &n_loc);
+        uint32_t unloc_before = i_lo - loc_before;
+        for (uint32_t i0 = i_lo; i0 < i_hi; i0 += kPgThreads) {
+          const uint32_t i = i0 + tid;
+          const bool in = i < i_hi;
+          const uint32_t e = in ? pg_ld(p.list + i) : 0u;
+          uint32_t r_loc, r_un, t_loc, t_un;
+          pg_block_rank2(sh, in && (e & kLocBit), in && !(e & kLocBit), &r_loc, &r_un, &t_loc, &t_un);
+          if (in) {
+            const uint32_t gi = (e & kLocBit) ? loc_before + r_loc : n_loc + unloc_before + r_un;
+            const uint32_t w = e & kIdxMask;
+            p.group_ask[g + gi] = c;
+            p.group_off[g + gi] = mpos + gi;
+            p.members[mpos + gi] = w;
+            p.worker_group[w] = g + gi;
+            p.worker_ask[w] = c;
+          }
+          loc_before += t_loc;
+          unloc_before += t_un;
+        }
+        g += n;
+        mpos += n;
+        if (extra) {
+          if (lead && tid == 0) { p.group_ask[g] = c; p.group_off[g] = mpos; }
+          ++g;
+        }
+      }
+      if (lead && tid == 0) { p.base_len[c] = 0; p.xcount[c] = 0; p.xhead[c] = kNone; }
+      __threadfence();
+      grid.sync();
+      c_lo = c + 1;
+      continue;
+    }
+
+    // ---- the group loop of mod.rs:507-609 for this configuration (max_group_size >= 2)
+    uint32_t remaining = n, ploc = 0, pany = 0;
+    for (;;) {
+      if (remaining < mn) break;                                           // :507 / :517
+      uint32_t seed_pos = n;
+      bool seed_loc = false;
+      if (remaining) {
+        if (ploc < n) {
+          seed_pos = pg_find_first(sh, p.list, n, ploc, kTakenBit | kLocBit, kLocBit);
+          ploc = seed_pos;
+        }
+        if (seed_pos < n) {
+          seed_loc = true;
+        } else {                                                           // .or(compatible_nodes.first())
+          seed_pos = pg_find_first(sh, p.list, n, pany, kTakenBit, 0u);
+          pany = seed_pos;
+        }
+      }
+      const bool have_seed = seed_pos < n;
+      const uint32_t size = have_seed ? min(mx, remaining) : 0u;
+      if (size < mn) break;                                                // :564
+      if (g >= p.group_cap) { overflow = true; break; }
+      if (lead && tid == 0) { p.group_ask[g] = c; p.group_off[g] = mpos; }
+      if (!have_seed) {                                                    // min_group_size == 0: the empty group
+        ++g;
+        break;                                                             // :606 no progress
+      }
+      const uint32_t seed_w = pg_ld(p.list + seed_pos) & kIdxMask;
+      uint32_t need = size - 1u, written = 1u;   // members written so far (the seed is written with the first marks)
+      bool seed_marked = false;
+      if (need && seed_loc) {
+        const double slat = p.lat[seed_w], slon = p.lon[seed_w];
+        bool first_pass = true;
+        while (need) {
+          const uint32_t kk = min(need, kPgTopK);
+          const bool keep = first_pass ? need > kk || kk > 1u : true;     // distances are re-read in later rounds
+          parity ^= 1u;
+          double* my_d = gp.part_d + ((size_t)parity * ncta + cta) * kPgTopK;
+          uint32_t* my_i = gp.part_i + ((size_t)parity * ncta + cta) * kPgTopK;
+          // 2. this CTA's kk best by (distance, position): round r takes the smallest pair above round r-1's
+          double prev_d = -1.0;
+          uint32_t prev_i = 0;
+          for (uint32_t r = 0; r < kk; ++r) {
+            double bd = kPgMax;
+            uint32_t bi = kNone;
+            for (uint32_t i = gtid; i < n; i += nthr) {
+              const uint32_t e = pg_ld(p.list + i);
+              if ((e & kTakenBit) || i == seed_pos) continue;
+              double d;
+              if (first_pass && r == 0u) {
+                d = (e & kLocBit) ? haversine_km(slat, slon, p.lat[e & kIdxMask], p.lon[e & kIdxMask]) : kPgMax;
+                if (keep) p.dist[i] = d;                                  // owner-private: read back by this thread only
+              } else {
+                d = p.dist[i];
+              }
+              if (r && !(d > prev_d || (d == prev_d && i > prev_i))) continue;
+              if (bi == kNone || d < bd) { bd = d; bi = i; }              // i increases: ties keep the smaller position
+            }
+            double wd;
+            const uint32_t wi = pg_block_argmin(sh, bd, bi, &wd);
+            if (tid == 0) { my_d[r] = wd; my_i[r] = wi; }
+            prev_d = wd;
+            prev_i = wi;
+            if (wi == kNone) {                                            // this CTA has no more candidates
+              if (tid == 0) for (uint32_t q = r + 1; q < kk; ++q) { my_d[q] = kPgMax; my_i[q] = kNone; }
+              break;
+            }
+          }
+          __threadfence();
+          grid.sync();                                                     // 3. the group's one barrier
+          // 4. every CTA merges all partial lists to the same kk winners
+          const double* all_d = gp.part_d + (size_t)parity * ncta * kPgTopK;
+          const uint32_t* all_i = gp.part_i + (size_t)parity * ncta * kPgTopK;
+          prev_d = -1.0;
+          prev_i = 0;
+          for (uint32_t r = 0; r < kk; ++r) {
+            double bd = kPgMax;
+            uint32_t bi = kNone;
+            for (uint32_t e = tid; e < ncta * kk; e += kPgThreads) {
+              const uint32_t slot = (e / kk) * kPgTopK + (e % kk);
+              const uint32_t i = __ldcg(all_i + slot);
+              if (i == kNone) continue;
+              const double d = __ldcg(all_d + slot);
+              if (r && !(d > prev_d || (d == prev_d && i > prev_i))) continue;
+              if (bi == kNone || d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+            }
+            double wd;
+            const uint32_t wi = pg_block_argmin(sh, bd, bi, &wd);
+            if (tid == 0) sh.picks[r] = wi;
+            prev_d = wd;
+            prev_i = wi;
+          }
+          __syncthreads();
+          // marks: only now, after the barrier — every CTA sets the same bits; the lead CTA writes the tables
+          if (tid < kk) {
+            const uint32_t pos = sh.picks[tid];
+            if (pos != kNone) {
+              atomicOr(p.list + pos, kTakenBit);
+              if (lead) {
+                const uint32_t w = pg_ld(p.list + pos) & kIdxMask;
+                p.members[mpos + written + tid] = w;
+                p.worker_group[w] = g;
+                p.worker_ask[w] = c;
+              }
+            }
+          }
+          if (!seed_marked && tid == kPgThreads - 1) {
+            atomicOr(p.list + seed_pos, kTakenBit);
+            if (lead) { p.members[mpos] = seed_w; p.worker_group[seed_w] = g; p.worker_ask[seed_w] = c; }
+          }
+          seed_marked = true;
+          __syncthreads();
+          need -= kk;
+          written += kk;
+          first_pass = false;
+        }
+      } else {
+        // no distances involved: a group of one, or a seed without location (then nobody left has one): the next
+        // `need` live candidates in list order, taken in chunks of the pick buffer; marks after a barrier as above
+        uint32_t pos = pany;
+        bool first = true;
+        while (first || need) {
+          uint32_t got = 0;
+          const uint32_t want = min(need, (uint32_t)kPgThreads);
+          while (got < want && pos < n) {
+            const uint32_t i = pos + tid;
+            const bool live = i < n && i != seed_pos && (pg_ld(p.list + i) & kTakenBit) == 0u;
+            uint32_t tile = 0;
+            const uint32_t r = pg_block_rank(sh, live, &tile);
+            if (live && got + r < want) sh.picks[got + r] = i;
+            if (got + tile > want) {
+              // the chunk ends inside this tile: continue right after its last pick (uniform: read back below)
+              __syncthreads();
+              const uint32_t last = sh.picks[want - 1];
+              got = want;
+              pos = last + 1u;
+              __syncthreads();
+            } else {
+              got += tile;
+              pos += kPgThreads;
+            }
+          }
+          __syncthreads();
+          __threadfence();
+          grid.sync();
+          for (uint32_t j = tid; j < got; j += kPgThreads) {
+            const uint32_t q = sh.picks[j];
+            atomicOr(p.list + q, kTakenBit);
+            if (lead) {
+              const uint32_t w = pg_ld(p.list + q) & kIdxMask;
+              p.members[mpos + written + j] = w;
+              p.worker_group[w] = g;
+              p.worker_ask[w] = c;
+            }
+          }
+          if (!seed_marked && tid == kPgThreads - 1) {
+            atomicOr(p.list + seed_pos, kTakenBit);
+            if (lead) { p.members[mpos] = seed_w; p.worker_group[seed_w] = g; p.worker_ask[seed_w] = c; }
+          }
+          seed_marked = true;
+          __syncthreads();
+          need -= got;
+          written += got;
+          first = false;
+          if (got == 0u) break;   // cannot happen (remaining >= size); keeps the loop finite
+        }
+      }
+      remaining -= size;
+      mpos += size;
+      ++g;
+    }
+
+    // ---- leftovers move on to their next feasible configuration
+    if (!overflow) {
+      for (uint32_t i = gtid; i < n; i += nthr) {
+        const uint32_t e = pg_ld(p.list + i);
+        if ((e & kTakenBit) == 0u) p.popped[atomicAdd(gp.gctl, 1u)] = e & kIdxMask;
+      }
+      __threadfence();
+      grid.sync();
+      const uint32_t npop = pg_ld(gp.gctl);
+      const uint32_t gwarp = cta * kPgWarps + warp, nwarp = ncta * kPgWarps;
+      for (uint32_t i = gwarp; i < npop; i += nwarp) {
+        const uint32_t w = pg_ld(p.popped + i);
+        const WorkerReg wr = make_worker(p.ev.wa[w], p.ev.wb[w]);
+        uint32_t found = kNone;
+        for (uint32_t cbase = c + 1; cbase < T; cbase += 32) {
+          const uint32_t c2 = cbase + lane;
+          bool ok = false;
+          if (c2 < T) ok = ask_meets(p.ev.asks[c2], p.ev.opts, wr, p.ev.bits, p.ev.words);
+          const uint32_t b = __ballot_sync(0xffffffffu, ok);
+          if (b) { found = cbase + (uint32_t)__ffs(b) - 1u; break; }
+        }
+        if (lane == 0) {
+          p.cur[w] = found;
+          if (found != kNone) {
+            const uint32_t old = atomicExch(&p.xhead[found], w);
+            p.xnext[w] = old;
+            atomicAdd(&p.xcount[found], 1u);
+          }
+          atomicAdd(&p.out_counts[2], 1u);
+        }
+      }
+      __threadfence();
+      grid.sync();
+      if (lead && tid == 0) { p.base_len[c] = 0; p.xcount[c] = 0; p.xhead[c] = kNone; gp.gctl[0] = 0; }
+    }
+    c_lo = c + 1;
+  }
+  if (lead && tid == 0) {
+    p.out_counts[0] = g;
+    p.out_counts[1] = mpos;
+    if (overflow) p.out_counts[3] = 1u;
+    if (g < p.group_cap + 1) p.group_off[g] = mpos;
+  }
+}
+
+}  // namespace pm

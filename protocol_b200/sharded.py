@@ -73,6 +73,40 @@ def exchange(first_ask, ask_best, ask_count, lo: int, hi: int, group=None):
     dist.all_reduce(ask_count, op=dist.ReduceOp.SUM, group=group)
 
 
+def packed_stride(n_workers: int, n_asks: int, world: int):
+    """(per, stride): the library's exchange layout (pm_xchg_pack in csrc/pm_kernels.cuh) — one buffer per rank,
+    [ask_best int64[T] | ask_count u32[T] | first_ask of the rank's own range u32[per]], rounded up to 16 bytes."""
+    per = (n_workers + world - 1) // world
+    return per, ((n_asks * 12 + per * 4) + 15) & ~15
+
+
+def packed_exchange(first_ask, ask_best, ask_count, lo: int, hi: int, group=None):
+    """The exchange as the library does it inside pm_match (pm_comm): pack, ONE all-gather of bytes, fold.  Same
+    arguments and result as `exchange`; used on CPU/gloo to pin the layout and the fold rules the CUDA kernels follow."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    W, T = first_ask.numel(), ask_best.numel()
+    per, stride = packed_stride(W, T, world)
+    send = np.zeros(stride, dtype=np.uint8)
+    send[:T * 8] = ask_best.numpy().view(np.uint8)
+    send[T * 8:T * 12] = ask_count.numpy().view(np.uint8)
+    mine = np.full(per, 0xFFFFFFFF, dtype=np.uint32)
+    mine[:hi - lo] = first_ask.numpy()[lo:hi].view(np.uint32)
+    send[T * 12:T * 12 + per * 4] = mine.view(np.uint8)
+    recv = torch.empty(stride * world, dtype=torch.uint8)
+    dist.all_gather_into_tensor(recv, torch.from_numpy(send), group=group)
+    r = recv.numpy().reshape(world, stride)
+    best = r[:, :T * 8].copy().view(np.int64).reshape(world, T).min(axis=0)
+    cnt = r[:, T * 8:T * 12].copy().view(np.uint32).reshape(world, T).sum(axis=0, dtype=np.uint32)
+    first = r[:, T * 12:T * 12 + per * 4].copy().view(np.uint32).reshape(world * per)[:W]
+    ask_best.copy_(torch.from_numpy(best))
+    ask_count.copy_(torch.from_numpy(cnt.view(np.int32)))
+    first_ask.copy_(torch.from_numpy(first.view(np.int32).copy()))
+
+
 class ShardedMatcher:
     """One rank's view of a sharded pass over an Engine created with this rank's shard range."""
 

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import pm_oracle as orc
 from protocol_b200 import synth
-from protocol_b200.sharded import exchange, shard_range
+from protocol_b200.sharded import exchange, packed_exchange, shard_range
 
 
 def _free_port():
@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _rank_main(rank, world, port, n_workers, n_asks, out_dir):
+def _rank_main(rank, world, port, n_workers, n_asks, out_dir, packed):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -36,17 +36,19 @@ def _rank_main(rank, world, port, n_workers, n_asks, out_dir):
     first[lo:hi] = torch.from_numpy(ev["col_first"].view(np.int32))
     best = torch.from_numpy(ev["row_best"].copy())
     cnt = torch.from_numpy(ev["row_count"].view(np.int32).copy())
-    exchange(first, best, cnt, lo, hi)
+    (packed_exchange if packed else exchange)(first, best, cnt, lo, hi)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), first=first.numpy(), best=best.numpy(), cnt=cnt.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["three_collectives", "one_packed_all_gather"])
 @pytest.mark.parametrize("n_workers", [4000, 4001])   # even split and ragged last shard
-def test_two_rank_exchange_matches_single_shard(tmp_path, n_workers):
+def test_two_rank_exchange_matches_single_shard(tmp_path, n_workers, packed):
+    """packed=True is the layout and fold the library uses inside pm_match (pm_comm, one all-gather per pass)."""
     n_asks, world = 300, 2
     port = _free_port()
-    mp.spawn(_rank_main, args=(world, port, n_workers, n_asks, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, port, n_workers, n_asks, str(tmp_path), packed), nprocs=world, join=True)
     w = synth.make_workers(n_workers)
     a = synth.make_asks(n_asks, "mixed")
     bits, npat, nmod, words = synth.intern_tables(w, a)
