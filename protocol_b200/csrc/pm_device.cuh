@@ -58,11 +58,16 @@ struct __align__(16) DevOpt {
 
 // Fast-path form of an option (same 32 B slot as DevOpt, separate array).  Valid
 // when every numeric operand on both sides is < 2^31 and every gpu count < 2^16
-// (checked at upload; otherwise the generic predicate is used).  The worker's
-// presence flags and gpu count are packed into one `key` word (count in bits
-// 13..28), so presence + count is ONE masked equality ((key & m) ^ v) == 0, where
-// m/v also carry the owning ask's `need` bits; range clauses are sign tests of
-// (x - lo) | (hi - x), which run on the FMA pipe (IMAD) instead of the ALU pipe.
+// (checked at upload; otherwise the generic predicate is used).  Every clause ends as a SIGN BIT ("set = fails"),
+// so clauses combine with OR (AND across the OR-options of an ask) and nothing is compared or selected until the
+// very end:
+//   * the worker's presence flags and gpu count are packed into one `key` word of 29 bits (layout below), so
+//     presence + count is one masked equality z = (key & m) ^ v, with m/v also carrying the owning ask's `need`;
+//     the model clause adds ~word & mmask (device acceptance words hold 31 models, so z < 2^31), and
+//     0 - z has its sign set exactly when z != 0 — a subtraction, which issues on the FMA pipe (IMAD);
+//   * range clauses are the signs of (x - lo) | (hi - x): IMAD subtractions again.
+// What is left for the ALU pipe per (option, worker) is five LOP3; the int64 cost is then formed with one shift
+// and two IMADs (pm_kernels.cuh) — the integer work is split evenly over the two pipes instead of 2:1 on the ALU.
 struct __align__(16) DevOptF {
   uint32_t m, v;
   uint32_t mem_lo, mem_hi;
@@ -70,14 +75,22 @@ struct __align__(16) DevOptF {
   uint32_t pattern_row;
   uint32_t pad;
 };
+// key = flags bits 3..12 (PM_W_HAS_*) in bits 0..9, candidate 10, never 11, total-memory-skipped 12, gpu count 13..28
 constexpr uint32_t kKeyCountShift = 13;
-constexpr uint32_t kKeyFlagMask = 0xE0001FFFu;
+constexpr uint32_t kKeyCandBit = 1u << 10, kKeyNeverBit = 1u << 11, kKeyTotInvalidBit = 1u << 12;
 constexpr uint32_t kSign = 0x80000000u;
+constexpr uint32_t kModelsPerWord = 31;   // device acceptance words keep bit 31 clear (see DevOptF)
+
+// presence bits (ABI flags + the synthetic bits 29..31) -> their positions in `key`
+__host__ __device__ __forceinline__ uint32_t key_bits(uint32_t f) {
+  return ((f >> 3) & 0x3FFu) | ((f & (1u << 31)) ? kKeyCandBit : 0u) | ((f & (1u << 30)) ? kKeyNeverBit : 0u) |
+         ((f & (1u << 29)) ? kKeyTotInvalidBit : 0u);
+}
 
 // One worker held in registers.
 struct WorkerReg {
   uint32_t flags;      // ABI presence bits + kCandBit / kTotInvalidBit
-  uint32_t key;        // fast path: flags | count << 13
+  uint32_t key;        // fast path: key_bits(flags) | count << 13
   uint32_t count_eff;  // None behaves exactly like Some(0) in the count clause (node.rs:447-461)
   uint32_t mem_eff;
   uint32_t tot;        // count * memory_mb, wrapping (release-build u32 multiply, node.rs:509,518)
@@ -93,7 +106,7 @@ __device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
   const bool cand = (a.w & (PM_W_HEALTHY | PM_W_P2P | PM_W_ASSIGNED)) == (PM_W_HEALTHY | PM_W_P2P);
   w.flags = (a.w & 0x1FFFFFFFu) | (cand ? kCandBit : 0u) | ((hc && hm) ? 0u : kTotInvalidBit);
   w.count_eff = hc ? a.x : 0u;
-  w.key = (w.flags & kKeyFlagMask) | (w.count_eff << kKeyCountShift);
+  w.key = key_bits(w.flags) | (w.count_eff << kKeyCountShift);
   w.mem_eff = hm ? a.y : 0u;
   w.tot = a.x * a.y;
   w.tot_keep = (hc && hm) ? 0xFFFFFFFFu : 0u;
@@ -102,14 +115,14 @@ __device__ __forceinline__ WorkerReg make_worker(uint4 a, uint4 b) {
   w.storage = b.z;
   w.price = b.w;
   const uint32_t mid = (a.w & PM_W_HAS_GPU_MODEL) ? a.z : 0u;
-  w.mword = mid >> 5;
-  w.mmask = 1u << (mid & 31u);
+  w.mword = mid / kModelsPerWord;
+  w.mmask = 1u << (mid % kModelsPerWord);
   return w;
 }
 
 __device__ __forceinline__ WorkerReg null_worker() {
   WorkerReg w;
-  w.flags = kTotInvalidBit; w.key = kTotInvalidBit; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_keep = 0;
+  w.flags = kTotInvalidBit; w.key = kKeyTotInvalidBit; w.count_eff = 0; w.mem_eff = 0; w.tot = 0; w.tot_keep = 0;
   w.cores = 0; w.ram = 0; w.storage = 0; w.mword = 0; w.mmask = 1u; w.price = 0;
   return w;
 }

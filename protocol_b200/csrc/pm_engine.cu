@@ -297,6 +297,7 @@ pm::EvalParams eval_params(pm_engine* e) {
   p.n_asks = e->n_asks;
   p.n_opts = e->n_opts;
   p.n_bits_rows = e->have_bits ? e->n_patterns + 1 : 1;
+  p.sign_shift = 31;
   return p;
 }
 
@@ -427,7 +428,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   // asks may share or overlap option rows, so the converted table (one private range per ask) can be longer than
   // the caller's: size it by the sum of the per-ask counts
   uint64_t opt_rows = 0;
-  for (uint32_t i = 0; i < n_asks; ++i) opt_rows += asks[i].n_opts;
+  for (uint32_t i = 0; i < n_asks; ++i) opt_rows += std::max<uint32_t>(asks[i].n_opts, 1u);   // an ask without options gets a neutral row
   if (opt_rows >= (1ull << 31)) return e->fail(PM_E_INVALID, "pm_set_asks: too many option rows");
   const size_t opt_cap = std::max<size_t>(n_opts, (size_t)opt_rows);
   PM_CUDA(e->opts.ensure(opt_cap)); PM_CUDA(e->opts_fast.ensure(opt_cap));
@@ -477,9 +478,24 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
   if (words == 0) words = 1;
   if (n_patterns && !bits) return e->fail(PM_E_INVALID, "pm_set_model_table: null table");
   if ((uint64_t)words * 32 < n_models) return e->fail(PM_E_INVALID, "pm_set_model_table: words too small");
-  std::vector<uint32_t> tbl((size_t)(n_patterns + 1) * words, 0u);
-  for (uint32_t i = 0; i < words; ++i) tbl[i] = 0xFFFFFFFFu;  // row 0: no model clause
-  if (n_patterns) std::memcpy(tbl.data() + words, bits, (size_t)n_patterns * words * 4);
+  // device layout: 31 models per word (bit 31 stays clear: the fast predicate turns "non-zero" into a sign bit by
+  // an addition, pm_device.cuh DevOptF), row 0 = no model clause = accepts everything
+  const uint32_t dwords = std::max<uint32_t>((n_models + pm::kModelsPerWord - 1) / pm::kModelsPerWord, 1u);
+  std::vector<uint32_t> tbl((size_t)(n_patterns + 1) * dwords, 0u);
+  for (uint32_t i = 0; i < dwords; ++i) tbl[i] = 0x7FFFFFFFu;
+  for (uint32_t p = 0; p < n_patterns; ++p) {
+    const uint32_t* src = bits + (size_t)p * words;
+    uint32_t* dst = tbl.data() + (size_t)(p + 1) * dwords;
+    for (uint32_t wi = 0; wi < words; ++wi) {
+      uint32_t v = src[wi];
+      while (v) {
+        const uint32_t m = wi * 32u + (uint32_t)__builtin_ctz(v);
+        v &= v - 1;
+        if (m < n_models) dst[m / pm::kModelsPerWord] |= 1u << (m % pm::kModelsPerWord);
+      }
+    }
+  }
+  words = dwords;
   PM_CUDA(cudaSetDevice(e->device));
   PM_CUDA(e->bits.ensure(tbl.size()));
   PM_CUDA(cudaMemcpyAsync(e->bits.p, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, e->stream));
@@ -706,7 +722,9 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
       tm.stop();
       e->stats.n_tiles = 1;
     } else {
-      const size_t ld = ((size_t)nw + 15) & ~(size_t)15;  // 128-byte rows
+      // leading dimension = whole CTA stripes of the build kernel (1024 columns): its stores need no bounds test;
+      // the columns past the shard hold "infeasible" and cost 0.05 % of a 1M-worker row
+      const size_t ld = (((size_t)nw + pm::kEvalCols - 1) / pm::kEvalCols) * pm::kEvalCols;
       uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
       if (rows == 0) rows = 1;
       rows = std::min<uint64_t>(rows, T);
@@ -734,8 +752,8 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
           ++e->stats.n_argmin_launches;
         }
         ++e->stats.n_tiles;
-        e->stats.cost_bytes_written += (uint64_t)nt * ld * 8;
-        e->stats.cost_bytes_read += (uint64_t)nt * ld * 8;
+        e->stats.cost_bytes_written += (uint64_t)nt * nw * 8;   // algorithmic: 8 B per evaluation (padding columns not counted)
+        e->stats.cost_bytes_read += (uint64_t)nt * nw * 8;
       }
     }
     e->stats.evals = (uint64_t)T * nw;
@@ -1347,7 +1365,7 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
     PM_CUDA(cudaMemsetAsync(e->bits.p, 0xFF, 4, e->stream));
     e->words = 1;
   }
-  const size_t ld = ((size_t)nw + 15) & ~(size_t)15;
+  const size_t ld = (((size_t)nw + pm::kEvalCols - 1) / pm::kEvalCols) * pm::kEvalCols;
   if (nt > 65535u * pm::kEvalRows) return e->fail(PM_E_INVALID, "pm_build_cost_tile: too many rows");
   if (e->cost.ensure((size_t)nt * ld) != cudaSuccess) {
     cudaGetLastError();

@@ -27,6 +27,9 @@ struct EvalParams {
   uint32_t n_asks;
   uint32_t n_opts;
   uint32_t n_bits_rows;               // n_patterns + 1
+  uint32_t sign_shift;                // always 31.  A run-time value on purpose: with a literal shift ptxas proves the
+                                      // result is 0/1 and turns the two multiply-adds that form the packed cost back
+                                      // into a compare and two selects on the (busier) ALU pipe
 };
 
 // ------------------------------------------------------------------ evaluation core
@@ -121,44 +124,43 @@ __device__ __forceinline__ void eval_row(const EvalStage& s, const DevAsk& a, ui
   }
 }
 
-// Fast path (all operands < 2^31, counts < 2^16): `fail == 0` <=> feasible.
-// Per worker and option: 2 LOP3 for presence+count+model, 4 IMAD subtractions and
-// 2 LOP3 for the two range clauses, 1 LOP3 to merge — half the ALU-pipe work of the
-// generic chain, which is what bounds pm_build_cost on the integer side.
+// Fast path (all operands < 2^31, counts < 2^16; layout and derivation at DevOptF in pm_device.cuh): the SIGN BIT of
+// fail[k] is set <=> worker k does not meet the ask.  Per worker and option: 5 LOP3 on the ALU pipe, 7 IMAD-pipe
+// adds/subtractions; clauses are never compared, only OR-ed (AND across the ask's OR-options).  Every converted ask
+// has at least one option row (pm_ask_convert adds a neutral one), so there is no option-less special case.
+template <int WPT, int BITS>
+__device__ __forceinline__ void eval_opt_fast(const EvalStage& s, const DevOptF& q, const WorkerReg (&w)[WPT],
+                                              const uint32_t* __restrict__ gbits, uint32_t words, uint32_t (&u)[WPT]) {
+  const uint32_t rowoff = q.pattern_row * words;
+  const uint32_t uword = (BITS == 2) ? s.bits[q.pattern_row] : 0u;
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const uint32_t word = (BITS == 2) ? uword
+                          : (BITS == 1) ? s.bits[rowoff + w[k].mword] : __ldg(gbits + rowoff + w[k].mword);
+    const uint32_t z = ((w[k].key & q.m) ^ q.v) | (~word & w[k].mmask);          // < 2^31, non-zero = fails
+    const uint32_t r = (w[k].mem_eff - q.mem_lo) | (q.mem_hi - w[k].mem_eff) |
+                       (((w[k].tot - q.tot_lo) | (q.tot_hi - w[k].tot)) & w[k].tot_keep);
+    u[k] = (0u - z) | r;    // z < 2^31: the negation has its sign set exactly when z != 0
+  }
+}
+
 template <int WPT, int BITS>
 __device__ __forceinline__ void eval_row_fast(const EvalStage& s, const DevAsk& a, uint32_t obegin,
                                               const WorkerReg (&w)[WPT],
                                               const uint32_t* __restrict__ gbits, uint32_t words,
                                               uint32_t (&fail)[WPT]) {
-  uint32_t sb[WPT];
+  const DevOptF* optf = reinterpret_cast<const DevOptF*>(s.opt) + (a.opt_off - obegin);
+  uint32_t um[WPT];
+  eval_opt_fast<WPT, BITS>(s, optf[0], w, gbits, words, um);
+  for (uint32_t o = 1; o < a.n_opts; ++o) {   // OR-options (node.rs:420-438): the ask fails only if every option does
+    uint32_t u[WPT];
+    eval_opt_fast<WPT, BITS>(s, optf[o], w, gbits, words, u);
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) um[k] &= u[k];
+  }
 #pragma unroll
   for (int k = 0; k < WPT; ++k)
-    sb[k] = ((w[k].cores - a.cpu_cores) | (w[k].ram - a.ram_mb) | (w[k].storage - a.storage_gb)) & kSign;
-  if (a.n_opts == 0u) {
-#pragma unroll
-    for (int k = 0; k < WPT; ++k) fail[k] = (~w[k].key & a.need) | sb[k];
-    return;
-  }
-  const DevOptF* optf = reinterpret_cast<const DevOptF*>(s.opt);
-  const uint32_t o0 = a.opt_off - obegin;
-  uint32_t um[WPT];
-  for (uint32_t o = 0; o < a.n_opts; ++o) {
-    const DevOptF q = optf[o0 + o];
-    const uint32_t rowoff = q.pattern_row * words;
-    const uint32_t uword = (BITS == 2) ? s.bits[q.pattern_row] : 0u;
-#pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-      const uint32_t word = (BITS == 2) ? uword
-                            : (BITS == 1) ? s.bits[rowoff + w[k].mword] : __ldg(gbits + rowoff + w[k].mword);
-      const uint32_t z = ((w[k].key & q.m) ^ q.v) | (~word & w[k].mmask);
-      const uint32_t r = (w[k].mem_eff - q.mem_lo) | (q.mem_hi - w[k].mem_eff) |
-                         (((w[k].tot - q.tot_lo) | (q.tot_hi - w[k].tot)) & w[k].tot_keep);
-      const uint32_t u = z | (r & kSign);
-      um[k] = (o == 0u) ? u : min(um[k], u);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < WPT; ++k) fail[k] = um[k] | sb[k];
+    fail[k] = um[k] | (w[k].cores - a.cpu_cores) | (w[k].ram - a.ram_mb) | (w[k].storage - a.storage_gb);
 }
 
 // Slow path for an ask whose option list alone exceeds the staging capacity.
@@ -228,9 +230,12 @@ __device__ __forceinline__ void for_each_staged_row(EvalStage& s, const EvalPara
 }
 
 // ------------------------------------------------------------------ build
-// grid = (ceil(ld / 1024), ceil(nt / 128)); each thread owns 4 workers in registers and walks
+// grid = (ld / 1024, ceil(nt / 128)); each thread owns 4 workers in registers and walks
 // the staged asks, emitting two 128-bit streaming stores per row: a warp writes 1 KB
 // contiguous (two fully coalesced 512-byte stores), the CTA 8 KB contiguous per row.
+// ld is a multiple of the CTA's 1024 columns (columns past the shard hold the "infeasible" pattern of a null
+// worker), so the stores need no bounds test.  Fast form: the packed cost is formed from the predicate's sign bit
+// with one shift and two multiply-adds per worker — no compare, no select (see DevOptF).
 template <int BITS, bool FAST, int MINB = 2>
 __global__ void __launch_bounds__(kEvalThreads, MINB)
 pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
@@ -243,16 +248,17 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t cbase = blockIdx.x * kEvalCols + (threadIdx.x >> 5) * 128u + lane * 2u;
   WorkerReg w[kEvalWPT];
-  uint32_t gw[kEvalWPT];
+  uint32_t gw[kEvalWPT], dx[kEvalWPT], dy[kEvalWPT];
 #pragma unroll
   for (int k = 0; k < kEvalWPT; ++k) {
     const uint32_t col = cbase + (k >> 1) * 64u + (k & 1);
     gw[k] = w0 + col;
     if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
     else w[k] = null_worker();
+    dx[k] = 0xFFFFFFFFu - gw[k];          // infeasible: 0x7FFFFFFF_FFFFFFFF = feasible word + (0/1) * difference
+    dy[k] = 0x7FFFFFFFu - w[k].price;
   }
-  const bool in0 = cbase < ld, in1 = cbase + 64u < ld;   // ld is a multiple of 16: a pair is all in or all out
-  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + (in0 ? cbase : 0));
+  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + cbase);
   const size_t row_stride = ld / 2;   // in 16-byte units; rows are visited in increasing order
   for_each_staged_row(s, p, FAST, t0, r0, r1, [&](uint32_t, const DevAsk& a, uint32_t obegin, bool staged) {
     uint4 v0, v1;
@@ -260,10 +266,12 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
     if (FAST && staged) {
       uint32_t fail[kEvalWPT];
       eval_row_fast<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, fail);
-      v0.x = fail[0] ? 0xFFFFFFFFu : gw[0]; v0.y = fail[0] ? 0x7FFFFFFFu : w[0].price;
-      v0.z = fail[1] ? 0xFFFFFFFFu : gw[1]; v0.w = fail[1] ? 0x7FFFFFFFu : w[1].price;
-      v1.x = fail[2] ? 0xFFFFFFFFu : gw[2]; v1.y = fail[2] ? 0x7FFFFFFFu : w[2].price;
-      v1.z = fail[3] ? 0xFFFFFFFFu : gw[3]; v1.w = fail[3] ? 0x7FFFFFFFu : w[3].price;
+      const uint32_t sh = p.sign_shift;
+      const uint32_t b0 = fail[0] >> sh, b1 = fail[1] >> sh, b2 = fail[2] >> sh, b3 = fail[3] >> sh;
+      v0.x = b0 * dx[0] + gw[0]; v0.y = b0 * dy[0] + w[0].price;
+      v0.z = b1 * dx[1] + gw[1]; v0.w = b1 * dy[1] + w[1].price;
+      v1.x = b2 * dx[2] + gw[2]; v1.y = b2 * dy[2] + w[2].price;
+      v1.z = b3 * dx[3] + gw[3]; v1.w = b3 * dy[3] + w[3].price;
     } else {
       uint32_t f[kEvalWPT];
       if (staged) eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
@@ -273,8 +281,8 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
       v1.x = gw[2] | ~f[2]; v1.y = (w[2].price & f[2]) | (0x7FFFFFFFu & ~f[2]);
       v1.z = gw[3] | ~f[3]; v1.w = (w[3].price & f[3]) | (0x7FFFFFFFu & ~f[3]);
     }
-    if (in0) __stcs(out, v0);
-    if (in1) __stcs(out + 32, v1);     // + 64 columns
+    __stcs(out, v0);
+    __stcs(out + 32, v1);     // + 64 columns
     out += row_stride;
   });
 }
@@ -402,7 +410,7 @@ pm_fused_eval(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
       uint32_t fail[kEvalWPT];
       eval_row_fast<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, fail);
 #pragma unroll
-      for (int k = 0; k < kEvalWPT; ++k) f[k] = fail[k] ? 0u : 0xFFFFFFFFu;
+      for (int k = 0; k < kEvalWPT; ++k) f[k] = ~(uint32_t)((int32_t)fail[k] >> 31);   // all-ones <=> feasible
     } else if (staged) {
       eval_row<kEvalWPT, BITS>(s, a, obegin, w, p.bits, p.words, f);
     } else {
@@ -462,7 +470,8 @@ __global__ void pm_ask_counts(const pm_ask* __restrict__ asks, uint32_t n_asks, 
   if (!(a.min_group_size == 1 && a.max_group_size == 1)) st |= kAskNotSolo;
   if (a.max_group_size == 0) st |= kAskMaxZero;
   if (st) atomicOr(status, st);
-  counts[t] = ((a.flags & PM_A_HAS_REQ) && !(st & kAskBadRange)) ? a.n_opts : 0u;
+  // every converted ask owns at least one option row: an ask without GPU options gets a neutral one (pm_ask_convert)
+  counts[t] = max(((a.flags & PM_A_HAS_REQ) && !(st & kAskBadRange)) ? a.n_opts : 0u, 1u);
 }
 
 __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt* __restrict__ opts,
@@ -478,7 +487,10 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
   d.n_opts = 0; d.cpu_cores = 0; d.ram_mb = 0; d.storage_gb = 0; d.pad0 = 0; d.pad1 = 0;
   const bool has_req = (a.flags & PM_A_HAS_REQ) != 0;
   uint32_t need = kCandBit;
-  const uint32_t n_eff = new_off[t + 1] - new_off[t];
+  const uint32_t n_rows = new_off[t + 1] - new_off[t];                  // >= 1
+  // option rows that come from the caller (none are read when pm_ask_counts found a range out of bounds: the call fails)
+  const bool bad_range = (*reinterpret_cast<volatile uint32_t*>(status) & kAskBadRange) != 0u;
+  const uint32_t n_eff = (has_req && !bad_range) ? min(a.n_opts, n_rows) : 0u;
   if (has_req) {
     need |= PM_W_HAS_SPECS;
     if (a.flags & PM_A_REQ_CPU) need |= PM_W_HAS_CPU;
@@ -486,8 +498,8 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
     if (a.flags & PM_A_REQ_RAM) { need |= PM_W_HAS_RAM; d.ram_mb = a.ram_mb; }
     if (a.flags & PM_A_REQ_STORAGE) { need |= PM_W_HAS_STORAGE; d.storage_gb = a.storage_gb; }
     if (a.n_opts) need |= PM_W_HAS_GPU;
-    d.n_opts = n_eff;
   }
+  d.n_opts = n_rows;
   if (a.max_group_size == 0) need |= kNeverBit;   // first-fit with max_group_size == 0 takes nobody (mod.rs:555-556)
   d.need = need;
   d.opt_off = new_off[t];
@@ -519,7 +531,7 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
     dopts[d.opt_off + o] = x;
     DevOptF f;
     const uint32_t need_all = need | x.need;
-    f.m = need_all; f.v = need_all;
+    f.m = key_bits(need_all); f.v = f.m;
     if (q.present & PM_O_COUNT) {
       if (q.count >= 65536u) st |= kAskNotSmall;
       f.m |= 0xFFFFu << kKeyCountShift;
@@ -530,6 +542,19 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
     f.tot_lo = tot_lo; f.tot_hi = min(tot_hi, 0x7FFFFFFFu);
     f.pattern_row = x.pattern_row; f.pad = 0;
     doptsf[d.opt_off + o] = f;
+  }
+  if (n_eff == 0u) {
+    // no GPU clause (requirements.gpu empty, or no requirements at all): one neutral option row — it accepts every
+    // worker, so the ask's presence bits and scalar thresholds decide alone — keeps the evaluation loops free of an
+    // option-less special case
+    DevOpt x;
+    x.need = 0; x.count_mask = 0; x.count = 0; x.mem_lo = 0; x.mem_span = 0xFFFFFFFFu; x.tot_lo = 0; x.tot_span = 0xFFFFFFFFu;
+    x.pattern_row = 0;
+    dopts[d.opt_off] = x;
+    DevOptF f;
+    f.m = key_bits(need); f.v = f.m;
+    f.mem_lo = 0; f.mem_hi = 0x7FFFFFFFu; f.tot_lo = 0; f.tot_hi = 0x7FFFFFFFu; f.pattern_row = 0; f.pad = 0;
+    doptsf[d.opt_off] = f;
   }
   dasks[t] = d;
   amin[t] = a.min_group_size;

@@ -71,7 +71,7 @@ def run(kernel, w, a, checker="banded"):
     t = tables_for(w, a)
     os.environ["PM_TUNE_PROX"] = kernel   # read at pm_create
     try:
-        eng = Engine()
+        eng = Engine(timing=True)
     finally:
         os.environ.pop("PM_TUNE_PROX", None)
     load_engine(eng, t, addr_rank=w.addr_rank, locations=True)

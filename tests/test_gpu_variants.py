@@ -67,8 +67,9 @@ def run_all_paths(w, a, obits, pbits, npat, nmod, words, expect_bits, check_cost
     T, W = len(a), len(w)
     og = orc.soa_form_groups(w.a, w.b, a.asks, a.opts, obits, words)
     ev = orc.soa_eval_matrix(w.a, w.b, a.asks, a.opts, obits, words, 0, T, 0, W, threads=8)
-    bits_rows_words = (npat + 1) * words
-    got_bits = 2 if (bits_rows_words <= 2048 and words == 1) else 1 if bits_rows_words <= 2048 else 0
+    dwords = max((nmod + 30) // 31, 1)            # the device keeps 31 models per acceptance word
+    bits_rows_words = (npat + 1) * dwords
+    got_bits = 2 if (bits_rows_words <= 2048 and dwords == 1) else 1 if bits_rows_words <= 2048 else 0
     assert got_bits == expect_bits, f"table shape selects BITS={got_bits}, the test is meant for BITS={expect_bits}"
     for generic in ("0", "1"):
         os.environ["PM_TUNE_GENERIC"] = generic   # read at pm_create
@@ -161,4 +162,4 @@ def test_asks_with_more_options_than_the_stage_holds(n_models):
     ev = orc.soa_eval_matrix(w.a, w.b, a.asks, a.opts, obits, words, 0, 300, 0, 5000, threads=8)
     for t in big:
         assert 0 < ev["row_count"][t] < 4500
-    run_all_paths(w, a, obits, pbits, npat, nmod, words, expect_bits=2 if n_models <= 32 else 1, check_cost_rows=300)
+    run_all_paths(w, a, obits, pbits, npat, nmod, words, expect_bits=2 if n_models <= 31 else 1, check_cost_rows=300)
