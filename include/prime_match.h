@@ -204,6 +204,19 @@ int pm_set_worker_addr_rank(pm_engine*, const uint32_t* rank, uint32_t first, ui
 /* status / assigned deltas (status_update_impl.rs:8-39, mod.rs:1423-1487)   */
 int pm_set_flags(pm_engine*, const uint32_t* idx, const uint32_t* flags, uint32_t n);
 
+/* Resident tables with deltas: a long-running host keeps the worker table on the device between management passes and
+ * sends only the rows that changed (status / assigned / specs / location), instead of NodeStore::get_nodes' full
+ * read per pass (store/domains/node_store.rs:163-209).
+ *   pm_resize_workers   grow (or shrink) the table, keeping the rows it holds; new rows are empty (no candidate)
+ *   pm_update_workers   scatter n rows by index; lat/lon both NULL or both given
+ *   pm_table_version    changes whenever any table call ran: lets a caller detect that someone else used the engine
+ *   pm_create_sibling   a second engine on the same device with the same configuration (own stream and tables)   */
+int      pm_resize_workers(pm_engine*, uint32_t n_workers);
+int      pm_update_workers(pm_engine*, const uint32_t* idx, const pm_worker_a* a, const pm_worker_b* b,
+                           const double* lat, const double* lon, uint32_t n);
+uint64_t pm_table_version(const pm_engine*);
+int      pm_create_sibling(const pm_engine*, pm_engine** out);
+
 /* NORTH-STAR EXTENSION columns (no reference counterpart; only PM_MODE_AUCTION reads them):
  * per-ask price cap against pm_worker_b.ext_ask_price, and the auction's parameters
  * (value = -(ask_price * cost_scale) - price; eps runs eps_start, /eps_div, ..., 1).       */

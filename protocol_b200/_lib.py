@@ -66,6 +66,10 @@ def load() -> C.CDLL:
         "pm_device_buffer": (i32, [vp, u32, P(vp), P(sz)]),
         "pm_stream_sync": (i32, [vp]),
         "pm_set_shard": (i32, [vp, u32, u32]),
+        "pm_resize_workers": (i32, [vp, u32]),
+        "pm_update_workers": (i32, [vp, vp, vp, vp, vp, vp, u32]),
+        "pm_table_version": (C.c_uint64, [vp]),
+        "pm_create_sibling": (i32, [vp, P(vp)]),
         "pm_comm_unique_id": (i32, [vp]),
         "pm_comm_create": (i32, [vp, u32, u32, C.c_int32, P(vp)]),
         "pm_comm_destroy": (None, [vp]),

@@ -114,6 +114,7 @@ EXPORTS = [
     "pm_set_ask_price_caps", "pm_set_auction_params",
     "pm_match", "pm_fetch_result", "pm_get_stats", "pm_build_cost_tile",
     "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync", "pm_set_shard",
+    "pm_resize_workers", "pm_update_workers", "pm_table_version", "pm_create_sibling",
     "pm_comm_unique_id", "pm_comm_create", "pm_comm_destroy", "pm_attach_comm",
     "pm_multi_create", "pm_multi_destroy", "pm_multi_size", "pm_multi_engine", "pm_multi_last_error",
     "pm_multi_set_asks", "pm_multi_set_model_table", "pm_multi_set_worker_count", "pm_multi_upsert_workers",

@@ -57,6 +57,23 @@ template <class T> struct DevBuf {
     p = nullptr;
     n = 0;
   }
+  // capacity >= want, the first `keep` elements preserved, everything after them zero
+  cudaError_t grow_keep(size_t want, size_t keep, cudaStream_t st) {
+    if (want <= n && p) return cudaSuccess;
+    const size_t cap = std::max<size_t>(want + want / 4, 1);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, cap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    keep = p ? std::min(keep, n) : 0;
+    if (keep) e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(q + keep, 0, (cap - keep) * sizeof(T), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(q); return e; }
+    if (p) cudaFree(p);
+    p = q;
+    n = cap;
+    return cudaSuccess;
+  }
 };
 template <class T> struct PinBuf {
   T* p = nullptr;
@@ -147,6 +164,9 @@ struct pm_engine {
   bool workers_checked = false;
   DevBuf<uint32_t> amin, amax, bits;
   DevBuf<uint32_t> scratch_idx, scratch_flags;
+  DevBuf<uint4> upd_a, upd_b;          // staging of pm_update_workers
+  DevBuf<double> upd_lat, upd_lon;
+  uint64_t table_version = 0;          // bumped by every call that changes a table (pm_table_version)
 
   // evaluation
   DevBuf<long long> cost;
@@ -381,6 +401,7 @@ void pm_destroy(pm_engine* e) {
   e->asks.release(); e->opts.release(); e->opts_fast.release();
   e->raw_asks.release(); e->raw_opts.release(); e->ask_counts.release(); e->ask_newoff.release(); e->amin.release(); e->amax.release(); e->bits.release();
   e->scratch_idx.release(); e->scratch_flags.release();
+  e->upd_a.release(); e->upd_b.release(); e->upd_lat.release(); e->upd_lon.release();
   e->cost.release(); e->first_ask.release(); e->ask_count.release(); e->ask_best.release();
   e->keys.release(); e->keys_sorted.release(); e->iota.release(); e->order.release();
   e->hist.release(); e->seg_start.release(); e->ngroups.release(); e->group_base.release();
@@ -418,6 +439,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
                 uint32_t n_opts) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if ((n_asks && !asks) || (n_opts && !opts)) return e->fail(PM_E_INVALID, "pm_set_asks: null table");
   if (n_asks >= (1u << 30)) return e->fail(PM_E_INVALID, "pm_set_asks: too many asks");
   PM_CUDA(cudaSetDevice(e->device));
@@ -475,6 +497,7 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
                        uint32_t words) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if (words == 0) words = 1;
   if (n_patterns && !bits) return e->fail(PM_E_INVALID, "pm_set_model_table: null table");
   if ((uint64_t)words * 32 < n_models) return e->fail(PM_E_INVALID, "pm_set_model_table: words too small");
@@ -511,6 +534,7 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
 int pm_set_worker_count(pm_engine* e, uint32_t n_workers) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   PM_CUDA(cudaSetDevice(e->device));
   if (n_workers > e->wa.n || !e->wa.p) {
     // grow, preserving nothing: callers upsert after (re)sizing
@@ -531,6 +555,7 @@ int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, 
                       uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_upsert_workers: call pm_set_worker_count first");
   if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_upsert_workers: range out of bounds");
   if (n && (!a || !b)) return e->fail(PM_E_INVALID, "pm_upsert_workers: null plane");
@@ -548,6 +573,7 @@ int pm_set_worker_locations(pm_engine* e, const double* lat, const double* lon, 
                             uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_locations: no worker table");
   if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_set_worker_locations: range");
   PM_CUDA(cudaSetDevice(e->device));
@@ -564,6 +590,7 @@ int pm_set_worker_locations(pm_engine* e, const double* lat, const double* lon, 
 int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_addr_rank: no worker table");
   if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_set_worker_addr_rank: range");
   PM_CUDA(cudaSetDevice(e->device));
@@ -576,6 +603,7 @@ int pm_set_worker_addr_rank(pm_engine* e, const uint32_t* rank, uint32_t first, 
 int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint32_t n) try {
   if (!e) return PM_E_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
   if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_flags: no worker table");
   if (n == 0) return PM_OK;
   if (!idx || !flags) return e->fail(PM_E_INVALID, "pm_set_flags: null");
@@ -589,6 +617,80 @@ int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint3
   e->workers_checked = false;
   e->matched = e->local_done = false;
   return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+// Resident tables with deltas (the management pass of a long-running host: only rows that changed travel).
+int pm_resize_workers(pm_engine* e, uint32_t n_workers) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
+  PM_CUDA(cudaSetDevice(e->device));
+  const size_t keep = e->have_workers ? e->n_workers : 0;
+  PM_CUDA(e->wa.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+  PM_CUDA(e->wb.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+  if (e->have_loc) {
+    PM_CUDA(e->lat.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+    PM_CUDA(e->lon.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+  }
+  if (e->have_rank) PM_CUDA(e->addr_rank.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+  if (n_workers > keep) {   // rows that were beyond the old table (or were cut off earlier) start empty
+    PM_CUDA(cudaMemsetAsync(e->wa.p + keep, 0, (size_t)(n_workers - keep) * 16, e->stream));
+    PM_CUDA(cudaMemsetAsync(e->wb.p + keep, 0, (size_t)(n_workers - keep) * 16, e->stream));
+    if (e->have_loc) {
+      PM_CUDA(cudaMemsetAsync(e->lat.p + keep, 0, (size_t)(n_workers - keep) * 8, e->stream));
+      PM_CUDA(cudaMemsetAsync(e->lon.p + keep, 0, (size_t)(n_workers - keep) * 8, e->stream));
+    }
+    if (e->have_rank) PM_CUDA(cudaMemsetAsync(e->addr_rank.p + keep, 0, (size_t)(n_workers - keep) * 4, e->stream));
+  }
+  e->n_workers = n_workers;
+  e->have_workers = true;
+  e->workers_checked = false;
+  e->matched = e->local_done = false;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+int pm_update_workers(pm_engine* e, const uint32_t* idx, const pm_worker_a* a, const pm_worker_b* b, const double* lat,
+                      const double* lon, uint32_t n) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_update_workers: no worker table");
+  if (n == 0) return PM_OK;
+  if (!idx || !a || !b || ((lat == nullptr) != (lon == nullptr))) return e->fail(PM_E_INVALID, "pm_update_workers: null");
+  ++e->table_version;
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->scratch_idx.ensure(n)); PM_CUDA(e->upd_a.ensure(n)); PM_CUDA(e->upd_b.ensure(n));
+  PM_CUDA(cudaMemcpyAsync(e->scratch_idx.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->upd_a.p, a, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaMemcpyAsync(e->upd_b.p, b, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  if (lat) {
+    if (!e->have_loc) {
+      PM_CUDA(e->lat.ensure(e->wa.n)); PM_CUDA(e->lon.ensure(e->wa.n));
+      PM_CUDA(cudaMemsetAsync(e->lat.p, 0, e->wa.n * 8, e->stream));
+      PM_CUDA(cudaMemsetAsync(e->lon.p, 0, e->wa.n * 8, e->stream));
+      e->have_loc = true;
+    }
+    PM_CUDA(e->upd_lat.ensure(n)); PM_CUDA(e->upd_lon.ensure(n));
+    PM_CUDA(cudaMemcpyAsync(e->upd_lat.p, lat, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaMemcpyAsync(e->upd_lon.p, lon, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  }
+  pm::pm_scatter_rows<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->wa.p, e->wb.p, lat ? e->lat.p : nullptr, lat ? e->lon.p : nullptr,
+                                                                 e->scratch_idx.p, e->upd_a.p, e->upd_b.p, e->upd_lat.p, e->upd_lon.p, n,
+                                                                 e->n_workers);
+  PM_LAUNCH_CHECK("pm_scatter_rows");
+  e->workers_checked = false;
+  e->matched = e->local_done = false;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+uint64_t pm_table_version(const pm_engine* e) { return e ? e->table_version : 0; }
+
+// A second engine on the same device with the same configuration and its own stream and tables.
+int pm_create_sibling(const pm_engine* e, pm_engine** out) try {
+  if (!e || !out) return PM_E_INVALID;
+  pm_cfg c = e->cfg;
+  c.stream = nullptr;
+  c.shard_first = c.shard_count = 0;
+  return pm_create(&c, out);
 } catch (...) { return pm_guard_rc(); }
 
 // ------------------------------------------------------------------ evaluation

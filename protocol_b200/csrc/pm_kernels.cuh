@@ -578,6 +578,19 @@ __global__ void pm_scatter_flags(uint4* wa, const uint32_t* idx, const uint32_t*
   if (i < n && idx[i] < n_workers) wa[idx[i]].w = flags[i];
 }
 
+// pm_update_workers: rows that changed since the last pass, scattered into the resident table
+__global__ void pm_scatter_rows(uint4* wa, uint4* wb, double* lat, double* lon, const uint32_t* __restrict__ idx,
+                                const uint4* __restrict__ a, const uint4* __restrict__ b, const double* __restrict__ la,
+                                const double* __restrict__ lo, uint32_t n, uint32_t n_workers) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t w = idx[i];
+  if (w >= n_workers) return;
+  wa[w] = a[i];
+  wb[w] = b[i];
+  if (lat) { lat[w] = la[i]; lon[w] = lo[i]; }
+}
+
 // Do all workers satisfy the fast-path operand limits (values < 2^31, gpu count < 2^16,
 // count * memory_mb < 2^31 without wrapping)?  Clears *ok otherwise.
 __global__ void pm_check_worker_ranges(const uint4* __restrict__ wa, const uint4* __restrict__ wb,

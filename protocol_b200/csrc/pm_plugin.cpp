@@ -82,6 +82,7 @@ struct NodeRec {
   double lat = 0, lon = 0;
   uint64_t sync_gen = 0;               // the discovery fetch that last touched the node (de-dup by id within a fetch)
   bool grouped = false;                // mirrors node_to_group.count(address): read by the table snapshot
+  bool dirty = false;                  // changed since the engine's resident copy of its row was written
 };
 
 struct Group {  // NodeGroup, mod.rs:63-69
@@ -178,6 +179,18 @@ struct pm_plugin {
   // (ip, port) -> number of Healthy nodes: replaces the per-node full scan of
   // count_healthy_nodes_with_same_endpoint (discovery/monitor.rs:218-234, Theta(N^2) per sync)
   std::unordered_map<std::string, uint32_t> healthy_at;
+  // The engine keeps the worker table between management passes (rows in table order: candidates are all Healthy,
+  // so their relative order equals the canonical status-sorted order of node_store.rs:195-206); a pass uploads only
+  // the rows touched since the previous one.  `resident_version` detects anybody else using the engine in between.
+  std::vector<uint32_t> dirty_list;
+  uint32_t resident_rows = 0;
+  uint64_t resident_version = ~0ull;
+  std::string resident_asks_sig;
+  uint32_t resident_npat = ~0u, resident_nmod = ~0u;
+  pm_engine* merge_engine = nullptr;   // solo-group merging works on its own small table: a sibling engine, created on demand
+  void touch(size_t i) {
+    if (!nodes[i].dirty) { nodes[i].dirty = true; dirty_list.push_back((uint32_t)i); }
+  }
   uint64_t sync_gen = 0;
   uint64_t sync_skipped = 0;   // discovery entries without id / ip, skipped (the reference logs them)
   // BTreeSet<String> rank of every node's address: addresses never change and nodes are only appended, so the ranks
@@ -200,6 +213,7 @@ struct pm_plugin {
     n.status = status;
     n.last_status_change_ms = now_ms;
     index_add(n);
+    touch(size_t(&n - nodes.data()));
     if (status == kDead || status == kLowBalance) {
       auto g = node_to_group.find(n.address);
       if (g != node_to_group.end()) {
@@ -241,12 +255,12 @@ struct pm_plugin {
   void map_node(const std::string& addr, const std::string& gid) {
     node_to_group[addr] = gid;
     auto it = node_index.find(addr);
-    if (it != node_index.end()) nodes[it->second].grouped = true;
+    if (it != node_index.end()) { nodes[it->second].grouped = true; touch(it->second); }
   }
   void unmap_node(const std::string& addr) {
     node_to_group.erase(addr);
     auto it = node_index.find(addr);
-    if (it != node_index.end()) nodes[it->second].grouped = false;
+    if (it != node_index.end()) { nodes[it->second].grouped = false; touch(it->second); }
   }
 
   void dissolve(const std::string& group_id) {  // mod.rs:1423-1487
@@ -288,6 +302,7 @@ int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugi
 void pm_plugin_destroy(pm_plugin* p) {
   if (!p) return;
   pm_interner_destroy(p->interner);
+  if (p->merge_engine) pm_destroy(p->merge_engine);
   delete p;
 }
 
@@ -384,6 +399,7 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) try {
   r->lat = d->lat;
   r->lon = d->lon;
   p->index_add(*r);
+  p->touch(size_t(r - p->nodes.data()));
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
 
@@ -467,6 +483,7 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
         node.has_loc = true;
         node.lat = d.node.lat;
         node.lon = d.node.lon;
+        p->touch(it->second);
       }
       if (existing.status == kDead && existing.last_status_change_ms >= 0 && d.last_updated_ms >= 0 &&
           existing.last_status_change_ms < d.last_updated_ms) {                                          // :364-389
@@ -510,6 +527,7 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
       node.grouped = p->node_to_group.count(addr) != 0;
       p->node_index.emplace(addr, p->nodes.size());
       p->nodes.push_back(std::move(node));
+      p->touch(p->nodes.size() - 1);
       if (n_new) ++*n_new;
     }
   }
@@ -983,25 +1001,68 @@ int pm_plugin_export_tables(pm_plugin* p, pm_worker_a* a, pm_worker_b* b, double
 } catch (...) { return pm_guard_rc(); }
 
 // try_form_new_groups (mod.rs:478-628): the evaluation and the allocation run on the GPU.
+//
+// The worker table stays RESIDENT on the engine between passes, rows in table (insertion) order — every candidate is
+// Healthy, so the candidates' relative order is the canonical order of the status-sorted node list
+// (node_store.rs:195-206) and the groups are the same — and a pass sends only the rows touched since the previous one
+// (status changes, new group members, new nodes): the reference re-reads and re-parses every node per pass.  Asks and
+// the model table travel only when the configurations or the interner changed.  Members of a group are put in
+// BTreeSet<String> order here at publication (the address strings are at hand), so no address ranks travel at all.
 int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) try {
   if (!p) return PM_E_INVALID;
   if (n_formed) *n_formed = 0;
   std::lock_guard<std::mutex> loop_lk(p->loop_mu);
-  // ---- phase 1 (tables locked): snapshot what the pass reads, like the reference's reads at loop start
-  uint32_t W = 0;
-  TableSnapshot snap;
+  // ---- phase 1 (tables locked): what changed since the previous pass
+  uint32_t W = 0, mode = PM_MODE_FIRST_FIT;
+  bool full = false, send_asks = false, send_bits = false;
+  std::vector<uint32_t> idx;
+  std::vector<pm_worker_a> ua;
+  std::vector<pm_worker_b> ub;
+  std::vector<double> ulat, ulon;
   std::vector<std::string> cfg_names;
   std::vector<pm_ask> asks;
   std::vector<pm_gpu_opt> opts;
   std::vector<uint32_t> bits_copy;
-  uint32_t npat = 0, nmod = 0, words = 1, mode = PM_MODE_FIRST_FIT;
+  uint32_t npat = 0, nmod = 0, words = 1;
   {
     std::lock_guard<std::shared_mutex> lk(p->mu);
     if (!p->engine) return p->fail(PM_E_NO_DEVICE, "no engine attached: group formation has no CPU path");
     if (!p->sealed) return p->fail(PM_E_STATE, "configurations not sealed");
+    W = (uint32_t)p->nodes.size();
+    full = pm_table_version(p->engine) != p->resident_version || p->resident_rows > W;
+    auto row_of = [&](uint32_t i, pm_worker_a* a, pm_worker_b* b, double* la, double* lo) {
+      const NodeRec& n = p->nodes[i];
+      *a = n.a;
+      *b = n.b;
+      uint32_t f = n.a.flags;
+      if (n.status == kHealthy) f |= PM_W_HEALTHY;                         // mod.rs:494
+      if (n.has_p2p) f |= PM_W_P2P;                                        // :495
+      if (n.grouped) f |= PM_W_ASSIGNED;                                   // :496 (get_node_group is Some)
+      if (n.has_loc) f |= PM_W_HAS_LOC;
+      a->flags = f;
+      *la = n.lat;
+      *lo = n.lon;
+    };
+    if (full) {
+      idx.resize(W); ua.resize(W); ub.resize(W); ulat.resize(W); ulon.resize(W);
+      for (uint32_t i = 0; i < W; ++i) {
+        idx[i] = i;
+        row_of(i, &ua[i], &ub[i], &ulat[i], &ulon[i]);
+        p->nodes[i].dirty = false;
+      }
+    } else {
+      const size_t nd = p->dirty_list.size();
+      idx.resize(nd); ua.resize(nd); ub.resize(nd); ulat.resize(nd); ulon.resize(nd);
+      for (size_t k = 0; k < nd; ++k) {
+        const uint32_t i = p->dirty_list[k];
+        idx[k] = i;
+        row_of(i, &ua[k], &ub[k], &ulat[k], &ulon[k]);
+        p->nodes[i].dirty = false;
+      }
+    }
+    p->dirty_list.clear();
     const auto configs = p->available_configurations();
-    build_table_snapshot(p, &snap);
-    W = (uint32_t)snap.wa.size();
+    std::string sig;
     for (const Config* c : configs) {
       pm_ask a = c->ask;
       a.opt_off = (uint32_t)opts.size();
@@ -1010,14 +1071,22 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) try {
       opts.insert(opts.end(), c->opts.begin(), c->opts.end());
       asks.push_back(a);
       cfg_names.push_back(c->name);
+      sig += c->name;
+      sig += '\x1f';
     }
+    send_asks = full || sig != p->resident_asks_sig;
+    p->resident_asks_sig = sig;
     const uint32_t* bits = nullptr;
     int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
     if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
-    bits_copy.assign(bits, bits + (size_t)std::max<uint32_t>(npat, 1) * words);
+    send_bits = full || npat != p->resident_npat || nmod != p->resident_nmod;   // rows and columns are only ever added
+    if (send_bits) bits_copy.assign(bits, bits + (size_t)std::max<uint32_t>(npat, 1) * words);
+    p->resident_npat = npat;
+    p->resident_nmod = nmod;
     // the pass needs the per-worker first feasible configuration only: evaluate and reduce on chip, skip the per-ask
     // statistics (same groups as the materialised pass, ~20 MB of DRAM traffic instead of 16 B per pair)
     mode = (p->policy.proximity_enabled ? PM_MODE_PROXIMITY : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS;
+    p->resident_version = ~0ull;   // not valid again until this pass has put its rows on the device
   }
   // ---- phase 2 (tables unlocked: heartbeats keep being served): the pass on the GPU
   auto chk = [&](int r, const char* what) {
@@ -1029,31 +1098,41 @@ int pm_plugin_try_form_new_groups(pm_plugin* p, uint32_t* n_formed) try {
     return r;
   };
   int rc;
-  if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
-  if ((rc = chk(pm_set_model_table(p->engine, bits_copy.data(), npat, nmod, words), "pm_set_model_table"))) return rc;
-  if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
-  if ((rc = chk(pm_upsert_workers(p->engine, snap.wa.data(), snap.wb.data(), 0, W), "pm_upsert_workers"))) return rc;
-  if ((rc = chk(pm_set_worker_locations(p->engine, snap.lat.data(), snap.lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
-  if ((rc = chk(pm_set_worker_addr_rank(p->engine, snap.arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
-  if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;   // staging vectors are read asynchronously
+  if (send_asks && (rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
+  if (send_bits && (rc = chk(pm_set_model_table(p->engine, bits_copy.data(), npat, nmod, words), "pm_set_model_table"))) return rc;
+  if (full) {
+    if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
+  } else if (W != p->resident_rows) {
+    if ((rc = chk(pm_resize_workers(p->engine, W), "pm_resize_workers"))) return rc;
+  }
+  if (!idx.empty()) {
+    if ((rc = chk(pm_update_workers(p->engine, idx.data(), ua.data(), ub.data(), ulat.data(), ulon.data(), (uint32_t)idx.size()), "pm_update_workers"))) return rc;
+    if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;   // staging vectors are read asynchronously
+  } else if (full) {   // an empty table still needs its location columns for the proximity mode
+    if ((rc = chk(pm_set_worker_locations(p->engine, nullptr, nullptr, 0, 0), "pm_set_worker_locations"))) return rc;
+  }
+  p->resident_rows = W;
+  const uint64_t version_after_upload = pm_table_version(p->engine);
   if ((rc = chk(pm_match(p->engine, mode), "pm_match"))) return rc;
   pm_result res{};
   if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
 
   // ---- phase 3 (tables locked): publish the groups (create_group_atomically, mod.rs:299-322, 568-581)
   std::lock_guard<std::shared_mutex> lk(p->mu);
+  p->resident_version = version_after_upload;
   uint32_t formed = 0;
   for (uint32_t g = 0; g < res.n_groups; ++g) {
     Group grp;
     grp.configuration_name = cfg_names[res.group_ask[g]];
     grp.created_at_ms = (int64_t)std::time(nullptr) * 1000;
-    bool stale = false;   // a member was removed from the table while the pass ran
+    bool stale = false;   // a member joined another group while the pass ran
     for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m) {
-      const std::string& addr = p->nodes[snap.row_node[res.group_members[m]]].address;   // nodes are never removed
+      const std::string& addr = p->nodes[res.group_members[m]].address;   // row == index in the node table; nodes are never removed
       if (p->node_to_group.count(addr)) stale = true;
       grp.nodes.push_back(addr);
     }
     if (stale) continue;
+    std::sort(grp.nodes.begin(), grp.nodes.end());                         // NodeGroup.nodes: BTreeSet<String> (mod.rs:63-69)
     char idbuf[32];
     std::snprintf(idbuf, sizeof idbuf, "%llx", (unsigned long long)p->next_group_id++);  // format!("{:x}", ..)
     grp.id = idbuf;
@@ -1123,23 +1202,30 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
   uint32_t npat = 0, nmod = 0, words = 1;
   int rc = pm_interner_table(p->interner, &bits, &npat, &nmod, &words);
   if (rc != PM_OK) return p->fail(rc, "pm_interner_table");
+  // merging works on its own small table (the nodes of solo groups only): a sibling engine, so that the formation
+  // pass's resident worker table stays where it is
+  if (!p->merge_engine) {
+    rc = pm_create_sibling(p->engine, &p->merge_engine);
+    if (rc != PM_OK) return p->fail(rc, "pm_create_sibling");
+  }
+  pm_engine* const eng = p->merge_engine;
   auto chk = [&](int r, const char* what) {
     if (r != PM_OK) {
-      const char* m = pm_last_error(p->engine);
+      const char* m = pm_last_error(eng);
       p->err = std::string(what) + ": " + (m ? m : "");
     }
     return r;
   };
-  if ((rc = chk(pm_set_asks(p->engine, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
-  if ((rc = chk(pm_set_model_table(p->engine, bits, npat, nmod, words), "pm_set_model_table"))) return rc;
-  if ((rc = chk(pm_set_worker_count(p->engine, W), "pm_set_worker_count"))) return rc;
-  if ((rc = chk(pm_upsert_workers(p->engine, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
-  if ((rc = chk(pm_set_worker_locations(p->engine, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
-  if ((rc = chk(pm_set_worker_addr_rank(p->engine, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
-  if ((rc = chk(pm_stream_sync(p->engine), "pm_stream_sync"))) return rc;
-  if ((rc = chk(pm_match(p->engine, (prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS), "pm_match"))) return rc;
+  if ((rc = chk(pm_set_asks(eng, asks.data(), (uint32_t)asks.size(), opts.data(), (uint32_t)opts.size()), "pm_set_asks"))) return rc;
+  if ((rc = chk(pm_set_model_table(eng, bits, npat, nmod, words), "pm_set_model_table"))) return rc;
+  if ((rc = chk(pm_set_worker_count(eng, W), "pm_set_worker_count"))) return rc;
+  if ((rc = chk(pm_upsert_workers(eng, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
+  if ((rc = chk(pm_set_worker_locations(eng, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
+  if ((rc = chk(pm_set_worker_addr_rank(eng, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
+  if ((rc = chk(pm_stream_sync(eng), "pm_stream_sync"))) return rc;
+  if ((rc = chk(pm_match(eng, (prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS), "pm_match"))) return rc;
   pm_result res{};
-  if ((rc = chk(pm_fetch_result(p->engine, &res), "pm_fetch_result"))) return rc;
+  if ((rc = chk(pm_fetch_result(eng, &res), "pm_fetch_result"))) return rc;
   for (uint32_t g = 0; g < res.n_groups; ++g) {
     std::vector<std::string> ids;
     for (uint32_t m = res.group_off[g]; m < res.group_off[g + 1]; ++m) ids.push_back(solo_ids[res.group_members[m]]);

@@ -177,6 +177,24 @@ class Engine:
         self._check(self._lib.pm_set_worker_addr_rank(self._h, _ptr(rank), 0, len(rank)))
         self.sync()
 
+    def resize_workers(self, n: int):
+        self._check(self._lib.pm_resize_workers(self._h, n))
+        self.n_workers = n
+
+    def update_workers(self, idx, a, b, lat=None, lon=None):
+        """Scatter changed rows into the resident table (pm_update_workers)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        a = np.ascontiguousarray(a, dtype=abi.WORKER_A)
+        b = np.ascontiguousarray(b, dtype=abi.WORKER_B)
+        la = np.ascontiguousarray(lat, dtype=np.float64) if lat is not None else None
+        lo = np.ascontiguousarray(lon, dtype=np.float64) if lon is not None else None
+        self._check(self._lib.pm_update_workers(self._h, _ptr(idx), _ptr(a), _ptr(b), _ptr(la) if la is not None else None,
+                                                _ptr(lo) if lo is not None else None, len(idx)))
+        self.sync()
+
+    def table_version(self) -> int:
+        return int(self._lib.pm_table_version(self._h))
+
     def set_flags(self, idx: np.ndarray, flags: np.ndarray):
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         flags = np.ascontiguousarray(flags, dtype=np.uint32)

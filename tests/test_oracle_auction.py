@@ -67,3 +67,55 @@ def test_infeasible_asks_withdraw():
     bits = np.array([0xFFFFFFFF], dtype=np.uint32)
     out, _, rounds = orc.soa_auction(a, b, asks, opts, bits, 1, cap)
     assert (out == NONE).all() and rounds == 1
+
+
+def lsa_optimum(price, cap, feasible, scale=1):
+    """Minimum of sum over asks of (price * scale if assigned to a feasible worker within the cap, else the outside
+    option (cap + 1) * scale) — scipy's Hungarian solver on the masked matrix: an anchor that is NOT this repo's code."""
+    from scipy.optimize import linear_sum_assignment
+
+    T, W = feasible.shape
+    BIG = 1 << 40
+    C = np.full((T, W + T), BIG, dtype=np.int64)
+    ok = feasible & (price[None, :] <= cap[:, None])
+    C[:, :W][ok] = np.broadcast_to(price[None, :].astype(np.int64) * scale, (T, W))[ok]
+    C[np.arange(T), W + np.arange(T)] = (cap.astype(np.int64) + 1) * scale        # ask t stays out
+    r, c = linear_sum_assignment(C)
+    return int(C[r, c].sum())
+
+
+def assignment_cost(out, price, cap, scale=1):
+    return sum((int(price[out[t]]) if out[t] != NONE else int(cap[t]) + 1) * scale for t in range(len(cap)))
+
+
+@pytest.mark.parametrize("T,W,seed", [(60, 200, 1), (300, 2000, 2), (500, 300, 3)])
+def test_auction_total_cost_against_scipy_linear_sum_assignment(T, W, seed):
+    """External anchor: with cost_scale = 1, eps = 1 the auction's total cost is within T * eps of
+    the optimum of the feasibility-masked, cap-filtered assignment problem; with cost_scale = T + 1 it IS the optimum."""
+    from protocol_b200 import synth
+
+    w = synth.make_workers(W, seed=synth.SEED_WORKERS + seed, price="loguniform")
+    a = synth.make_asks(T, "mixed", seed=synth.SEED_ASKS + seed)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    cap = np.exp(np.log(20) + synth._unit(synth.SEED_EXT + seed, T, 3) * np.log(60)).astype(np.uint32)
+    ev = orc.soa_eval_matrix(w.a, w.b, a.asks, a.opts, bits, words, 0, T, 0, W, want_cost=True)
+    feasible = ev["cost"] != abi.PM_COST_INF
+    price = w.b["ext_ask_price"].astype(np.int64)
+    opt = lsa_optimum(price, cap, feasible)
+    out, _, rounds = orc.soa_auction(w.a, w.b, a.asks, a.opts, bits, words, cap, cost_scale=1)
+    for t in np.flatnonzero(out != NONE):
+        assert feasible[t, out[t]] and price[out[t]] <= cap[t]
+    used = out[out != NONE]
+    assert len(set(used.tolist())) == len(used)
+    got = assignment_cost(out, price, cap)
+    assert opt <= got <= opt + T, (opt, got)
+    out2, _, _ = orc.soa_auction(w.a, w.b, a.asks, a.opts, bits, words, cap, cost_scale=T + 1)
+    assert assignment_cost(out2, price, cap) == opt
+    # eps-scaling (phases 64, 16, 4, 1; assignment cleared, prices kept) is NOT covered by that bound here: prices only
+    # rise, a coarse phase overshoots them, and with price caps (an outside option per ask) the asks that were outbid at
+    # inflated prices withdraw for good in the eps = 1 phase.  The result stays feasible but can be far from the optimum
+    # (54 % above it on the first instance) — which is why eps_start = 1 stays the engine's default (VERDICT r1 item 8c).
+    out3, _, rounds3 = orc.soa_auction(w.a, w.b, a.asks, a.opts, bits, words, cap, cost_scale=1, eps_start=64, eps_div=4)
+    for t in np.flatnonzero(out3 != NONE):
+        assert feasible[t, out3[t]] and price[out3[t]] <= cap[t]
+    assert assignment_cost(out3, price, cap) >= opt
