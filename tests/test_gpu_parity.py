@@ -624,3 +624,39 @@ def test_cfg4_shape_one_million_asks_x_250k_workers():
     for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_count"):
         assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
     eng.close()
+
+
+def test_extension_auction_against_scipy_at_2k_x_2k():
+    """An anchor that is not this repo's code: at 2000 asks x 2000 workers the engine's auction (default
+    parameters: cost_scale 1, eps 1) must land within T * eps of scipy.optimize.linear_sum_assignment's optimum on the
+    feasibility-masked, cap-filtered cost matrix (unassigned asks pay their outside option cap + 1)."""
+    from scipy.optimize import linear_sum_assignment
+
+    T = W = 2000
+    w = synth.make_workers(W, seed=synth.SEED_WORKERS + 31, price="loguniform")
+    a = synth.make_asks(T, "mixed", seed=synth.SEED_ASKS + 31)
+    bits, npat, nmod, words = synth.intern_tables(w, a)
+    t = dict(asks=a.asks, opts=a.opts, wa=w.a, wb=w.b, bits=bits, n_patterns=npat, n_models=nmod, words=words)
+    cap = np.exp(np.log(20) + synth._unit(synth.SEED_EXT + 31, T, 3) * np.log(60)).astype(np.uint32)
+    eng = Engine()
+    load_engine(eng, t)
+    eng.set_price_caps(cap)
+    eng.match(abi.PM_MODE_AUCTION)
+    res = eng.fetch()
+    eng.close()
+    got = np.full(T, abi.PM_NONE, dtype=np.uint32)
+    for ask, members in res.groups():
+        got[ask] = members[0]
+    price = w.b["ext_ask_price"].astype(np.int64)
+    feasible = orc.soa_eval_matrix(w.a, w.b, a.asks, a.opts, bits, words, 0, T, 0, W, threads=8, want_cost=True)["cost"] != abi.PM_COST_INF
+    ok = feasible & (price[None, :] <= cap[:, None])
+    BIG = 1 << 40
+    C = np.full((T, W + T), BIG, dtype=np.int64)
+    C[:, :W][ok] = np.broadcast_to(price[None, :], (T, W))[ok]
+    C[np.arange(T), W + np.arange(T)] = cap.astype(np.int64) + 1
+    r, c = linear_sum_assignment(C)
+    opt = int(C[r, c].sum())
+    sold = np.flatnonzero(got != abi.PM_NONE)
+    assert ok[sold, got[sold]].all() and len(np.unique(got[sold])) == len(sold)
+    total = int(price[got[sold]].sum() + (cap.astype(np.int64) + 1)[got == abi.PM_NONE].sum())
+    assert opt <= total <= opt + T, (opt, total)

@@ -135,6 +135,22 @@ int main(int argc, char** argv) {
     CHECK(pm_plugin_try_form_new_groups(plugin, &n_formed));
     dt = now_s() - t0;
     std::printf("try_form_new_groups (steady state: everybody grouped) groups_formed=%u  %.3f s\n", n_formed, dt);
+    // churn: 1000 nodes die (their groups dissolve) and come back healthy; the pass re-forms what it can from row deltas
+    for (uint32_t k = 0; k < 1000 && k * 997u < N; ++k) CHECK(pm_plugin_set_node_status(plugin, addrs[k * 997u].c_str(), 4));
+    for (uint32_t k = 0; k < 1000 && k * 997u < N; ++k) CHECK(pm_plugin_set_node_status(plugin, addrs[k * 997u].c_str(), 2));
+    t0 = now_s();
+    CHECK(pm_plugin_try_form_new_groups(plugin, &n_formed));
+    dt = now_s() - t0;
+    std::printf("try_form_new_groups (after 1000 nodes died and came back) groups_formed=%u  %.3f s\n", n_formed, dt);
+    t0 = now_s();
+    uint32_t n_merged = 0;
+    CHECK(pm_plugin_try_merge_solo_groups(plugin, &n_merged));
+    dt = now_s() - t0;
+    std::printf("try_merge_solo_groups groups_merged=%u  %.3f s\n", n_merged, dt);
+    t0 = now_s();
+    CHECK(pm_plugin_try_form_new_groups(plugin, &n_formed));
+    dt = now_s() - t0;
+    std::printf("try_form_new_groups (steady state again) groups_formed=%u  %.3f s\n", n_formed, dt);
   }
 
   if (!engine && !no_configs) {   // no GPU here: groups come in the way they do at start-up, from the stored state
