@@ -180,7 +180,7 @@ struct pm_engine {
   DevBuf<uint32_t> prox_list, prox_xs, members_raw;
   DevBuf<double> prox_dist, prox_lat_key;
   DevBuf<uint32_t> prox_lat_ord, prox_rank_of;
-  DevBuf<double> pg_part_d;
+  DevBuf<double> pg_part_d, pg_clat, pg_clon, pg_ccos;
   DevBuf<uint32_t> pg_part_i, pg_cta_cnt, pg_ctl;
   int coop_blocks = -1;   // co-resident CTAs of pm_proximity_grid on this device (0: cooperative launch unavailable)
   bool any_max_zero = false;
@@ -410,6 +410,7 @@ void pm_destroy(pm_engine* e) {
   e->prox_list.release(); e->prox_xs.release(); e->members_raw.release(); e->prox_dist.release();
   e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
   e->pg_part_d.release(); e->pg_part_i.release(); e->pg_cta_cnt.release(); e->pg_ctl.release();
+  e->pg_clat.release(); e->pg_clon.release(); e->pg_ccos.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
@@ -951,10 +952,12 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
       const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)e->coop_blocks, blocks_for(std::max<uint32_t>(W, 1), pm::kPgThreads)));
       PM_CUDA(e->pg_part_d.ensure((size_t)2 * grid * pm::kPgTopK)); PM_CUDA(e->pg_part_i.ensure((size_t)2 * grid * pm::kPgTopK));
       PM_CUDA(e->pg_cta_cnt.ensure((size_t)2 * grid)); PM_CUDA(e->pg_ctl.ensure(4));
+      PM_CUDA(e->pg_clat.ensure(W)); PM_CUDA(e->pg_clon.ensure(W)); PM_CUDA(e->pg_ccos.ensure(W));
       PM_CUDA(cudaMemsetAsync(e->pg_ctl.p, 0, 16, e->stream));
       pm::GridProxParams gp;
       gp.p = pp;
       gp.part_d = e->pg_part_d.p; gp.part_i = e->pg_part_i.p; gp.cta_cnt = e->pg_cta_cnt.p; gp.gctl = e->pg_ctl.p;
+      gp.clat = e->pg_clat.p; gp.clon = e->pg_clon.p; gp.ccos = e->pg_ccos.p;
       gp.n_workers = W;
       void* args[] = {&gp};
       PM_CUDA(cudaLaunchCooperativeKernel((const void*)pm::pm_proximity_grid, dim3(grid), dim3(pm::kPgThreads), args, 0, e->stream));

@@ -42,6 +42,9 @@ constexpr int kPgWarps = kPgThreads / 32;
 constexpr uint32_t kPgTopK = 16;        // neighbours selected per grid barrier (larger groups take several)
 constexpr uint32_t kPgXsSmem = 128;     // hand-downs up to this long are walked and sorted in shared memory
 constexpr double kPgMax = 1.7976931348623157e308;   // f64::MAX: distance of a candidate without location
+constexpr uint32_t kPgBatchK = 4;       // seed-parallel phase: neighbours listed per seed (group size - 1 plus spares)
+constexpr uint32_t kPgHash = 4096;      // slots of the per-CTA "taken in this batch" set (<= 296 * 4 keys)
+constexpr uint32_t kPgMaxSeeds = 304;   // >= co-resident CTAs of a B200 (148 SMs x 2)
 
 struct GridProxParams {
   ProxParams p;
@@ -49,6 +52,9 @@ struct GridProxParams {
   uint32_t* part_i;      // [2][grid][kPgTopK]
   uint32_t* cta_cnt;     // [2 * grid] per-CTA counts for the ordered compactions
   uint32_t* gctl;        // [4] [0] leftover count
+  double* clat;          // [W] candidate-ordered copies of latitude / longitude / cos(latitude in radians), written with
+  double* clon;          //     the list: the seed-parallel phase streams them instead of gathering through the index
+  double* ccos;
   uint32_t n_workers;
 };
 
@@ -60,7 +66,41 @@ struct PgShared {
   uint32_t red_i[kPgWarps];
   uint32_t picks[kPgThreads];     // positions chosen in the current pass (<= kPgTopK, or a chunk of list-order picks)
   uint32_t xs[kPgXsSmem];
+  uint32_t seeds[kPgMaxSeeds];                 // seed-parallel phase: list positions of the batch's seeds
+  uint32_t grp[kPgMaxSeeds * kPgBatchK];       // resolved groups: [seed, up to 3 neighbours] positions
+  uint32_t taken[kPgHash];                     // positions taken by earlier groups of the batch (open addressing)
 };
+
+__device__ __forceinline__ bool pg_set_has(const uint32_t* tab, uint32_t key) {
+  uint32_t h = (key * 2654435761u) >> 20;
+  for (;;) {
+    const uint32_t v = tab[h];
+    if (v == key) return true;
+    if (v == kNone) return false;
+    h = (h + 1u) & (kPgHash - 1u);
+  }
+}
+__device__ __forceinline__ void pg_set_put(uint32_t* tab, uint32_t key) {
+  uint32_t h = (key * 2654435761u) >> 20;
+  for (;;) {
+    const uint32_t old = atomicCAS(&tab[h], kNone, key);
+    if (old == kNone || old == key) return;
+    h = (h + 1u) & (kPgHash - 1u);
+  }
+}
+
+// calculate_distance (mod.rs:218-231) with the two cosines already taken: same operations in the same order as
+// haversine_km, cos(lat1_rad) and cos(lat2_rad) are the cached values of exactly those expressions.
+__device__ __forceinline__ double haversine_km_cached(double lat1, double lon1, double cos1, double lat2, double lon2, double cos2) {
+  const double kRadsPerDeg = 3.14159265358979323846264338327950288 / 180.0;
+  const double delta_lat = __dmul_rn(__dsub_rn(lat2, lat1), kRadsPerDeg);
+  const double delta_lon = __dmul_rn(__dsub_rn(lon2, lon1), kRadsPerDeg);
+  const double s1 = sin(__dmul_rn(delta_lat, 0.5));
+  const double s2 = sin(__dmul_rn(delta_lon, 0.5));
+  const double a = __dadd_rn(__dmul_rn(s1, s1), __dmul_rn(__dmul_rn(cos1, cos2), __dmul_rn(s2, s2)));
+  const double c = __dmul_rn(2.0, atan2(sqrt(a), sqrt(__dsub_rn(1.0, a))));
+  return __dmul_rn(6371.0, c);
+}
 
 __device__ __forceinline__ uint32_t pg_ld(const uint32_t* p) { return __ldcg(p); }
 
@@ -178,6 +218,19 @@ __device__ __forceinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* 
   *total = pg_block_sum(sh, t);
 }
 
+// one list entry and its candidate-ordered coordinate copies
+__device__ __forceinline__ void pg_put_entry(const GridProxParams& gp, uint32_t pos, uint32_t w, bool coords) {
+  const ProxParams& p = gp.p;
+  const bool loc = (p.ev.wa[w].w & PM_W_HAS_LOC) != 0u;
+  p.list[pos] = w | (loc ? kLocBit : 0u);
+  if (coords && loc) {
+    const double la = p.lat[w];
+    gp.clat[pos] = la;
+    gp.clon[pos] = p.lon[w];
+    gp.ccos[pos] = cos(__dmul_rn(la, 3.14159265358979323846264338327950288 / 180.0));
+  }
+}
+
 __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams gp) {
   __shared__ PgShared sh;
   cg::grid_group grid = cg::this_grid();
@@ -206,6 +259,8 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
     const uint32_t bl = pg_ld(p.base_len + c), xc = pg_ld(p.xcount + c);
     const uint32_t n = bl + xc;
     const uint32_t* base = p.order + p.seg_start[c];
+    // groups of 2..4 (1..3 neighbours) go through the seed-parallel phase first
+    const bool batchable = mx >= 2u && mx - 1u < kPgBatchK && ncta >= 2u;
 
     // ---- the configuration's candidate list in canonical order, located candidates tagged
     if (xc <= kPgXsSmem) {
@@ -232,11 +287,11 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
       }
       for (uint32_t i = gtid; i < bl; i += nthr) {
         const uint32_t w = base[i];
-        p.list[i + lower_bound_u32(sh.xs, xc, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+        pg_put_entry(gp, i + lower_bound_u32(sh.xs, xc, w), w, batchable);
       }
       for (uint32_t j = gtid; j < xc; j += nthr) {
         const uint32_t w = sh.xs[j];
-        p.list[j + lower_bound_u32(base, bl, w)] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+        pg_put_entry(gp, j + lower_bound_u32(base, bl, w), w, batchable);
       }
     } else {
       // long hand-down: the list is {w : cur[w] == c} in index order — an ordered compaction over the whole table
@@ -255,7 +310,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
         const bool f = w < w_hi && pg_ld(p.cur + w) == c;
         uint32_t tile = 0;
         const uint32_t r = pg_block_rank(sh, f, &tile);
-        if (f) p.list[off + r] = w | ((p.ev.wa[w].w & PM_W_HAS_LOC) ? kLocBit : 0u);
+        if (f) pg_put_entry(gp, off + r, w, batchable);
         off += tile;
       }
     }
@@ -313,6 +368,121 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
 
     // ---- the group loop of mod.rs:507-609 for this configuration (max_group_size >= 2)
     uint32_t remaining = n, ploc = 0, pany = 0;
+
+    // Seed-parallel phase.  The next B seeds are the first B live located candidates (canonical order).  CTA j lists,
+    // for seed j, its kPgBatchK nearest live candidates as of the START of the batch — over ALL candidates, so a batch is
+    // one pass of distance work per CTA and one grid barrier for up to `grid` groups.  Every CTA then replays the
+    // sequential loop over the batch: a seed already taken by an earlier group of the batch is no seed any more; a
+    // group's members are the first k entries of its list not taken earlier in the batch — exactly the k nearest of what
+    // is left, because the list is the head of the order "by (distance, position)" over a superset.  A list that runs
+    // out of spare entries ends the batch there (the first group of a batch can never run out).  Full-size groups only:
+    // the last few of a configuration, larger groups and unlocated seeds go through the per-group loop below.
+    if (batchable) {
+      const uint32_t k = mx - 1u;
+      for (;;) {
+        const uint32_t room = p.group_cap > g ? p.group_cap - g : 0u;
+        uint32_t B = min(min(ncta, (uint32_t)kPgMaxSeeds), min(remaining / mx, room));
+        if (B < 2u || ploc >= n) break;
+        // the batch's seeds: first B live located positions from ploc (same scan on every CTA)
+        uint32_t nb = 0, pos = ploc;
+        while (nb < B && pos < n) {
+          const uint32_t i = pos + tid;
+          const bool f = i < n && (pg_ld(p.list + i) & (kTakenBit | kLocBit)) == kLocBit;
+          uint32_t tile = 0;
+          const uint32_t r = pg_block_rank(sh, f, &tile);
+          if (f && nb + r < B) sh.seeds[nb + r] = i;
+          nb = min(B, nb + tile);
+          pos += kPgThreads;
+        }
+        __syncthreads();
+        if (nb == 0u) { ploc = n; break; }   // nobody located is left: the per-group loop takes the rest in list order
+        parity ^= 1u;
+        if (cta < nb) {
+          const uint32_t sp = sh.seeds[cta];
+          const double slat = __ldcg(gp.clat + sp), slon = __ldcg(gp.clon + sp), scos = __ldcg(gp.ccos + sp);
+          double bd[kPgBatchK];
+          uint32_t bi[kPgBatchK];
+#pragma unroll
+          for (uint32_t q = 0; q < kPgBatchK; ++q) { bd[q] = kPgMax; bi[q] = kNone; }
+          for (uint32_t i = tid; i < n; i += kPgThreads) {
+            const uint32_t e = pg_ld(p.list + i);
+            if ((e & kTakenBit) || i == sp) continue;
+            const double d = (e & kLocBit) ? haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + i), __ldcg(gp.clon + i), __ldcg(gp.ccos + i))
+                                           : kPgMax;
+            // i only grows in this thread: an equal distance never displaces an entry already held
+            if (bi[kPgBatchK - 1] == kNone || d < bd[kPgBatchK - 1]) {
+              bd[kPgBatchK - 1] = d;
+              bi[kPgBatchK - 1] = i;
+#pragma unroll
+              for (int q = (int)kPgBatchK - 1; q > 0; --q) {
+                const bool up = bi[q - 1] == kNone || bd[q] < bd[q - 1];
+                if (up) {
+                  const double td = bd[q]; bd[q] = bd[q - 1]; bd[q - 1] = td;
+                  const uint32_t ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
+                }
+              }
+            }
+          }
+          uint32_t* my_i = gp.part_i + ((size_t)parity * ncta + cta) * kPgTopK;
+          for (uint32_t r = 0; r < kPgBatchK; ++r) {   // merge the per-thread lists: the winner pops its head
+            double wd;
+            const uint32_t wi = pg_block_argmin(sh, bd[0], bi[0], &wd);
+            if (wi != kNone && bi[0] == wi) {
+#pragma unroll
+              for (uint32_t q = 0; q + 1 < kPgBatchK; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
+              bd[kPgBatchK - 1] = kPgMax;
+              bi[kPgBatchK - 1] = kNone;
+            }
+            if (tid == 0) my_i[r] = wi;
+          }
+        }
+        __threadfence();
+        grid.sync();
+        // replay of the sequential loop over the batch, identically on every CTA (warp 0; the set is per CTA)
+        for (uint32_t h = tid; h < kPgHash; h += kPgThreads) sh.taken[h] = kNone;
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t formed = 0, next = nb;
+          const uint32_t* all_i = gp.part_i + (size_t)parity * ncta * kPgTopK;
+          for (uint32_t j = 0; j < nb; ++j) {
+            const uint32_t sp = sh.seeds[j];
+            if (pg_set_has(sh.taken, sp)) continue;                        // became a member of an earlier group
+            const uint32_t cand = lane < kPgBatchK ? __ldcg(all_i + (size_t)j * kPgTopK + lane) : kNone;
+            const bool free_ = cand != kNone && !pg_set_has(sh.taken, cand);
+            const uint32_t fb = __ballot_sync(0xffffffffu, free_);
+            if ((uint32_t)__popc(fb) < k) { next = j; break; }             // out of spares: this seed opens the next batch
+            const uint32_t rank = (uint32_t)__popc(fb & ((1u << lane) - 1u));
+            if (free_ && rank < k) { sh.grp[formed * kPgBatchK + 1u + rank] = cand; pg_set_put(sh.taken, cand); }
+            if (lane == 0) { sh.grp[formed * kPgBatchK] = sp; pg_set_put(sh.taken, sp); }
+            __syncwarp();
+            ++formed;
+          }
+          if (lane == 0) { sh.u[4] = formed; sh.u[5] = next < nb ? sh.seeds[next] : sh.seeds[nb - 1u] + 1u; }
+        }
+        __syncthreads();
+        const uint32_t formed = sh.u[4];
+        ploc = sh.u[5];
+        // marks (after the barrier, same bits from every CTA) and, on the lead CTA, the group tables
+        for (uint32_t t = tid; t < formed * mx; t += kPgThreads) {
+          const uint32_t gi = t / mx, m = t % mx;
+          const uint32_t q = sh.grp[gi * kPgBatchK + m];
+          atomicOr(p.list + q, kTakenBit);
+          if (lead) {
+            const uint32_t w = pg_ld(p.list + q) & kIdxMask;
+            p.members[mpos + t] = w;
+            p.worker_group[w] = g + gi;
+            p.worker_ask[w] = c;
+            if (m == 0u) { p.group_ask[g + gi] = c; p.group_off[g + gi] = mpos + gi * mx; }
+          }
+        }
+        __syncthreads();
+        g += formed;
+        mpos += formed * mx;
+        remaining -= formed * mx;
+        if (formed == 0u) break;
+      }
+    }
+
     for (;;) {
       if (remaining < mn) break;                                           // :507 / :517
       uint32_t seed_pos = n;

@@ -40,8 +40,9 @@ def test_resident_pass_equals_full_upload_pass(proximity):
     e1, e2 = Engine(), Engine()
     a = NodeGroupsPlugin(cfgs, engine=e1, proximity_enabled=proximity)
     b = NodeGroupsPlugin(cfgs, engine=e2, proximity_enabled=proximity)
+    task = Task(allowed_topologies=["pair", "flex", "h100-trio"])   # one task (one id) known to both plugins
     for p in (a, b):
-        p.add_task(Task(allowed_topologies=["pair", "flex", "h100-trio"]))
+        p.add_task(task)
     rng = np.random.default_rng(17)
     n = 0
     for step in range(40):
