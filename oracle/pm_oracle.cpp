@@ -374,6 +374,10 @@ double calculate_distance(const Location& loc1, const Location& loc2) {
   double s1 = std::sin(delta_lat / 2.0);
   double s2 = std::sin(delta_lon / 2.0);
   double a = s1 * s1 + std::cos(lat1_rad) * std::cos(lat2_rad) * (s2 * s2);
+  // determinisation rule 7: for (near-)antipodal points rounding can push a above 1, sqrt(1 - a) is NaN, and the
+  // reference's stable sort with partial_cmp(..).unwrap_or(Equal) is then no total order (its result depends on the
+  // sort's internal comparison sequence).  a is clamped to 1 — the mathematically exact value — here and on the device.
+  if (a > 1.0) a = 1.0;
   double c = 2.0 * std::atan2(std::sqrt(a), std::sqrt(1.0 - a));
   return EARTH_RADIUS_KM * c;
 }

@@ -75,6 +75,16 @@ struct __align__(16) DevOptF {
   uint32_t pattern_row;
   uint32_t pad;
 };
+// One ask as the fast build kernel reads it (48 B = three 128-bit shared-memory loads at an address that depends on
+// the row number only, so the next row's operands are fetched while the current row is evaluated): the first OR-option
+// inline, the scalar thresholds, and where the remaining options are.  `wp` is the option's pattern row until
+// pm_bind_rows replaces it, when every acceptance row is a single word, by the word itself.
+struct __align__(16) FastRow {
+  uint32_t m, v, mem_lo, mem_hi;
+  uint32_t tot_lo, tot_hi, wp, n_opts;
+  uint32_t cpu_cores, ram_mb, storage_gb, opt_off;
+};
+
 // key = flags bits 3..12 (PM_W_HAS_*) in bits 0..9, candidate 10, never 11, total-memory-skipped 12, gpu count 13..28
 constexpr uint32_t kKeyCountShift = 13;
 constexpr uint32_t kKeyCandBit = 1u << 10, kKeyNeverBit = 1u << 11, kKeyTotInvalidBit = 1u << 12;

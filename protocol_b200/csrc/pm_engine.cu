@@ -156,6 +156,8 @@ struct pm_engine {
   DevBuf<pm::DevAsk> asks;
   DevBuf<pm::DevOpt> opts;
   DevBuf<pm::DevOptF> opts_fast;
+  DevBuf<pm::FastRow> frows;
+  bool rows_bound = false;     // FastRow.wp matches the current model table (pm_bind_rows)
   DevBuf<pm_ask> raw_asks;
   DevBuf<pm_gpu_opt> raw_opts;
   DevBuf<uint32_t> ask_counts, ask_newoff;
@@ -311,6 +313,7 @@ pm::EvalParams eval_params(pm_engine* e) {
   p.asks = e->asks.p;
   p.opts = e->opts.p;
   p.opts_fast = e->opts_fast.p;
+  p.frows = e->frows.p;
   p.bits = e->bits.p;
   p.words = e->words;
   p.n_workers = e->n_workers;
@@ -398,7 +401,7 @@ void pm_destroy(pm_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->wa.release(); e->wb.release(); e->lat.release(); e->lon.release(); e->addr_rank.release();
-  e->asks.release(); e->opts.release(); e->opts_fast.release();
+  e->asks.release(); e->opts.release(); e->opts_fast.release(); e->frows.release();
   e->raw_asks.release(); e->raw_opts.release(); e->ask_counts.release(); e->ask_newoff.release(); e->amin.release(); e->amax.release(); e->bits.release();
   e->scratch_idx.release(); e->scratch_flags.release();
   e->upd_a.release(); e->upd_b.release(); e->upd_lat.release(); e->upd_lon.release();
@@ -454,7 +457,8 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   for (uint32_t i = 0; i < n_asks; ++i) opt_rows += std::max<uint32_t>(asks[i].n_opts, 1u);   // an ask without options gets a neutral row
   if (opt_rows >= (1ull << 31)) return e->fail(PM_E_INVALID, "pm_set_asks: too many option rows");
   const size_t opt_cap = std::max<size_t>(n_opts, (size_t)opt_rows);
-  PM_CUDA(e->opts.ensure(opt_cap)); PM_CUDA(e->opts_fast.ensure(opt_cap));
+  PM_CUDA(e->opts.ensure(opt_cap)); PM_CUDA(e->opts_fast.ensure(opt_cap)); PM_CUDA(e->frows.ensure(n_asks));
+  e->rows_bound = false;
   if (n_asks) PM_CUDA(cudaMemcpyAsync(e->raw_asks.p, asks, (size_t)n_asks * sizeof(pm_ask), cudaMemcpyHostToDevice, e->stream));
   if (n_opts) PM_CUDA(cudaMemcpyAsync(e->raw_opts.p, opts, (size_t)n_opts * sizeof(pm_gpu_opt), cudaMemcpyHostToDevice, e->stream));
   PM_CUDA(cudaMemsetAsync(e->counters.p + 12, 0, 8, e->stream));
@@ -469,7 +473,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   if (n_asks) {
     pm::pm_ask_convert<<<blocks_for(n_asks, 256), 256, 0, e->stream>>>(e->raw_asks.p, e->raw_opts.p, n_asks, e->ask_newoff.p, e->asks.p,
                                                                         e->opts.p, e->opts_fast.p, e->amin.p, e->amax.p,
-                                                                        e->counters.p + 12, e->counters.p + 13);
+                                                                        e->counters.p + 12, e->counters.p + 13, e->frows.p);
     PM_LAUNCH_CHECK("pm_ask_convert");
   }
   PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 20, e->counters.p + 12, 8, cudaMemcpyDeviceToHost, e->stream));
@@ -528,6 +532,7 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
   e->n_models = n_models;
   e->words = words;
   e->have_bits = true;
+  e->rows_bound = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -715,6 +720,17 @@ static int decide_fast(pm_engine* e, bool* fast) {
   return PM_OK;
 }
 
+// FastRow.wp follows the model table: (re)bound after either table changed
+static int bind_rows(pm_engine* e) {
+  if (e->rows_bound) return PM_OK;
+  if (e->n_asks) {
+    pm::pm_bind_rows<<<blocks_for(e->n_asks, 256), 256, 0, e->stream>>>(e->frows.p, e->opts_fast.p, e->bits.p, e->words, e->n_asks);
+    PM_LAUNCH_CHECK("pm_bind_rows");
+  }
+  e->rows_bound = true;
+  return PM_OK;
+}
+
 static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, bool fast, dim3 grid,
                          uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw, size_t ld) {
 #define PM_BUILD_CASE(B, F) pm::pm_build_cost<B, F><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld)
@@ -722,6 +738,12 @@ static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, b
     pm::pm_build_cost<2, true, 3><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
   } else if (fast && bits_mode == 2 && e->tune_build == 4) {
     pm::pm_build_cost<2, true, 4><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+  } else if (fast && e->tune_build != 1) {   // the round-2 kernel; PM_TUNE_BUILD=1 keeps the staged-CSR form for A/B runs
+    // one-word acceptance rows are bound into the FastRows (pm_bind_rows) however many rows there are
+    if (p.words == 1) bits_mode = 2;
+    if (bits_mode == 2) pm::pm_build_cost_fast<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    else if (bits_mode == 1) pm::pm_build_cost_fast<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    else pm::pm_build_cost_fast<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
   } else if (fast) {
     if (bits_mode == 2) PM_BUILD_CASE(2, true); else if (bits_mode == 1) PM_BUILD_CASE(1, true); else PM_BUILD_CASE(0, true);
   } else {
@@ -828,6 +850,10 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
       // leading dimension = whole CTA stripes of the build kernel (1024 columns): its stores need no bounds test;
       // the columns past the shard hold "infeasible" and cost 0.05 % of a 1M-worker row
       const size_t ld = (((size_t)nw + pm::kEvalCols - 1) / pm::kEvalCols) * pm::kEvalCols;
+      {
+        const int rc = bind_rows(e);
+        if (rc != PM_OK) return rc;
+      }
       uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
       if (rows == 0) rows = 1;
       rows = std::min<uint64_t>(rows, T);
@@ -1481,6 +1507,8 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
   bool fast = false;
   {
     int rc = decide_fast(e, &fast);
+    if (rc != PM_OK) return rc;
+    rc = bind_rows(e);
     if (rc != PM_OK) return rc;
   }
   launch_build(e, p, ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0, fast, grid, t0, nt, w0, nw, ld);

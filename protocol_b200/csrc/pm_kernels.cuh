@@ -21,6 +21,7 @@ struct EvalParams {
   const DevAsk* __restrict__ asks;    // [n_asks] priority order
   const DevOpt* __restrict__ opts;    // CSR, ask order
   const DevOptF* __restrict__ opts_fast;  // same CSR, fast-path form
+  const FastRow* __restrict__ frows;      // [n_asks] fast build kernel's view of an ask (first option inline)
   const uint32_t* __restrict__ bits;  // [(n_patterns+1) * words], row 0 all-ones
   uint32_t words;
   uint32_t n_workers;                 // global
@@ -287,6 +288,124 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
   });
 }
 
+// ------------------------------------------------------------------ build, fast form
+// Same decomposition and output as pm_build_cost, for tables that fit the fast predicate.  What changed after the
+// round-2 profile (profiles/r02_summary.md: ALU pipe no longer the limiter, warps waiting on chained shared-memory
+// loads — ask -> its option -> the option's acceptance word — and on the previous row's store reading its registers):
+//   * one FastRow per ask: everything a single-option ask needs in three 128-bit loads whose address depends only on
+//     the row number; the rows of the CTA arrive by ONE 1-D TMA bulk copy;
+//   * the next row's FastRow is loaded while the current row is evaluated (explicit double buffer in registers);
+//   * further OR-options (one ask in ten) are read straight from global memory, warp-uniform and L1-resident.
+template <int WPT, int BITS>
+__device__ __forceinline__ void eval_fast_first(const FastRow& q, const uint32_t* sbits, const WorkerReg (&w)[WPT],
+                                                const uint32_t* __restrict__ gbits, uint32_t words, uint32_t (&u)[WPT]) {
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const uint32_t word = (BITS == 2) ? q.wp
+                          : (BITS == 1) ? sbits[q.wp * words + w[k].mword] : __ldg(gbits + q.wp * words + w[k].mword);
+    const uint32_t z = ((w[k].key & q.m) ^ q.v) | (~word & w[k].mmask);
+    const uint32_t r = (w[k].mem_eff - q.mem_lo) | (q.mem_hi - w[k].mem_eff) |
+                       (((w[k].tot - q.tot_lo) | (q.tot_hi - w[k].tot)) & w[k].tot_keep);
+    u[k] = (0u - z) | r;
+  }
+}
+
+template <int WPT, int BITS>
+__device__ __forceinline__ void eval_fast_more(const DevOptF* __restrict__ gopts, uint32_t n_more, const uint32_t* sbits,
+                                               const WorkerReg (&w)[WPT], const uint32_t* __restrict__ gbits,
+                                               uint32_t words, uint32_t (&um)[WPT]) {
+  for (uint32_t o = 0; o < n_more; ++o) {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(gopts + o));
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(gopts + o) + 1);   // {tot_lo, tot_hi, pattern_row, pad}
+    const uint32_t uword = (BITS == 2) ? __ldg(gbits + q1.z) : 0u;
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const uint32_t word = (BITS == 2) ? uword
+                            : (BITS == 1) ? sbits[q1.z * words + w[k].mword] : __ldg(gbits + q1.z * words + w[k].mword);
+      const uint32_t z = ((w[k].key & q0.x) ^ q0.y) | (~word & w[k].mmask);
+      const uint32_t r = (w[k].mem_eff - q0.z) | (q0.w - w[k].mem_eff) |
+                         (((w[k].tot - q1.x) | (q1.y - w[k].tot)) & w[k].tot_keep);
+      um[k] &= (0u - z) | r;
+    }
+  }
+}
+
+struct __align__(128) FastStage {
+  FastRow row[kEvalRows];
+  uint32_t bits[kBitsCap];
+  uint64_t bar;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(kEvalThreads, 2)
+pm_build_cost_fast(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw, long long* __restrict__ cost, size_t ld) {
+  __shared__ FastStage s;
+  const uint32_t r0 = blockIdx.y * kEvalRows;
+  const uint32_t nrows = min(nt - r0, (uint32_t)kEvalRows);
+  if (threadIdx.x == 0) {
+    mbar_init(&s.bar, 1);
+    mbar_expect_tx(&s.bar, nrows * (uint32_t)sizeof(FastRow));
+    bulk_g2s(s.row, p.frows + t0 + r0, nrows * (uint32_t)sizeof(FastRow), &s.bar);
+  }
+  if (BITS == 1) {
+    const uint32_t total_words = p.n_bits_rows * p.words;
+    for (uint32_t i = threadIdx.x; i < total_words; i += blockDim.x) s.bits[i] = __ldg(p.bits + i);
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t cbase = blockIdx.x * kEvalCols + (threadIdx.x >> 5) * 128u + lane * 2u;
+  WorkerReg w[kEvalWPT];
+  uint32_t gw[kEvalWPT], dx[kEvalWPT], dy[kEvalWPT];
+#pragma unroll
+  for (int k = 0; k < kEvalWPT; ++k) {
+    const uint32_t col = cbase + (k >> 1) * 64u + (k & 1);
+    gw[k] = w0 + col;
+    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+    else w[k] = null_worker();
+    dx[k] = 0xFFFFFFFFu - gw[k];          // infeasible: 0x7FFFFFFF_FFFFFFFF = feasible word + (0/1) * difference
+    dy[k] = 0x7FFFFFFFu - w[k].price;
+  }
+  uint4* out = reinterpret_cast<uint4*>(cost + (size_t)r0 * ld + cbase);
+  const size_t row_stride = ld / 2;
+  const uint32_t sh = p.sign_shift;
+  __syncthreads();            // mbarrier initialised, acceptance words staged
+  mbar_wait(&s.bar, 0);
+  FastRow cur = s.row[0];
+  for (uint32_t r = 0; r < nrows; ++r) {
+    FastRow nxt = cur;
+    if (r + 1 < nrows) nxt = s.row[r + 1];    // in flight while this row is evaluated
+    uint32_t um[kEvalWPT];
+    eval_fast_first<kEvalWPT, BITS>(cur, s.bits, w, p.bits, p.words, um);
+    if (cur.n_opts > 1u)                      // OR-options (node.rs:420-438): the ask fails only if every option does
+      eval_fast_more<kEvalWPT, BITS>(p.opts_fast + cur.opt_off + 1, cur.n_opts - 1u, s.bits, w, p.bits, p.words, um);
+    uint4 v0, v1;
+    {
+      uint32_t o[2 * kEvalWPT];
+#pragma unroll
+      for (int k = 0; k < kEvalWPT; ++k) {
+        const uint32_t fail = um[k] | (w[k].cores - cur.cpu_cores) | (w[k].ram - cur.ram_mb) | (w[k].storage - cur.storage_gb);
+        const uint32_t b = fail >> sh;                                    // 1 when infeasible (sh == 31)
+        o[2 * k] = b * dx[k] + gw[k];                                     // feasible: (price << 32) | worker
+        o[2 * k + 1] = b * dy[k] + w[k].price;                            // infeasible: 0x7FFFFFFF_FFFFFFFF
+      }
+      v0 = make_uint4(o[0], o[1], o[2], o[3]);
+      v1 = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __stcs(out, v0);
+    __stcs(out + 32, v1);     // + 64 columns
+    out += row_stride;
+    cur = nxt;
+  }
+}
+
+// `wp` of every FastRow: the first option's acceptance WORD when rows are one word wide, else its pattern row.
+__global__ void pm_bind_rows(FastRow* __restrict__ rows, const DevOptF* __restrict__ opts_fast,
+                             const uint32_t* __restrict__ bits, uint32_t words, uint32_t n_asks) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_asks) return;
+  const uint32_t prow = opts_fast[rows[t].opt_off].pattern_row;
+  rows[t].wp = words == 1u ? bits[prow] : prow;
+}
+
 // ------------------------------------------------------------------ argmin
 constexpr int kArgThreads = 256;
 constexpr int kArgWarps = kArgThreads / 32;
@@ -479,7 +598,7 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
                                DevAsk* __restrict__ dasks, DevOpt* __restrict__ dopts,
                                DevOptF* __restrict__ doptsf, uint32_t* __restrict__ amin,
                                uint32_t* __restrict__ amax, uint32_t* __restrict__ status,
-                               uint32_t* __restrict__ max_row) {
+                               uint32_t* __restrict__ max_row, FastRow* __restrict__ frows) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_asks) return;
   const pm_ask a = asks[t];
@@ -557,6 +676,14 @@ __global__ void pm_ask_convert(const pm_ask* __restrict__ asks, const pm_gpu_opt
     doptsf[d.opt_off] = f;
   }
   dasks[t] = d;
+  {
+    const DevOptF f = doptsf[d.opt_off];   // written above by this thread
+    FastRow fr;
+    fr.m = f.m; fr.v = f.v; fr.mem_lo = f.mem_lo; fr.mem_hi = f.mem_hi;
+    fr.tot_lo = f.tot_lo; fr.tot_hi = f.tot_hi; fr.wp = f.pattern_row; fr.n_opts = n_rows;
+    fr.cpu_cores = d.cpu_cores; fr.ram_mb = d.ram_mb; fr.storage_gb = d.storage_gb; fr.opt_off = d.opt_off;
+    frows[t] = fr;
+  }
   amin[t] = a.min_group_size;
   amax[t] = a.max_group_size;
   if (st) atomicOr(status, st);

@@ -19,6 +19,7 @@
 // Redis"); the reference's random choices follow the determinisation
 // rules of SURVEY 8c (newest applicable task; group id = running counter).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <ctime>
@@ -395,9 +396,10 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) try {
   r->b.ram_mb = d->ram_mb;
   r->b.storage_gb = d->storage_gb;
   r->b.ext_ask_price = 0;
-  r->has_loc = d->has_location != 0;
-  r->lat = d->lat;
-  r->lon = d->lon;
+  // a location the distance function cannot use (NaN / infinite coordinates) is no location
+  r->has_loc = d->has_location != 0 && std::isfinite(d->lat) && std::isfinite(d->lon);
+  r->lat = r->has_loc ? d->lat : 0.0;
+  r->lon = r->has_loc ? d->lon : 0.0;
   p->index_add(*r);
   p->touch(size_t(r - p->nodes.data()));
   return PM_OK;
@@ -479,7 +481,7 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
         node.ip_address = ip;
         p->index_add(node);
       }
-      if (!existing.has_loc && d.node.has_location) {                                                    // :349-362
+      if (!existing.has_loc && d.node.has_location && std::isfinite(d.node.lat) && std::isfinite(d.node.lon)) {   // :349-362
         node.has_loc = true;
         node.lat = d.node.lat;
         node.lon = d.node.lon;
@@ -521,9 +523,9 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
       node.b.cpu_cores = d.node.cpu_cores;
       node.b.ram_mb = d.node.ram_mb;
       node.b.storage_gb = d.node.storage_gb;
-      node.has_loc = d.node.has_location != 0;
-      node.lat = d.node.lat;
-      node.lon = d.node.lon;
+      node.has_loc = d.node.has_location != 0 && std::isfinite(d.node.lat) && std::isfinite(d.node.lon);
+      node.lat = node.has_loc ? d.node.lat : 0.0;
+      node.lon = node.has_loc ? d.node.lon : 0.0;
       node.grouped = p->node_to_group.count(addr) != 0;
       p->node_index.emplace(addr, p->nodes.size());
       p->nodes.push_back(std::move(node));

@@ -62,8 +62,9 @@ __device__ __forceinline__ double haversine_km(double lat1, double lon1, double 
   const double delta_lon = __dmul_rn(__dsub_rn(lon2, lon1), kRadsPerDeg);
   const double s1 = sin(__dmul_rn(delta_lat, 0.5));
   const double s2 = sin(__dmul_rn(delta_lon, 0.5));
-  const double a = __dadd_rn(__dmul_rn(s1, s1),
+  double a = __dadd_rn(__dmul_rn(s1, s1),
                              __dmul_rn(__dmul_rn(cos(lat1_rad), cos(lat2_rad)), __dmul_rn(s2, s2)));
+  if (a > 1.0) a = 1.0;   // antipodal rounding pushes a above 1 (NaN in the reference, no total order): clamped, DESIGN.md determinisation rule 7
   const double c = __dmul_rn(2.0, atan2(sqrt(a), sqrt(__dsub_rn(1.0, a))));
   return __dmul_rn(6371.0, c);
 }

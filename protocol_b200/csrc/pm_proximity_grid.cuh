@@ -51,7 +51,7 @@ struct GridProxParams {
   double* part_d;        // [2][grid][kPgTopK] per-CTA partial selections, double-buffered by pass parity
   uint32_t* part_i;      // [2][grid][kPgTopK]
   uint32_t* cta_cnt;     // [2 * grid] per-CTA counts for the ordered compactions
-  uint32_t* gctl;        // [4] [0] leftover count
+  uint32_t* gctl;        // [4] [0] leftover count  [1],[2] "a located candidate has |latitude| > 90", by configuration parity
   double* clat;          // [W] candidate-ordered copies of latitude / longitude / cos(latitude in radians), written with
   double* clon;          //     the list: the seed-parallel phase streams them instead of gathering through the index
   double* ccos;
@@ -97,12 +97,37 @@ __device__ __forceinline__ double haversine_km_cached(double lat1, double lon1, 
   const double delta_lon = __dmul_rn(__dsub_rn(lon2, lon1), kRadsPerDeg);
   const double s1 = sin(__dmul_rn(delta_lat, 0.5));
   const double s2 = sin(__dmul_rn(delta_lon, 0.5));
-  const double a = __dadd_rn(__dmul_rn(s1, s1), __dmul_rn(__dmul_rn(cos1, cos2), __dmul_rn(s2, s2)));
+  double a = __dadd_rn(__dmul_rn(s1, s1), __dmul_rn(__dmul_rn(cos1, cos2), __dmul_rn(s2, s2)));
+  if (a > 1.0) a = 1.0;   // antipodal rounding pushes a above 1 (NaN in the reference, no total order): clamped, DESIGN.md determinisation rule 7
   const double c = __dmul_rn(2.0, atan2(sqrt(a), sqrt(__dsub_rn(1.0, a))));
   return __dmul_rn(6371.0, c);
 }
 
 __device__ __forceinline__ uint32_t pg_ld(const uint32_t* p) { return __ldcg(p); }
+
+// keep the kPgBatchK smallest (d, i) pairs, sorted; `mono` = positions arrive in increasing order (ties keep the holder)
+template <bool MONO>
+__device__ __forceinline__ void pg_top_insert(double (&bd)[kPgBatchK], uint32_t (&bi)[kPgBatchK], double d, uint32_t i) {
+  const int L = (int)kPgBatchK - 1;
+  if (!(bi[L] == kNone || d < bd[L] || (!MONO && d == bd[L] && i < bi[L]))) return;
+  bd[L] = d;
+  bi[L] = i;
+#pragma unroll
+  for (int q = L; q > 0; --q) {
+    const bool up = bi[q - 1] == kNone || bd[q] < bd[q - 1] || (!MONO && bd[q] == bd[q - 1] && bi[q] < bi[q - 1]);
+    if (up) {
+      const double td = bd[q]; bd[q] = bd[q - 1]; bd[q - 1] = td;
+      const uint32_t ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
+    }
+  }
+}
+
+// haversine distance >= R * |delta latitude| (a >= sin^2(dlat / 2) when both latitudes are real); the margins are
+// those of the checker's latitude-pruned mode (oracle/): nine orders of magnitude above f64 rounding
+__device__ __forceinline__ double pg_lat_bound(double slat, double lat) {
+  const double dl = fabs(lat - slat) * (3.14159265358979323846264338327950288 / 180.0);
+  return 6371.0 * dl * (1.0 - 1e-9) - 1e-9;
+}
 
 // smallest position >= start whose entry satisfies (e & mask) == want, or n.  Uniform over the CTA and — because every
 // CTA reads the same list — over the grid.
@@ -149,6 +174,18 @@ __device__ __forceinline__ uint32_t pg_block_argmin(PgShared& sh, double bd, uin
   *out_d = sh.red_d[0];
   __syncthreads();
   return r;
+}
+
+// pop the CTA-wide smallest head of the threads' sorted lists; returns its position (kNone: all empty), *out_d its key
+__device__ __forceinline__ uint32_t pg_pop_min(PgShared& sh, double (&bd)[kPgBatchK], uint32_t (&bi)[kPgBatchK], double* out_d) {
+  const uint32_t wi = pg_block_argmin(sh, bd[0], bi[0], out_d);
+  if (wi != kNone && bi[0] == wi) {
+#pragma unroll
+    for (uint32_t q = 0; q + 1 < kPgBatchK; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
+    bd[kPgBatchK - 1] = kPgMax;
+    bi[kPgBatchK - 1] = kNone;
+  }
+  return wi;
 }
 
 // exclusive rank of this thread's flag inside the CTA and the CTA total
@@ -219,12 +256,13 @@ __device__ __forceinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* 
 }
 
 // one list entry and its candidate-ordered coordinate copies
-__device__ __forceinline__ void pg_put_entry(const GridProxParams& gp, uint32_t pos, uint32_t w, bool coords) {
+__device__ __forceinline__ void pg_put_entry(const GridProxParams& gp, uint32_t pos, uint32_t w, bool coords, uint32_t flag_slot) {
   const ProxParams& p = gp.p;
   const bool loc = (p.ev.wa[w].w & PM_W_HAS_LOC) != 0u;
   p.list[pos] = w | (loc ? kLocBit : 0u);
   if (coords && loc) {
     const double la = p.lat[w];
+    if (!(fabs(la) <= 90.0)) atomicOr(gp.gctl + flag_slot, 1u);   // the latitude bound of the pruning needs real latitudes
     gp.clat[pos] = la;
     gp.clon[pos] = p.lon[w];
     gp.ccos[pos] = cos(__dmul_rn(la, 3.14159265358979323846264338327950288 / 180.0));
@@ -240,7 +278,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
   const uint32_t cta = blockIdx.x, ncta = gridDim.x;
   const uint32_t gtid = cta * kPgThreads + tid, nthr = ncta * kPgThreads;
   const bool lead = cta == 0;   // the CTA that writes the group tables
-  uint32_t g = 0, mpos = 0, c_lo = 0, parity = 0;
+  uint32_t g = 0, mpos = 0, c_lo = 0, parity = 0, cfgno = 0;
   bool overflow = false;
 
   while (c_lo < T && !overflow) {
@@ -261,6 +299,9 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
     const uint32_t* base = p.order + p.seg_start[c];
     // groups of 2..4 (1..3 neighbours) go through the seed-parallel phase first
     const bool batchable = mx >= 2u && mx - 1u < kPgBatchK && ncta >= 2u;
+    // "a located candidate has |latitude| > 90" flag of this configuration; two slots used alternately, so that the lead
+    // CTA can clear the next configuration's slot without racing the writers of this one
+    const uint32_t flag_slot = 1u + (cfgno & 1u);
 
     // ---- the configuration's candidate list in canonical order, located candidates tagged
     if (xc <= kPgXsSmem) {
@@ -287,11 +328,11 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
       }
       for (uint32_t i = gtid; i < bl; i += nthr) {
         const uint32_t w = base[i];
-        pg_put_entry(gp, i + lower_bound_u32(sh.xs, xc, w), w, batchable);
+        pg_put_entry(gp, i + lower_bound_u32(sh.xs, xc, w), w, batchable, flag_slot);
       }
       for (uint32_t j = gtid; j < xc; j += nthr) {
         const uint32_t w = sh.xs[j];
-        pg_put_entry(gp, j + lower_bound_u32(base, bl, w), w, batchable);
+        pg_put_entry(gp, j + lower_bound_u32(base, bl, w), w, batchable, flag_slot);
       }
     } else {
       // long hand-down: the list is {w : cur[w] == c} in index order — an ordered compaction over the whole table
@@ -310,12 +351,15 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
         const bool f = w < w_hi && pg_ld(p.cur + w) == c;
         uint32_t tile = 0;
         const uint32_t r = pg_block_rank(sh, f, &tile);
-        if (f) pg_put_entry(gp, off + r, w, batchable);
+        if (f) pg_put_entry(gp, off + r, w, batchable, flag_slot);
         off += tile;
       }
     }
     __threadfence();
     grid.sync();
+    const bool prune = batchable && pg_ld(gp.gctl + flag_slot) == 0u;
+    if (lead && tid == 0) gp.gctl[1u + ((cfgno + 1u) & 1u)] = 0u;   // nobody touches that slot before the next configuration
+    ++cfgno;
 
     if (mx == 1u) {
       // ---- solo groups: located candidates first, then the others, each its own group (mod.rs:526-530)
@@ -402,37 +446,51 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
           const double slat = __ldcg(gp.clat + sp), slon = __ldcg(gp.clon + sp), scos = __ldcg(gp.ccos + sp);
           double bd[kPgBatchK];
           uint32_t bi[kPgBatchK];
+          // Pruning.  An upper bound T of the CTA's final 4th-best distance comes from a cheap first pass: every thread
+          // keeps its 4 candidates with the smallest LATITUDE lower bound, their exact distances are taken, and the
+          // 4th smallest of those over the CTA is T (exact distances of real candidates: the true 4th best cannot be
+          // larger).  The second pass then computes a haversine only where the lower bound does not already exceed T —
+          // a candidate with bound > T is farther than T and can neither enter the list nor win a tie.
+          double T = kPgMax;
+          if (prune) {
+            double lv[kPgBatchK];
+            uint32_t li[kPgBatchK];
+#pragma unroll
+            for (uint32_t q = 0; q < kPgBatchK; ++q) { lv[q] = kPgMax; li[q] = kNone; bd[q] = kPgMax; bi[q] = kNone; }
+            for (uint32_t i = tid; i < n; i += kPgThreads) {
+              const uint32_t e = pg_ld(p.list + i);
+              if ((e & (kTakenBit | kLocBit)) != kLocBit || i == sp) continue;
+              pg_top_insert<true>(lv, li, pg_lat_bound(slat, __ldcg(gp.clat + i)), i);
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < kPgBatchK; ++q)
+              if (li[q] != kNone)
+                pg_top_insert<false>(bd, bi, haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + li[q]), __ldcg(gp.clon + li[q]), __ldcg(gp.ccos + li[q])), li[q]);
+            uint32_t got = 0;
+            double wd = kPgMax;
+            for (uint32_t r = 0; r < kPgBatchK; ++r)
+              if (pg_pop_min(sh, bd, bi, &wd) != kNone) ++got;
+            if (got == kPgBatchK) T = wd;       // fewer than 4 located candidates exist: no pruning, unlocated ones may be needed
+          }
 #pragma unroll
           for (uint32_t q = 0; q < kPgBatchK; ++q) { bd[q] = kPgMax; bi[q] = kNone; }
           for (uint32_t i = tid; i < n; i += kPgThreads) {
             const uint32_t e = pg_ld(p.list + i);
             if ((e & kTakenBit) || i == sp) continue;
-            const double d = (e & kLocBit) ? haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + i), __ldcg(gp.clon + i), __ldcg(gp.ccos + i))
-                                           : kPgMax;
-            // i only grows in this thread: an equal distance never displaces an entry already held
-            if (bi[kPgBatchK - 1] == kNone || d < bd[kPgBatchK - 1]) {
-              bd[kPgBatchK - 1] = d;
-              bi[kPgBatchK - 1] = i;
-#pragma unroll
-              for (int q = (int)kPgBatchK - 1; q > 0; --q) {
-                const bool up = bi[q - 1] == kNone || bd[q] < bd[q - 1];
-                if (up) {
-                  const double td = bd[q]; bd[q] = bd[q - 1]; bd[q - 1] = td;
-                  const uint32_t ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
-                }
-              }
+            double d = kPgMax;
+            if (e & kLocBit) {
+              const double la = __ldcg(gp.clat + i);
+              if (pg_lat_bound(slat, la) > T) continue;
+              d = haversine_km_cached(slat, slon, scos, la, __ldcg(gp.clon + i), __ldcg(gp.ccos + i));
+            } else if (T != kPgMax) {
+              continue;                          // at least 4 located candidates exist: a candidate without location cannot be among the 4 nearest
             }
+            pg_top_insert<true>(bd, bi, d, i);   // i only grows in this thread: an equal distance never displaces a holder
           }
           uint32_t* my_i = gp.part_i + ((size_t)parity * ncta + cta) * kPgTopK;
           for (uint32_t r = 0; r < kPgBatchK; ++r) {   // merge the per-thread lists: the winner pops its head
             double wd;
-            const uint32_t wi = pg_block_argmin(sh, bd[0], bi[0], &wd);
-            if (wi != kNone && bi[0] == wi) {
-#pragma unroll
-              for (uint32_t q = 0; q + 1 < kPgBatchK; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
-              bd[kPgBatchK - 1] = kPgMax;
-              bi[kPgBatchK - 1] = kNone;
-            }
+            const uint32_t wi = pg_pop_min(sh, bd, bi, &wd);
             if (tid == 0) my_i[r] = wi;
           }
         }
