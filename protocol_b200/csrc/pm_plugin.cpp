@@ -1167,7 +1167,7 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
   std::vector<pm_worker_a> wa(W);
   std::vector<pm_worker_b> wb(W);
   std::vector<double> lat(W), lon(W);
-  std::vector<uint32_t> by_addr(W), arank(W);
+  // (no address ranks: execute_group_merge puts the merged group's nodes in BTreeSet order from the strings themselves)
   std::vector<const NodeRec*> recs(W);
   for (uint32_t i = 0; i < W; ++i) {
     const Group& g = p->groups.at(solo_ids[i]);
@@ -1179,10 +1179,7 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
     wa[i].flags = n.a.flags | PM_W_HEALTHY | PM_W_P2P | (n.has_loc ? PM_W_HAS_LOC : 0u);
     lat[i] = n.lat;
     lon[i] = n.lon;
-    by_addr[i] = i;
   }
-  std::sort(by_addr.begin(), by_addr.end(), [&](uint32_t a, uint32_t b) { return recs[a]->address < recs[b]->address; });
-  for (uint32_t i = 0; i < W; ++i) arank[by_addr[i]] = i;
 
   const bool prox = p->policy.proximity_enabled != 0;
   std::vector<pm_ask> asks;
@@ -1223,7 +1220,6 @@ static int merge_pass(pm_plugin* p, const std::vector<const Config*>& configs, c
   if ((rc = chk(pm_set_worker_count(eng, W), "pm_set_worker_count"))) return rc;
   if ((rc = chk(pm_upsert_workers(eng, wa.data(), wb.data(), 0, W), "pm_upsert_workers"))) return rc;
   if ((rc = chk(pm_set_worker_locations(eng, lat.data(), lon.data(), 0, W), "pm_set_worker_locations"))) return rc;
-  if ((rc = chk(pm_set_worker_addr_rank(eng, arank.data(), 0, W), "pm_set_worker_addr_rank"))) return rc;
   if ((rc = chk(pm_stream_sync(eng), "pm_stream_sync"))) return rc;
   if ((rc = chk(pm_match(eng, (prox ? PM_MODE_PROXIMITY_MERGE : PM_MODE_FIRST_FIT) | PM_PATH_FUSED | PM_NO_ASK_STATS), "pm_match"))) return rc;
   pm_result res{};
@@ -1248,7 +1244,12 @@ int pm_plugin_try_merge_solo_groups(pm_plugin* p, uint32_t* n_merged) try {
       if (kv.second.nodes.size() == 1) ids.push_back(kv.first);
     return ids;
   };
-  if (solo_list().size() < 2) return PM_OK;                      // mod.rs:640-644
+  {
+    size_t n_solo = 0;
+    for (const auto& kv : p->groups)
+      if (kv.second.nodes.size() == 1 && ++n_solo >= 2) break;
+    if (n_solo < 2) return PM_OK;                                  // mod.rs:640-644
+  }
   if (!p->policy.task_switching_enabled) return PM_OK;            // should_switch_tasks, mod.rs:263-265
   const auto configs = p->available_configurations();
 

@@ -45,6 +45,7 @@ constexpr double kPgMax = 1.7976931348623157e308;   // f64::MAX: distance of a c
 constexpr uint32_t kPgBatchK = 4;       // seed-parallel phase: neighbours listed per seed (group size - 1 plus spares)
 constexpr uint32_t kPgHash = 4096;      // slots of the per-CTA "taken in this batch" set (<= 296 * 4 keys)
 constexpr uint32_t kPgMaxSeeds = 304;   // >= co-resident CTAs of a B200 (148 SMs x 2)
+constexpr uint32_t kPgUnroll = 8;       // candidates per thread in flight while the list streams from L2
 
 struct GridProxParams {
   ProxParams p;
@@ -68,6 +69,7 @@ struct PgShared {
   uint32_t xs[kPgXsSmem];
   uint32_t seeds[kPgMaxSeeds];                 // seed-parallel phase: list positions of the batch's seeds
   uint32_t grp[kPgMaxSeeds * kPgBatchK];       // resolved groups: [seed, up to 3 neighbours] positions
+  uint32_t cand[kPgMaxSeeds * kPgBatchK];      // the batch's neighbour lists, staged for the replay
   uint32_t taken[kPgHash];                     // positions taken by earlier groups of the batch (open addressing)
 };
 
@@ -452,15 +454,27 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
           // larger).  The second pass then computes a haversine only where the lower bound does not already exceed T —
           // a candidate with bound > T is farther than T and can neither enter the list nor win a tie.
           double T = kPgMax;
+          // Both passes stream the whole list from L2; kPgUnroll candidates per thread are in flight at a time (the
+          // loads of a chunk are issued before anything is decided), otherwise every candidate costs a full L2 round trip.
           if (prune) {
             double lv[kPgBatchK];
             uint32_t li[kPgBatchK];
 #pragma unroll
             for (uint32_t q = 0; q < kPgBatchK; ++q) { lv[q] = kPgMax; li[q] = kNone; bd[q] = kPgMax; bi[q] = kNone; }
-            for (uint32_t i = tid; i < n; i += kPgThreads) {
-              const uint32_t e = pg_ld(p.list + i);
-              if ((e & (kTakenBit | kLocBit)) != kLocBit || i == sp) continue;
-              pg_top_insert<true>(lv, li, pg_lat_bound(slat, __ldcg(gp.clat + i)), i);
+            for (uint32_t base = tid; base < n; base += kPgThreads * kPgUnroll) {
+              uint32_t e[kPgUnroll];
+              double la[kPgUnroll];
+#pragma unroll
+              for (uint32_t u = 0; u < kPgUnroll; ++u) {
+                const uint32_t i = base + u * kPgThreads;
+                e[u] = (i < n && i != sp) ? pg_ld(p.list + i) : kTakenBit;
+              }
+#pragma unroll
+              for (uint32_t u = 0; u < kPgUnroll; ++u)
+                la[u] = (e[u] & (kTakenBit | kLocBit)) == kLocBit ? __ldcg(gp.clat + base + u * kPgThreads) : 0.0;
+#pragma unroll
+              for (uint32_t u = 0; u < kPgUnroll; ++u)
+                if ((e[u] & (kTakenBit | kLocBit)) == kLocBit) pg_top_insert<true>(lv, li, pg_lat_bound(slat, la[u]), base + u * kPgThreads);
             }
 #pragma unroll
             for (uint32_t q = 0; q < kPgBatchK; ++q)
@@ -474,18 +488,30 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
           }
 #pragma unroll
           for (uint32_t q = 0; q < kPgBatchK; ++q) { bd[q] = kPgMax; bi[q] = kNone; }
-          for (uint32_t i = tid; i < n; i += kPgThreads) {
-            const uint32_t e = pg_ld(p.list + i);
-            if ((e & kTakenBit) || i == sp) continue;
-            double d = kPgMax;
-            if (e & kLocBit) {
-              const double la = __ldcg(gp.clat + i);
-              if (pg_lat_bound(slat, la) > T) continue;
-              d = haversine_km_cached(slat, slon, scos, la, __ldcg(gp.clon + i), __ldcg(gp.ccos + i));
-            } else if (T != kPgMax) {
-              continue;                          // at least 4 located candidates exist: a candidate without location cannot be among the 4 nearest
+          for (uint32_t base = tid; base < n; base += kPgThreads * kPgUnroll) {
+            uint32_t e[kPgUnroll];
+            double la[kPgUnroll];
+#pragma unroll
+            for (uint32_t u = 0; u < kPgUnroll; ++u) {
+              const uint32_t i = base + u * kPgThreads;
+              e[u] = (i < n && i != sp) ? pg_ld(p.list + i) : kTakenBit;
             }
-            pg_top_insert<true>(bd, bi, d, i);   // i only grows in this thread: an equal distance never displaces a holder
+#pragma unroll
+            for (uint32_t u = 0; u < kPgUnroll; ++u)
+              la[u] = (e[u] & (kTakenBit | kLocBit)) == kLocBit ? __ldcg(gp.clat + base + u * kPgThreads) : 0.0;
+#pragma unroll
+            for (uint32_t u = 0; u < kPgUnroll; ++u) {
+              if (e[u] & kTakenBit) continue;
+              const uint32_t i = base + u * kPgThreads;
+              double d = kPgMax;
+              if (e[u] & kLocBit) {
+                if (pg_lat_bound(slat, la[u]) > T) continue;
+                d = haversine_km_cached(slat, slon, scos, la[u], __ldcg(gp.clon + i), __ldcg(gp.ccos + i));
+              } else if (T != kPgMax) {
+                continue;                        // at least 4 located candidates exist: one without location cannot be among the 4 nearest
+              }
+              pg_top_insert<true>(bd, bi, d, i); // i only grows in this thread: an equal distance never displaces a holder
+            }
           }
           uint32_t* my_i = gp.part_i + ((size_t)parity * ncta + cta) * kPgTopK;
           for (uint32_t r = 0; r < kPgBatchK; ++r) {   // merge the per-thread lists: the winner pops its head
@@ -498,14 +524,17 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
         grid.sync();
         // replay of the sequential loop over the batch, identically on every CTA (warp 0; the set is per CTA)
         for (uint32_t h = tid; h < kPgHash; h += kPgThreads) sh.taken[h] = kNone;
+        {   // the batch's lists into shared memory in one go (a load per seed inside the replay would serialise L2 round trips)
+          const uint32_t* all_i = gp.part_i + (size_t)parity * ncta * kPgTopK;
+          for (uint32_t t = tid; t < nb * kPgBatchK; t += kPgThreads) sh.cand[t] = __ldcg(all_i + (size_t)(t / kPgBatchK) * kPgTopK + (t % kPgBatchK));
+        }
         __syncthreads();
         if (warp == 0) {
           uint32_t formed = 0, next = nb;
-          const uint32_t* all_i = gp.part_i + (size_t)parity * ncta * kPgTopK;
           for (uint32_t j = 0; j < nb; ++j) {
             const uint32_t sp = sh.seeds[j];
             if (pg_set_has(sh.taken, sp)) continue;                        // became a member of an earlier group
-            const uint32_t cand = lane < kPgBatchK ? __ldcg(all_i + (size_t)j * kPgTopK + lane) : kNone;
+            const uint32_t cand = lane < kPgBatchK ? sh.cand[j * kPgBatchK + lane] : kNone;
             const bool free_ = cand != kNone && !pg_set_has(sh.taken, cand);
             const uint32_t fb = __ballot_sync(0xffffffffu, free_);
             if ((uint32_t)__popc(fb) < k) { next = j; break; }             // out of spares: this seed opens the next batch
