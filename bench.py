@@ -210,7 +210,7 @@ def run_reference(args):
         "note": "reference = C++ restatement of crates/orchestrator node_groups scheduler (Rust toolchain absent); "
                 "Redis/JSON/HTTP time of the real orchestrator excluded",
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def faithful_sample(orc, w, a, n_nodes=4000, n_cfgs=400):
@@ -428,7 +428,9 @@ def run_ours(args):
         if ranks_agree is not None:
             line["ranks_agree"] = ranks_agree
         line.update(extras)
-        print(json.dumps(line))
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
+    if world > 1:
+        dist.barrier()          # nobody tears its communicator down while another rank is still in a pass
     eng.close()
     if comm is not None:
         comm.close()
@@ -485,7 +487,15 @@ def cpu_baseline(args, w, a, bits, words, T, W):
             "faithful_single_thread": faithful_sample(orc, w, a)}
 
 
+RESULT_OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE line, the result: native libraries write banners to file descriptor 1 (NCCL prints its
+    # version there when a communicator is created), so fd 1 is pointed at stderr and the line goes to a saved copy
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -502,10 +512,16 @@ def main():
         args.workload = "cfg3" if args.gpus <= 1 else "cfg5"
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
 
 
 if __name__ == "__main__":

@@ -741,9 +741,18 @@ static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, b
   } else if (fast && e->tune_build != 1) {   // the round-2 kernel; PM_TUNE_BUILD=1 keeps the staged-CSR form for A/B runs
     // one-word acceptance rows are bound into the FastRows (pm_bind_rows) however many rows there are
     if (p.words == 1) bits_mode = 2;
-    if (bits_mode == 2) pm::pm_build_cost_fast<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
-    else if (bits_mode == 1) pm::pm_build_cost_fast<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
-    else pm::pm_build_cost_fast<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    if (bits_mode == 2 && e->tune_build == 5) {          // rows-per-CTA experiments (profiles/)
+      grid.y = blocks_for(nt, 128);
+      pm::pm_build_cost_fast<2, 128><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    } else if (bits_mode == 2 && e->tune_build == 6) {
+      grid.y = blocks_for(nt, 512);
+      pm::pm_build_cost_fast<2, 512><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    } else {
+      grid.y = blocks_for(nt, pm::kFastRows);
+      if (bits_mode == 2) pm::pm_build_cost_fast<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+      else if (bits_mode == 1) pm::pm_build_cost_fast<1><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+      else pm::pm_build_cost_fast<0><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+    }
   } else if (fast) {
     if (bits_mode == 2) PM_BUILD_CASE(2, true); else if (bits_mode == 1) PM_BUILD_CASE(1, true); else PM_BUILD_CASE(0, true);
   } else {
@@ -858,6 +867,7 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
       if (rows == 0) rows = 1;
       rows = std::min<uint64_t>(rows, T);
       rows = std::min<uint64_t>(rows, 65535ull * pm::kArgRows);
+      if (rows >= 1024) rows &= ~(uint64_t)511;   // whole row bands of the build kernel (no ragged last band in every tile)
       cudaError_t ce = e->cost.ensure((size_t)rows * ld);
       if (ce != cudaSuccess) {
         cudaGetLastError();

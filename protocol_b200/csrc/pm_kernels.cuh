@@ -330,18 +330,20 @@ __device__ __forceinline__ void eval_fast_more(const DevOptF* __restrict__ gopts
   }
 }
 
+template <int ROWS>
 struct __align__(128) FastStage {
-  FastRow row[kEvalRows];
+  FastRow row[ROWS];
   uint32_t bits[kBitsCap];
   uint64_t bar;
 };
+constexpr int kFastRows = 256;   // asks per CTA: the prologue (worker rows from L2, the TMA of the FastRows) is paid once per CTA
 
-template <int BITS>
+template <int BITS, int ROWS = kFastRows>
 __global__ void __launch_bounds__(kEvalThreads, 2)
 pm_build_cost_fast(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw, long long* __restrict__ cost, size_t ld) {
-  __shared__ FastStage s;
-  const uint32_t r0 = blockIdx.y * kEvalRows;
-  const uint32_t nrows = min(nt - r0, (uint32_t)kEvalRows);
+  __shared__ FastStage<ROWS> s;
+  const uint32_t r0 = blockIdx.y * ROWS;
+  const uint32_t nrows = min(nt - r0, (uint32_t)ROWS);
   if (threadIdx.x == 0) {
     mbar_init(&s.bar, 1);
     mbar_expect_tx(&s.bar, nrows * (uint32_t)sizeof(FastRow));
