@@ -745,8 +745,8 @@ static void launch_build(pm_engine* e, const pm::EvalParams& p, int bits_mode, b
       grid.y = blocks_for(nt, 128);
       pm::pm_build_cost_fast<2, 128><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
     } else if (bits_mode == 2 && e->tune_build == 6) {
-      grid.y = blocks_for(nt, 512);
-      pm::pm_build_cost_fast<2, 512><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
+      grid.y = blocks_for(nt, 256);
+      pm::pm_build_cost_fast<2, 256><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
     } else {
       grid.y = blocks_for(nt, pm::kFastRows);
       if (bits_mode == 2) pm::pm_build_cost_fast<2><<<grid, pm::kEvalThreads, 0, e->stream>>>(p, t0, nt, w0, nw, e->cost.p, ld);
@@ -947,6 +947,7 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   int rc = sort_and_scan(e, n_bins, shift);
   if (rc != PM_OK) return rc;
   uint32_t* const scal = e->counters.p + 8;   // device mailbox {groups, members, bumped, overflow}
+  bool prox_grid_ran = false;
 
   if (prox_general) {
     // sequential-per-group nearest-neighbour formation (pm_proximity.cuh)
@@ -987,9 +988,9 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
       // all SMs: one grid barrier per group instead of one CTA doing everything (pm_proximity_grid.cuh)
       const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)e->coop_blocks, blocks_for(std::max<uint32_t>(W, 1), pm::kPgThreads)));
       PM_CUDA(e->pg_part_d.ensure((size_t)2 * grid * pm::kPgTopK)); PM_CUDA(e->pg_part_i.ensure((size_t)2 * grid * pm::kPgTopK));
-      PM_CUDA(e->pg_cta_cnt.ensure((size_t)2 * grid)); PM_CUDA(e->pg_ctl.ensure(4));
+      PM_CUDA(e->pg_cta_cnt.ensure((size_t)2 * grid)); PM_CUDA(e->pg_ctl.ensure(8));
       PM_CUDA(e->pg_clat.ensure(W)); PM_CUDA(e->pg_clon.ensure(W)); PM_CUDA(e->pg_ccos.ensure(W));
-      PM_CUDA(cudaMemsetAsync(e->pg_ctl.p, 0, 16, e->stream));
+      PM_CUDA(cudaMemsetAsync(e->pg_ctl.p, 0, 32, e->stream));
       pm::GridProxParams gp;
       gp.p = pp;
       gp.part_d = e->pg_part_d.p; gp.part_i = e->pg_part_i.p; gp.cta_cnt = e->pg_cta_cnt.p; gp.gctl = e->pg_ctl.p;
@@ -997,6 +998,8 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
       gp.n_workers = W;
       void* args[] = {&gp};
       PM_CUDA(cudaLaunchCooperativeKernel((const void*)pm::pm_proximity_grid, dim3(grid), dim3(pm::kPgThreads), args, 0, e->stream));
+      PM_CUDA(cudaMemcpyAsync(e->h_scalars.p + 24, e->pg_ctl.p + 4, 12, cudaMemcpyDeviceToHost, e->stream));
+      prox_grid_ran = true;
     }
     else if (e->tune_prox & 1) {   // experimental: same groups from a latitude-ordered view (pm_proximity_band.cuh)
       PM_CUDA(e->prox_lat_key.ensure(P)); PM_CUDA(e->prox_lat_ord.ensure(P)); PM_CUDA(e->prox_rank_of.ensure(W));
@@ -1079,6 +1082,11 @@ static int match_finish_locked(pm_engine* e, uint32_t mode) {
   e->n_groups = e->h_scalars.p[8];
   e->n_assigned = e->h_scalars.p[9];
   e->stats.n_bumped = e->h_scalars.p[10];
+  if (prox_grid_ran) {   // cooperative proximity sweep: seed-parallel batches, groups formed in them, groups formed one at a time
+    e->stats.n_tiles = e->h_scalars.p[24];
+    e->stats.n_rounds = e->h_scalars.p[25];
+    e->stats.n_build_launches = e->h_scalars.p[26];
+  }
   if (e->cfg.flags & PM_CFG_TIMING) {
     PM_CUDA(cudaEventElapsedTime(&e->stats.ms_total, e->ev0, e->ev1));
     e->resolve_timers();

@@ -336,7 +336,8 @@ struct __align__(128) FastStage {
   uint32_t bits[kBitsCap];
   uint64_t bar;
 };
-constexpr int kFastRows = 256;   // asks per CTA: the prologue (worker rows from L2, the TMA of the FastRows) is paid once per CTA
+constexpr int kFastRows = 512;   // asks per CTA: the prologue (worker rows from L2, the TMA of the FastRows) is paid once per CTA
+                                 // (measured on cfg3: 128 rows 119.1 ms/step, 256 rows 116.3, 512 rows 113.8 — profiles/r02_build_rows.txt)
 
 template <int BITS, int ROWS = kFastRows>
 __global__ void __launch_bounds__(kEvalThreads, 2)

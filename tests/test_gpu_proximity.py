@@ -135,7 +135,8 @@ def test_pairs_then_solo_at_100k_nodes(kernel):
     w = swarm(100_000, "cities", seed_shift=0)
     a = custom_asks([("gpu:count=8;gpu:count=4", 2, 2), (None, 1, 1)])   # 35 % of the candidates compete for pairs
     res, og = run(kernel, w, a)
-    print(f"\n[proximity {dict(KERNELS)[kernel]}] 100k nodes: {res.n_groups} groups, ms_resolve = {res.stats['ms_resolve']:.2f}")
+    print(f"\n[proximity {dict(KERNELS)[kernel]}] 100k nodes: {res.n_groups} groups, ms_resolve = {res.stats['ms_resolve']:.2f}, "
+          f"batches = {res.stats['n_tiles']}, groups formed in batches = {res.stats['n_rounds']}, one at a time = {res.stats['n_build_launches']}")
     assert (np.diff(res.group_off) == 2).sum() > 10_000
 
 
@@ -146,4 +147,5 @@ def test_pairs_then_solo_at_1m_nodes():
     a = custom_asks([("gpu:count=8;gpu:count=4", 2, 2), (None, 1, 1)])
     res, og = run("0", w, a)
     print(f"\n[proximity grid] 1M nodes: {res.n_groups} groups ({int((np.diff(res.group_off) == 2).sum())} pairs), "
-          f"ms_resolve = {res.stats['ms_resolve']:.1f}")
+          f"ms_resolve = {res.stats['ms_resolve']:.1f}, batches = {res.stats['n_tiles']}, groups formed in batches = {res.stats['n_rounds']}, "
+          f"one at a time = {res.stats['n_build_launches']}")
