@@ -54,7 +54,7 @@ struct ProxParams {
 // calculate_distance, mod.rs:218-231.  Same operation order as the reference in
 // IEEE f64; explicit _rn intrinsics keep nvcc from contracting a*b+c into FMA
 // (rustc never does).  Only the ORDER of distances is observable.
-__device__ __forceinline__ double haversine_km(double lat1, double lon1, double lat2, double lon2) {
+__device__ __noinline__ double haversine_km(double lat1, double lon1, double lat2, double lon2) {
   const double kRadsPerDeg = 3.14159265358979323846264338327950288 / 180.0;
   const double lat1_rad = __dmul_rn(lat1, kRadsPerDeg);
   const double lat2_rad = __dmul_rn(lat2, kRadsPerDeg);

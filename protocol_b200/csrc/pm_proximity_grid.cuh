@@ -73,7 +73,7 @@ struct PgShared {
   uint32_t taken[kPgHash];                     // positions taken by earlier groups of the batch (open addressing)
 };
 
-__device__ __forceinline__ bool pg_set_has(const uint32_t* tab, uint32_t key) {
+__device__ __noinline__ bool pg_set_has(const uint32_t* tab, uint32_t key) {
   uint32_t h = (key * 2654435761u) >> 20;
   for (;;) {
     const uint32_t v = tab[h];
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool pg_set_has(const uint32_t* tab, uint32_t key) {
     h = (h + 1u) & (kPgHash - 1u);
   }
 }
-__device__ __forceinline__ void pg_set_put(uint32_t* tab, uint32_t key) {
+__device__ __noinline__ void pg_set_put(uint32_t* tab, uint32_t key) {
   uint32_t h = (key * 2654435761u) >> 20;
   for (;;) {
     const uint32_t old = atomicCAS(&tab[h], kNone, key);
@@ -93,7 +93,7 @@ __device__ __forceinline__ void pg_set_put(uint32_t* tab, uint32_t key) {
 
 // calculate_distance (mod.rs:218-231) with the two cosines already taken: same operations in the same order as
 // haversine_km, cos(lat1_rad) and cos(lat2_rad) are the cached values of exactly those expressions.
-__device__ __forceinline__ double haversine_km_cached(double lat1, double lon1, double cos1, double lat2, double lon2, double cos2) {
+__device__ __noinline__ double haversine_km_cached(double lat1, double lon1, double cos1, double lat2, double lon2, double cos2) {
   const double kRadsPerDeg = 3.14159265358979323846264338327950288 / 180.0;
   const double delta_lat = __dmul_rn(__dsub_rn(lat2, lat1), kRadsPerDeg);
   const double delta_lon = __dmul_rn(__dsub_rn(lon2, lon1), kRadsPerDeg);
@@ -133,7 +133,7 @@ __device__ __forceinline__ double pg_lat_bound(double slat, double lat) {
 
 // smallest position >= start whose entry satisfies (e & mask) == want, or n.  Uniform over the CTA and — because every
 // CTA reads the same list — over the grid.
-__device__ __forceinline__ uint32_t pg_find_first(PgShared& sh, const uint32_t* list, uint32_t n, uint32_t start,
+__device__ __noinline__ uint32_t pg_find_first(PgShared& sh, const uint32_t* list, uint32_t n, uint32_t start,
                                                   uint32_t mask, uint32_t want) {
   for (uint32_t base = start; base < n; base += kPgThreads) {
     if (threadIdx.x == 0) sh.u[7] = kNone;
@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t pg_find_first(PgShared& sh, const uint32_t* 
 
 // lexicographic (distance, position) minimum over the CTA; kNone when no thread has a candidate.  Uniform result in
 // *out_d / return value.
-__device__ __forceinline__ uint32_t pg_block_argmin(PgShared& sh, double bd, uint32_t bi, double* out_d) {
+__device__ __noinline__ uint32_t pg_block_argmin(PgShared& sh, double bd, uint32_t bi, double* out_d) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, bd, off);
@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t pg_pop_min(PgShared& sh, double (&bd)[kPgBat
 }
 
 // exclusive rank of this thread's flag inside the CTA and the CTA total
-__device__ __forceinline__ uint32_t pg_block_rank(PgShared& sh, bool flag, uint32_t* total) {
+__device__ __noinline__ uint32_t pg_block_rank(PgShared& sh, bool flag, uint32_t* total) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t b = __ballot_sync(0xffffffffu, flag);
   if (lane == 0) sh.warp_cnt[warp] = (uint32_t)__popc(b);
@@ -209,7 +209,7 @@ __device__ __forceinline__ uint32_t pg_block_rank(PgShared& sh, bool flag, uint3
 }
 
 // two flags ranked in one pass (located / not located)
-__device__ __forceinline__ void pg_block_rank2(PgShared& sh, bool f0, bool f1, uint32_t* r0, uint32_t* r1,
+__device__ __noinline__ void pg_block_rank2(PgShared& sh, bool f0, bool f1, uint32_t* r0, uint32_t* r1,
                                                uint32_t* t0, uint32_t* t1) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
@@ -231,7 +231,7 @@ __device__ __forceinline__ void pg_block_rank2(PgShared& sh, bool f0, bool f1, u
 }
 
 // sum over the CTA
-__device__ __forceinline__ uint32_t pg_block_sum(PgShared& sh, uint32_t v) {
+__device__ __noinline__ uint32_t pg_block_sum(PgShared& sh, uint32_t v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -245,7 +245,7 @@ __device__ __forceinline__ uint32_t pg_block_sum(PgShared& sh, uint32_t v) {
 }
 
 // sum of cnt[0 .. upto) and of cnt[0 .. all), both CTA-uniform
-__device__ __forceinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* cnt, uint32_t upto, uint32_t all,
+__device__ __noinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* cnt, uint32_t upto, uint32_t all,
                                                   uint32_t* before, uint32_t* total) {
   uint32_t a = 0, t = 0;
   for (uint32_t b = threadIdx.x; b < all; b += kPgThreads) {
@@ -258,7 +258,7 @@ __device__ __forceinline__ void pg_prefix_of_ctas(PgShared& sh, const uint32_t* 
 }
 
 // one list entry and its candidate-ordered coordinate copies
-__device__ __forceinline__ void pg_put_entry(const GridProxParams& gp, uint32_t pos, uint32_t w, bool coords, uint32_t flag_slot) {
+__device__ __noinline__ void pg_put_entry(const GridProxParams& gp, uint32_t pos, uint32_t w, bool coords, uint32_t flag_slot) {
   const ProxParams& p = gp.p;
   const bool loc = (p.ev.wa[w].w & PM_W_HAS_LOC) != 0u;
   p.list[pos] = w | (loc ? kLocBit : 0u);
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
       }
       for (uint32_t i = gtid; i < bl; i += nthr) {
         const uint32_t w = base[i];
-        pg_put_entry(gp, i + lower_bound_u32(sh.xs, xc, w), w, batchable, flag_slot);
+        pg_put_entry(gp, i + lower_bound_u32(sh.xs, xc, w), w, mx >= 2u, flag_slot);
       }
       for (uint32_t j = gtid; j < xc; j += nthr) {
         const uint32_t w = sh.xs[j];
-        pg_put_entry(gp, j + lower_bound_u32(base, bl, w), w, batchable, flag_slot);
+        pg_put_entry(gp, j + lower_bound_u32(base, bl, w), w, mx >= 2u, flag_slot);
       }
     } else {
       // long hand-down: the list is {w : cur[w] == c} in index order — an ordered compaction over the whole table
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
         const bool f = w < w_hi && pg_ld(p.cur + w) == c;
         uint32_t tile = 0;
         const uint32_t r = pg_block_rank(sh, f, &tile);
-        if (f) pg_put_entry(gp, off + r, w, batchable, flag_slot);
+        if (f) pg_put_entry(gp, off + r, w, mx >= 2u, flag_slot);
         off += tile;
       }
     }
@@ -457,17 +457,19 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
           double T = kPgMax;
           // Both passes stream the whole list from L2; kPgUnroll candidates per thread are in flight at a time (the
           // loads of a chunk are issued before anything is decided), otherwise every candidate costs a full L2 round trip.
-          // Every CTA starts at a different chunk and wraps around: all CTAs read the same arrays, and in lock step they
-          // would all hit the same few L2 slices at any moment (measured: 1.5 TB/s of L2 throughput before the stagger).
+          // (Staggering the CTAs' starting offsets was measured and made it slower: 2.15 s -> 2.92 s at 1M nodes.)
+          // Code size matters here: the first version of these loops inlined the haversine and the insertion network at
+          // every unrolled site, the kernel grew to 13k instructions (208 KB) and 58 % of its warp-stall samples were
+          // instruction-cache misses (profiles/r02_proximity_1m_stalls.txt).  Hence: loads unrolled, processing rolled,
+          // one out-of-line haversine.
           const uint32_t n_chunks = (n + kPgThreads * kPgUnroll - 1) / (kPgThreads * kPgUnroll);
-          const uint32_t first_chunk = (uint32_t)(((uint64_t)cta * n_chunks) / nb);
           if (prune) {
             double lv[kPgBatchK];
             uint32_t li[kPgBatchK];
 #pragma unroll
             for (uint32_t q = 0; q < kPgBatchK; ++q) { lv[q] = kPgMax; li[q] = kNone; bd[q] = kPgMax; bi[q] = kNone; }
             for (uint32_t ck = 0; ck < n_chunks; ++ck) {
-              const uint32_t base = ((ck + first_chunk) % n_chunks) * (kPgThreads * kPgUnroll) + tid;
+              const uint32_t base = ck * (kPgThreads * kPgUnroll) + tid;
               uint32_t e[kPgUnroll];
               double la[kPgUnroll];
 #pragma unroll
@@ -478,14 +480,16 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
 #pragma unroll
               for (uint32_t u = 0; u < kPgUnroll; ++u)
                 la[u] = (e[u] & (kTakenBit | kLocBit)) == kLocBit ? __ldcg(gp.clat + base + u * kPgThreads) : 0.0;
-#pragma unroll
+#pragma unroll 1
               for (uint32_t u = 0; u < kPgUnroll; ++u)
-                if ((e[u] & (kTakenBit | kLocBit)) == kLocBit) pg_top_insert<false>(lv, li, pg_lat_bound(slat, la[u]), base + u * kPgThreads);
+                if ((e[u] & (kTakenBit | kLocBit)) == kLocBit) pg_top_insert<true>(lv, li, pg_lat_bound(slat, la[u]), base + u * kPgThreads);
             }
-#pragma unroll
-            for (uint32_t q = 0; q < kPgBatchK; ++q)
-              if (li[q] != kNone)
-                pg_top_insert<false>(bd, bi, haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + li[q]), __ldcg(gp.clon + li[q]), __ldcg(gp.ccos + li[q])), li[q]);
+#pragma unroll 1
+            for (uint32_t q = 0; q < kPgBatchK; ++q) {
+              const uint32_t i = li[q];
+              if (i != kNone)
+                pg_top_insert<false>(bd, bi, haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + i), __ldcg(gp.clon + i), __ldcg(gp.ccos + i)), i);
+            }
             uint32_t got = 0;
             double wd = kPgMax;
             for (uint32_t r = 0; r < kPgBatchK; ++r)
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
 #pragma unroll
           for (uint32_t q = 0; q < kPgBatchK; ++q) { bd[q] = kPgMax; bi[q] = kNone; }
           for (uint32_t ck = 0; ck < n_chunks; ++ck) {
-            const uint32_t base = ((ck + first_chunk) % n_chunks) * (kPgThreads * kPgUnroll) + tid;
+            const uint32_t base = ck * (kPgThreads * kPgUnroll) + tid;
             uint32_t e[kPgUnroll];
             double la[kPgUnroll];
 #pragma unroll
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
 #pragma unroll
             for (uint32_t u = 0; u < kPgUnroll; ++u)
               la[u] = (e[u] & (kTakenBit | kLocBit)) == kLocBit ? __ldcg(gp.clat + base + u * kPgThreads) : 0.0;
-#pragma unroll
+#pragma unroll 1
             for (uint32_t u = 0; u < kPgUnroll; ++u) {
               if (e[u] & kTakenBit) continue;
               const uint32_t i = base + u * kPgThreads;
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
               } else if (T != kPgMax) {
                 continue;                        // at least 4 located candidates exist: one without location cannot be among the 4 nearest
               }
-              pg_top_insert<false>(bd, bi, d, i);
+              pg_top_insert<true>(bd, bi, d, i);   // positions only grow in this thread: an equal distance never displaces a holder
             }
           }
           uint32_t* my_i = gp.part_i + ((size_t)parity * ncta + cta) * kPgTopK;
@@ -608,7 +612,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
       uint32_t need = size - 1u, written = 1u;   // members written so far (the seed is written with the first marks)
       bool seed_marked = false;
       if (need && seed_loc) {
-        const double slat = p.lat[seed_w], slon = p.lon[seed_w];
+        const double slat = __ldcg(gp.clat + seed_pos), slon = __ldcg(gp.clon + seed_pos), scos = __ldcg(gp.ccos + seed_pos);
         bool first_pass = true;
         while (need) {
           const uint32_t kk = min(need, kPgTopK);
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
               if ((e & kTakenBit) || i == seed_pos) continue;
               double d;
               if (first_pass && r == 0u) {
-                d = (e & kLocBit) ? haversine_km(slat, slon, p.lat[e & kIdxMask], p.lon[e & kIdxMask]) : kPgMax;
+                d = (e & kLocBit) ? haversine_km_cached(slat, slon, scos, __ldcg(gp.clat + i), __ldcg(gp.clon + i), __ldcg(gp.ccos + i)) : kPgMax;
                 if (keep) p.dist[i] = d;                                  // owner-private: read back by this thread only
               } else {
                 d = p.dist[i];
