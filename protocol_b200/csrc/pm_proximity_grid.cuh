@@ -600,6 +600,47 @@ __global__ void __launch_bounds__(kPgThreads) pm_proximity_grid(GridProxParams g
         }
       }
       const bool have_seed = seed_pos < n;
+      if (have_seed && !seed_loc && remaining >= mx) {
+        // Nobody located is left: from here on every group is its seed (the first live candidate) plus the next max-1
+        // live candidates in list order (the stable sort leaves f64::MAX distances in list order) — consecutive runs of
+        // `max` live candidates.  All full groups at once by an ordered partition (two barriers) instead of a barrier
+        // per group; what remains afterwards (fewer than `max`) goes through the loop below.
+        const uint32_t n_full = remaining / mx;
+        if ((uint64_t)g + n_full > (uint64_t)p.group_cap) { overflow = true; break; }
+        const uint32_t chunk = ((n + ncta - 1) / ncta + kPgThreads - 1) / kPgThreads * kPgThreads;
+        const uint32_t i_lo = min(n, cta * chunk), i_hi = min(n, i_lo + chunk);
+        uint32_t mine = 0;
+        for (uint32_t i = i_lo + tid; i < i_hi; i += kPgThreads) mine += (pg_ld(p.list + i) & kTakenBit) ? 0u : 1u;
+        const uint32_t cnt = pg_block_sum(sh, mine);
+        if (tid == 0) gp.cta_cnt[ncta + cta] = cnt;
+        __threadfence();
+        grid.sync();
+        uint32_t before = 0, total = 0;
+        pg_prefix_of_ctas(sh, gp.cta_cnt + ncta, cta, ncta, &before, &total);   // total == remaining
+        for (uint32_t i0 = i_lo; i0 < i_hi; i0 += kPgThreads) {
+          const uint32_t i = i0 + tid;
+          const uint32_t e = i < i_hi ? pg_ld(p.list + i) : kTakenBit;
+          const bool live = (e & kTakenBit) == 0u;
+          uint32_t tile = 0;
+          const uint32_t r = before + pg_block_rank(sh, live, &tile);
+          if (live && r < n_full * mx) {
+            const uint32_t w = e & kIdxMask, gi = r / mx;
+            atomicOr(p.list + i, kTakenBit);
+            p.members[mpos + r] = w;
+            p.worker_group[w] = g + gi;
+            p.worker_ask[w] = c;
+            if (r % mx == 0u) { p.group_ask[g + gi] = c; p.group_off[g + gi] = mpos + r; }
+          }
+          before += tile;
+        }
+        g += n_full;
+        mpos += n_full * mx;
+        remaining -= n_full * mx;
+        n_single += n_full;
+        __threadfence();
+        grid.sync();          // the marks of every CTA are in place before anybody looks at the list again
+        continue;
+      }
       const uint32_t size = have_seed ? min(mx, remaining) : 0u;
       if (size < mn) break;                                                // :564
       if (g >= p.group_cap) { overflow = true; break; }

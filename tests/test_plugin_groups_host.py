@@ -256,3 +256,23 @@ def test_assigned_flag_follows_every_membership_change():
     assert assigned() == [False, True, False]
     plugin.delete_task(task.id)                                           # the group working on it goes
     assert assigned() == [False, False, False]
+
+
+def test_idle_group_without_applicable_task_is_answered_without_a_claim():
+    """A group whose configuration no task allows (allowed_topologies) heartbeats to `current_task: null` every time —
+    from the cached per-configuration choice, without writing a claim — and gets the task as soon as one applies
+    (scheduler_impl.rs:42-70; ADVICE r1: this path used to fall back to the exclusive lock on every heartbeat)."""
+    plugin = make([NodeGroupConfiguration("a", 1, 2), NodeGroupConfiguration("b", 1, 2)])
+    sched = Scheduler(plugin)
+    plugin.add_node(OrchestratorNode(A1, p2p_id="p1"))
+    plugin.add_node(OrchestratorNode(A2, p2p_id="p2"))
+    plugin.restore_group("1", "a", [A1, A2])
+    other = Task(image="img", name="only-b", allowed_topologies=["b"])
+    plugin.add_task(other)
+    for _ in range(5):
+        assert sched.get_task_for_node(A1) is None and sched.get_task_for_node(A2) is None
+    assert plugin.get_node_group(A1)["task_id"] is None                 # nothing was claimed
+    mine = Task(image="img", name="for-a", allowed_topologies=["a"])
+    plugin.add_task(mine)                                               # the task list changed: the cache is rebuilt
+    assert sched.get_task_for_node(A1)["id"] == mine.id and sched.get_task_for_node(A2)["id"] == mine.id
+    assert plugin.get_node_group(A1)["task_id"] == mine.id

@@ -276,3 +276,28 @@ def test_json_and_struct_ingest_agree_on_random_fetches():
                 assert a.get_node(f"0x{i:040x}") == b.get_node(f"0x{i:040x}")
 
     check()
+
+
+def test_entry_without_id_or_ip_is_skipped_and_the_rest_of_the_fetch_applies():
+    """The monitor logs a node it cannot sync and goes on with the others (monitor.rs:425-429); the struct entry point
+    used to return PM_E_INVALID at the first such entry and drop the rest of the fetch."""
+    import ctypes as C
+
+    from protocol_b200 import abi
+
+    plugin = NodeGroupsPlugin([])
+    arr = (abi.PmDiscoveryNode * 3)()
+    keep = []
+    for i, (addr, ip) in enumerate([("0x" + "1" * 40, "10.0.0.1"), ("0x" + "2" * 40, None), ("0x" + "3" * 40, "10.0.0.3")]):
+        d = arr[i]
+        keep.append((addr.encode(), ip.encode() if ip else None))
+        d.node.address = keep[-1][0]
+        d.ip_address = keep[-1][1]
+        d.port = 8000 + i
+        d.is_validated, d.is_active, d.is_provider_whitelisted = 1, 1, 1
+        d.last_updated_ms = -1
+    n_new = C.c_uint32()
+    rc = plugin._lib.pm_plugin_sync_discovery(plugin._h, arr, 3, NOW, 1, C.byref(n_new))
+    assert rc == abi.PM_OK and n_new.value == 2
+    assert plugin.get_node("0x" + "1" * 40) is not None and plugin.get_node("0x" + "3" * 40) is not None
+    assert plugin.get_node("0x" + "2" * 40) is None
