@@ -222,6 +222,12 @@ int      pm_create_sibling(const pm_engine*, pm_engine** out);
  * (value = -(ask_price * cost_scale) - price; eps runs eps_start, /eps_div, ..., 1).       */
 int pm_set_ask_price_caps(pm_engine*, const uint32_t* price_cap, uint32_t n_asks);
 int pm_set_auction_params(pm_engine*, uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div);
+/* `reputation` (north_star worker column; SURVEY 8 A21 side column ext_reputation:u32) and the per-ask floor on it:
+ *   feasible(t,w) additionally requires reputation[w] >= min_reputation[t]   (PM_MODE_AUCTION only).
+ * Both default to 0 (no clause).  The worker column follows the worker table: pm_resize_workers keeps it,
+ * pm_set_worker_count drops it.  min_reputation is per ask, after pm_set_asks, like the price caps.      */
+int pm_set_worker_reputation(pm_engine*, const uint32_t* reputation, uint32_t first, uint32_t n);
+int pm_set_ask_min_reputation(pm_engine*, const uint32_t* min_reputation, uint32_t n_asks);
 
 enum pm_mode {
   PM_MODE_FIRST_FIT = 0,   /* try_form_new_groups, ProximityOptimizationPolicy{enabled:false} */

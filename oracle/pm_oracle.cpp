@@ -1121,6 +1121,18 @@ uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_
                          const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
                          uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
                          uint32_t* ask_worker_out, int64_t* worker_price_out) {
+  return orc_soa_auction_rep(a, b, n_workers, asks, n_asks, opts, model_bits, words, price_cap, nullptr, nullptr, cost_scale,
+                             eps_start, eps_div, ask_worker_out, worker_price_out);
+}
+
+// ... with the `reputation` worker column (north-star extension): a pair is feasible only when
+// reputation[w] >= min_reputation[t]; either pointer may be null (column of zeros).
+uint32_t orc_soa_auction_rep(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                             const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                             const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
+                             const uint32_t* reputation, const uint32_t* min_reputation,
+                             uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
+                             uint32_t* ask_worker_out, int64_t* worker_price_out) {
   const int64_t S = cost_scale ? int64_t(cost_scale) : 1;
   const int64_t NEG = INT64_MIN / 4;
   std::vector<int64_t> price(n_workers, 0);
@@ -1131,6 +1143,7 @@ uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_
   for (u32 t = 0; t < n_asks; ++t)
     for (u32 w = 0; w < n_workers; ++w)
       if (soa_candidate(a[w].flags) && b[w].ext_ask_price <= price_cap[t] &&
+          (reputation ? reputation[w] : 0u) >= (min_reputation ? min_reputation[t] : 0u) &&
           orc_soa_compatible(&a[w], &b[w], &asks[t], opts, model_bits, words))
         feas[t].push_back(w);
   u32 rounds = 0;

@@ -193,6 +193,14 @@ uint32_t orc_soa_auction(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_
                          const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
                          uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
                          uint32_t* ask_worker_out, int64_t* worker_price_out);
+/* ... plus the north-star `reputation` worker column: feasible(t,w) also needs
+ * reputation[w] >= min_reputation[t]; either pointer may be null (all zeros).              */
+uint32_t orc_soa_auction_rep(const pm_worker_a* a, const pm_worker_b* b, uint32_t n_workers,
+                             const pm_ask* asks, uint32_t n_asks, const pm_gpu_opt* opts,
+                             const uint32_t* model_bits, uint32_t words, const uint32_t* price_cap,
+                             const uint32_t* reputation, const uint32_t* min_reputation,
+                             uint64_t cost_scale, uint64_t eps_start, uint32_t eps_div,
+                             uint32_t* ask_worker_out, int64_t* worker_price_out);
 
 #ifdef __cplusplus
 }

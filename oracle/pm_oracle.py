@@ -88,6 +88,7 @@ def load() -> C.CDLL:
         "orc_soa_compatible": (i32, [vp, vp, vp, vp, vp, u32]),
         "orc_soa_form_groups": (vp, [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, i32]),
         "orc_soa_auction": (u32, [vp, vp, u32, vp, u32, vp, vp, u32, vp, C.c_uint64, C.c_uint64, u32, vp, vp]),
+        "orc_soa_auction_rep": (u32, [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, C.c_uint64, C.c_uint64, u32, vp, vp]),
         "orc_model_table": (None, [P(cp), u32, P(cp), u32, u32, u32, vp]),
         "orc_soa_first_feasible": (None, [vp, vp, u32, vp, u32, vp, vp, u32, u32, vp]),
         "orc_soa_eval_matrix": (C.c_uint64, [vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, vp]),
@@ -363,15 +364,22 @@ def soa_first_feasible(a, b, asks, opts, bits, words, threads=8):
     return out
 
 
-def soa_auction(a, b, asks, opts, bits, words, price_cap, cost_scale=1, eps_start=1, eps_div=4):
-    """EXTENSION self-oracle (no reference counterpart): returns (ask_worker u32[T], worker_price i64[W], rounds)."""
+def soa_auction(a, b, asks, opts, bits, words, price_cap, cost_scale=1, eps_start=1, eps_div=4, reputation=None,
+                min_reputation=None):
+    """EXTENSION self-oracle (no reference counterpart): returns (ask_worker u32[T], worker_price i64[W], rounds).
+    reputation u32[W] / min_reputation u32[T] (north-star column, optional): feasible only if reputation >= floor."""
     a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
     asks = np.ascontiguousarray(asks); opts = np.ascontiguousarray(opts)
     bits = np.ascontiguousarray(bits, dtype=np.uint32)
     cap = np.ascontiguousarray(price_cap, dtype=np.uint32)
+    rep = None if reputation is None else np.ascontiguousarray(reputation, dtype=np.uint32)
+    floor = None if min_reputation is None else np.ascontiguousarray(min_reputation, dtype=np.uint32)
+    assert rep is None or len(rep) == len(a)
+    assert floor is None or len(floor) == len(asks)
     out = np.empty(len(asks), dtype=np.uint32)
     price = np.empty(len(a), dtype=np.int64)
-    rounds = load().orc_soa_auction(a.ctypes.data, b.ctypes.data, len(a), asks.ctypes.data, len(asks), opts.ctypes.data,
-                                    bits.ctypes.data, words, cap.ctypes.data, cost_scale, eps_start, eps_div, out.ctypes.data,
-                                    price.ctypes.data)
+    rounds = load().orc_soa_auction_rep(a.ctypes.data, b.ctypes.data, len(a), asks.ctypes.data, len(asks), opts.ctypes.data,
+                                        bits.ctypes.data, words, cap.ctypes.data, None if rep is None else rep.ctypes.data,
+                                        None if floor is None else floor.ctypes.data, cost_scale, eps_start, eps_div,
+                                        out.ctypes.data, price.ctypes.data)
     return out, price, rounds

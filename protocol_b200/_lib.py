@@ -56,6 +56,8 @@ def load() -> C.CDLL:
         "pm_set_worker_addr_rank": (i32, [vp, vp, u32, u32]),
         "pm_set_flags": (i32, [vp, vp, vp, u32]),
         "pm_set_ask_price_caps": (i32, [vp, vp, u32]),
+        "pm_set_worker_reputation": (i32, [vp, vp, u32, u32]),
+        "pm_set_ask_min_reputation": (i32, [vp, vp, u32]),
         "pm_set_auction_params": (i32, [vp, C.c_uint64, C.c_uint64, u32]),
         "pm_match": (i32, [vp, u32]),
         "pm_fetch_result": (i32, [vp, P(abi.PmResult)]),

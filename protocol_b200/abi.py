@@ -111,7 +111,7 @@ EXPORTS = [
     "pm_create", "pm_destroy", "pm_last_error", "pm_alloc_pinned", "pm_free_pinned",
     "pm_set_asks", "pm_set_model_table", "pm_set_worker_count", "pm_upsert_workers",
     "pm_set_worker_locations", "pm_set_worker_addr_rank", "pm_set_flags",
-    "pm_set_ask_price_caps", "pm_set_auction_params",
+    "pm_set_ask_price_caps", "pm_set_auction_params", "pm_set_worker_reputation", "pm_set_ask_min_reputation",
     "pm_match", "pm_fetch_result", "pm_get_stats", "pm_build_cost_tile",
     "pm_match_local", "pm_match_finish", "pm_device_buffer", "pm_stream_sync", "pm_set_shard",
     "pm_resize_workers", "pm_update_workers", "pm_table_version", "pm_create_sibling",

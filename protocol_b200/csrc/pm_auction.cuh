@@ -8,6 +8,8 @@
 //
 // Synchronous (Jacobi) Bertsekas auction:
 //   feasible(t,w) = candidate(w) && compatible(t,w) && ask_price[w] <= price_cap[t]
+//                   && reputation[w] >= min_reputation[t]   (the north-star `reputation` column; both default to 0.
+//                   The floor is part of the ask's class, so cached and pooled workers never need the test again.)
 //   value(t,w)    = -(ask_price[w] * S) - price[w]      outside(t) = -((price_cap[t] + 1) * S)
 //   bid(t)        = price[w1] + (best - max(second, outside)) + eps    on the best worker w1
 //   a worker takes the highest bid (ties: lowest ask index), releasing its previous owner.
@@ -89,6 +91,8 @@ struct AuctionParams {
   long long* price_s;          // [W + 2] price mirror in sorted order
   const unsigned long long* csort_s;  // [W] the sort key: ask_price * S + price at the time of the last sort
   const uint32_t* price_cap;   // [T]
+  const uint32_t* rep_s;       // [W + 4] `reputation` column in sorted order, or null (no reputation clause)
+  const uint32_t* min_rep;     // [T] per-ask floor on it (part of the ask's class); null with rep_s
   long long* price;            // [W] dual price of each worker
   uint32_t* owner;             // [W] ask currently holding the worker
   uint32_t* assigned;          // [T] worker held by the ask
@@ -124,6 +128,7 @@ struct __align__(128) AuctionStage {
   uint4 b[kAucStripe];
   long long price[kAucStripe];
   uint32_t perm[kAucStripe];
+  uint32_t rep[kAucStripe];
   uint64_t bar;
 };
 
@@ -303,6 +308,8 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   const uint32_t t = live ? (cls_mode ? p.class_rep[item] : item) : 0u;
   const DevAsk ask = p.ev.asks[t];
   const uint32_t cap = cls_mode ? 0xFFFFFFFFu : p.price_cap[t];
+  const bool use_rep = p.rep_s != nullptr;
+  const uint32_t floor_rep = use_rep ? p.min_rep[t] : 0u;
   // per lane: its 4 best (value, worker) in order, and the best (value, worker) it did not keep
   long long cv[4] = {kAucNeg, kAucNeg, kAucNeg, kAucNeg};
   uint32_t cw[4] = {kNone, kNone, kNone, kNone};
@@ -323,11 +330,12 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price_s[] and perm[] are padded
     const uint32_t nq = (n + 3u) & ~3u;
-    mbar_expect_tx(&s.bar, n * 32u + np * 8u + nq * 4u);
+    mbar_expect_tx(&s.bar, n * 32u + np * 8u + nq * 4u + (use_rep ? nq * 4u : 0u));
     bulk_g2s(s.a, p.wa_s + w0, n * 16u, &s.bar);
     bulk_g2s(s.b, p.wb_s + w0, n * 16u, &s.bar);
     bulk_g2s(s.price, p.price_s + w0, np * 8u, &s.bar);
     bulk_g2s(s.perm, p.perm + w0, nq * 4u, &s.bar);
+    if (use_rep) bulk_g2s(s.rep, p.rep_s + w0, nq * 4u, &s.bar);
   };
   auto wait_stage = [&](uint32_t j) {
     const uint32_t b = j % kAucStages;   // bit b of phase_bits = parity of the buffer's next completed phase
@@ -352,7 +360,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
       scanned += n;
       for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
-        if (wr.price <= cap && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words))
+        if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words))
           auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
       }
     }
@@ -636,12 +644,13 @@ __device__ __forceinline__ uint64_t auc_mix(uint64_t h, uint32_t v) {
   h *= 0x9E3779B97F4A7C15ull;
   return h ^ (h >> 29);
 }
-__global__ void pm_auction_ask_hash(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts, uint32_t n_asks,
-                                    uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+__global__ void pm_auction_ask_hash(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts, const uint32_t* __restrict__ min_rep,
+                                    uint32_t n_asks, uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_asks) return;
   const DevAsk a = asks[t];
   uint64_t h = 0x243F6A8885A308D3ull;
+  if (min_rep) h = auc_mix(h, min_rep[t]);
   h = auc_mix(h, a.need); h = auc_mix(h, a.n_opts); h = auc_mix(h, a.cpu_cores); h = auc_mix(h, a.ram_mb); h = auc_mix(h, a.storage_gb);
   for (uint32_t o = 0; o < a.n_opts; ++o) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>(opts + a.opt_off + o);
@@ -651,8 +660,9 @@ __global__ void pm_auction_ask_hash(const DevAsk* __restrict__ asks, const DevOp
   key[t] = h;
   idx[t] = t;
 }
-__device__ __forceinline__ bool auc_same_ask(const DevAsk* asks, const DevOpt* opts, uint32_t x, uint32_t y) {
+__device__ __forceinline__ bool auc_same_ask(const DevAsk* asks, const DevOpt* opts, const uint32_t* min_rep, uint32_t x, uint32_t y) {
   const DevAsk a = asks[x], b = asks[y];
+  if (min_rep && min_rep[x] != min_rep[y]) return false;
   if (a.need != b.need || a.n_opts != b.n_opts || a.cpu_cores != b.cpu_cores || a.ram_mb != b.ram_mb ||
       a.storage_gb != b.storage_gb)
     return false;
@@ -665,11 +675,11 @@ __device__ __forceinline__ bool auc_same_ask(const DevAsk* asks, const DevOpt* o
   return true;
 }
 // flag[i] = 1 where the i-th ask in hash order starts a new class (content compared, not the hash)
-__global__ void pm_auction_class_flags(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts,
+__global__ void pm_auction_class_flags(const DevAsk* __restrict__ asks, const DevOpt* __restrict__ opts, const uint32_t* __restrict__ min_rep,
                                        const uint32_t* __restrict__ sorted, uint32_t n_asks, uint32_t* __restrict__ flag) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_asks) return;
-  flag[i] = (i == 0 || !auc_same_ask(asks, opts, sorted[i - 1], sorted[i])) ? 1u : 0u;
+  flag[i] = (i == 0 || !auc_same_ask(asks, opts, min_rep, sorted[i - 1], sorted[i])) ? 1u : 0u;
 }
 __global__ void pm_auction_class_assign(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ flag,
                                         const uint32_t* __restrict__ incl, uint32_t n_asks, uint32_t* __restrict__ class_of,
@@ -692,7 +702,7 @@ __global__ void pm_auction_cost_keys(const uint4* __restrict__ wb, const long lo
 __global__ void pm_auction_gather_sorted(const uint4* __restrict__ wa, const uint4* __restrict__ wb,
                                          const uint32_t* __restrict__ perm, const long long* __restrict__ price, uint32_t n,
                                          uint4* __restrict__ wa_s, uint4* __restrict__ wb_s, uint32_t* __restrict__ pos_of,
-                                         long long* __restrict__ price_s) {
+                                         long long* __restrict__ price_s, const uint32_t* __restrict__ rep, uint32_t* __restrict__ rep_s) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t w = perm[i];
@@ -700,6 +710,7 @@ __global__ void pm_auction_gather_sorted(const uint4* __restrict__ wa, const uin
   wb_s[i] = wb[w];
   pos_of[w] = i;
   price_s[i] = price[w];
+  if (rep_s) rep_s[i] = rep[w];
 }
 
 // result in the engine's group form: one solo group per assigned ask, in ask order

@@ -203,6 +203,8 @@ struct pm_engine {
   uint32_t auc_n_classes = 0;
   bool auc_classes_valid = false;
   bool have_caps = false;
+  DevBuf<uint32_t> reputation, ask_min_rep, auc_rep_s;   // extension: worker reputation column, per-ask floor, sorted copy
+  bool have_rep = false, have_min_rep = false;
   uint64_t auc_scale = 1, auc_eps_start = 1;
   uint32_t auc_eps_div = 4;
   DevBuf<uint32_t> worker_group, worker_ask, group_ask, group_off, members;
@@ -414,6 +416,7 @@ void pm_destroy(pm_engine* e) {
   e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
   e->pg_part_d.release(); e->pg_part_i.release(); e->pg_cta_cnt.release(); e->pg_ctl.release();
   e->pg_clat.release(); e->pg_clon.release(); e->pg_ccos.release();
+  e->reputation.release(); e->ask_min_rep.release(); e->auc_rep_s.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
@@ -492,6 +495,7 @@ int pm_set_asks(pm_engine* e, const pm_ask* asks, uint32_t n_asks, const pm_gpu_
   e->asks_small = (st & pm::kAskNotSmall) == 0;
   e->any_max_zero = (st & pm::kAskMaxZero) != 0;
   e->have_caps = false;
+  e->have_min_rep = false;
   e->auc_classes_valid = false;
   e->have_asks = true;
   e->matched = e->local_done = false;
@@ -553,6 +557,7 @@ int pm_set_worker_count(pm_engine* e, uint32_t n_workers) try {
   e->workers_checked = false;
   e->have_workers = true;
   e->have_loc = e->have_rank = false;
+  e->have_rep = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -639,6 +644,7 @@ int pm_resize_workers(pm_engine* e, uint32_t n_workers) try {
     PM_CUDA(e->lon.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
   }
   if (e->have_rank) PM_CUDA(e->addr_rank.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
+  if (e->have_rep) PM_CUDA(e->reputation.grow_keep(std::max<uint32_t>(n_workers, 1), keep, e->stream));
   if (n_workers > keep) {   // rows that were beyond the old table (or were cut off earlier) start empty
     PM_CUDA(cudaMemsetAsync(e->wa.p + keep, 0, (size_t)(n_workers - keep) * 16, e->stream));
     PM_CUDA(cudaMemsetAsync(e->wb.p + keep, 0, (size_t)(n_workers - keep) * 16, e->stream));
@@ -647,6 +653,7 @@ int pm_resize_workers(pm_engine* e, uint32_t n_workers) try {
       PM_CUDA(cudaMemsetAsync(e->lon.p + keep, 0, (size_t)(n_workers - keep) * 8, e->stream));
     }
     if (e->have_rank) PM_CUDA(cudaMemsetAsync(e->addr_rank.p + keep, 0, (size_t)(n_workers - keep) * 4, e->stream));
+    if (e->have_rep) PM_CUDA(cudaMemsetAsync(e->reputation.p + keep, 0, (size_t)(n_workers - keep) * 4, e->stream));
   }
   e->n_workers = n_workers;
   e->have_workers = true;
@@ -1104,7 +1111,7 @@ static int auction_build_classes(pm_engine* e) {
   PM_CUDA(e->auc_hash_out.ensure(T)); PM_CUDA(e->auc_idx.ensure(T)); PM_CUDA(e->auc_sorted.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_incl.ensure(T));
   if (T == 0) { e->auc_classes_valid = true; return PM_OK; }
-  pm::pm_auction_ask_hash<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, T, e->auc_hash.p, e->auc_idx.p);
+  pm::pm_auction_ask_hash<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, e->have_min_rep ? e->ask_min_rep.p : nullptr, T, e->auc_hash.p, e->auc_idx.p);
   PM_LAUNCH_CHECK("pm_auction_ask_hash");
   size_t tmp_sort = 0, tmp_scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, e->auc_hash.p, e->auc_hash_out.p, e->auc_idx.p, e->auc_sorted.p, (int)T, 0, 64, e->stream);
@@ -1112,7 +1119,7 @@ static int auction_build_classes(pm_engine* e) {
   size_t tmp = std::max(tmp_sort, tmp_scan);
   PM_CUDA(e->cub_tmp.ensure(tmp));
   PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_hash.p, e->auc_hash_out.p, e->auc_idx.p, e->auc_sorted.p, (int)T, 0, 64, e->stream));
-  pm::pm_auction_class_flags<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, e->auc_sorted.p, T, e->auc_flag.p);
+  pm::pm_auction_class_flags<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->asks.p, e->opts.p, e->have_min_rep ? e->ask_min_rep.p : nullptr, e->auc_sorted.p, T, e->auc_flag.p);
   PM_LAUNCH_CHECK("pm_auction_class_flags");
   PM_CUDA(cub::DeviceScan::InclusiveSum(e->cub_tmp.p, tmp, e->auc_flag.p, e->auc_incl.p, (int)T, e->stream));
   pm::pm_auction_class_assign<<<blocks_for(T, 256), 256, 0, e->stream>>>(e->auc_sorted.p, e->auc_flag.p, e->auc_incl.p, T,
@@ -1170,6 +1177,17 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(cudaMemsetAsync(e->auc_ctl.p, 0, sizeof(pm::AuctionCtl), e->stream));
   PM_CUDA(cudaMemsetAsync(e->auc_class_req.p, 0, (size_t)std::max<uint32_t>(C, 1) * 4, e->stream));
   PM_CUDA(e->auc_ckey.ensure(W)); PM_CUDA(e->auc_ckey_s.ensure(W));
+  // `reputation` clause: only when a floor was given; a missing worker column is a column of zeros
+  const bool use_rep = e->have_min_rep;
+  if (use_rep) {
+    if (!e->have_rep) {
+      PM_CUDA(e->reputation.ensure(std::max<size_t>(e->wa.n, 1)));
+      PM_CUDA(cudaMemsetAsync(e->reputation.p, 0, std::max<size_t>(e->wa.n, 1) * 4, e->stream));
+      e->have_rep = true;
+    }
+    PM_CUDA(e->auc_rep_s.ensure((size_t)W + 4));
+    PM_CUDA(cudaMemsetAsync(e->auc_rep_s.p, 0, ((size_t)W + 4) * 4, e->stream));
+  }
   if (W) {
     pm::pm_fill_i64<<<std::min(blocks_for(W, 256), 1184u), 256, 0, e->stream>>>(e->auc_bid_max.p, pm::kAucNeg, W);
     PM_LAUNCH_CHECK("pm_fill_i64");
@@ -1184,7 +1202,8 @@ static int match_auction_locked(pm_engine* e) {
     PM_CUDA(e->cub_tmp.ensure(tmp));
     PM_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, e->auc_ckey.p, e->auc_ckey_s.p, e->auc_idx.p, e->auc_perm.p, (int)W, 0, 64, e->stream));
     pm::pm_auction_gather_sorted<<<blocks_for(W, 256), 256, 0, e->stream>>>(e->wa.p, e->wb.p, e->auc_perm.p, e->auc_price.p, W, e->auc_wa_s.p,
-                                                                            e->auc_wb_s.p, e->auc_pos_of.p, e->auc_price_s.p);
+                                                                            e->auc_wb_s.p, e->auc_pos_of.p, e->auc_price_s.p,
+                                                                            use_rep ? e->reputation.p : nullptr, use_rep ? e->auc_rep_s.p : nullptr);
     PM_LAUNCH_CHECK("pm_auction_gather_sorted");
     return PM_OK;
   };
@@ -1198,6 +1217,7 @@ static int match_auction_locked(pm_engine* e) {
   ap.ev = eval_params(e);
   ap.wa_s = e->auc_wa_s.p; ap.wb_s = e->auc_wb_s.p; ap.perm = e->auc_perm.p; ap.pos_of = e->auc_pos_of.p; ap.price_s = e->auc_price_s.p;
   ap.csort_s = reinterpret_cast<const unsigned long long*>(e->auc_ckey_s.p);
+  ap.rep_s = use_rep ? e->auc_rep_s.p : nullptr; ap.min_rep = use_rep ? e->ask_min_rep.p : nullptr;
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
   ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
@@ -1342,6 +1362,41 @@ int pm_set_ask_price_caps(pm_engine* e, const uint32_t* price_cap, uint32_t n_as
   if (n_asks) PM_CUDA(cudaMemcpyAsync(e->price_cap.p, price_cap, (size_t)n_asks * 4, cudaMemcpyHostToDevice, e->stream));
   PM_CUDA(cudaStreamSynchronize(e->stream));
   e->have_caps = true;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+// `reputation` worker column and the per-ask floor on it (north-star extension; PM_MODE_AUCTION only)
+int pm_set_worker_reputation(pm_engine* e, const uint32_t* reputation, uint32_t first, uint32_t n) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  ++e->table_version;
+  if (!e->have_workers) return e->fail(PM_E_STATE, "pm_set_worker_reputation: no worker table");
+  if ((uint64_t)first + n > e->n_workers) return e->fail(PM_E_INVALID, "pm_set_worker_reputation: range");
+  if (n && !reputation) return e->fail(PM_E_INVALID, "pm_set_worker_reputation: null");
+  PM_CUDA(cudaSetDevice(e->device));
+  if (!e->have_rep) {
+    PM_CUDA(e->reputation.ensure(std::max<size_t>(e->wa.n, 1)));
+    PM_CUDA(cudaMemsetAsync(e->reputation.p, 0, std::max<size_t>(e->wa.n, 1) * 4, e->stream));
+  }
+  if (n) PM_CUDA(cudaMemcpyAsync(e->reputation.p + first, reputation, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_rep = true;
+  e->matched = e->local_done = false;
+  return PM_OK;
+} catch (...) { return pm_guard_rc(); }
+
+int pm_set_ask_min_reputation(pm_engine* e, const uint32_t* min_reputation, uint32_t n_asks) try {
+  if (!e) return PM_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_asks || n_asks != e->n_asks) return e->fail(PM_E_INVALID, "pm_set_ask_min_reputation: one floor per ask, after pm_set_asks");
+  if (n_asks && !min_reputation) return e->fail(PM_E_INVALID, "pm_set_ask_min_reputation: null");
+  PM_CUDA(cudaSetDevice(e->device));
+  PM_CUDA(e->ask_min_rep.ensure(std::max<uint32_t>(n_asks, 1)));
+  if (n_asks) PM_CUDA(cudaMemcpyAsync(e->ask_min_rep.p, min_reputation, (size_t)n_asks * 4, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_min_rep = true;
+  e->auc_classes_valid = false;   // the floor is part of an ask's class
+  e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
 

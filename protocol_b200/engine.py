@@ -206,6 +206,15 @@ class Engine:
         caps = np.ascontiguousarray(caps, dtype=np.uint32)
         self._check(self._lib.pm_set_ask_price_caps(self._h, _ptr(caps), len(caps)))
 
+    def set_worker_reputation(self, reputation: np.ndarray, first: int = 0):
+        """north_star worker column `reputation` (u32 per worker); read by PM_MODE_AUCTION through the per-ask floor."""
+        reputation = np.ascontiguousarray(reputation, dtype=np.uint32)
+        self._check(self._lib.pm_set_worker_reputation(self._h, _ptr(reputation), first, len(reputation)))
+
+    def set_min_reputation(self, floors: np.ndarray):
+        floors = np.ascontiguousarray(floors, dtype=np.uint32)
+        self._check(self._lib.pm_set_ask_min_reputation(self._h, _ptr(floors), len(floors)))
+
     def set_auction_params(self, cost_scale: int = 1, eps_start: int = 1, eps_div: int = 4):
         self._check(self._lib.pm_set_auction_params(self._h, cost_scale, eps_start, eps_div))
 

@@ -483,6 +483,89 @@ def test_extension_auction_cfg3_100k_x_1m_properties():
     eng.close()
 
 
+def _check_auction_rep(t, cap, reputation, floors, **params):
+    eng = Engine()
+    load_engine(eng, t)
+    eng.set_price_caps(cap)
+    if reputation is not None:
+        eng.set_worker_reputation(reputation)
+    if floors is not None:
+        eng.set_min_reputation(floors)
+    if params:
+        eng.set_auction_params(**params)
+    eng.match(abi.PM_MODE_AUCTION)
+    res = eng.fetch()
+    want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap,
+                                          reputation=reputation, min_reputation=floors, **params)
+    got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
+    for ask, members in res.groups():
+        assert len(members) == 1
+        got[ask] = members[0]
+    assert np.array_equal(got, want)
+    assert res.stats["n_rounds"] == rounds
+    eng.close()
+    return got
+
+
+@pytest.mark.parametrize("n_asks,n_workers,seed", [(50, 700, 12), (300, 2500, 13), (64, 1025, 14), (400, 20000, 15)])
+def test_extension_auction_reputation_floor_matches_self_oracle(n_asks, n_workers, seed):
+    """north_star worker column `reputation`: a pair is feasible only when reputation[w] >= the ask's floor.  The floor
+    is part of the ask's class (two asks with the same requirement row and different floors do not share a cache)."""
+    t, cap = _auction_tables(n_asks, n_workers, seed)
+    rng = np.random.default_rng(seed)
+    reputation = rng.integers(0, 1000, n_workers).astype(np.uint32)
+    floors = np.where(rng.random(n_asks) < 0.5, 0, rng.integers(1, 1100, n_asks)).astype(np.uint32)
+    got = _check_auction_rep(t, cap, reputation, floors)
+    sold = got != abi.PM_NONE
+    assert np.all(reputation[got[sold]] >= floors[sold])
+    assert not np.any(sold & (floors > reputation.max()))          # a floor nobody reaches: the ask withdraws
+    # the clause bites: without it the same market sells differently
+    want0, _, _ = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap)
+    assert not np.array_equal(got, want0)
+
+
+def test_extension_auction_reputation_duplicated_asks_and_ties():
+    """Duplicated requirement rows that differ ONLY in the floor, narrow price range (every tie rule), few reputation levels."""
+    w, a, t = synth_tables(10, 3000, "mixed", seed_shift=21)
+    rng = np.random.default_rng(21)
+    idx = rng.permutation(np.repeat(np.arange(10), 40))
+    t["asks"] = np.ascontiguousarray(t["asks"][idx])
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = rng.integers(10, 15, 3000).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(8, 18, len(idx)).astype(np.uint32)
+    reputation = rng.integers(0, 4, 3000).astype(np.uint32)
+    floors = rng.integers(0, 5, len(idx)).astype(np.uint32)
+    _check_auction_rep(t, cap, reputation, floors)
+    _check_auction_rep(t, cap, reputation, floors, cost_scale=3)
+
+
+def test_extension_auction_reputation_defaults_are_inert():
+    """No floor -> the worker column is never read; a floor without a worker column is a column of zeros."""
+    t, cap = _auction_tables(120, 1500, 31)
+    rng = np.random.default_rng(31)
+    reputation = rng.integers(0, 100, 1500).astype(np.uint32)
+    base = _check_auction_rep(t, cap, None, None)
+    assert np.array_equal(_check_auction_rep(t, cap, reputation, None), base)
+    assert np.array_equal(_check_auction_rep(t, cap, reputation, np.zeros(120, dtype=np.uint32)), base)
+    floors = np.zeros(120, dtype=np.uint32)
+    floors[::3] = 1
+    got = _check_auction_rep(t, cap, None, floors)
+    assert np.all(got[::3] == abi.PM_NONE)
+    # reference modes ignore both columns
+    eng = Engine()
+    load_engine(eng, t)
+    eng.match()
+    r0 = eng.fetch()
+    eng.set_worker_reputation(reputation)
+    eng.set_min_reputation(floors)
+    eng.match()
+    r1 = eng.fetch()
+    for f in ("worker_group", "worker_ask", "group_ask", "group_off", "group_members", "ask_count"):
+        assert np.array_equal(getattr(r0, f), getattr(r1, f)), f
+    eng.close()
+
+
 def test_extension_columns_are_neutral_in_reference_modes():
     """ext_ask_price only occupies the high word of the packed cost; groups do not depend on it."""
     w, a, t = synth_tables(200, 3000, "mixed")

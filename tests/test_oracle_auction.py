@@ -69,6 +69,44 @@ def test_infeasible_asks_withdraw():
     assert (out == NONE).all() and rounds == 1
 
 
+def brute_force_best_surplus_masked(price, cap, ok):
+    T, W = len(cap), len(price)
+    best = 0
+    for k in range(0, min(T, W) + 1):
+        for ts in itertools.combinations(range(T), k):
+            for ws in itertools.permutations(range(W), k):
+                if all(ok[t, w] and price[w] <= cap[t] for t, w in zip(ts, ws)):
+                    best = max(best, sum(int(cap[t]) + 1 - int(price[w]) for t, w in zip(ts, ws)))
+    return best
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_reputation_floor_is_a_feasibility_clause(seed):
+    """north_star worker column `reputation`: reputation[w] >= min_reputation[t] joins the feasibility predicate;
+    with the exact cost scale the result is the optimum of the masked problem (brute force)."""
+    T, W = 4, 5
+    a, b, asks, opts, cap = tiny(200 + seed, T, W)
+    rng = np.random.default_rng(seed)
+    rep = rng.integers(0, 4, W).astype(np.uint32)
+    floor = rng.integers(0, 5, T).astype(np.uint32)
+    bits = np.array([0xFFFFFFFF], dtype=np.uint32)
+    out, _, _ = orc.soa_auction(a, b, asks, opts, bits, 1, cap, cost_scale=T + 1, reputation=rep, min_reputation=floor)
+    ok = rep[None, :] >= floor[:, None]
+    for t in range(T):
+        if out[t] != NONE:
+            assert ok[t, out[t]] and b["ext_ask_price"][out[t]] <= cap[t]
+    used = out[out != NONE]
+    assert len(set(used.tolist())) == len(used)
+    surplus = sum(int(cap[t]) + 1 - int(b["ext_ask_price"][out[t]]) for t in range(T) if out[t] != NONE)
+    assert surplus == brute_force_best_surplus_masked(b["ext_ask_price"], cap, ok)
+    # missing columns are columns of zeros
+    base, _, r0 = orc.soa_auction(a, b, asks, opts, bits, 1, cap)
+    z, _, r1 = orc.soa_auction(a, b, asks, opts, bits, 1, cap, reputation=rep, min_reputation=np.zeros(T, dtype=np.uint32))
+    assert np.array_equal(base, z) and r0 == r1
+    none, _, _ = orc.soa_auction(a, b, asks, opts, bits, 1, cap, min_reputation=np.ones(T, dtype=np.uint32))
+    assert (none == NONE).all()
+
+
 def lsa_optimum(price, cap, feasible, scale=1):
     """Minimum of sum over asks of (price * scale if assigned to a feasible worker within the cap, else the outside
     option (cap + 1) * scale) — scipy's Hungarian solver on the masked matrix: an anchor that is NOT this repo's code."""
