@@ -78,6 +78,8 @@ struct AuctionCtl {
   uint32_t n_retry;      // asks that bid again after the class rescans
   uint32_t n_fallback;   // asks that need their own scan
   uint32_t rounds;       // rounds in which at least one ask was active
+  uint32_t flip;         // which half of active[] holds the current round's list (the other half collects the next one)
+  uint32_t ticket;       // blocks of pm_auction_apply that are through: the last one advances the round
   unsigned long long evals;
   unsigned long long n_class_scans, n_ask_scans, n_refills;
 };
@@ -97,7 +99,8 @@ struct AuctionParams {
   uint32_t* owner;             // [W] ask currently holding the worker
   uint32_t* assigned;          // [T] worker held by the ask
   uint32_t* withdrawn;         // [T]
-  uint32_t* active;            // [T]
+  uint32_t* active;            // [2 * T] the round's active asks | the next round's, roles swapped by ctl->flip
+  uint32_t n_asks;
   uint32_t* bid_w;             // [T]
   long long* bid_p;            // [T]
   long long* bid_max;          // [W] highest bid of the round (reset by the winner)
@@ -120,6 +123,7 @@ struct AuctionParams {
   uint32_t* fallback;          // [T]
   AuctionCtl* ctl;
   long long scale, eps;
+  uint32_t pool_good, pool_extra;   // pool fill of a class walk (kAucPoolGood / kAucPoolExtra unless PM_TUNE_AUCTION_POOL=good,extra)
   uint32_t dbg;                // PM_TUNE_AUCTION: 1 = no early exit, 2 = every ask scans for itself
 };
 
@@ -131,6 +135,20 @@ struct __align__(128) AuctionStage {
   uint32_t rep[kAucStripe];
   uint64_t bar;
 };
+
+__device__ __forceinline__ const uint32_t* auc_active(const AuctionParams& p) { return p.active + (p.ctl->flip ? p.n_asks : 0u); }
+__device__ __forceinline__ uint32_t* auc_next(const AuctionParams& p) { return p.active + (p.ctl->flip ? 0u : p.n_asks); }
+__device__ __forceinline__ void auc_advance(AuctionCtl* ctl, int first) {
+  if (!first && ctl->n_active) ++ctl->rounds;
+  ctl->n_active = ctl->n_next;
+  ctl->n_next = 0;
+  ctl->n_cls = 0;
+  ctl->n_walk = 0;
+  ctl->n_retry = 0;
+  ctl->n_fallback = 0;
+  ctl->flip ^= 1u;
+  ctl->ticket = 0;
+}
 
 __device__ __forceinline__ bool auc_better(long long v1, uint32_t w1, long long v2, uint32_t w2) {
   return v1 > v2 || (v1 == v2 && w1 < w2);
@@ -288,6 +306,70 @@ __device__ __forceinline__ AuctionPick auction_select(long long (&cv)[4], uint32
   return r;
 }
 
+// CTA-wide selection (all 256 threads, one item): the 1024 kept candidates are sorted by (value desc, worker asc) in
+// shared memory with a bitonic network — 52 compare-exchange stages of two pairs per thread, the stages whose pairs
+// stay inside a warp's own 64 entries separated by a warp barrier only — instead of 2 x 32 dependent warp arg-max
+// rounds (a quarter of the instructions, a tenth of the dependent shuffle chain).  A thread's 4 candidates arrive
+// sorted, so the network is entered at run length 4 (odd threads store their run reversed: every 8 entries are then a
+// bitonic sequence).  The result is valid in warp 0.
+struct __align__(16) AuctionSort {
+  long long v[kAucPool];
+  uint32_t w[kAucPool];
+  long long drop_v[kAucWarps];
+  uint32_t drop_w[kAucWarps];
+};
+static_assert(kAucPool == 4 * kAucThreads, "one sorted run of 4 per thread");
+
+__device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[4], const uint32_t (&cw)[4], long long dropped,
+                                                          uint32_t dropped_w, AuctionSort& ss) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  {
+    const bool rev = (tid & 1u) != 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t at = tid * 4u + (rev ? 3u - (uint32_t)j : (uint32_t)j);
+      ss.v[at] = cv[j];
+      ss.w[at] = cw[j];
+    }
+    long long dv;
+    uint32_t dw;
+    warp_argbest(dropped, dropped_w, &dv, &dw);
+    if (lane == 0) { ss.drop_v[warp] = dv; ss.drop_w[warp] = dw; }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t k = 8; k <= (uint32_t)kAucPool; k <<= 1) {
+#pragma unroll 1
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (uint32_t r = 0; r < 2; ++r) {
+        const uint32_t idx = tid + r * (uint32_t)kAucThreads;
+        const uint32_t i = 2u * idx - (idx & (j - 1u));   // the pair (i, i + j): bit j of i is clear
+        const long long va = ss.v[i], vb = ss.v[i + j];
+        const uint32_t wa = ss.w[i], wb = ss.w[i + j];
+        const bool desc = (i & k) == 0u;
+        const bool swap = desc ? auc_better(vb, wb, va, wa) : auc_better(va, wa, vb, wb);
+        if (swap) { ss.v[i] = vb; ss.w[i] = wb; ss.v[i + j] = va; ss.w[i + j] = wa; }
+      }
+      // pairs at distance <= 32 stay inside the 64 entries a warp owns per half (idx -> i maps 32 consecutive idx
+      // onto one aligned block of 64): only a change to or from a wider stage needs the whole CTA
+      if (j > 32u || (j == 1u && k >= 64u)) __syncthreads();
+      else __syncwarp();
+    }
+  }
+  AuctionPick r;
+  r.b1 = ss.v[0]; r.w1 = ss.w[0]; r.b2 = ss.v[1];
+  r.mine = (ss.v[lane] > kAucNeg) ? ss.w[lane] : kNone;
+  const long long next_v = ss.v[32];
+  const uint32_t next_w = ss.w[32];
+  warp_argbest(lane < (uint32_t)kAucWarps ? ss.drop_v[lane] : kAucNeg, lane < (uint32_t)kAucWarps ? ss.drop_w[lane] : kNone, &r.drop_v, &r.drop_w);
+  const bool use_next = auc_better(next_v, next_w, r.drop_v, r.drop_w);
+  r.bound_v = use_next ? next_v : r.drop_v;
+  r.bound_w = use_next ? next_w : r.drop_w;
+  __syncthreads();   // ss may be rewritten by the next select
+  return r;
+}
+
 // One scan item (a class, or a single ask in fallback mode) per 8/TPC warps.
 //
 // Class mode keeps, next to the 32-entry cache the asks bid from, a POOL: every candidate the lanes
@@ -367,8 +449,9 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     // The table is sorted by the cost ask_price * S + price each worker had at the last sort; prices only rise, so
     // every later worker has value <= U = -(the stripe's last sort key).  Once 33 of the item's kept candidates beat the
     // unseen workers, at least one of them stays outside the 32-entry cache, so the bound (best candidate not cached) beats
-    // every unseen worker and the walk may stop; a class walks a little further to fill its pool; a single ask also
-    // stops once the unseen workers cannot reach its outside option.
+    // every unseen worker and the walk may stop; a class walks a little further to fill its pool (not a part of a split
+    // walk: it leaves its top 32 only, and those are final at this point); a single ask also stops once the unseen
+    // workers cannot reach its outside option.
     const long long u = -(long long)p.csort_s[w0 + n - 1];
     const bool past_cap = !cls_mode && u < -(((long long)cap + 1) * p.scale);
     // ... and a later worker whose value still equals U has the same sort key as the stripe's last worker, hence a
@@ -386,7 +469,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     }
     if (cnt > (uint32_t)kAucCache && first_good == kNone) first_good = k;
     bool done = !scan || past_cap ||
-                (first_good != kNone && (!cls_mode || cnt > (uint32_t)kAucPoolGood || k - first_good >= (uint32_t)kAucPoolExtra));
+                (first_good != kNone && (!cls_mode || G > 1u || cnt > p.pool_good || k - first_good >= p.pool_extra));
     if (p.dbg & 1u) done = false;
     if (kWpt == 1) done = __syncthreads_and(done) != 0;
     // (the barrier above also means: stripe k fully consumed, its buffer may be refilled)
@@ -403,7 +486,12 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     if (kWpt == 1)
       for (uint32_t j = 32u + lane; j < (uint32_t)(kAucPool / 4); j += 32u) pool[j] = make_uint4(kNone, kNone, kNone, kNone);
   }
-  AuctionPick r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+  // the stage buffers are idle from here to the item's end (every copy issued was waited for): the sort scratch lives there
+  AuctionSort& ss = *reinterpret_cast<AuctionSort*>(&stage[0]);
+  static_assert(sizeof(AuctionSort) <= sizeof(AuctionStage), "sort scratch aliases one stage");
+  AuctionPick r;
+  if constexpr (kWpt == kAucWarps) r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+  else r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
   if (scan && sub == 0 && lane == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
   long long pb_v = kAucNeg;   // outside the pool: what no lane kept, and the part of the table the walk did not reach
   uint32_t pb_w = kNone;
@@ -448,7 +536,8 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
         if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
     }
     if (in_item == 0) { dropped = pb_v; dropped_w = pb_w; }
-    r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+    if constexpr (kWpt == kAucWarps) r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+    else r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
     if (threadIdx.x == 0) p.split_ticket[slot] = 0u;
   } else if (scan && sub == 0) {
     pb_v = r.drop_v;
@@ -476,7 +565,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
 // Rescan requests first re-rank the class pool at the current prices (a few gathers per thread); the classes
 // whose pool cannot decide go on the walk list.
 __global__ void __launch_bounds__(kAucThreads) pm_auction_refill(AuctionParams p) {
-  __shared__ AuctionMerge mg;
+  __shared__ AuctionSort ss;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n = p.ctl->n_cls;
   for (uint32_t slot = blockIdx.x; slot < n; slot += gridDim.x) {
@@ -496,7 +585,7 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_refill(AuctionParams p
     for (int j = 0; j < 4; ++j)
       if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
     if (threadIdx.x == 0) { dropped = pool_bound; dropped_w = p.pool_bound_w[item]; }   // everything outside the pool
-    const AuctionPick r = auction_select<kAucWarps>(cv, cw, dropped, dropped_w, mg);
+    const AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
     if (warp == 0) {
       const bool ok = !(p.dbg & 16u) && (r.bound_v == kAucNeg || (r.b2 >= r.bound_v && auc_better(r.b1, r.w1, r.bound_v, r.bound_w)));
       if (ok) {
@@ -548,7 +637,7 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_scan(AuctionParams p, 
 __global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionParams p, int pass) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n = pass ? p.ctl->n_retry : p.ctl->n_active;
-  const uint32_t* list = pass ? p.retry : p.active;
+  const uint32_t* list = pass ? p.retry : auc_active(p);
   const uint32_t stamp = p.ctl->rounds + 1u;
   for (uint32_t slot = blockIdx.x * kAucWarps + warp; slot < n; slot += gridDim.x * kAucWarps) {
     const uint32_t t = list[slot];
@@ -600,43 +689,55 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionPara
 // the claim: among the highest bidders of a worker the lowest ask index wins
 __global__ void pm_auction_claim(AuctionParams p) {
   const uint32_t n = p.ctl->n_active;
+  const uint32_t* __restrict__ active = auc_active(p);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t t = p.active[i], w = p.bid_w[t];
+    const uint32_t t = active[i], w = p.bid_w[t];
     if (w != kNone && p.bid_p[t] == p.bid_max[w]) atomicMin(p.winner + w, t);
   }
 }
 
+// Winners take their workers; the next round's active list is written on the way: an active ask that did not win and
+// did not withdraw stays, and the ask a winner displaces comes back (it held a worker, so it was not active: no
+// duplicates).  The block that finishes last advances the round — no pass over all asks, no separate launches.
 __global__ void pm_auction_apply(AuctionParams p) {
   const uint32_t n = p.ctl->n_active;
+  const uint32_t* __restrict__ active = auc_active(p);
+  uint32_t* __restrict__ next = auc_next(p);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t t = p.active[i], w = p.bid_w[t];
-    if (w == kNone || p.winner[w] != t) continue;
-    const uint32_t prev = p.owner[w];
-    if (prev != kNone) p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
-    p.owner[w] = t;
-    p.assigned[t] = w;
-    p.price[w] = p.bid_p[t];
-    p.price_s[p.pos_of[w]] = p.bid_p[t];
-    p.bid_max[w] = kAucNeg;
-    p.winner[w] = kNone;
+    const uint32_t t = active[i], w = p.bid_w[t];
+    if (w != kNone && p.winner[w] == t) {
+      const uint32_t prev = p.owner[w];
+      if (prev != kNone) {
+        p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
+        next[atomicAdd(&p.ctl->n_next, 1u)] = prev;
+      }
+      p.owner[w] = t;
+      p.assigned[t] = w;
+      p.price[w] = p.bid_p[t];
+      p.price_s[p.pos_of[w]] = p.bid_p[t];
+      p.bid_max[w] = kAucNeg;
+      p.winner[w] = kNone;
+    } else if (!p.withdrawn[t]) {
+      next[atomicAdd(&p.ctl->n_next, 1u)] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&p.ctl->ticket, 1u) == gridDim.x - 1u) {
+      __threadfence();
+      auc_advance(p.ctl, 0);
+    }
   }
 }
 
-// next round's active list
+// the first active list of an eps phase: every ask that holds no worker and has not withdrawn
 __global__ void pm_auction_compact(AuctionParams p, uint32_t n_asks) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_asks) return;
-  if (p.assigned[t] == kNone && !p.withdrawn[t]) p.active[atomicAdd(&p.ctl->n_next, 1u)] = t;
+  if (p.assigned[t] == kNone && !p.withdrawn[t]) auc_next(p)[atomicAdd(&p.ctl->n_next, 1u)] = t;
 }
-__global__ void pm_auction_advance(AuctionCtl* ctl, int first) {
-  if (!first && ctl->n_active) ++ctl->rounds;
-  ctl->n_active = ctl->n_next;
-  ctl->n_next = 0;
-  ctl->n_cls = 0;
-  ctl->n_walk = 0;
-  ctl->n_retry = 0;
-  ctl->n_fallback = 0;
-}
+__global__ void pm_auction_advance(AuctionCtl* ctl, int first) { auc_advance(ctl, first); }
 
 // ---- ask classes -----------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t auc_mix(uint64_t h, uint32_t v) {

@@ -149,7 +149,7 @@ struct pm_engine {
   uint32_t max_pattern_row = 0;
   bool have_workers = false, have_asks = false, have_bits = false, have_loc = false, have_rank = false;
   bool all_solo = true;  // every ask has min == max == 1
-  int tune_argmin = 0, tune_generic = 0, tune_build = 0, tune_auction = 0, tune_prox = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
+  int tune_argmin = 0, tune_generic = 0, tune_build = 0, tune_auction = 0, tune_prox = 0, tune_auc_good = 0, tune_auc_extra = 0;   // PM_TUNE_ARGMIN: kernel-shape experiments (see profiles/)
   DevBuf<uint4> wa, wb;
   DevBuf<double> lat, lon;
   DevBuf<uint32_t> addr_rank;
@@ -378,6 +378,7 @@ int pm_create(const pm_cfg* cfg, pm_engine** out) try {
   if (const char* t = std::getenv("PM_TUNE_GENERIC")) e->tune_generic = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_BUILD")) e->tune_build = std::atoi(t);
   if (const char* t = std::getenv("PM_TUNE_AUCTION")) e->tune_auction = std::atoi(t);
+  if (const char* t = std::getenv("PM_TUNE_AUCTION_POOL")) std::sscanf(t, "%d,%d", &e->tune_auc_good, &e->tune_auc_extra);   // pool fill of a class walk
   if (const char* t = std::getenv("PM_TUNE_PROX")) e->tune_prox = std::atoi(t);   // 0: all-SM cooperative sweep; 2: single-CTA sweep; 1: latitude-banded single-CTA sweep (experimental)
   bool ok = cudaSetDevice(e->device) == cudaSuccess;
   if (ok && cfg->stream) {
@@ -1158,7 +1159,7 @@ static int match_auction_locked(pm_engine* e) {
   constexpr unsigned kScanGrid = 296u;   // two scanning CTAs per SM (shared memory)
   PM_CUDA(e->auc_price.ensure((size_t)W + 2)); PM_CUDA(e->auc_owner.ensure(W)); PM_CUDA(e->auc_bid_max.ensure(W));
   PM_CUDA(e->auc_winner.ensure(W)); PM_CUDA(e->auc_assigned.ensure(T)); PM_CUDA(e->auc_withdrawn.ensure(T));
-  PM_CUDA(e->auc_active.ensure(T)); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
+  PM_CUDA(e->auc_active.ensure((size_t)2 * std::max<uint32_t>(T, 1))); PM_CUDA(e->auc_bid_w.ensure(T)); PM_CUDA(e->auc_bid_p.ensure(T));
   PM_CUDA(e->auc_flag.ensure((size_t)T + 1)); PM_CUDA(e->auc_gidx.ensure((size_t)T + 1));
   PM_CUDA(e->auc_theta.ensure(C)); PM_CUDA(e->auc_theta_w.ensure(C)); PM_CUDA(e->auc_cand.ensure((size_t)C * pm::kAucCache));
   PM_CUDA(e->auc_pool.ensure((size_t)C * pm::kAucPool)); PM_CUDA(e->auc_pool_bound_v.ensure(C)); PM_CUDA(e->auc_pool_bound_w.ensure(C));
@@ -1219,7 +1220,7 @@ static int match_auction_locked(pm_engine* e) {
   ap.csort_s = reinterpret_cast<const unsigned long long*>(e->auc_ckey_s.p);
   ap.rep_s = use_rep ? e->auc_rep_s.p : nullptr; ap.min_rep = use_rep ? e->ask_min_rep.p : nullptr;
   ap.price_cap = e->price_cap.p; ap.price = e->auc_price.p; ap.owner = e->auc_owner.p; ap.assigned = e->auc_assigned.p;
-  ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
+  ap.withdrawn = e->auc_withdrawn.p; ap.active = e->auc_active.p; ap.n_asks = T; ap.bid_w = e->auc_bid_w.p; ap.bid_p = e->auc_bid_p.p;
   ap.bid_max = e->auc_bid_max.p; ap.winner = e->auc_winner.p; ap.scale = (long long)e->auc_scale;
   ap.class_of = e->auc_class_of.p; ap.class_rep = e->auc_class_rep.p; ap.class_req = e->auc_class_req.p;
   ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p;
@@ -1227,6 +1228,8 @@ static int match_auction_locked(pm_engine* e) {
   ap.walk_list = e->auc_walk_list.p; ap.split_bound_v = e->auc_split_v.p; ap.split_bound_w = e->auc_split_w.p; ap.split_ticket = e->auc_split_ticket.p;
   ap.class_list = e->auc_class_list.p; ap.retry = e->auc_retry.p; ap.fallback = e->auc_fallback.p; ap.ctl = e->auc_ctl.p;
   ap.dbg = (uint32_t)e->tune_auction;
+  ap.pool_good = e->tune_auc_good > 0 ? (uint32_t)e->tune_auc_good : (uint32_t)pm::kAucPoolGood;
+  ap.pool_extra = e->tune_auc_extra > 0 ? (uint32_t)e->tune_auc_extra : (uint32_t)pm::kAucPoolExtra;
   const size_t smem = pm::kAucStages * sizeof(pm::AuctionStage) + sizeof(pm::AuctionMerge);
   PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // fixed grids: every kernel strides over a list whose length it reads from the control block
@@ -1261,9 +1264,7 @@ static int match_auction_locked(pm_engine* e) {
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 1);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 0);
         pm::pm_auction_claim<<<g_thr, 256, 0, e->stream>>>(ap);
-        pm::pm_auction_apply<<<g_thr, 256, 0, e->stream>>>(ap);
-        pm::pm_auction_compact<<<blocks_for(T, 256), 256, 0, e->stream>>>(ap, T);
-        pm::pm_auction_advance<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, 0);
+        pm::pm_auction_apply<<<g_thr, 256, 0, e->stream>>>(ap);   // ... and the next round's active list, and the advance
       }
     };
     // a batch of rounds is one CUDA graph (the kernels are a few microseconds each: launch-bound otherwise);
@@ -1314,7 +1315,7 @@ static int match_auction_locked(pm_engine* e) {
   e->stats.evals = e->h_ctl.p->evals;
   e->stats.n_tiles = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_class_scans, 0xFFFFFFFFull);
   e->stats.n_fused_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_ask_scans, 0xFFFFFFFFull);
-  e->stats.n_launches = e->h_ctl.p->rounds * 9u;
+  e->stats.n_launches = e->h_ctl.p->rounds * 7u;
   e->stats.n_build_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_refills, 0xFFFFFFFFull);
   tm.stop();
   Timer tr(e, &e->stats.ms_resolve);

@@ -1,5 +1,7 @@
 """Parity of the CUDA path against the CPU oracle, through the C ABI.  Bit-exact
 (integer/index work).  Run with `pytest -m gpu` on a B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -401,23 +403,34 @@ def test_extension_auction_matches_self_oracle(n_asks, n_workers, seed):
     eng.close()
 
 
-def _check_auction(t, cap, **params):
-    eng = Engine()
-    load_engine(eng, t)
-    eng.set_price_caps(cap)
-    if params:
-        eng.set_auction_params(**params)
-    eng.match(abi.PM_MODE_AUCTION)
-    res = eng.fetch()
+def _tuned_engine(tune):
+    """PM_TUNE_AUCTION is read at pm_create."""
+    if tune:
+        os.environ["PM_TUNE_AUCTION"] = str(tune)
+    try:
+        return Engine()
+    finally:
+        os.environ.pop("PM_TUNE_AUCTION", None)
+
+
+def _check_auction(t, cap, tunes=(0,), **params):
     want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap, **params)
-    got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
-    for g, (ask, members) in enumerate(res.groups()):
-        assert len(members) == 1
-        got[ask] = members[0]
-    assert np.array_equal(got, want)
-    assert res.stats["n_rounds"] == rounds
-    stats = res.stats
-    eng.close()
+    for tune in tunes:
+        eng = _tuned_engine(tune)
+        load_engine(eng, t)
+        eng.set_price_caps(cap)
+        if params:
+            eng.set_auction_params(**params)
+        eng.match(abi.PM_MODE_AUCTION)
+        res = eng.fetch()
+        got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
+        for g, (ask, members) in enumerate(res.groups()):
+            assert len(members) == 1
+            got[ask] = members[0]
+        assert np.array_equal(got, want), tune
+        assert res.stats["n_rounds"] == rounds, tune
+        stats = res.stats
+        eng.close()
     return got, stats
 
 
@@ -445,6 +458,40 @@ def test_extension_auction_identical_bidders_and_ties(n_base, copies, n_workers,
     n_classes = len({(int(r["flags"]), int(r["cpu_cores"]), int(r["ram_mb"]), int(r["storage_gb"]),
                       t["opts"][r["opt_off"]:r["opt_off"] + r["n_opts"]].tobytes()) for r in t["asks"]})
     assert n_classes <= stats["n_tiles"] <= n_classes * max(stats["n_rounds"], 1)
+
+
+@pytest.mark.parametrize("tune", [1, 2, 8, 16, 32, 8 | 32, 0x200, 0x100 | 16])
+def test_extension_auction_every_shortcut_can_be_switched_off(tune):
+    """PM_TUNE_AUCTION bits: 1 walks never stop early, 2 every ask scans for itself (the checker's algorithm on the device),
+    8 no class pool, 16 pool re-ranked but never trusted, 32 walks never split, bits 8+ batches between re-sorts of the
+    worker copy.  Every setting must give the checker's assignment and round count."""
+    w, a, t = synth_tables(25, 20000, "mixed", seed_shift=7)
+    rng = np.random.default_rng(70)
+    idx = rng.permutation(np.repeat(np.arange(25), 20))
+    t["asks"] = np.ascontiguousarray(t["asks"][idx])
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = rng.integers(5, 120, 20000).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(3, 140, len(idx)).astype(np.uint32)
+    _check_auction(t, cap, tunes=(tune,))
+
+
+def test_extension_auction_scarce_and_broad_classes_side_by_side():
+    """60k workers: classes with a handful, a few thousand and tens of thousands of compatible workers in one market
+    (59 stripes: pooled classes, early exits, split walks); more asks than scarce workers, so the scarce classes fight
+    to their caps."""
+    w, a, t = synth_tables(60, 60000, "mixed", seed_shift=17)
+    rng = np.random.default_rng(170)
+    idx = rng.permutation(np.repeat(np.arange(60), 30))
+    t["asks"] = np.ascontiguousarray(t["asks"][idx])
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = rng.integers(10, 60, 60000).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(8, 70, len(idx)).astype(np.uint32)
+    ev = orc.soa_eval_matrix(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], 0, len(idx), 0, 60000, want_cols=False)
+    counts = ev["row_count"]
+    assert (counts <= 8192).any() and (counts > 8192).any() and ((counts > 32) & (counts <= 8192)).any()
+    _check_auction(t, cap)
 
 
 @pytest.mark.parametrize("params", [dict(cost_scale=3), dict(cost_scale=4, eps_start=16, eps_div=4)])
@@ -483,27 +530,28 @@ def test_extension_auction_cfg3_100k_x_1m_properties():
     eng.close()
 
 
-def _check_auction_rep(t, cap, reputation, floors, **params):
-    eng = Engine()
-    load_engine(eng, t)
-    eng.set_price_caps(cap)
-    if reputation is not None:
-        eng.set_worker_reputation(reputation)
-    if floors is not None:
-        eng.set_min_reputation(floors)
-    if params:
-        eng.set_auction_params(**params)
-    eng.match(abi.PM_MODE_AUCTION)
-    res = eng.fetch()
+def _check_auction_rep(t, cap, reputation, floors, tunes=(0,), **params):
     want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap,
                                           reputation=reputation, min_reputation=floors, **params)
-    got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
-    for ask, members in res.groups():
-        assert len(members) == 1
-        got[ask] = members[0]
-    assert np.array_equal(got, want)
-    assert res.stats["n_rounds"] == rounds
-    eng.close()
+    for tune in tunes:
+        eng = _tuned_engine(tune)
+        load_engine(eng, t)
+        eng.set_price_caps(cap)
+        if reputation is not None:
+            eng.set_worker_reputation(reputation)
+        if floors is not None:
+            eng.set_min_reputation(floors)
+        if params:
+            eng.set_auction_params(**params)
+        eng.match(abi.PM_MODE_AUCTION)
+        res = eng.fetch()
+        got = np.full(len(cap), abi.PM_NONE, dtype=np.uint32)
+        for ask, members in res.groups():
+            assert len(members) == 1
+            got[ask] = members[0]
+        assert np.array_equal(got, want), tune
+        assert res.stats["n_rounds"] == rounds, tune
+        eng.close()
     return got
 
 
