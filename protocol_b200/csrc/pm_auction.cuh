@@ -37,6 +37,11 @@
 //    stripe's last worker no later worker can enter the top 32 or the bound, and the walk stops —
 //    after a stripe or two for most classes, because the workers whose prices were bid up have
 //    moved back in the order.
+//  * SKIP TO THE CLASS'S COST LEVEL.  A class whose compatible workers are all expensive (eight H100s) would walk
+//    through the cheap end of the table every time — tens of stripes with nobody in them.  Compatibility of a
+//    (class, worker) pair never changes during an auction and sort keys only rise, so "no compatible worker has a
+//    key below K" stays true for good once a walk has seen it: every walk records the key at which it met its first
+//    compatible worker and the next one starts at the stripe that key falls into (a 32-ary search over stripe ends).
 //  * CLASS POOL.  The candidates the lanes held at the end of a walk (up to 1024) stay as the
 //    class's pool; a rescan request first re-ranks the pool at the current prices and walks the
 //    table only when the pool's best two no longer beat the bound on everything outside it.
@@ -119,6 +124,8 @@ struct AuctionParams {
   long long* split_bound_v;    // [grid * 16] per-part bounds of a walk split over several CTAs
   uint32_t* split_bound_w;
   uint32_t* split_ticket;      // [grid]
+  uint32_t* split_first;       // [grid] first stripe in which any part of a split walk met a compatible worker
+  unsigned long long* skip_key;  // [C] every compatible worker of the class has a sort key >= this (keys only rise)
   uint32_t* retry;             // [T]
   uint32_t* fallback;          // [T]
   AuctionCtl* ctl;
@@ -201,6 +208,8 @@ struct AuctionMerge {
   uint32_t drop_w[kAucWarps];
   uint32_t cnt[3];
   uint32_t flag;
+  uint32_t j0;      // first stripe of the walk (class mode: where the class's compatible workers begin)
+  uint32_t first;   // first stripe in which the CTA met a compatible worker
 };
 
 struct AuctionPick {
@@ -397,18 +406,39 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   uint32_t cw[4] = {kNone, kNone, kNone, kNone};
   long long dropped = kAucNeg;
   uint32_t dropped_w = kNone;
-  if (threadIdx.x == 0) { mg.cnt[0] = 0; mg.cnt[1] = 0; mg.cnt[2] = 0; mg.flag = 0; }
+  const uint32_t W = p.ev.n_workers;
+  const uint32_t n_all = (W + kAucStripe - 1) / kAucStripe;
+  // one class per CTA: start where its compatible workers begin — the first stripe whose last key reaches skip_key
+  const bool skipping = cls_mode && kWpt == kAucWarps && !(p.dbg & 64u);
+  if (threadIdx.x == 0) { mg.cnt[0] = 0; mg.cnt[1] = 0; mg.cnt[2] = 0; mg.flag = 0; mg.first = kNone; mg.j0 = 0; }
+  if (skipping && warp == 0) {
+    const unsigned long long key = p.skip_key[item];
+    uint32_t lo = 0, hi = n_all;   // every stripe below lo ends under the key; stripe hi (if any) does not
+    while (lo < hi) {
+      const uint32_t step = (hi - lo + 31u) / 32u;
+      const uint32_t j = lo + lane * step;
+      bool ge = true;
+      if (j < hi) ge = p.csort_s[min((j + 1u) * (uint32_t)kAucStripe, W) - 1u] >= key;
+      const uint32_t m = __ballot_sync(0xffffffffu, ge);
+      const uint32_t f = m ? (uint32_t)__ffs((int)m) - 1u : 32u;   // ge is monotone in the lane
+      if (f == 0u) { hi = lo; break; }
+      const uint32_t nlo = lo + (f - 1u) * step + 1u;
+      if (f < 32u && lo + f * step < hi) hi = lo + f * step;
+      lo = nlo;
+    }
+    __syncwarp();
+    if (lane == 0) mg.j0 = min(lo, hi);
+  }
   __syncthreads();
+  const uint32_t j0 = mg.j0;
 
   const bool scan = live;
 
-  const uint32_t W = p.ev.n_workers;
-  const uint32_t n_all = (W + kAucStripe - 1) / kAucStripe;
-  // a walk split over G CTAs: part `part` takes the stripes part, part + G, part + 2G, ...
-  const uint32_t n_stripes = n_all > part ? (n_all - part + G - 1u) / G : 0u;
+  // a walk split over G CTAs: part `part` takes the stripes j0 + part, j0 + part + G, j0 + part + 2G, ...
+  const uint32_t n_stripes = n_all > j0 + part ? (n_all - j0 - part + G - 1u) / G : 0u;
   auto issue = [&](uint32_t j) {
     AuctionStage& s = stage[j % kAucStages];
-    const uint32_t w0 = (part + j * G) * kAucStripe;
+    const uint32_t w0 = (j0 + part + j * G) * kAucStripe;
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     const uint32_t np = (n + 1u) & ~1u;   // bulk copies move multiples of 16 B; price_s[] and perm[] are padded
     const uint32_t nq = (n + 3u) & ~3u;
@@ -425,6 +455,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     phase_bits ^= 1u << b;
   };
   uint32_t scanned = 0;
+  uint32_t first_hit = kNone;    // first stripe in which this thread met a compatible worker
   uint32_t first_good = kNone;   // first stripe after which 33 candidates beat every unseen worker
   bool unseen = false;           // the walk stopped before the end of its stripes ...
   long long unseen_u = kAucNeg;  // ... where every remaining worker ranks at or below (unseen_u, unseen_w)
@@ -436,14 +467,16 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     if (threadIdx.x == 0 && k + kAucStages - 1 < n_stripes) issue(k + kAucStages - 1);
     AuctionStage& s = stage[k % kAucStages];
     wait_stage(k);
-    const uint32_t w0 = (part + k * G) * kAucStripe;
+    const uint32_t w0 = (j0 + part + k * G) * kAucStripe;
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     if (scan) {
       scanned += n;
       for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
-        if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words))
+        if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
           auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
+          if (first_hit == kNone) first_hit = j0 + part + k * G;
+        }
       }
     }
     // The table is sorted by the cost ask_price * S + price each worker had at the last sort; prices only rise, so
@@ -480,6 +513,10 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
       break;
     }
   }
+  if (skipping) {   // (the selections below have CTA barriers: mg.first is complete when it is read)
+    const uint32_t fh = __reduce_min_sync(0xffffffffu, first_hit);
+    if (lane == 0 && fh != kNone) atomicMin(&mg.first, fh);
+  }
   if (cls_mode && scan && G == 1u) {   // the new pool: what the lanes hold now
     uint4* pool = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
     pool[in_item] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
@@ -515,10 +552,18 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) mg.flag = (atomicAdd(p.split_ticket + slot, 1u) == G - 1u) ? 1u : 0u;
+    if (threadIdx.x == 0) {
+      if (skipping && mg.first != kNone) atomicMin(p.split_first + slot, mg.first);
+      __threadfence();
+      mg.flag = (atomicAdd(p.split_ticket + slot, 1u) == G - 1u) ? 1u : 0u;
+    }
     __syncthreads();
     if (mg.flag == 0u) return;   // uniform; the CTA has no further item in split mode
     __threadfence();
+    if (skipping && threadIdx.x == 0) {   // all parts are in: the earliest stripe any of them met a compatible worker in
+      mg.first = __ldcg(p.split_first + slot);
+      p.split_first[slot] = kNone;
+    }
     long long bv = kAucNeg;
     uint32_t bw = kNone;
     if (sub == 0) {
@@ -547,6 +592,12 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   if (scan && sub == 0) {
     if (cls_mode) {
       p.cand[(size_t)item * kAucCache + lane] = r.mine;
+      if (skipping && lane == 0) {
+        // nobody compatible before stripe mg.first (none at all if the walk ran to the end without meeting one)
+        const uint32_t fs = mg.first;
+        const unsigned long long k_new = (fs == kNone) ? ~0ull : p.csort_s[(size_t)fs * kAucStripe];
+        if (k_new > p.skip_key[item]) p.skip_key[item] = k_new;
+      }
       if (lane == 0) {
         p.theta[item] = (r.bound_v == kAucNeg) ? kThetaComplete : r.bound_v;
         p.theta_w[item] = r.bound_w;

@@ -203,6 +203,8 @@ struct pm_engine {
   uint32_t auc_n_classes = 0;
   bool auc_classes_valid = false;
   bool have_caps = false;
+  DevBuf<uint32_t> auc_split_first;
+  DevBuf<uint64_t> auc_skip_key;
   DevBuf<uint32_t> reputation, ask_min_rep, auc_rep_s;   // extension: worker reputation column, per-ask floor, sorted copy
   bool have_rep = false, have_min_rep = false;
   uint64_t auc_scale = 1, auc_eps_start = 1;
@@ -417,7 +419,7 @@ void pm_destroy(pm_engine* e) {
   e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
   e->pg_part_d.release(); e->pg_part_i.release(); e->pg_cta_cnt.release(); e->pg_ctl.release();
   e->pg_clat.release(); e->pg_clon.release(); e->pg_ccos.release();
-  e->reputation.release(); e->ask_min_rep.release(); e->auc_rep_s.release();
+  e->reputation.release(); e->ask_min_rep.release(); e->auc_rep_s.release(); e->auc_split_first.release(); e->auc_skip_key.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
   e->auc_price.release(); e->auc_bid_p.release(); e->auc_bid_max.release();
@@ -1166,6 +1168,9 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(e->auc_walk_list.ensure(C)); PM_CUDA(e->auc_split_v.ensure(kScanGrid * 16)); PM_CUDA(e->auc_split_w.ensure(kScanGrid * 16));
   PM_CUDA(e->auc_split_ticket.ensure(kScanGrid));
   PM_CUDA(cudaMemsetAsync(e->auc_split_ticket.p, 0, kScanGrid * 4, e->stream));
+  PM_CUDA(e->auc_split_first.ensure(kScanGrid)); PM_CUDA(e->auc_skip_key.ensure(std::max<uint32_t>(C, 1)));
+  PM_CUDA(cudaMemsetAsync(e->auc_split_first.p, 0xFF, kScanGrid * 4, e->stream));
+  PM_CUDA(cudaMemsetAsync(e->auc_skip_key.p, 0, (size_t)std::max<uint32_t>(C, 1) * 8, e->stream));
   PM_CUDA(e->auc_class_req.ensure(C)); PM_CUDA(e->auc_class_list.ensure(C)); PM_CUDA(e->auc_retry.ensure(T)); PM_CUDA(e->auc_fallback.ensure(T));
   PM_CUDA(e->auc_perm.ensure((size_t)W + 4)); PM_CUDA(e->auc_pos_of.ensure(W));
   PM_CUDA(e->auc_idx.ensure(std::max(W, T))); PM_CUDA(e->auc_wa_s.ensure(W)); PM_CUDA(e->auc_wb_s.ensure(W)); PM_CUDA(e->auc_price_s.ensure((size_t)W + 2));
@@ -1225,7 +1230,8 @@ static int match_auction_locked(pm_engine* e) {
   ap.class_of = e->auc_class_of.p; ap.class_rep = e->auc_class_rep.p; ap.class_req = e->auc_class_req.p;
   ap.cand = e->auc_cand.p; ap.theta = e->auc_theta.p; ap.theta_w = e->auc_theta_w.p;
   ap.pool = e->auc_pool.p; ap.pool_bound_v = e->auc_pool_bound_v.p; ap.pool_bound_w = e->auc_pool_bound_w.p;
-  ap.walk_list = e->auc_walk_list.p; ap.split_bound_v = e->auc_split_v.p; ap.split_bound_w = e->auc_split_w.p; ap.split_ticket = e->auc_split_ticket.p;
+  ap.walk_list = e->auc_walk_list.p; ap.split_bound_v = e->auc_split_v.p; ap.split_bound_w = e->auc_split_w.p; ap.split_ticket = e->auc_split_ticket.p; ap.split_first = e->auc_split_first.p;
+  ap.skip_key = reinterpret_cast<unsigned long long*>(e->auc_skip_key.p);
   ap.class_list = e->auc_class_list.p; ap.retry = e->auc_retry.p; ap.fallback = e->auc_fallback.p; ap.ctl = e->auc_ctl.p;
   ap.dbg = (uint32_t)e->tune_auction;
   ap.pool_good = e->tune_auc_good > 0 ? (uint32_t)e->tune_auc_good : (uint32_t)pm::kAucPoolGood;
