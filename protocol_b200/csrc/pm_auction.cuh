@@ -53,8 +53,8 @@
 //    and only polls the number of unassigned asks.
 //
 // pm_auction_scan: stripes of the sorted worker planes, their prices and original indices are
-// staged into shared memory with 1-D TMA bulk copies, double-buffered; 8 items share a stripe
-// (one warp each) when the list is long, otherwise the CTA's 8 warps split one item.
+// staged into shared memory with 1-D TMA bulk copies, double-buffered; one item per CTA (its 8 warps split
+// each stripe), items drawn from a counter because their lengths differ by two orders of magnitude.
 // Collisions are resolved by atomicMax on the bid and atomicMin on the bidder (the claim),
 // applied by the single winner of each worker.
 #pragma once
@@ -85,6 +85,7 @@ struct AuctionCtl {
   uint32_t rounds;       // rounds in which at least one ask was active
   uint32_t flip;         // which half of active[] holds the current round's list (the other half collects the next one)
   uint32_t ticket;       // blocks of pm_auction_apply that are through: the last one advances the round
+  uint32_t walk_taken, fb_taken;   // items of the round's walk / fallback list already drawn by a scanning CTA
   unsigned long long evals;
   unsigned long long n_class_scans, n_ask_scans, n_refills;
 };
@@ -155,6 +156,8 @@ __device__ __forceinline__ void auc_advance(AuctionCtl* ctl, int first) {
   ctl->n_fallback = 0;
   ctl->flip ^= 1u;
   ctl->ticket = 0;
+  ctl->walk_taken = 0;
+  ctl->fb_taken = 0;
 }
 
 __device__ __forceinline__ bool auc_better(long long v1, uint32_t w1, long long v2, uint32_t w2) {
@@ -199,14 +202,8 @@ __device__ __forceinline__ long long warp_max_i64(long long v) {
   return v;
 }
 
-struct AuctionMerge {
-  long long v[kAucWarps][32];
-  uint32_t w[kAucWarps][32];
-  long long bound_v[kAucWarps];
-  uint32_t bound_w[kAucWarps];
-  long long drop_v[kAucWarps];
-  uint32_t drop_w[kAucWarps];
-  uint32_t cnt[3];
+struct AuctionMerge {   // per-CTA control words of a walk
+  uint32_t cnt[3];  // good candidates after stripe k (three slots in rotation: one barrier per stripe)
   uint32_t flag;
   uint32_t j0;      // first stripe of the walk (class mode: where the class's compatible workers begin)
   uint32_t first;   // first stripe in which the CTA met a compatible worker
@@ -236,83 +233,6 @@ __device__ __forceinline__ void auc_insert(long long (&cv)[4], uint32_t (&cw)[4]
   } else if (auc_better(v, w, dropped, dropped_w)) {
     dropped = v; dropped_w = w;
   }
-}
-
-// Top 32 of an item's candidates (4 sorted per lane, kWpt warps per item) in (value desc, worker asc)
-// order, plus the bounds.  Consumes cv/cw.  With kWpt > 1 the result is valid in the item's warp 0 only and
-// every thread of the CTA must call (two barriers).
-template <int kWpt>
-__device__ __forceinline__ AuctionPick auction_select(long long (&cv)[4], uint32_t (&cw)[4], long long dropped, uint32_t dropped_w,
-                                                      AuctionMerge& mg) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t sub = warp % kWpt;
-  AuctionPick r;
-  r.b1 = kAucNeg; r.b2 = kAucNeg; r.w1 = kNone; r.mine = kNone;
-  long long mine_v = kAucNeg;
-  // 32 selection rounds over the warp's 128 candidates: lane i keeps the i-th best
-#pragma unroll 1
-  for (int i = 0; i < kAucCache; ++i) {
-    long long bv;
-    uint32_t bw;
-    const uint32_t win = warp_argbest(cv[0], cw[0], &bv, &bw);
-    if (i == 0) { r.b1 = bv; r.w1 = bw; }
-    if (i == 1) r.b2 = bv;
-    if ((int)lane == i) { r.mine = (bv > kAucNeg) ? bw : kNone; mine_v = bv; }
-    if (lane == win) { cv[0] = cv[1]; cw[0] = cw[1]; cv[1] = cv[2]; cw[1] = cw[2]; cv[2] = cv[3]; cw[2] = cw[3]; cv[3] = kAucNeg; cw[3] = kNone; }
-  }
-  long long next_v;
-  uint32_t next_w;
-  warp_argbest(cv[0], cw[0], &next_v, &next_w);           // the warp's 33rd best candidate
-  warp_argbest(dropped, dropped_w, &r.drop_v, &r.drop_w); // the best worker no lane kept
-  const bool use_next = auc_better(next_v, next_w, r.drop_v, r.drop_w);
-  r.bound_v = use_next ? next_v : r.drop_v;
-  r.bound_w = use_next ? next_w : r.drop_w;
-  if (kWpt > 1) {
-    // merge the kWpt warps of the item: warp `sub == 0` re-selects from kWpt sorted lists
-    mg.v[warp][lane] = mine_v;
-    mg.w[warp][lane] = r.mine;
-    if (lane == 0) { mg.bound_v[warp] = r.bound_v; mg.bound_w[warp] = r.bound_w; mg.drop_v[warp] = r.drop_v; mg.drop_w[warp] = r.drop_w; }
-    __syncthreads();
-    if (sub == 0) {
-      long long lv[kWpt];
-      uint32_t lw[kWpt];
-#pragma unroll
-      for (int q = 0; q < kWpt; ++q) { lv[q] = mg.v[warp + q][lane]; lw[q] = mg.w[warp + q][lane]; }
-#pragma unroll
-      for (int i = 1; i < kWpt; ++i)      // sort the lane's kWpt entries by (value desc, worker asc)
-#pragma unroll
-        for (int j = i; j > 0; --j)
-          if (auc_better(lv[j], lw[j], lv[j - 1], lw[j - 1])) {
-            const long long tv = lv[j]; const uint32_t tw = lw[j];
-            lv[j] = lv[j - 1]; lw[j] = lw[j - 1]; lv[j - 1] = tv; lw[j - 1] = tw;
-          }
-      r.b1 = kAucNeg; r.b2 = kAucNeg; r.w1 = kNone; r.mine = kNone;
-#pragma unroll 1
-      for (int i = 0; i < kAucCache; ++i) {
-        long long bv;
-        uint32_t bw;
-        const uint32_t win = warp_argbest(lv[0], lw[0], &bv, &bw);
-        if (i == 0) { r.b1 = bv; r.w1 = bw; }
-        if (i == 1) r.b2 = bv;
-        if ((int)lane == i) r.mine = (bv > kAucNeg) ? bw : kNone;
-        if (lane == win) {
-#pragma unroll
-          for (int q = 0; q + 1 < kWpt; ++q) { lv[q] = lv[q + 1]; lw[q] = lw[q + 1]; }
-          lv[kWpt - 1] = kAucNeg; lw[kWpt - 1] = kNone;
-        }
-      }
-      warp_argbest(lv[0], lw[0], &r.bound_v, &r.bound_w);   // 33rd of the merged lists ...
-#pragma unroll
-      for (int q = 0; q < kWpt; ++q) {                      // ... against everything the warps left out
-        const long long qv = mg.bound_v[warp + q];
-        const uint32_t qw = mg.bound_w[warp + q];
-        if (auc_better(qv, qw, r.bound_v, r.bound_w)) { r.bound_v = qv; r.bound_w = qw; }
-        if (q > 0 && auc_better(mg.drop_v[warp + q], mg.drop_w[warp + q], r.drop_v, r.drop_w)) { r.drop_v = mg.drop_v[warp + q]; r.drop_w = mg.drop_w[warp + q]; }
-      }
-    }
-    __syncthreads();   // mg may be rewritten by the next select
-  }
-  return r;
 }
 
 // CTA-wide selection (all 256 threads, one item): the 1024 kept candidates are sorted by (value desc, worker asc) in
@@ -379,21 +299,18 @@ __device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[
   return r;
 }
 
-// One scan item (a class, or a single ask in fallback mode) per 8/TPC warps.
+// One scan item (a class, or a single ask in fallback mode) per CTA.
 //
 // Class mode keeps, next to the 32-entry cache the asks bid from, a POOL: every candidate the lanes
 // held at the end of the class's last full scan (up to 1024 workers) and a bound on everything else.
 // A rescan request first re-ranks the pool at the current prices (a few gathers per thread); only when
 // the pool's best two no longer beat its bound does the class walk the price-sorted worker table again.
-template <int TPC>
 __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, AuctionStage* stage, AuctionMerge& mg,
                                                    uint32_t& phase_bits, uint32_t base, const uint32_t* __restrict__ list,
                                                    uint32_t n_list, bool cls_mode, uint32_t part, uint32_t G) {
-  constexpr int kWpt = kAucWarps / TPC;           // warps per item
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t slot = base + warp / kWpt;
-  const uint32_t sub = warp % kWpt;
-  const uint32_t in_item = sub * 32u + lane;      // this thread's pool slot (4 workers)
+  const uint32_t slot = base;
+  const uint32_t in_item = threadIdx.x;           // this thread's pool slot (4 workers)
   const bool live = slot < n_list;
   const uint32_t item = live ? list[slot] : 0u;
   const uint32_t t = live ? (cls_mode ? p.class_rep[item] : item) : 0u;
@@ -409,7 +326,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   const uint32_t W = p.ev.n_workers;
   const uint32_t n_all = (W + kAucStripe - 1) / kAucStripe;
   // one class per CTA: start where its compatible workers begin — the first stripe whose last key reaches skip_key
-  const bool skipping = cls_mode && kWpt == kAucWarps && !(p.dbg & 64u);
+  const bool skipping = cls_mode && !(p.dbg & 64u);
   if (threadIdx.x == 0) { mg.cnt[0] = 0; mg.cnt[1] = 0; mg.cnt[2] = 0; mg.flag = 0; mg.first = kNone; mg.j0 = 0; }
   if (skipping && warp == 0) {
     const unsigned long long key = p.skip_key[item];
@@ -471,7 +388,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     const uint32_t n = min((uint32_t)kAucStripe, W - w0);
     if (scan) {
       scanned += n;
-      for (uint32_t i = sub * 32 + lane; i < n; i += kWpt * 32) {
+      for (uint32_t i = threadIdx.x; i < n; i += (uint32_t)kAucThreads) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
         if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
           auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
@@ -494,18 +411,14 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     auto beats = [&](long long v, uint32_t w) { return v > u || (v == u && w <= il); };
     uint32_t cnt = __popc(__ballot_sync(0xffffffffu, beats(cv[0], cw[0]))) + __popc(__ballot_sync(0xffffffffu, beats(cv[1], cw[1]))) +
                    __popc(__ballot_sync(0xffffffffu, beats(cv[2], cw[2]))) + __popc(__ballot_sync(0xffffffffu, beats(cv[3], cw[3])));
-    if (kWpt > 1) {
-      if (lane == 0) atomicAdd(&mg.cnt[k % 3u], cnt);
-      if (threadIdx.x == 0) mg.cnt[(k + 1u) % 3u] = 0;
-      __syncthreads();
-      cnt = mg.cnt[k % 3u];
-    }
+    if (lane == 0) atomicAdd(&mg.cnt[k % 3u], cnt);
+    if (threadIdx.x == 0) mg.cnt[(k + 1u) % 3u] = 0;
+    __syncthreads();   // (also: stripe k fully consumed, its buffer may be refilled)
+    cnt = mg.cnt[k % 3u];
     if (cnt > (uint32_t)kAucCache && first_good == kNone) first_good = k;
     bool done = !scan || past_cap ||
                 (first_good != kNone && (!cls_mode || G > 1u || cnt > p.pool_good || k - first_good >= p.pool_extra));
     if (p.dbg & 1u) done = false;
-    if (kWpt == 1) done = __syncthreads_and(done) != 0;
-    // (the barrier above also means: stripe k fully consumed, its buffer may be refilled)
     if (done) {
       if (k + 1 < n_stripes) { unseen = true; unseen_u = u; unseen_w = il + 1u; }
       // the copies already in flight must land before the buffers are reused
@@ -520,23 +433,19 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   if (cls_mode && scan && G == 1u) {   // the new pool: what the lanes hold now
     uint4* pool = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
     pool[in_item] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-    if (kWpt == 1)
-      for (uint32_t j = 32u + lane; j < (uint32_t)(kAucPool / 4); j += 32u) pool[j] = make_uint4(kNone, kNone, kNone, kNone);
   }
   // the stage buffers are idle from here to the item's end (every copy issued was waited for): the sort scratch lives there
   AuctionSort& ss = *reinterpret_cast<AuctionSort*>(&stage[0]);
   static_assert(sizeof(AuctionSort) <= sizeof(AuctionStage), "sort scratch aliases one stage");
-  AuctionPick r;
-  if constexpr (kWpt == kAucWarps) r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
-  else r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
-  if (scan && sub == 0 && lane == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
+  AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+  if (scan && threadIdx.x == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
   long long pb_v = kAucNeg;   // outside the pool: what no lane kept, and the part of the table the walk did not reach
   uint32_t pb_w = kNone;
-  if (kWpt > 1 && G > 1u) {
+  if (G > 1u) {
     // Split walk: this part's top 32 become its slice of the pool, everything else it saw or skipped is summed up in
     // one bound; the part that arrives last re-ranks the G slices into the class cache.
     uint4* pool4 = reinterpret_cast<uint4*>(p.pool) + (size_t)item * (kAucPool / 4);
-    if (sub == 0) {
+    if (warp == 0) {
       p.pool[(size_t)item * kAucPool + part * 32u + lane] = r.mine;
       if (lane == 0) {
         long long bv = r.bound_v;
@@ -566,7 +475,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
     }
     long long bv = kAucNeg;
     uint32_t bw = kNone;
-    if (sub == 0) {
+    if (warp == 0) {
       if (lane < G) { bv = __ldcg(p.split_bound_v + slot * 16u + lane); bw = __ldcg(p.split_bound_w + slot * 16u + lane); }
       warp_argbest(bv, bw, &pb_v, &pb_w);
     }
@@ -581,15 +490,14 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
         if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
     }
     if (in_item == 0) { dropped = pb_v; dropped_w = pb_w; }
-    if constexpr (kWpt == kAucWarps) r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
-    else r = auction_select<kWpt>(cv, cw, dropped, dropped_w, mg);
+    r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
     if (threadIdx.x == 0) p.split_ticket[slot] = 0u;
-  } else if (scan && sub == 0) {
+  } else if (scan && warp == 0) {
     pb_v = r.drop_v;
     pb_w = r.drop_w;
     if (unseen && auc_better(unseen_u, unseen_w, pb_v, pb_w)) { pb_v = unseen_u; pb_w = unseen_w; }
   }
-  if (scan && sub == 0) {
+  if (scan && warp == 0) {
     if (cls_mode) {
       p.cand[(size_t)item * kAucCache + lane] = r.mine;
       if (skipping && lane == 0) {
@@ -672,13 +580,19 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_scan(AuctionParams p, 
   __syncthreads();
   uint32_t phase_bits = 0u;
   if (G > 1u) {
-    auction_scan_items<1>(p, stage, mg, phase_bits, blockIdx.x / G, list, n, true, blockIdx.x % G, G);
-  } else if (n >= 8u * gridDim.x) {
-    for (uint32_t base = blockIdx.x * 8u; base < n; base += gridDim.x * 8u)
-      auction_scan_items<8>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0, 0u, 1u);
+    auction_scan_items(p, stage, mg, phase_bits, blockIdx.x / G, list, n, true, blockIdx.x % G, G);
   } else {
-    for (uint32_t base = blockIdx.x; base < n; base += gridDim.x)
-      auction_scan_items<1>(p, stage, mg, phase_bits, base, list, n, cls_mode != 0, 0u, 1u);
+    // items differ by two orders of magnitude in length (a broad class is done after a few stripes, a scarce one walks
+    // to the end of the table): the CTAs draw them from a counter instead of taking every gridDim-th
+    uint32_t* next = cls_mode ? &p.ctl->walk_taken : &p.ctl->fb_taken;
+    for (;;) {
+      if (threadIdx.x == 0) mg.flag = atomicAdd(next, 1u);
+      __syncthreads();
+      const uint32_t base = mg.flag;
+      __syncthreads();   // (auction_scan_items resets mg.flag)
+      if (base >= n) break;
+      auction_scan_items(p, stage, mg, phase_bits, base, list, n, cls_mode != 0, 0u, 1u);
+    }
   }
 }
 

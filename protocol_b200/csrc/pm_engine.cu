@@ -1240,6 +1240,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // fixed grids: every kernel strides over a list whose length it reads from the control block
   const unsigned g_scan = kScanGrid;
+  const unsigned g_refill = std::max(1u, std::min(C, 1184u));   // 12 KB of shared memory per CTA: eight per SM
   const unsigned g_warp = std::max(1u, std::min(blocks_for(T, pm::kAucWarps), 1184u));
   const unsigned g_thr = std::max(1u, std::min(blocks_for(T, 256), 592u));
   const uint32_t kBatch = 32;  // rounds launched between polls of the control block
@@ -1265,7 +1266,7 @@ static int match_auction_locked(pm_engine* e) {
     auto launch_rounds = [&]() {
       for (uint32_t r = 0; r < kBatch; ++r) {
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 0);
-        pm::pm_auction_refill<<<g_scan, pm::kAucThreads, 0, e->stream>>>(ap);
+        pm::pm_auction_refill<<<g_refill, pm::kAucThreads, 0, e->stream>>>(ap);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 1);
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 1);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 0);
