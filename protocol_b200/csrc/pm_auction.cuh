@@ -144,6 +144,22 @@ struct __align__(128) AuctionStage {
   uint64_t bar;
 };
 
+// The scan's predicate: the generic clause masks of pm_kernels.cuh (predicated PTX, no branches) with the class's
+// first option row held in registers for the whole walk (nine asks in ten have one option); same result as ask_meets.
+__device__ __forceinline__ bool auc_meets(const DevAsk& a, const DevOpt& q0, const DevOpt* __restrict__ opts, const WorkerReg& w,
+                                          const uint32_t* __restrict__ bits, uint32_t words) {
+  uint32_t ok = base_mask(a, w);
+  if (a.n_opts != 0u) {
+    uint32_t any = opt_mask(q0, w, q0.pattern_row ? bits[q0.pattern_row * words + w.mword] : 0xFFFFFFFFu);   // row 0: no model clause
+    for (uint32_t o = 1; o < a.n_opts; ++o) {
+      const DevOpt q = opts[a.opt_off + o];
+      any |= opt_mask(q, w, q.pattern_row ? bits[q.pattern_row * words + w.mword] : 0xFFFFFFFFu);
+    }
+    ok &= any;
+  }
+  return ok != 0u;
+}
+
 __device__ __forceinline__ const uint32_t* auc_active(const AuctionParams& p) { return p.active + (p.ctl->flip ? p.n_asks : 0u); }
 __device__ __forceinline__ uint32_t* auc_next(const AuctionParams& p) { return p.active + (p.ctl->flip ? 0u : p.n_asks); }
 __device__ __forceinline__ void auc_advance(AuctionCtl* ctl, int first) {
@@ -235,12 +251,11 @@ __device__ __forceinline__ void auc_insert(long long (&cv)[4], uint32_t (&cw)[4]
   }
 }
 
-// CTA-wide selection (all 256 threads, one item): the 1024 kept candidates are sorted by (value desc, worker asc) in
-// shared memory with a bitonic network — 52 compare-exchange stages of two pairs per thread, the stages whose pairs
-// stay inside a warp's own 64 entries separated by a warp barrier only — instead of 2 x 32 dependent warp arg-max
-// rounds (a quarter of the instructions, a tenth of the dependent shuffle chain).  A thread's 4 candidates arrive
-// sorted, so the network is entered at run length 4 (odd threads store their run reversed: every 8 entries are then a
-// bitonic sequence).  The result is valid in warp 0.
+// CTA-wide selection (all 256 threads, one item): the best 64 of the 1024 kept candidates, in (value desc, worker asc)
+// order, by a bitonic network in shared memory that sorts blocks of 64 and then merges them keeping the better half
+// (below) — instead of 2 x 32 dependent warp arg-max rounds (round 1).  A thread's 4 candidates arrive sorted, so
+// the network is entered at run length 4 (odd threads store their run reversed: every 8 entries are then a bitonic
+// sequence).  The result is valid in warp 0.
 struct __align__(16) AuctionSort {
   long long v[kAucPool];
   uint32_t w[kAucPool];
@@ -266,26 +281,53 @@ __device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[
     if (lane == 0) { ss.drop_v[warp] = dv; ss.drop_w[warp] = dw; }
   }
   __syncthreads();
+  auto cmpx = [&](uint32_t i, uint32_t j, bool desc) {   // compare-exchange of the entries i and i + j
+    const long long va = ss.v[i], vb = ss.v[i + j];
+    const uint32_t wa = ss.w[i], wb = ss.w[i + j];
+    const bool swap = desc ? auc_better(vb, wb, va, wa) : auc_better(va, wa, vb, wb);
+    if (swap) { ss.v[i] = vb; ss.w[i] = wb; ss.v[i + j] = va; ss.w[i + j] = wa; }
+  };
+  // phase 1: the sixteen blocks of 64 entries, each sorted (even blocks descending, odd ones ascending).  A warp owns
+  // the blocks `warp` and `8 + warp` (idx -> i maps 32 consecutive idx onto one aligned block of 64): warp barriers only.
 #pragma unroll 1
-  for (uint32_t k = 8; k <= (uint32_t)kAucPool; k <<= 1) {
+  for (uint32_t k = 8; k <= 64u; k <<= 1) {
 #pragma unroll 1
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
       for (uint32_t r = 0; r < 2; ++r) {
         const uint32_t idx = tid + r * (uint32_t)kAucThreads;
-        const uint32_t i = 2u * idx - (idx & (j - 1u));   // the pair (i, i + j): bit j of i is clear
-        const long long va = ss.v[i], vb = ss.v[i + j];
-        const uint32_t wa = ss.w[i], wb = ss.w[i + j];
-        const bool desc = (i & k) == 0u;
-        const bool swap = desc ? auc_better(vb, wb, va, wa) : auc_better(va, wa, vb, wb);
-        if (swap) { ss.v[i] = vb; ss.w[i] = wb; ss.v[i + j] = va; ss.w[i + j] = wa; }
+        const uint32_t i = 2u * idx - (idx & (j - 1u));   // bit j of i is clear
+        cmpx(i, j, (i & k) == 0u);
       }
-      // pairs at distance <= 32 stay inside the 64 entries a warp owns per half (idx -> i maps 32 consecutive idx
-      // onto one aligned block of 64): only a change to or from a wider stage needs the whole CTA
-      if (j > 32u || (j == 1u && k >= 64u)) __syncthreads();
-      else __syncwarp();
+      __syncwarp();
     }
   }
+  // phase 2: only the best 64 are wanted, so a merge keeps the better half and drops the rest: of a descending block A
+  // and an ascending block B the entry-wise better one goes to A (a bitonic sequence holding the 64 best of both),
+  // six more stages sort it — descending or ascending by turns, so that the survivors pair up again.  8 + 4 + 2 + 1
+  // merges by one warp each instead of the four full-width merge passes of a complete sort (half the instructions).
+#pragma unroll 1
+  for (uint32_t S = 64u, P = 8u; P > 0u; S <<= 1, P >>= 1) {
+    __syncthreads();
+    if (warp < P) {
+      const uint32_t A = warp * 2u * S, B = A + S;
+#pragma unroll
+      for (uint32_t r = 0; r < 2; ++r) {
+        const uint32_t i = lane + 32u * r;
+        const long long vb = ss.v[B + i];
+        const uint32_t wb = ss.w[B + i];
+        if (auc_better(vb, wb, ss.v[A + i], ss.w[A + i])) { ss.v[A + i] = vb; ss.w[A + i] = wb; }
+      }
+      __syncwarp();
+      const bool desc = (warp & 1u) == 0u;
+#pragma unroll 1
+      for (uint32_t j = 32u; j > 0; j >>= 1) {
+        cmpx(A + 2u * lane - (lane & (j - 1u)), j, desc);
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
   AuctionPick r;
   r.b1 = ss.v[0]; r.w1 = ss.w[0]; r.b2 = ss.v[1];
   r.mine = (ss.v[lane] > kAucNeg) ? ss.w[lane] : kNone;
@@ -315,6 +357,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   const uint32_t item = live ? list[slot] : 0u;
   const uint32_t t = live ? (cls_mode ? p.class_rep[item] : item) : 0u;
   const DevAsk ask = p.ev.asks[t];
+  const DevOpt opt0 = p.ev.opts[ask.n_opts ? ask.opt_off : 0u];
   const uint32_t cap = cls_mode ? 0xFFFFFFFFu : p.price_cap[t];
   const bool use_rep = p.rep_s != nullptr;
   const uint32_t floor_rep = use_rep ? p.min_rep[t] : 0u;
@@ -390,7 +433,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
       scanned += n;
       for (uint32_t i = threadIdx.x; i < n; i += (uint32_t)kAucThreads) {
         const WorkerReg wr = make_worker(s.a[i], s.b[i]);
-        if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && ask_meets(ask, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
+        if (wr.price <= cap && (!use_rep || s.rep[i] >= floor_rep) && auc_meets(ask, opt0, p.ev.opts, wr, p.ev.bits, p.ev.words)) {
           auc_insert(cv, cw, dropped, dropped_w, -((long long)wr.price * p.scale) - s.price[i], s.perm[i]);
           if (first_hit == kNone) first_hit = j0 + part + k * G;
         }
