@@ -86,6 +86,8 @@ struct AuctionCtl {
   uint32_t flip;         // which half of active[] holds the current round's list (the other half collects the next one)
   uint32_t ticket;       // blocks of pm_auction_apply that are through: the last one advances the round
   uint32_t walk_taken, fb_taken;   // items of the round's walk / fallback list already drawn by a scanning CTA
+  uint32_t max_ask_price, max_cap; // over the worker table / the asks (pm_auction_limits)
+  uint32_t packed;                 // every reachable cost < 2^40 and fewer than 2^24 workers: selections sort packed keys
   unsigned long long evals;
   unsigned long long n_class_scans, n_ask_scans, n_refills;
 };
@@ -264,16 +266,32 @@ struct __align__(16) AuctionSort {
 };
 static_assert(kAucPool == 4 * kAucThreads, "one sorted run of 4 per thread");
 
-__device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[4], const uint32_t (&cw)[4], long long dropped,
-                                                          uint32_t dropped_w, AuctionSort& ss) {
+// PACKED: (value, worker) as ONE sortable 64-bit key, (-value) << 24 | worker — ascending key = value descending,
+// worker ascending; an empty slot is all ones.  Valid when every cost the auction can reach is below 2^40 and there are
+// fewer than 2^24 workers (pm_auction_limits decides once per auction; ctl->packed): a compare-exchange is then two
+// 64-bit loads, one compare and two stores instead of four loads, a two-word compare and four stores.
+constexpr int kAucPackShift = 24;
+__device__ __forceinline__ unsigned long long auc_pack(long long v, uint32_t w) {
+  return (w == kNone || v <= kAucNeg) ? ~0ull : (((unsigned long long)(-v)) << kAucPackShift) | (unsigned long long)w;
+}
+__device__ __forceinline__ void auc_unpack(unsigned long long k, long long* v, uint32_t* w) {
+  const bool none = k == ~0ull;
+  *v = none ? kAucNeg : -(long long)(k >> kAucPackShift);
+  *w = none ? kNone : (uint32_t)(k & ((1ull << kAucPackShift) - 1ull));
+}
+
+template <bool PACKED>
+__device__ __forceinline__ AuctionPick auction_select_cta_t(const long long (&cv)[4], const uint32_t (&cw)[4], long long dropped,
+                                                            uint32_t dropped_w, AuctionSort& ss) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  unsigned long long* const kk = reinterpret_cast<unsigned long long*>(ss.v);
   {
     const bool rev = (tid & 1u) != 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t at = tid * 4u + (rev ? 3u - (uint32_t)j : (uint32_t)j);
-      ss.v[at] = cv[j];
-      ss.w[at] = cw[j];
+      if (PACKED) kk[at] = auc_pack(cv[j], cw[j]);
+      else { ss.v[at] = cv[j]; ss.w[at] = cw[j]; }
     }
     long long dv;
     uint32_t dw;
@@ -282,10 +300,15 @@ __device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[
   }
   __syncthreads();
   auto cmpx = [&](uint32_t i, uint32_t j, bool desc) {   // compare-exchange of the entries i and i + j
-    const long long va = ss.v[i], vb = ss.v[i + j];
-    const uint32_t wa = ss.w[i], wb = ss.w[i + j];
-    const bool swap = desc ? auc_better(vb, wb, va, wa) : auc_better(va, wa, vb, wb);
-    if (swap) { ss.v[i] = vb; ss.w[i] = wb; ss.v[i + j] = va; ss.w[i + j] = wa; }
+    if (PACKED) {
+      const unsigned long long ka = kk[i], kb = kk[i + j];
+      if (desc ? kb < ka : ka < kb) { kk[i] = kb; kk[i + j] = ka; }
+    } else {
+      const long long va = ss.v[i], vb = ss.v[i + j];
+      const uint32_t wa = ss.w[i], wb = ss.w[i + j];
+      const bool swap = desc ? auc_better(vb, wb, va, wa) : auc_better(va, wa, vb, wb);
+      if (swap) { ss.v[i] = vb; ss.w[i] = wb; ss.v[i + j] = va; ss.w[i + j] = wa; }
+    }
   };
   // phase 1: the sixteen blocks of 64 entries, each sorted (even blocks descending, odd ones ascending).  A warp owns
   // the blocks `warp` and `8 + warp` (idx -> i maps 32 consecutive idx onto one aligned block of 64): warp barriers only.
@@ -314,9 +337,14 @@ __device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[
 #pragma unroll
       for (uint32_t r = 0; r < 2; ++r) {
         const uint32_t i = lane + 32u * r;
-        const long long vb = ss.v[B + i];
-        const uint32_t wb = ss.w[B + i];
-        if (auc_better(vb, wb, ss.v[A + i], ss.w[A + i])) { ss.v[A + i] = vb; ss.w[A + i] = wb; }
+        if (PACKED) {
+          const unsigned long long kb = kk[B + i];
+          if (kb < kk[A + i]) kk[A + i] = kb;
+        } else {
+          const long long vb = ss.v[B + i];
+          const uint32_t wb = ss.w[B + i];
+          if (auc_better(vb, wb, ss.v[A + i], ss.w[A + i])) { ss.v[A + i] = vb; ss.w[A + i] = wb; }
+        }
       }
       __syncwarp();
       const bool desc = (warp & 1u) == 0u;
@@ -329,16 +357,30 @@ __device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[
   }
   __syncthreads();
   AuctionPick r;
-  r.b1 = ss.v[0]; r.w1 = ss.w[0]; r.b2 = ss.v[1];
-  r.mine = (ss.v[lane] > kAucNeg) ? ss.w[lane] : kNone;
-  const long long next_v = ss.v[32];
-  const uint32_t next_w = ss.w[32];
+  long long mine_v, next_v;
+  uint32_t mine_w, next_w;
+  if (PACKED) {
+    uint32_t w2;
+    auc_unpack(kk[0], &r.b1, &r.w1);
+    auc_unpack(kk[1], &r.b2, &w2);
+    auc_unpack(kk[lane], &mine_v, &mine_w);
+    auc_unpack(kk[32], &next_v, &next_w);
+  } else {
+    r.b1 = ss.v[0]; r.w1 = ss.w[0]; r.b2 = ss.v[1];
+    mine_v = ss.v[lane]; mine_w = ss.w[lane];
+    next_v = ss.v[32]; next_w = ss.w[32];
+  }
+  r.mine = (mine_v > kAucNeg) ? mine_w : kNone;
   warp_argbest(lane < (uint32_t)kAucWarps ? ss.drop_v[lane] : kAucNeg, lane < (uint32_t)kAucWarps ? ss.drop_w[lane] : kNone, &r.drop_v, &r.drop_w);
   const bool use_next = auc_better(next_v, next_w, r.drop_v, r.drop_w);
   r.bound_v = use_next ? next_v : r.drop_v;
   r.bound_w = use_next ? next_w : r.drop_w;
   __syncthreads();   // ss may be rewritten by the next select
   return r;
+}
+__device__ __forceinline__ AuctionPick auction_select_cta(const long long (&cv)[4], const uint32_t (&cw)[4], long long dropped,
+                                                          uint32_t dropped_w, AuctionSort& ss, bool packed) {
+  return packed ? auction_select_cta_t<true>(cv, cw, dropped, dropped_w, ss) : auction_select_cta_t<false>(cv, cw, dropped, dropped_w, ss);
 }
 
 // One scan item (a class, or a single ask in fallback mode) per CTA.
@@ -480,7 +522,8 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
   // the stage buffers are idle from here to the item's end (every copy issued was waited for): the sort scratch lives there
   AuctionSort& ss = *reinterpret_cast<AuctionSort*>(&stage[0]);
   static_assert(sizeof(AuctionSort) <= sizeof(AuctionStage), "sort scratch aliases one stage");
-  AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+  const bool packed = p.ctl->packed != 0u && !(p.dbg & 128u);
+  AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss, packed);
   if (scan && threadIdx.x == 0) atomicAdd(&p.ctl->evals, (unsigned long long)scanned);
   long long pb_v = kAucNeg;   // outside the pool: what no lane kept, and the part of the table the walk did not reach
   uint32_t pb_w = kNone;
@@ -533,7 +576,7 @@ __device__ __forceinline__ void auction_scan_items(const AuctionParams& p, Aucti
         if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
     }
     if (in_item == 0) { dropped = pb_v; dropped_w = pb_w; }
-    r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+    r = auction_select_cta(cv, cw, dropped, dropped_w, ss, packed);
     if (threadIdx.x == 0) p.split_ticket[slot] = 0u;
   } else if (scan && warp == 0) {
     pb_v = r.drop_v;
@@ -587,7 +630,7 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_refill(AuctionParams p
     for (int j = 0; j < 4; ++j)
       if (pw[j] != kNone) auc_insert(cv, cw, dropped, dropped_w, -((long long)p.ev.wb[pw[j]].w * p.scale) - p.price[pw[j]], pw[j]);
     if (threadIdx.x == 0) { dropped = pool_bound; dropped_w = p.pool_bound_w[item]; }   // everything outside the pool
-    const AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss);
+    const AuctionPick r = auction_select_cta(cv, cw, dropped, dropped_w, ss, p.ctl->packed != 0u && !(p.dbg & 128u));
     if (warp == 0) {
       const bool ok = !(p.dbg & 16u) && (r.bound_v == kAucNeg || (r.b2 >= r.bound_v && auc_better(r.b1, r.w1, r.bound_v, r.bound_w)));
       if (ok) {
@@ -746,6 +789,24 @@ __global__ void pm_auction_compact(AuctionParams p, uint32_t n_asks) {
   if (p.assigned[t] == kNone && !p.withdrawn[t]) auc_next(p)[atomicAdd(&p.ctl->n_next, 1u)] = t;
 }
 __global__ void pm_auction_advance(AuctionCtl* ctl, int first) { auc_advance(ctl, first); }
+
+// Can (value, worker) be sorted as one 64-bit key?  A bid never exceeds (cap + 1) * S + eps (an ask pays at most its outside
+// option), so every cost ask_price * S + price stays below (max ask_price + max cap + 2) * S + eps.
+__global__ void pm_auction_limits(const uint4* __restrict__ wb, uint32_t n_workers, const uint32_t* __restrict__ cap, uint32_t n_asks,
+                                  AuctionCtl* ctl) {
+  uint32_t ma = 0, mc = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_workers; i += gridDim.x * blockDim.x) ma = max(ma, wb[i].w);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_asks; i += gridDim.x * blockDim.x) mc = max(mc, cap[i]);
+  ma = __reduce_max_sync(0xffffffffu, ma);
+  mc = __reduce_max_sync(0xffffffffu, mc);
+  if ((threadIdx.x & 31u) == 0u) { atomicMax(&ctl->max_ask_price, ma); atomicMax(&ctl->max_cap, mc); }
+}
+__global__ void pm_auction_decide_packed(AuctionCtl* ctl, uint32_t n_workers, unsigned long long scale, unsigned long long eps_start) {
+  const unsigned long long lim = 1ull << 40;
+  bool ok = n_workers < (1u << kAucPackShift) && scale < lim && eps_start < lim;
+  if (ok) ok = ((unsigned long long)ctl->max_ask_price + ctl->max_cap + 2ull) < (lim - eps_start) / scale;
+  ctl->packed = ok ? 1u : 0u;
+}
 
 // ---- ask classes -----------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t auc_mix(uint64_t h, uint32_t v) {

@@ -460,11 +460,12 @@ def test_extension_auction_identical_bidders_and_ties(n_base, copies, n_workers,
     assert n_classes <= stats["n_tiles"] <= n_classes * max(stats["n_rounds"], 1)
 
 
-@pytest.mark.parametrize("tune", [1, 2, 8, 16, 32, 64, 8 | 32, 64 | 32, 1 | 64, 0x200, 0x100 | 16])
+@pytest.mark.parametrize("tune", [1, 2, 8, 16, 32, 64, 128, 8 | 32, 64 | 32, 1 | 64, 128 | 32, 0x200, 0x100 | 16])
 def test_extension_auction_every_shortcut_can_be_switched_off(tune):
     """PM_TUNE_AUCTION bits: 1 walks never stop early, 2 every ask scans for itself (the checker's algorithm on the device),
     8 no class pool, 16 pool re-ranked but never trusted, 32 walks never split, 64 walks start at the top of the table
-    (no skip to the class's cost level), bits 8+ batches between re-sorts of the worker copy.  Every setting must give the checker's assignment and round count."""
+    (no skip to the class's cost level), 128 selections sort (value, worker) pairs instead of packed 64-bit keys,
+    bits 8+ batches between re-sorts of the worker copy.  Every setting must give the checker's assignment and round count."""
     w, a, t = synth_tables(25, 20000, "mixed", seed_shift=7)
     rng = np.random.default_rng(70)
     idx = rng.permutation(np.repeat(np.arange(25), 20))
@@ -494,7 +495,10 @@ def test_extension_auction_scarce_and_broad_classes_side_by_side():
     _check_auction(t, cap)
 
 
-@pytest.mark.parametrize("params", [dict(cost_scale=3), dict(cost_scale=4, eps_start=16, eps_div=4)])
+@pytest.mark.parametrize("params", [dict(cost_scale=3), dict(cost_scale=4, eps_start=16, eps_div=4),
+                                    # a first eps beyond 2^40: bids can exceed what a packed sort key holds, the selections
+                                    # sort (value, worker) pairs (decided on the device, pm_auction_decide_packed)
+                                    dict(cost_scale=1, eps_start=1 << 41, eps_div=1 << 20)])
 def test_extension_auction_scaled_costs_and_eps_phases(params):
     t, cap = _auction_tables(300, 2500, 9)
     _check_auction(t, cap, **params)
