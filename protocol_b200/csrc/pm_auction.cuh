@@ -71,6 +71,8 @@ constexpr int kAucCache = 32;
 constexpr int kAucPool = 1024;       // pool slots per class (4 per thread of the scanning CTA)
 constexpr int kAucPoolGood = 256;    // a class walk goes on until this many candidates beat every unseen worker ...
 constexpr int kAucPoolExtra = 8;     // ... or for this many stripes past the point where it could have stopped
+constexpr int kAucClaimShift = 23;                       // packed claim: bids below 2^40, fewer than 2^23 asks
+constexpr uint32_t kAucClaimMask = (1u << kAucClaimShift) - 1u;
 constexpr long long kThetaComplete = (long long)0x8000000000000000ull;   // the cache holds every compatible worker
 constexpr long long kThetaInvalid = 0x7FFFFFFFFFFFFFFFll;                // no cache yet
 
@@ -88,6 +90,7 @@ struct AuctionCtl {
   uint32_t walk_taken, fb_taken;   // items of the round's walk / fallback list already drawn by a scanning CTA
   uint32_t max_ask_price, max_cap; // over the worker table / the asks (pm_auction_limits)
   uint32_t packed;                 // every reachable cost < 2^40 and fewer than 2^24 workers: selections sort packed keys
+  uint32_t packed_claim;           // ... and fewer than 2^23 asks: bid_max[] holds (bid, bidder), pm_auction_claim has nothing to do
   unsigned long long evals;
   unsigned long long n_class_scans, n_ask_scans, n_refills;
 };
@@ -190,7 +193,9 @@ __device__ __forceinline__ void auction_commit(const AuctionParams& p, uint32_t 
   const long long bid = p.price[w1] + (b1 - second) + p.eps;
   p.bid_w[t] = w1;
   p.bid_p[t] = bid;
-  atomicMax(p.bid_max + w1, bid);
+  // packed claim: bid and bidder in one word, (bid << 23) | (2^23 - 1 - ask) — the highest bid wins, among equal bids the
+  // lowest ask: the atomicMax IS the claim (no separate pass over the bidders)
+  atomicMax(p.bid_max + w1, p.ctl->packed_claim ? ((bid << kAucClaimShift) | (long long)(kAucClaimMask - t)) : bid);
 }
 // exact top-2 over the ask's feasible workers -> bid or withdrawal
 __device__ __forceinline__ void auction_place_bid(const AuctionParams& p, uint32_t t, uint32_t cap,
@@ -739,6 +744,7 @@ __global__ void __launch_bounds__(kAucThreads) pm_auction_bid_cached(AuctionPara
 
 // the claim: among the highest bidders of a worker the lowest ask index wins
 __global__ void pm_auction_claim(AuctionParams p) {
+  if (p.ctl->packed_claim) return;
   const uint32_t n = p.ctl->n_active;
   const uint32_t* __restrict__ active = auc_active(p);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -754,9 +760,12 @@ __global__ void pm_auction_apply(AuctionParams p) {
   const uint32_t n = p.ctl->n_active;
   const uint32_t* __restrict__ active = auc_active(p);
   uint32_t* __restrict__ next = auc_next(p);
+  const bool pc = p.ctl->packed_claim != 0u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t t = active[i], w = p.bid_w[t];
-    if (w != kNone && p.winner[w] == t) {
+    bool won = false;
+    if (w != kNone) won = pc ? (kAucClaimMask - (uint32_t)((unsigned long long)p.bid_max[w] & kAucClaimMask)) == t && p.bid_max[w] >= 0 : p.winner[w] == t;
+    if (won) {
       const uint32_t prev = p.owner[w];
       if (prev != kNone) {
         p.assigned[prev] = kNone;   // prev holds a worker, so it did not bid this round
@@ -801,11 +810,13 @@ __global__ void pm_auction_limits(const uint4* __restrict__ wb, uint32_t n_worke
   mc = __reduce_max_sync(0xffffffffu, mc);
   if ((threadIdx.x & 31u) == 0u) { atomicMax(&ctl->max_ask_price, ma); atomicMax(&ctl->max_cap, mc); }
 }
-__global__ void pm_auction_decide_packed(AuctionCtl* ctl, uint32_t n_workers, unsigned long long scale, unsigned long long eps_start) {
+__global__ void pm_auction_decide_packed(AuctionCtl* ctl, uint32_t n_workers, uint32_t n_asks, unsigned long long scale,
+                                         unsigned long long eps_start, uint32_t dbg) {
   const unsigned long long lim = 1ull << 40;
   bool ok = n_workers < (1u << kAucPackShift) && scale < lim && eps_start < lim;
   if (ok) ok = ((unsigned long long)ctl->max_ask_price + ctl->max_cap + 2ull) < (lim - eps_start) / scale;
   ctl->packed = ok ? 1u : 0u;
+  ctl->packed_claim = (ok && n_asks <= kAucClaimMask && !(dbg & 128u)) ? 1u : 0u;
 }
 
 // ---- ask classes -----------------------------------------------------------------------------

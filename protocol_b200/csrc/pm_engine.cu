@@ -1220,7 +1220,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(cudaMemsetAsync(e->auc_winner.p, 0xFF, (size_t)std::max<uint32_t>(W, 1) * 4, e->stream));
   // one packed 64-bit sort key per candidate when every reachable cost fits (decided on the device, read by the kernels)
   pm::pm_auction_limits<<<std::max(1u, std::min(blocks_for(std::max(W, T), 256), 592u)), 256, 0, e->stream>>>(e->wb.p, W, e->price_cap.p, T, e->auc_ctl.p);
-  pm::pm_auction_decide_packed<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, W, e->auc_scale, e->auc_eps_start ? e->auc_eps_start : 1);
+  pm::pm_auction_decide_packed<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, W, T, e->auc_scale, e->auc_eps_start ? e->auc_eps_start : 1, (uint32_t)e->tune_auction);
   PM_LAUNCH_CHECK("pm_auction_decide_packed");
 
   pm::AuctionParams ap;
