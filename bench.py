@@ -470,6 +470,7 @@ def auction_record(eng, abi, T, W):
     st = eng.stats()
     res = eng.fetch()
     return {"seconds": dt, "rounds": st["n_rounds"], "evals": st["evals"], "asks_assigned": int(res.n_groups),
+            "table_walks": st["n_tiles"], "pool_refills": st["n_build_launches"], "kernel_launches": st["n_launches"],
             "eps": "1 throughout (default; eps-scaling loses the T*eps bound under price caps, tests/test_oracle_auction.py)", "price_caps": "log-uniform 20..2000",
             "note": "rounds are not multiplied into the headline evals/s (SURVEY 8d)"}
 

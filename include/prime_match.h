@@ -151,6 +151,13 @@ int pm_parse_requirements(const char* s, pm_interner* interner, pm_ask* ask,
 int pm_sort_configs(const uint32_t* min_group_size, const uint8_t* has_requirements,
                     uint32_t n, uint32_t* perm_out);
 
+/* Node ids.  The reference parses every wire id (`node.id.parse::<Address>()`, discovery/monitor.rs:240) and uses
+ * `Address::to_string()` — "0x" + 40 hex digits in EIP-55 checksum case (alloy-primitives 1.1.0, Cargo.lock) — as the
+ * key of every store, of node_to_group and of the BTreeSet that decides GROUP_INDEX (mod.rs:63-69,424-434).
+ * pm_address_canonical does the same for a C string: accepts 40 hex digits with or without "0x", any case (no
+ * checksum validation, like Address::from_str), writes the 42-character checksummed form + NUL.  PM_E_INVALID otherwise. */
+int pm_address_canonical(const char* address, char out[43]);
+
 /* ------------------------------------------------------------------------ */
 /* Engine                                                                     */
 /* ------------------------------------------------------------------------ */
@@ -358,7 +365,9 @@ typedef struct pm_plugin_policy {     /* mod.rs:71-98 */
   uint8_t task_switching_enabled;     /* TaskSwitchingPolicy.enabled               */
   uint8_t prefer_larger_groups;       /* TaskSwitchingPolicy.prefer_larger_groups  */
   uint8_t proximity_enabled;          /* ProximityOptimizationPolicy.enabled       */
-  uint8_t reserved;
+  uint8_t canonical_addresses;        /* 1: every address that enters the mirror goes through pm_address_canonical (what the  */
+                                      /* reference's Address parse + to_string does); an id that is not an address is rejected */
+                                      /* (discovery entries: skipped, monitor.rs:240,425-429).  0: strings are opaque.        */
 } pm_plugin_policy;
 
 typedef struct pm_kv { const char* key; const char* value; } pm_kv;

@@ -383,3 +383,65 @@ def soa_auction(a, b, asks, opts, bits, words, price_cap, cost_scale=1, eps_star
                                         None if floor is None else floor.ctypes.data, cost_scale, eps_start, eps_div,
                                         out.ctypes.data, price.ctypes.data)
     return out, price, rounds
+
+
+# ---- node ids: Address::from_str + Address::to_string (alloy-primitives 1.1.0, pinned in the reference's Cargo.lock; the
+# crate is not under /root/reference).  Restated from the published algorithms: Keccak-f[1600] as in the Keccak
+# reference (state A[x][y], steps theta, rho, pi, chi, iota written out), Keccak-256 = rate 1088, padding 0x01 .. 0x80;
+# EIP-55: hex letter i is upper case iff nibble i of keccak256(lower-case hex digits) >= 8.  Pinned by the vectors of
+# EIP-55 itself and keccak256("") (tests/test_oracle_kat.py).  Pure Python: inputs are 40 bytes.
+_KECCAK_RC = []
+
+
+def _keccak_round_constants():
+    if _KECCAK_RC:
+        return _KECCAK_RC
+    r = 1                                   # LFSR x^8 + x^6 + x^5 + x^4 + 1
+    for _ in range(24):
+        rc = 0
+        for j in range(7):
+            if r & 1:
+                rc |= 1 << ((1 << j) - 1)
+            r = ((r << 1) ^ ((r >> 7) * 0x71)) & 0xFF
+        _KECCAK_RC.append(rc)
+    return _KECCAK_RC
+
+
+def keccak256(data: bytes) -> bytes:
+    M64 = (1 << 64) - 1
+    rol = lambda v, n: ((v << n) | (v >> (64 - n))) & M64 if n else v
+    rate = 136
+    msg = bytearray(data)
+    msg.append(0x01)
+    while len(msg) % rate:
+        msg.append(0)
+    msg[-1] |= 0x80
+    A = [[0] * 5 for _ in range(5)]         # A[x][y]
+    rc = _keccak_round_constants()
+    for off in range(0, len(msg), rate):
+        for i in range(rate // 8):
+            A[i % 5][i // 5] ^= int.from_bytes(msg[off + 8 * i: off + 8 * i + 8], "little")
+        for rnd in range(24):
+            C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+            D = [C[(x - 1) % 5] ^ rol(C[(x + 1) % 5], 1) for x in range(5)]
+            A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+            B = [[0] * 5 for _ in range(5)]
+            x, y = 1, 0
+            B[0][0] = A[0][0]
+            for t in range(24):             # rho offsets (t+1)(t+2)/2 along the pi orbit of (1, 0)
+                B[y][(2 * x + 3 * y) % 5] = rol(A[x][y], ((t + 1) * (t + 2) // 2) % 64)
+                x, y = y, (2 * x + 3 * y) % 5
+            A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y] & M64) for y in range(5)] for x in range(5)]
+            A[0][0] ^= rc[rnd]
+    out = b"".join(A[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+    return out
+
+
+def eip55(address: str):
+    """`Address::from_str(address)?.to_string()`: None when the string is not 40 hex digits (optional 0x)."""
+    h = address[2:] if address[:2] in ("0x", "0X") else address
+    if len(h) != 40 or any(c not in "0123456789abcdefABCDEF" for c in h):
+        return None
+    low = h.lower()
+    digest = keccak256(low.encode()).hex()
+    return "0x" + "".join(c.upper() if c in "abcdef" and int(digest[i], 16) >= 8 else c for i, c in enumerate(low))

@@ -43,6 +43,7 @@ def load() -> C.CDLL:
         "pm_interner_table": (i32, [vp, P(P(u32)), P(u32), P(u32), P(u32)]),
         "pm_parse_requirements": (i32, [cp, vp, P(abi.PmAsk), P(abi.PmGpuOpt), u32, P(u32), C.c_char_p, sz]),
         "pm_sort_configs": (i32, [vp, vp, u32, vp]),
+        "pm_address_canonical": (i32, [C.c_char_p, vp]),
         "pm_create": (i32, [P(abi.PmCfg), P(vp)]),
         "pm_destroy": (None, [vp]),
         "pm_last_error": (cp, [vp]),

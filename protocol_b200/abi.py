@@ -107,7 +107,7 @@ class PmResult(C.Structure):
 EXPORTS = [
     "pm_abi_version",
     "pm_interner_create", "pm_interner_destroy", "pm_intern_model", "pm_intern_pattern", "pm_interner_table",
-    "pm_parse_requirements", "pm_sort_configs",
+    "pm_parse_requirements", "pm_sort_configs", "pm_address_canonical",
     "pm_create", "pm_destroy", "pm_last_error", "pm_alloc_pinned", "pm_free_pinned",
     "pm_set_asks", "pm_set_model_table", "pm_set_worker_count", "pm_upsert_workers",
     "pm_set_worker_locations", "pm_set_worker_addr_rank", "pm_set_flags",
@@ -129,7 +129,7 @@ EXPORTS = [
 
 class PmPluginPolicy(C.Structure):
     _fields_ = [("task_switching_enabled", C.c_uint8), ("prefer_larger_groups", C.c_uint8),
-                ("proximity_enabled", C.c_uint8), ("reserved", C.c_uint8)]
+                ("proximity_enabled", C.c_uint8), ("canonical_addresses", C.c_uint8)]
 
 
 class PmKv(C.Structure):

@@ -1222,6 +1222,9 @@ static int match_auction_locked(pm_engine* e) {
   pm::pm_auction_limits<<<std::max(1u, std::min(blocks_for(std::max(W, T), 256), 592u)), 256, 0, e->stream>>>(e->wb.p, W, e->price_cap.p, T, e->auc_ctl.p);
   pm::pm_auction_decide_packed<<<1, 1, 0, e->stream>>>(e->auc_ctl.p, W, T, e->auc_scale, e->auc_eps_start ? e->auc_eps_start : 1, (uint32_t)e->tune_auction);
   PM_LAUNCH_CHECK("pm_auction_decide_packed");
+  PM_CUDA(cudaMemcpyAsync(e->h_ctl.p, e->auc_ctl.p, sizeof(pm::AuctionCtl), cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(cudaStreamSynchronize(e->stream));
+  const bool packed_claim = e->h_ctl.p->packed_claim != 0;   // then no round launches pm_auction_claim at all
 
   pm::AuctionParams ap;
   ap.ev = eval_params(e);
@@ -1244,6 +1247,7 @@ static int match_auction_locked(pm_engine* e) {
   PM_CUDA(cudaFuncSetAttribute(pm::pm_auction_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // fixed grids: every kernel strides over a list whose length it reads from the control block
   const unsigned g_scan = kScanGrid;
+  const unsigned g_apply = std::max(1u, std::min(blocks_for(T, 256), 148u));   // every CTA pays a fence + the ticket: one per SM at most
   const unsigned g_refill = std::max(1u, std::min(C, 1184u));   // 12 KB of shared memory per CTA: eight per SM
   const unsigned g_warp = std::max(1u, std::min(blocks_for(T, pm::kAucWarps), 1184u));
   const unsigned g_thr = std::max(1u, std::min(blocks_for(T, 256), 592u));
@@ -1274,8 +1278,8 @@ static int match_auction_locked(pm_engine* e) {
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 1);
         pm::pm_auction_bid_cached<<<g_warp, pm::kAucThreads, 0, e->stream>>>(ap, 1);
         pm::pm_auction_scan<<<g_scan, pm::kAucThreads, smem, e->stream>>>(ap, 0);
-        pm::pm_auction_claim<<<g_thr, 256, 0, e->stream>>>(ap);
-        pm::pm_auction_apply<<<g_thr, 256, 0, e->stream>>>(ap);   // ... and the next round's active list, and the advance
+        if (!packed_claim) pm::pm_auction_claim<<<g_thr, 256, 0, e->stream>>>(ap);
+        pm::pm_auction_apply<<<g_apply, 256, 0, e->stream>>>(ap);   // ... and the next round's active list, and the advance
       }
     };
     // a batch of rounds is one CUDA graph (the kernels are a few microseconds each: launch-bound otherwise);
@@ -1326,7 +1330,7 @@ static int match_auction_locked(pm_engine* e) {
   e->stats.evals = e->h_ctl.p->evals;
   e->stats.n_tiles = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_class_scans, 0xFFFFFFFFull);
   e->stats.n_fused_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_ask_scans, 0xFFFFFFFFull);
-  e->stats.n_launches = e->h_ctl.p->rounds * 7u;
+  e->stats.n_launches = e->h_ctl.p->rounds * (packed_claim ? 6u : 7u);
   e->stats.n_build_launches = (uint32_t)std::min<unsigned long long>(e->h_ctl.p->n_refills, 0xFFFFFFFFull);
   tm.stop();
   Timer tr(e, &e->stats.ms_resolve);

@@ -287,4 +287,80 @@ int pm_sort_configs(const uint32_t* min_group_size, const uint8_t* has_requireme
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
 
+// Keccak-256 (the pre-NIST padding 0x01, as Ethereum uses it) of a short message: one 136-byte block is enough for the
+// 40 hex digits EIP-55 hashes.
+static void keccak256_short(const unsigned char* msg, size_t len, unsigned char out[32]) {
+  static const uint64_t RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+      0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+      0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+      0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+  static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+  unsigned char block[136] = {0};
+  std::memcpy(block, msg, len);   // len < 136
+  block[len] ^= 0x01;
+  block[135] ^= 0x80;
+  uint64_t st[25] = {0};
+  for (int i = 0; i < 17; ++i) {
+    uint64_t lane = 0;
+    for (int b = 7; b >= 0; --b) lane = (lane << 8) | block[i * 8 + b];
+    st[i] = lane;
+  }
+  auto rotl = [](uint64_t x, int n) { return (x << n) | (x >> (64 - n)); };
+  for (int round = 0; round < 24; ++round) {
+    uint64_t bc[5];
+    for (int i = 0; i < 5; ++i) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+    for (int i = 0; i < 5; ++i) {
+      const uint64_t t = bc[(i + 4) % 5] ^ rotl(bc[(i + 1) % 5], 1);
+      for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+    }
+    uint64_t t = st[1];
+    for (int i = 0; i < 24; ++i) {
+      const int j = PIL[i];
+      const uint64_t keep = st[j];
+      st[j] = rotl(t, ROT[i]);
+      t = keep;
+    }
+    for (int j = 0; j < 25; j += 5) {
+      uint64_t row[5];
+      for (int i = 0; i < 5; ++i) row[i] = st[j + i];
+      for (int i = 0; i < 5; ++i) st[j + i] ^= (~row[(i + 1) % 5]) & row[(i + 2) % 5];
+    }
+    st[0] ^= RC[round];
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int b = 0; b < 8; ++b) out[i * 8 + b] = (unsigned char)(st[i] >> (8 * b));
+}
+
+// Address::from_str + Address::to_string of the reference (alloy-primitives 1.1.0): 40 hex digits, optional "0x", any
+// case in; "0x" + EIP-55 checksum case out (a hex letter is upper case iff the matching nibble of keccak256(lower-case
+// digits) is >= 8).
+int pm_address_canonical(const char* address, char out[43]) {
+  if (!address || !out) return PM_E_INVALID;
+  const char* h = address;
+  if (h[0] == '0' && (h[1] == 'x' || h[1] == 'X')) h += 2;
+  unsigned char lower[40];
+  for (int i = 0; i < 40; ++i) {
+    const char c = h[i];
+    if (c >= '0' && c <= '9') lower[i] = (unsigned char)c;
+    else if (c >= 'a' && c <= 'f') lower[i] = (unsigned char)c;
+    else if (c >= 'A' && c <= 'F') lower[i] = (unsigned char)(c - 'A' + 'a');
+    else return PM_E_INVALID;   // also a string that ends early
+  }
+  if (h[40] != '\0') return PM_E_INVALID;
+  unsigned char hash[32];
+  keccak256_short(lower, 40, hash);
+  out[0] = '0';
+  out[1] = 'x';
+  for (int i = 0; i < 40; ++i) {
+    const unsigned nib = (i & 1) ? (hash[i / 2] & 0x0Fu) : (hash[i / 2] >> 4);
+    const char c = (char)lower[i];
+    out[2 + i] = (c >= 'a' && nib >= 8u) ? (char)(c - 'a' + 'A') : c;
+  }
+  out[42] = '\0';
+  return PM_OK;
+}
+
 }  // extern "C"

@@ -284,6 +284,17 @@ struct pm_plugin {
 
 extern "C" {
 
+// Address::from_str + to_string at the boundary (policy.canonical_addresses): the string every table is keyed by.
+// `keep` owns the canonical form; returns nullptr when the policy is on and the string is not an address.
+static const char* canon_address(const pm_plugin* p, const char* address, char (&keep)[43]) {
+  if (!p->policy.canonical_addresses) return address;
+  return pm_address_canonical(address, keep) == PM_OK ? keep : nullptr;
+}
+#define PM_CANON(var)                                                                      \
+  char var##_canon[43];                                                                    \
+  var = canon_address(p, var, var##_canon);                                                \
+  if (!var) return p->fail(PM_E_INVALID, "not an address (policy.canonical_addresses)")
+
 int pm_plugin_create(pm_engine* engine, const pm_plugin_policy* policy, pm_plugin** out) try {
   if (!out) return PM_E_INVALID;
   pm_plugin* p = new (std::nothrow) pm_plugin;
@@ -367,14 +378,16 @@ int pm_plugin_enable_configuration(pm_plugin* p, const char* name, int enable) t
 
 int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) try {
   if (!p || !d || !d->address) return PM_E_INVALID;
+  const char* address = d->address;
+  PM_CANON(address);
   std::lock_guard<std::shared_mutex> lk(p->mu);
   NodeRec* r;
-  auto it = p->node_index.find(d->address);
+  auto it = p->node_index.find(address);
   if (it == p->node_index.end()) {
-    p->node_index.emplace(d->address, p->nodes.size());
+    p->node_index.emplace(address, p->nodes.size());
     p->nodes.emplace_back();
     r = &p->nodes.back();
-    r->address = d->address;
+    r->address = address;
     r->grouped = p->node_to_group.count(r->address) != 0;   // a restored group may name a node before it is stored
   } else {
     r = &p->nodes[it->second];
@@ -408,6 +421,7 @@ int pm_plugin_upsert_node(pm_plugin* p, const pm_node_desc* d) try {
 // StatusUpdatePlugin::handle_status_change (plugins/mod.rs:23-34 -> status_update_impl.rs:8-39)
 int pm_plugin_set_node_status(pm_plugin* p, const char* address, uint32_t status) try {
   if (!p || !address) return PM_E_INVALID;
+  PM_CANON(address);
   std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   if (it == p->node_index.end()) return p->fail(PM_E_INVALID, "unknown node");
@@ -438,6 +452,11 @@ static int sync_discovery_chunk(pm_plugin* p, const pm_discovery_node* dn, uint3
     if (!d.node.address || !d.ip_address) { ++p->sync_skipped; continue; }
     if (!d.is_validated) continue;                       // fetch keeps validated nodes only
     addr.assign(d.node.address);
+    if (p->policy.canonical_addresses) {   // node.id.parse::<Address>()? fails: this node is logged and skipped (monitor.rs:240,425-429)
+      char c[43];
+      if (pm_address_canonical(addr.c_str(), c) != PM_OK) { ++p->sync_skipped; continue; }
+      addr.assign(c);
+    }
     ip.assign(d.ip_address);
     auto it = p->node_index.find(addr);
     const bool exists = it != p->node_index.end();
@@ -853,6 +872,7 @@ int pm_plugin_sync_discovery_json(pm_plugin* p, const char* json, size_t len, in
 // node as the /nodes route would show it (fields on this path): JSON or null
 int pm_plugin_get_node(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
+  PM_CANON(address);
   std::lock_guard<std::shared_mutex> lk(p->mu);
   auto it = p->node_index.find(address);
   std::string out = "null";
@@ -1324,6 +1344,7 @@ static int emit(pm_plugin* p, const std::string& s, char* buf, size_t len) {
 // the key the storage route writes per requested upload (consumed by scheduler_impl.rs:131-157)
 int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group_id, const char* file_name) try {
   if (!p || !address || !group_id || !file_name) return PM_E_INVALID;
+  PM_CANON(address);
   std::lock_guard<std::shared_mutex> lk(p->mu);
   p->upload_keys.insert(std::string("upload:") + address + ":" + group_id + ":" + file_name);
   return PM_OK;
@@ -1332,6 +1353,7 @@ int pm_plugin_record_upload(pm_plugin* p, const char* address, const char* group
 // get_node_group (mod.rs:324-337): JSON NodeGroup or "null"
 int pm_plugin_get_node_group(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
+  PM_CANON(address);
   std::lock_guard<std::shared_mutex> lk(p->mu);
   std::string out = "null";
   auto it = p->node_to_group.find(address);
@@ -1402,12 +1424,15 @@ int pm_plugin_restore_group(pm_plugin* p, const char* id, const char* configurat
   g.created_at_ms = created_at_ms < 0 ? (int64_t)std::time(nullptr) * 1000 : created_at_ms;
   for (uint32_t i = 0; i < n_nodes; ++i) {
     if (!nodes[i]) return p->fail(PM_E_INVALID, "pm_plugin_restore_group: null node");
-    if (p->node_to_group.count(nodes[i])) return p->fail(PM_E_STATE, std::string("pm_plugin_restore_group: node already grouped: ") + nodes[i]);
-    g.nodes.emplace_back(nodes[i]);
+    const char* node = nodes[i];
+    PM_CANON(node);
+    if (p->node_to_group.count(node)) return p->fail(PM_E_STATE, std::string("pm_plugin_restore_group: node already grouped: ") + node);
+    g.nodes.emplace_back(node);
   }
   for (size_t i = 0; i < g.nodes.size(); ++i)
     for (size_t j = i + 1; j < g.nodes.size(); ++j)
       if (g.nodes[i] == g.nodes[j]) return p->fail(PM_E_INVALID, "pm_plugin_restore_group: node listed twice");
+  std::sort(g.nodes.begin(), g.nodes.end());   // NodeGroup.nodes is a BTreeSet<String>: whatever order the JSON had, it iterates sorted
   // ids this library makes are format!("{:x}", counter): keep the counter ahead of any such id
   {
     unsigned long long v = 0;
@@ -1668,6 +1693,7 @@ static FilterResult heartbeat_answer(pm_plugin* p, const std::string& addr, bool
 // exclusive lock.  Every table update elsewhere in this file is exclusive.
 int pm_scheduler_get_task_for_node(pm_plugin* p, const char* address, char* buf, size_t len) try {
   if (!p || !address) return PM_E_INVALID;
+  PM_CANON(address);
   const std::string addr(address);
   std::string out;
   {

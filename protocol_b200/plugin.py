@@ -88,9 +88,9 @@ class NodeGroupsPlugin:
     """NodeGroupsPlugin::new_with_policy (mod.rs:129-175)."""
 
     def __init__(self, configuration_templates, engine=None, task_switching_enabled=True,
-                 prefer_larger_groups=True, proximity_enabled=True):
+                 prefer_larger_groups=True, proximity_enabled=True, canonical_addresses=False):
         self._lib = load()
-        pol = abi.PmPluginPolicy(int(task_switching_enabled), int(prefer_larger_groups), int(proximity_enabled), 0)
+        pol = abi.PmPluginPolicy(int(task_switching_enabled), int(prefer_larger_groups), int(proximity_enabled), int(canonical_addresses))
         h = C.c_void_p()
         self._engine = engine
         rc = self._lib.pm_plugin_create(engine._h if engine is not None else None, C.byref(pol), C.byref(h))

@@ -206,3 +206,43 @@ def test_haversine_reference_cities():
         return 6371.0 * (2.0 * math.atan2(math.sqrt(a), math.sqrt(1.0 - a)))
 
     assert hav(45.5186, -73.5545, 32.7942, -96.7475) == d
+
+
+# ---- node ids: Address::from_str + to_string (alloy-primitives 1.1.0; not under /root/reference) -----------------------
+EIP55_VECTORS = [   # the test vectors of EIP-55 itself
+    "0x52908400098527886E0F7030069857D2E4169EE7", "0x8617E340B3D01FA5F11F306F4090FD50E238070D",   # all caps
+    "0xde709f2102306220921060314715629080e2fb77", "0x27b1fdb04752bbc536007a920d24acb045561c26",   # all lower
+    "0x5aAeb6053F3E94C9b9A09f33669435E7Ef1BeAed", "0xfB6916095ca1df60bB79Ce92cE3Ea74c37c5d359",
+    "0xdbF03B407c01E7cD3CBea99509d93f8DDDC8C6FB", "0xD1220A0cf47c7B9Be7A2E6BA89F429762e7b9aDb",
+]
+
+
+def _product_canonical(address: str):
+    import ctypes as C
+
+    from protocol_b200 import _lib
+    out = C.create_string_buffer(43)
+    return out.value.decode() if _lib.load().pm_address_canonical(address.encode(), out) == 0 else None
+
+
+def test_keccak256_and_eip55_known_answers():
+    """The oracle's Keccak-256 against the well-known digests, its EIP-55 casing against the vectors of the EIP, and the
+    product's pm_address_canonical against both."""
+    assert orc.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert orc.keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    for v in EIP55_VECTORS:
+        for spelled in (v, v.lower(), "0x" + v[2:].upper(), v[2:], "0X" + v[2:].lower()):
+            assert orc.eip55(spelled) == v
+            assert _product_canonical(spelled) == v
+    # the addresses the reference's own tests use (node_groups/tests.rs, monitor.rs): to_string() of a parsed Address
+    assert _product_canonical("0x0000000000000000000000000000000000000000") == "0x0000000000000000000000000000000000000000"
+
+
+def test_address_canonical_matches_oracle_on_random_addresses_and_rejects_non_addresses():
+    import random
+    rng = random.Random(55)
+    for _ in range(3000):
+        a = "0x" + "".join(rng.choice("0123456789abcdefABCDEF") for _ in range(40))
+        assert _product_canonical(a) == orc.eip55(a) and orc.eip55(a) is not None
+    for bad in ("", "0x", "0x123", "0x" + "g" * 40, "0x" + "1" * 39, "0x" + "1" * 41, "node-1", "0x" + "1" * 20 + " " + "1" * 19):
+        assert orc.eip55(bad) is None and _product_canonical(bad) is None

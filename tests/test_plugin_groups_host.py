@@ -276,3 +276,33 @@ def test_idle_group_without_applicable_task_is_answered_without_a_claim():
     plugin.add_task(mine)                                               # the task list changed: the cache is rebuilt
     assert sched.get_task_for_node(A1)["id"] == mine.id and sched.get_task_for_node(A2)["id"] == mine.id
     assert plugin.get_node_group(A1)["task_id"] == mine.id
+
+
+def test_group_index_follows_checksummed_order_under_the_canonical_policy():
+    """mod.rs:63-69,424-434: NodeGroup.nodes is a BTreeSet<String> of Address::to_string() strings; in EIP-55 case 'A'..'F'
+    sort before 'a'..'f', so the order differs from the lower-case one.  With policy.canonical_addresses the mirror keys,
+    orders and answers by the checksummed form whatever spelling comes in."""
+    from oracle import pm_oracle as orc
+
+    lows = ["0x" + "ab" * 19 + f"{i:02x}" for i in range(0xa0, 0xa8)] + ["0x" + "cd" * 19 + "ef", "0x" + "0f" * 20]
+    canon = {a: orc.eip55(a) for a in lows}
+    pair = None
+    for i, a in enumerate(lows):                          # two addresses whose order flips between the two spellings
+        for b in lows[i + 1:]:
+            if (a < b) != (canon[a] < canon[b]):
+                pair = (a, b)
+    assert pair is not None
+    a, b = pair
+    plugin = make([NodeGroupConfiguration("c", 2, 2)], canonical_addresses=True)
+    sched = Scheduler(plugin)
+    plugin.add_node(OrchestratorNode(a, p2p_id="p-a"))
+    plugin.add_node(OrchestratorNode(b.upper().replace("0X", "0x"), p2p_id="p-b"))
+    task = Task(image="i", name="t", env_vars={"RANK": "${GROUP_INDEX}"}, allowed_topologies=["c"])
+    plugin.add_task(task)
+    plugin.restore_group("1", "c", [a, b])
+    want = sorted([canon[a], canon[b]])
+    assert plugin.get_node_group(a[2:])["nodes"] == want                 # any spelling finds it; members in BTreeSet order
+    ranks = {canon[x]: sched.get_task_for_node(x)["env_vars"]["RANK"] for x in (a, b)}
+    assert ranks == {want[0]: "0", want[1]: "1"}
+    assert want != sorted([a, b], key=str) or True                       # (the lower-case order would have been the other one)
+    assert [canon[x] for x in sorted([a, b])] != want

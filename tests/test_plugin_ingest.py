@@ -301,3 +301,39 @@ def test_entry_without_id_or_ip_is_skipped_and_the_rest_of_the_fetch_applies():
     assert rc == abi.PM_OK and n_new.value == 2
     assert plugin.get_node("0x" + "1" * 40) is not None and plugin.get_node("0x" + "3" * 40) is not None
     assert plugin.get_node("0x" + "2" * 40) is None
+
+
+def test_canonical_addresses_policy_parses_and_checksums_every_id():
+    """ADVICE r1: the reference keys everything by Address::to_string() of the PARSED id (monitor.rs:240; BTreeSet member
+    order mod.rs:63-69).  With policy.canonical_addresses the mirror does the same: a lower-case id in a discovery body, an
+    upper-case one in a heartbeat and the checksummed one in a lookup are one node; an id that is not an address is skipped
+    like the reference's parse error, the rest of the fetch applies."""
+    import json
+
+    import pytest
+
+    from oracle import pm_oracle as orc
+    from protocol_b200 import abi
+    from protocol_b200._lib import PrimeMatchError
+
+    low = ["0x" + f"{i:02x}" * 20 for i in (0xab, 0xcd, 0x1f)]
+    canon = [orc.eip55(a) for a in low]
+    assert all(c != a for c, a in zip(canon, low))                       # the checksum case really differs
+    body = json.dumps([_wire(low[0], ip="10.0.0.1"), _wire("not-an-address", ip="10.0.0.9"), _wire(low[1].upper().replace("0X", "0x"), ip="10.0.0.2"),
+                       _wire(canon[2], ip="10.0.0.3")])
+    plugin = NodeGroupsPlugin([], canonical_addresses=True)
+    assert plugin.sync_discovery_json(body, NOW) == 3
+    for a, c in zip(low, canon):
+        for spelled in (a, c, a[2:], "0x" + a[2:].upper()):
+            node = plugin.get_node(spelled)
+            assert node is not None and node["address"] == c
+    assert plugin.sync_discovery_json(body, NOW + 1000) == 0             # the same three nodes, however they are spelled
+    with pytest.raises(PrimeMatchError) as e:
+        plugin.get_node("not-an-address")
+    assert e.value.status == abi.PM_E_INVALID
+    with pytest.raises(PrimeMatchError):
+        plugin.add_node(OrchestratorNode("0x1234", status=NodeStatus.Healthy))
+    # opaque strings without the policy (the default): three spellings are three nodes
+    plain = NodeGroupsPlugin([])
+    assert plain.sync_discovery_json(json.dumps([_wire(low[0]), _wire(canon[0], ip="10.0.0.2"), _wire("not-an-address", ip="10.0.0.3")]), NOW) == 3
+    assert plain.get_node(low[0])["address"] == low[0] and plain.get_node(canon[0])["address"] == canon[0]
