@@ -2,8 +2,9 @@
 checker (orc_soa_auction: every unassigned ask scans every worker every round): ask classes sharing one 32-entry cache
 and bound, the price cap folded into the outside option, the pool of candidates kept from the last table walk and
 re-ranked before any new walk, walks over a cost-sorted worker order (re-sorted every few rounds) that stop once enough
-kept candidates beat the composite bound on the unseen part, and the per-ask scan when a value ties exactly with the
-outside option.  Same assignments and the same number of rounds, on tie-heavy inputs.  This guards the ALGORITHM (the
+kept candidates beat the composite bound on the unseen part, walks that start at the class's cost level (skip keys:
+compatibility is static and sort keys only rise), and the per-ask scan when a value ties exactly with the outside
+option.  Same assignments and the same number of rounds, on tie-heavy inputs.  This guards the ALGORITHM (the
 exactness argument of DESIGN.md 4); the GPU tests guard the kernels."""
 import numpy as np
 import pytest
@@ -55,7 +56,8 @@ def auction_class_algorithm(t, cap, S=1, eps=1, K=32, stripe=1024, lanes=256, re
     theta = [(INVALID, NONE)] * C                             # ... and the bound on everything outside it
     pool = [None] * C                                         # what the lanes held after the class's last walk ...
     pool_bound = [(INVALID, NONE)] * C                        # ... and the bound on everything outside the pool
-    count = dict(full=0, refill=0, fb=0)
+    skip_key = [0] * C                                        # every compatible worker of the class has a sort key >= this
+    count = dict(full=0, refill=0, fb=0, skipped=0)
 
     def value(w):
         return int(-(ap[w] * S) - price[w])
@@ -90,12 +92,18 @@ def auction_class_algorithm(t, cap, S=1, eps=1, K=32, stripe=1024, lanes=256, re
         dropped = [(NEG, NONE)] * lanes
         unseen, first_good = None, None
         n_stripes = (W + stripe - 1) // stripe
-        for k in range(n_stripes):
+        # skip keys: the first stripe whose last key reaches the class's key (stripes before it hold nobody compatible)
+        j0 = next((j for j in range(n_stripes) if order["key"][min((j + 1) * stripe, W) - 1] >= skip_key[c]), n_stripes)
+        count["skipped"] += j0
+        first_hit = None
+        for k in range(j0, n_stripes):
             n = min(stripe, W - k * stripe)
             for i in range(n):
                 w = order["perm"][k * stripe + i]
                 if not compat[c, w]:
                     continue
+                if first_hit is None:
+                    first_hit = k
                 lane = i % lanes
                 lists[lane].append((value(w), int(w)))
                 lists[lane].sort(key=lambda e: (-e[0], e[1]))
@@ -110,6 +118,8 @@ def auction_class_algorithm(t, cap, S=1, eps=1, K=32, stripe=1024, lanes=256, re
                 if k + 1 < n_stripes:
                     unseen = (u, last + 1)
                 break
+        # nobody compatible before stripe first_hit (none at all if the walk ran to the end without meeting one); keys only rise
+        skip_key[c] = max(skip_key[c], int(order["key"][first_hit * stripe]) if first_hit is not None else (1 << 62))
         pool[c] = [[e[1] for e in lane] for lane in lists]
         best_dropped = (NEG, NONE)
         for d in dropped:
@@ -225,3 +235,110 @@ def test_class_cache_auction_equals_the_sequential_checker(n_base, copies, n_wor
     got, r, st = auction_class_algorithm(t, cap, stripe=stripe, lanes=lanes, resort_every=7)
     assert np.array_equal(got, want) and r == rounds
     assert st["full"] >= 1 and st["refill"] >= 1          # both refresh paths ran
+
+
+def test_skip_keys_leave_out_the_cheap_end_of_the_table():
+    """Prices that grow with the GPU count: the classes that want many GPUs have all their compatible workers deep in the
+    cost order, and every walk of theirs after the first starts there.  Same assignment and rounds as the checker."""
+    t, cap = _tables(20, 12, 2500, 10, 40, 16)
+    rng = np.random.default_rng(16)
+    wb = t["wb"].copy()
+    wb["ext_ask_price"] = (10 + 12 * np.log2(np.maximum(t["wa"]["gpu_count"], 1)) + rng.integers(0, 4, len(wb))).astype(np.uint32)
+    t["wb"] = wb
+    cap = rng.integers(8, 60, len(cap)).astype(np.uint32)
+    want, price, rounds = orc.soa_auction(t["wa"], t["wb"], t["asks"], t["opts"], t["bits"], t["words"], cap)
+    got, r, st = auction_class_algorithm(t, cap, K=4, stripe=32, lanes=2, resort_every=7)   # a tiny cache and pool: many walks
+    assert np.array_equal(got, want) and r == rounds
+    assert st["full"] > 2 * 20 and st["skipped"] > 5 * st["full"]   # classes walk again and again, and start deep in the table
+
+
+# ---- the two device formulations the selection and the skip rest on, restated and checked exhaustively enough on the CPU
+def _better(a, b):
+    return a[0] > b[0] or (a[0] == b[0] and a[1] < b[1])
+
+
+def best64_network(arr):
+    """auction_select_cta: 1024 entries, sorted runs of 4 (odd threads reversed) -> blocks of 64 sorted by the bitonic
+    network (even blocks descending, odd ascending) -> 8 + 4 + 2 + 1 merges that keep the entry-wise better half of a
+    descending and an ascending block and re-sort it (descending / ascending by turns).  Returns the first 64 entries."""
+    arr = list(arr)
+    k = 8
+    while k <= 64:
+        j = k >> 1
+        while j:
+            new = list(arr)
+            for idx in range(512):
+                i = 2 * idx - (idx & (j - 1))
+                a, b = arr[i], arr[i + j]
+                if (_better(b, a) if (i & k) == 0 else _better(a, b)):
+                    new[i], new[i + j] = b, a
+            arr, j = new, j >> 1
+        k <<= 1
+    S, P = 64, 8
+    while P:
+        new = list(arr)
+        for q in range(P):
+            A, B = q * 2 * S, q * 2 * S + S
+            for i in range(64):
+                if _better(arr[B + i], arr[A + i]):
+                    new[A + i] = arr[B + i]
+        arr, j = new, 32
+        while j:
+            new = list(arr)
+            for q in range(P):
+                A = q * 2 * S
+                for lane in range(32):
+                    i = A + 2 * lane - (lane & (j - 1))
+                    a, b = arr[i], arr[i + j]
+                    if (_better(b, a) if q % 2 == 0 else _better(a, b)):
+                        new[i], new[i + j] = b, a
+            arr, j = new, j >> 1
+        S, P = S * 2, P // 2
+    return arr[:64]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_selection_network_keeps_exactly_the_best_64(seed):
+    import random
+    rng = random.Random(seed)
+    arr = [None] * 1024
+    fill = [0, 1, 2, 3, 4, 4, 4] if seed % 3 else [0, 0, 0, 1]          # dense pools and nearly empty ones
+    workers = rng.sample(range(1 << 20), 1024)
+    for tid in range(256):
+        items = sorted(((rng.randint(-6, 0) if seed % 2 else -rng.randint(0, 1 << 30), workers[tid * 4 + q])
+                        for q in range(rng.choice(fill))), key=lambda e: (-e[0], e[1]))
+        items += [(NEG, NONE)] * (4 - len(items))
+        for q in range(4):
+            arr[tid * 4 + (3 - q if tid & 1 else q)] = items[q]
+    assert best64_network(arr) == sorted(arr, key=lambda e: (-e[0], e[1]))[:64]
+    # the packed form: one 64-bit key per entry, ascending = (value desc, worker asc); an empty slot is all ones
+    pack = lambda e: (1 << 64) - 1 if e[1] == NONE else ((-e[0]) << 24) | e[1]
+    assert sorted(arr, key=pack)[:64] == sorted(arr, key=lambda e: (-e[0], e[1]))[:64]
+
+
+def test_start_stripe_search_is_a_lower_bound_search():
+    """The 32-ary search one warp runs over the stripe ends: first stripe whose last key is >= the class's skip key."""
+    import bisect
+    import random
+
+    def search(ends, key):
+        lo, hi = 0, len(ends)
+        while lo < hi:
+            step = (hi - lo + 31) // 32
+            ge = [True if lo + lane * step >= hi else ends[lo + lane * step] >= key for lane in range(32)]
+            f = ge.index(True) if True in ge else 32
+            if f == 0:
+                hi = lo
+                break
+            nlo = lo + (f - 1) * step + 1
+            if f < 32 and lo + f * step < hi:
+                hi = lo + f * step
+            lo = nlo
+        return min(lo, hi)
+
+    rng = random.Random(3)
+    for _ in range(4000):
+        n = rng.choice([1, 2, 31, 32, 33, 64, 100, 977, 1024, 1025, 4000])
+        ends = sorted(rng.randint(0, 60) for _ in range(n))
+        key = rng.randint(-1, 62)
+        assert search(ends, key) == bisect.bisect_left(ends, key)
