@@ -50,13 +50,20 @@
 //    its top 32 and one bound, and the part that arrives last (a ticket) merges them.
 //  * DEVICE-DRIVEN ROUNDS.  List lengths live in device memory; every kernel of a round is
 //    launched with a fixed grid and strides over its list, so the host launches rounds in batches
-//    and only polls the number of unassigned asks.
+//    (32 rounds = one CUDA graph) and only polls the number of unassigned asks.  A round is 6 launches:
+//    bid from the caches, pool re-rank, class walks, bid again, per-ask scans, apply (which also
+//    writes the next round's active list and advances the round).
+//  * FEWER INSTRUCTIONS.  The kernels of a round are issue-bound, not memory-bound (ncu: kernel time =
+//    wall time, time follows the warp-instruction count): the selection of the top 32 is a bitonic
+//    network in shared memory that keeps the best 64 only, on ONE packed 64-bit key per candidate when
+//    every reachable cost fits 40 bits (auction_select_cta); the claim is the atomicMax itself when bid
+//    and bidder fit one word (auction_commit).
 //
 // pm_auction_scan: stripes of the sorted worker planes, their prices and original indices are
 // staged into shared memory with 1-D TMA bulk copies, double-buffered; one item per CTA (its 8 warps split
 // each stripe), items drawn from a counter because their lengths differ by two orders of magnitude.
-// Collisions are resolved by atomicMax on the bid and atomicMin on the bidder (the claim),
-// applied by the single winner of each worker.
+// Collisions are resolved by atomicMax on (bid, bidder) packed in one word — or, when they do not fit, by atomicMax on
+// the bid and atomicMin on the bidder (pm_auction_claim) — applied by the single winner of each worker.
 #pragma once
 #include "pm_kernels.cuh"
 
