@@ -142,12 +142,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_tables(workload: str, n_gpus: int):
+def make_tables(workload: str, n_gpus: int, n_models: int = 0):
     from protocol_b200 import synth
 
     T, Wg, kind, desc = WORKLOADS[workload]
     W = Wg * n_gpus
-    w = synth.make_workers(W, price=PRICES.get(workload))
+    # --models N: a permissionless pool's free-form model strings (node.rs:463-484) instead of the 16-entry catalogue;
+    # more than 31 distinct ones puts a per-worker acceptance word in shared memory (BITS=1), more than the shared-memory
+    # table holds leaves it in global memory (BITS=0)
+    cat = synth.wide_model_catalogue(n_models) if n_models else None
+    w = synth.make_workers(W, price=PRICES.get(workload), catalogue=cat)
     a = synth.make_asks(T, kind)
     bits, npat, nmod, words = synth.intern_tables(w, a)
     return w, a, (bits, npat, nmod, words), (T, W, Wg, desc)
@@ -155,7 +159,8 @@ def make_tables(workload: str, n_gpus: int):
 
 def config_dict(args, desc, T, W, Wg, world):
     """The workload, identical in both arms (the driver compares them); arm-specific detail goes under `detail`."""
-    return {"workload": f"{args.workload}: {desc}", "n_asks": T, "n_workers": W, "workers_per_gpu": Wg,
+    return {"workload": f"{args.workload}: {desc}" + (f", {args.models} distinct worker model strings" if args.models else ""),
+            "n_asks": T, "n_workers": W, "workers_per_gpu": Wg,
             "mode": "first_fit (try_form_new_groups)", "cost_tile_gib": args.tile_gib,
             "l2": "inputs larger than L2: each step streams the int64 cost matrix "
                   f"({T * Wg * 8 / 1e9:.0f} GB per GPU) through HBM in {args.tile_gib} GiB tiles",
@@ -174,7 +179,7 @@ def run_reference(args):
         return
     from oracle import pm_oracle as orc
 
-    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, max(args.gpus, 1))
+    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, max(args.gpus, 1), args.models)
     cpus = host_cpus()
     cores = cpus["threads"]
     # bounded sample: a band of asks against every worker, ~2e9 pair evaluations per step at most
@@ -277,7 +282,7 @@ def run_ours(args):
         dist.broadcast_object_list(box, src=0)
         comm = Comm(box[0], world, rank, local_rank)
 
-    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, world)
+    w, a, (bits, npat, nmod, words), (T, W, Wg, desc) = make_tables(args.workload, world, args.models)
     mode = abi.PM_MODE_FIRST_FIT | {"materialized": abi.PM_PATH_MATERIALIZED, "fused": abi.PM_PATH_FUSED,
                                     "fused-lean": abi.PM_PATH_FUSED | abi.PM_NO_ASK_STATS}[args.path]
 
@@ -509,6 +514,8 @@ def main():
                     help="default: cfg3 (BASELINE configs[2]) on one GPU, cfg5's per-GPU shape on several")
     ap.add_argument("--path", default="materialized", choices=["materialized", "fused", "fused-lean"])
     ap.add_argument("--tile-gib", dest="tile_gib", type=int, default=8)
+    ap.add_argument("--models", type=int, default=0,
+                    help="distinct worker model strings (0: the 16-entry catalogue; > 31 selects the wide-catalogue kernel variants)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the fused_lean / auction sub-records")
     args = ap.parse_args()
