@@ -158,6 +158,9 @@ struct pm_engine {
   DevBuf<pm::DevOptF> opts_fast;
   DevBuf<pm::FastRow> frows;
   bool rows_bound = false;     // FastRow.wp matches the current model table (pm_bind_rows)
+  bool rows_bound_wm = false;  // ... bound to the worker-major one-word table
+  DevBuf<uint32_t> nacc, bits_wm;   // worker-major acceptance (pm_worker_nacc) and its one-word table ~(1 << row)
+  bool nacc_valid = false;
   DevBuf<pm_ask> raw_asks;
   DevBuf<pm_gpu_opt> raw_opts;
   DevBuf<uint32_t> ask_counts, ask_newoff;
@@ -319,6 +322,7 @@ pm::EvalParams eval_params(pm_engine* e) {
   p.opts_fast = e->opts_fast.p;
   p.frows = e->frows.p;
   p.bits = e->bits.p;
+  p.nacc = nullptr;
   p.words = e->words;
   p.n_workers = e->n_workers;
   p.n_asks = e->n_asks;
@@ -419,6 +423,7 @@ void pm_destroy(pm_engine* e) {
   e->prox_lat_key.release(); e->prox_lat_ord.release(); e->prox_rank_of.release();
   e->pg_part_d.release(); e->pg_part_i.release(); e->pg_cta_cnt.release(); e->pg_ctl.release();
   e->pg_clat.release(); e->pg_clon.release(); e->pg_ccos.release();
+  e->nacc.release(); e->bits_wm.release();
   e->reputation.release(); e->ask_min_rep.release(); e->auc_rep_s.release(); e->auc_split_first.release(); e->auc_skip_key.release();
   e->price_cap.release(); e->auc_owner.release(); e->auc_assigned.release(); e->auc_withdrawn.release();
   e->auc_active.release(); e->auc_bid_w.release(); e->auc_winner.release(); e->auc_flag.release(); e->auc_gidx.release();
@@ -540,6 +545,7 @@ int pm_set_model_table(pm_engine* e, const uint32_t* bits, uint32_t n_patterns, 
   e->words = words;
   e->have_bits = true;
   e->rows_bound = false;
+  e->nacc_valid = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -558,6 +564,7 @@ int pm_set_worker_count(pm_engine* e, uint32_t n_workers) try {
   PM_CUDA(cudaMemsetAsync(e->wb.p, 0, (size_t)std::max<uint32_t>(n_workers, 1) * 16, e->stream));
   e->n_workers = n_workers;
   e->workers_checked = false;
+  e->nacc_valid = false;
   e->have_workers = true;
   e->have_loc = e->have_rank = false;
   e->have_rep = false;
@@ -579,6 +586,7 @@ int pm_upsert_workers(pm_engine* e, const pm_worker_a* a, const pm_worker_b* b, 
     PM_CUDA(cudaMemcpyAsync(e->wb.p + first, b, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
   }
   e->workers_checked = false;
+  e->nacc_valid = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -629,6 +637,7 @@ int pm_set_flags(pm_engine* e, const uint32_t* idx, const uint32_t* flags, uint3
   pm::pm_scatter_flags<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->wa.p, e->scratch_idx.p, e->scratch_flags.p, n, e->n_workers);
   PM_LAUNCH_CHECK("pm_scatter_flags");
   e->workers_checked = false;
+  e->nacc_valid = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -661,6 +670,7 @@ int pm_resize_workers(pm_engine* e, uint32_t n_workers) try {
   e->n_workers = n_workers;
   e->have_workers = true;
   e->workers_checked = false;
+  e->nacc_valid = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -694,6 +704,7 @@ int pm_update_workers(pm_engine* e, const uint32_t* idx, const pm_worker_a* a, c
                                                                  e->n_workers);
   PM_LAUNCH_CHECK("pm_scatter_rows");
   e->workers_checked = false;
+  e->nacc_valid = false;
   e->matched = e->local_done = false;
   return PM_OK;
 } catch (...) { return pm_guard_rc(); }
@@ -731,13 +742,40 @@ static int decide_fast(pm_engine* e, bool* fast) {
 }
 
 // FastRow.wp follows the model table: (re)bound after either table changed
-static int bind_rows(pm_engine* e) {
-  if (e->rows_bound) return PM_OK;
+static int bind_rows(pm_engine* e, bool wm) {
+  if (e->rows_bound && e->rows_bound_wm == wm) return PM_OK;
   if (e->n_asks) {
-    pm::pm_bind_rows<<<blocks_for(e->n_asks, 256), 256, 0, e->stream>>>(e->frows.p, e->opts_fast.p, e->bits.p, e->words, e->n_asks);
+    pm::pm_bind_rows<<<blocks_for(e->n_asks, 256), 256, 0, e->stream>>>(e->frows.p, e->opts_fast.p, wm ? e->bits_wm.p : e->bits.p,
+                                                                        wm ? 1u : e->words, e->n_asks);
     PM_LAUNCH_CHECK("pm_bind_rows");
   }
   e->rows_bound = true;
+  e->rows_bound_wm = wm;
+  return PM_OK;
+}
+
+// More distinct model strings than the shared-memory acceptance table holds (BITS == 0: one global-memory lookup per
+// (row, worker) pair, build kernel at 0.64 of the copy peak with 100k strings): turn the table around.  With at most 30
+// patterns a worker's acceptance over ALL of them is one word, computed once per table change; the kernels then run
+// their one-word form (BITS == 2) with the roles of row and worker swapped (EvalParams::nacc).  Fast predicate only.
+static int worker_major(pm_engine* e, pm::EvalParams* p, int* bits_mode) {
+  if (!e->nacc_valid) {
+    PM_CUDA(e->nacc.ensure(std::max<uint32_t>(e->n_workers, 1)));
+    PM_CUDA(e->bits_wm.ensure(32));
+    uint32_t host[32];
+    for (uint32_t r = 0; r < 32; ++r) host[r] = ~(1u << r);
+    PM_CUDA(cudaMemcpyAsync(e->bits_wm.p, host, sizeof host, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(cudaStreamSynchronize(e->stream));   // `host` is a local
+    if (e->n_workers) {
+      pm::pm_worker_nacc<<<blocks_for(e->n_workers, 256), 256, 0, e->stream>>>(e->wa.p, e->bits.p, e->words, p->n_bits_rows, e->n_workers, e->nacc.p);
+      PM_LAUNCH_CHECK("pm_worker_nacc");
+    }
+    e->nacc_valid = true;
+  }
+  p->bits = e->bits_wm.p;
+  p->words = 1;
+  p->nacc = e->nacc.p;
+  *bits_mode = 2;
   return PM_OK;
 }
 
@@ -847,10 +885,15 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
 
   if (T && nw) {
     pm::EvalParams p = eval_params(e);
-    const int bits_mode = ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0;
+    int bits_mode = ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0;
     bool fast = false;
     {
       int rc = decide_fast(e, &fast);
+      if (rc != PM_OK) return rc;
+    }
+    const bool wm = fast && bits_mode == 0 && p.n_bits_rows <= 31u && e->tune_build != 7;   // PM_TUNE_BUILD=7: keep the global-memory table
+    if (wm) {
+      const int rc = worker_major(e, &p, &bits_mode);
       if (rc != PM_OK) return rc;
     }
     if (mode & PM_PATH_FUSED) {
@@ -870,7 +913,7 @@ static int match_local_locked(pm_engine* e, uint32_t mode) {
       // the columns past the shard hold "infeasible" and cost 0.05 % of a 1M-worker row
       const size_t ld = (((size_t)nw + pm::kEvalCols - 1) / pm::kEvalCols) * pm::kEvalCols;
       {
-        const int rc = bind_rows(e);
+        const int rc = bind_rows(e, wm);
         if (rc != PM_OK) return rc;
       }
       uint64_t rows = e->cfg.cost_tile_bytes / (ld * 8);
@@ -1594,13 +1637,19 @@ int pm_build_cost_tile(pm_engine* e, uint32_t t0, uint32_t nt, int64_t* host_out
   pm::EvalParams p = eval_params(e);
   dim3 grid(blocks_for(ld, pm::kEvalCols), blocks_for(nt, pm::kEvalRows));
   bool fast = false;
+  int bits_mode = ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0;
   {
     int rc = decide_fast(e, &fast);
     if (rc != PM_OK) return rc;
-    rc = bind_rows(e);
+    const bool wm = fast && bits_mode == 0 && p.n_bits_rows <= 31u && e->tune_build != 7;   // as pm_match
+    if (wm) {
+      rc = worker_major(e, &p, &bits_mode);
+      if (rc != PM_OK) return rc;
+    }
+    rc = bind_rows(e, wm);
     if (rc != PM_OK) return rc;
   }
-  launch_build(e, p, ((uint64_t)p.n_bits_rows * p.words <= (uint64_t)pm::kBitsCap) ? (p.words == 1 ? 2 : 1) : 0, fast, grid, t0, nt, w0, nw, ld);
+  launch_build(e, p, bits_mode, fast, grid, t0, nt, w0, nw, ld);
   PM_LAUNCH_CHECK("pm_build_cost");
   PM_CUDA(cudaMemcpy2DAsync(host_out, (size_t)nw * 8, e->cost.p, ld * 8, (size_t)nw * 8, nt,
                             cudaMemcpyDeviceToHost, e->stream));

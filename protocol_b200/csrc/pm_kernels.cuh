@@ -23,6 +23,11 @@ struct EvalParams {
   const DevOptF* __restrict__ opts_fast;  // same CSR, fast-path form
   const FastRow* __restrict__ frows;      // [n_asks] fast build kernel's view of an ask (first option inline)
   const uint32_t* __restrict__ bits;  // [(n_patterns+1) * words], row 0 all-ones
+  const uint32_t* __restrict__ nacc;  // worker-major acceptance (pm_worker_nacc), or null: per worker the mask of the pattern
+                                      // rows that REJECT its model.  Then `bits` is the one-word table word[r] = ~(1 << r) and a
+                                      // worker's mmask is nacc[w]: the fast clause ~word & mmask = (1 << r) & nacc[w] is the same
+                                      // test with the roles of row and worker swapped — no table lookup per (row, worker) pair,
+                                      // however many distinct model strings the pool has (at most 30 patterns)
   uint32_t words;
   uint32_t n_workers;                 // global
   uint32_t n_asks;
@@ -178,8 +183,10 @@ __device__ __forceinline__ void load_workers(const EvalParams& p, uint32_t w0, u
 #pragma unroll
   for (int k = 0; k < WPT; ++k) {
     const uint32_t col = c + k;
-    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
-    else w[k] = null_worker();
+    if (col < nw) {
+      w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+      if (p.nacc) w[k].mmask = __ldg(p.nacc + w0 + col);
+    } else w[k] = null_worker();
   }
 }
 
@@ -254,8 +261,10 @@ pm_build_cost(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t nw,
   for (int k = 0; k < kEvalWPT; ++k) {
     const uint32_t col = cbase + (k >> 1) * 64u + (k & 1);
     gw[k] = w0 + col;
-    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
-    else w[k] = null_worker();
+    if (col < nw) {
+      w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+      if (p.nacc) w[k].mmask = __ldg(p.nacc + w0 + col);
+    } else w[k] = null_worker();
     dx[k] = 0xFFFFFFFFu - gw[k];          // infeasible: 0x7FFFFFFF_FFFFFFFF = feasible word + (0/1) * difference
     dy[k] = 0x7FFFFFFFu - w[k].price;
   }
@@ -362,8 +371,10 @@ pm_build_cost_fast(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t
   for (int k = 0; k < kEvalWPT; ++k) {
     const uint32_t col = cbase + (k >> 1) * 64u + (k & 1);
     gw[k] = w0 + col;
-    if (col < nw) w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
-    else w[k] = null_worker();
+    if (col < nw) {
+      w[k] = make_worker(__ldg(p.wa + w0 + col), __ldg(p.wb + w0 + col));
+      if (p.nacc) w[k].mmask = __ldg(p.nacc + w0 + col);
+    } else w[k] = null_worker();
     dx[k] = 0xFFFFFFFFu - gw[k];          // infeasible: 0x7FFFFFFF_FFFFFFFF = feasible word + (0/1) * difference
     dy[k] = 0x7FFFFFFFu - w[k].price;
   }
@@ -398,6 +409,20 @@ pm_build_cost_fast(EvalParams p, uint32_t t0, uint32_t nt, uint32_t w0, uint32_t
     out += row_stride;
     cur = nxt;
   }
+}
+
+// Worker-major acceptance: bit r of nacc[w] is set when pattern row r rejects worker w's model (row 0 never does).
+__global__ void pm_worker_nacc(const uint4* __restrict__ wa, const uint32_t* __restrict__ bits, uint32_t words, uint32_t n_rows,
+                               uint32_t n, uint32_t* __restrict__ nacc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 a = wa[i];
+  const uint32_t mid = (a.w & PM_W_HAS_GPU_MODEL) ? a.z : 0u;
+  const uint32_t mword = mid / kModelsPerWord, mmask = 1u << (mid % kModelsPerWord);
+  uint32_t rej = 0;
+  for (uint32_t r = 1; r < n_rows; ++r)
+    if (!(__ldg(bits + (size_t)r * words + mword) & mmask)) rej |= 1u << r;
+  nacc[i] = rej;
 }
 
 // `wp` of every FastRow: the first option's acceptance WORD when rows are one word wide, else its pattern row.

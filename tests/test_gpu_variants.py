@@ -111,6 +111,17 @@ def test_100k_models():
     run_all_paths(*t, expect_bits=0)
 
 
+@pytest.mark.parametrize("n_models,n_patterns", [(100_000, 24), (3000, 30), (3000, 31), (70_000, 12)])
+def test_wide_catalogue_few_patterns_worker_major_acceptance(n_models, n_patterns):
+    """More model strings than the shared-memory table holds, at most 30 patterns: the fast kernels turn the acceptance
+    table around (one word per WORKER over all patterns, pm_worker_nacc; EvalParams::nacc) instead of one global-memory
+    lookup per (row, worker) pair.  30 patterns is the last size that fits (31 rows with row 0), 31 falls back to the
+    global-memory table; the generic predicate always uses the table as it is.  Same groups, per-ask minima and cost rows
+    as the oracle on every path."""
+    t = wide_tables(500, 9000, n_models=n_models, n_patterns=n_patterns, seed_shift=11 + n_patterns, last_rows=True)
+    run_all_paths(*t, expect_bits=0)
+
+
 def test_few_models_many_patterns_still_uniform_word():
     """<= 32 models but many patterns: one warp-uniform word per row (BITS = 2), rows near the end of the table."""
     t = wide_tables(400, 5000, n_models=30, n_patterns=900, seed_shift=4, last_rows=True)
