@@ -337,3 +337,41 @@ def test_canonical_addresses_policy_parses_and_checksums_every_id():
     plain = NodeGroupsPlugin([])
     assert plain.sync_discovery_json(json.dumps([_wire(low[0]), _wire(canon[0], ip="10.0.0.2"), _wire("not-an-address", ip="10.0.0.3")]), NOW) == 3
     assert plain.get_node(low[0])["address"] == low[0] and plain.get_node(canon[0])["address"] == canon[0]
+
+
+def test_canonical_policy_is_the_opaque_mirror_fed_with_checksummed_ids():
+    """Differential property: a mirror with policy.canonical_addresses fed ids in random spellings (lower, upper, mixed, with
+    and without 0x) ends in the same node table as an opaque mirror fed Address::to_string() of the same ids — what the
+    Rust shim would pass — over several fetches through both ingest entry points."""
+    import json
+    import random
+
+    from oracle import pm_oracle as orc
+
+    rng = random.Random(7)
+    lows = ["0x" + "".join(rng.choice("0123456789abcdef") for _ in range(40)) for _ in range(10)]
+
+    def respell(a):
+        h = "".join(c.upper() if rng.random() < 0.5 else c for c in a[2:])
+        return rng.choice(["0x", "0X", ""]) + h
+
+    opaque, canon = NodeGroupsPlugin([]), NodeGroupsPlugin([], canonical_addresses=True)
+    for r in range(6):
+        picked = rng.sample(lows, rng.randint(1, len(lows)))
+        mk = lambda node_id, i: DiscoveryNode(node_id, f"10.0.{i}.1", 8000 + i, SPECS, is_validated=True, is_provider_whitelisted=rng.random() < 0.8,
+                                              is_active=rng.random() < 0.7)
+        state = rng.getstate()
+        a_nodes = [mk(orc.eip55(a), lows.index(a)) for a in picked]
+        rng.setstate(state)                                   # the same whitelisted / active draws for both mirrors
+        b_nodes = [mk("placeholder", lows.index(a)) for a in picked]
+        for n, a in zip(b_nodes, picked):
+            n.id = respell(a)
+        now = NOW + r * 400_000
+        if r % 2:
+            assert opaque.sync_discovery(a_nodes, now) == canon.sync_discovery(b_nodes, now)
+        else:
+            wire = lambda n: _wire(n.id, ip=n.ip_address, port=n.port, is_provider_whitelisted=n.is_provider_whitelisted, is_active=n.is_active)
+            assert (opaque.sync_discovery_json(json.dumps([wire(n) for n in a_nodes]), now)
+                    == canon.sync_discovery_json(json.dumps([wire(n) for n in b_nodes]), now))
+        for a in lows:
+            assert opaque.get_node(orc.eip55(a)) == canon.get_node(respell(a))
