@@ -66,7 +66,8 @@ enum pm_worker_flag {
 typedef struct pm_worker_a {   /* plane A, 16 B */
   uint32_t gpu_count;          /* GpuSpecs.count      */
   uint32_t gpu_mem_mb;         /* GpuSpecs.memory_mb  */
-  uint32_t model_id;           /* interned GpuSpecs.model (pm_intern_model)  */
+  uint32_t model_id;           /* interned GpuSpecs.model (pm_intern_model); must be < n_models of the model table in */
+                               /* force when PM_W_HAS_GPU_MODEL is set (a precondition: the kernels index the table by it) */
   uint32_t flags;              /* pm_worker_flag bits */
 } pm_worker_a;
 
