@@ -342,3 +342,19 @@ def test_start_stripe_search_is_a_lower_bound_search():
         ends = sorted(rng.randint(0, 60) for _ in range(n))
         key = rng.randint(-1, 62)
         assert search(ends, key) == bisect.bisect_left(ends, key)
+
+
+def test_packed_claim_orders_by_bid_then_lowest_ask():
+    """auction_commit: bid and bidder in one signed 64-bit word, (bid << 23) | (2^23 - 1 - ask): the maximum is the highest bid
+    and, among equal bids, the lowest ask — what atomicMax on the bid followed by atomicMin on the bidder gives; stays
+    positive (the 'no bid' value is negative) for bids below 2^40 and asks below 2^23."""
+    import random
+    rng = random.Random(23)
+    mask = (1 << 23) - 1
+    for _ in range(2000):
+        bids = [(rng.choice([1, 2, 3, rng.randrange(1, 1 << 40), (1 << 40) - 1]), rng.randrange(0, 1 << 23)) for _ in range(rng.randint(1, 12))]
+        keys = [(b << 23) | (mask - t) for b, t in bids]
+        assert all(0 < k < (1 << 63) for k in keys)
+        best = max(keys)
+        want = min((t for b, t in bids if b == max(b for b, _ in bids)))
+        assert best >> 23 == max(b for b, _ in bids) and mask - (best & mask) == want
